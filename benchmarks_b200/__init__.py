@@ -1,0 +1,12 @@
+"""benchmarks_b200 -- B200-native matrix-free high-order FE operator path.
+
+Python host-side mirror of the reference's operator interface over the C ABI in
+include/b200fe.h (libb200fe.so, hand-written sm_100a CUDA).  PyTorch is used only for device
+memory, streams and torch.distributed plumbing.  There is no CPU fallback: importing the
+package without the built library raises, and every compute call needs a CUDA device.
+"""
+from ._lib import lib, LIB_PATH, B200feError, check  # noqa: F401
+from .bk import bk1_apply, bk3_apply, bk5_apply, sum_squares, bk_launch_info  # noqa: F401
+
+__all__ = ["lib", "LIB_PATH", "B200feError", "check", "bk1_apply", "bk3_apply", "bk5_apply",
+           "sum_squares", "bk_launch_info"]

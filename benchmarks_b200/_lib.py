@@ -1,0 +1,45 @@
+"""ctypes binding of libb200fe.so (the C ABI of include/b200fe.h)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200fe.so")
+
+
+class B200feError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"b200fe error {code}: {msg}")
+        self.code = code
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "(or `make -C benchmarks_b200/csrc`).  b200fe has no CPU fallback.")
+
+lib = C.CDLL(LIB_PATH)
+
+_vp, _i, _u32, _u64 = C.c_void_p, C.c_int, C.c_uint32, C.c_uint64
+_pi = C.POINTER(C.c_int)
+_pd = C.POINTER(C.c_double)
+
+_SIGNATURES = {
+    "b200fe_version": (_i, []),
+    "b200fe_last_error": (C.c_char_p, []),
+    "b200fe_bk1_apply": (_i, [_i, _i, _u32, _vp, _vp, _vp, _vp, _vp]),
+    "b200fe_bk3_apply": (_i, [_i, _i, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200fe_bk5_apply": (_i, [_i, _u32, _vp, _vp, _vp, _vp, _vp]),
+    "b200fe_sum_squares": (_i, [_u64, _vp, _vp, _vp]),
+    "b200fe_bk_launch_info": (_i, [_i, _i, _i, _u32, _pi, _pi, _pi, _pi]),
+}
+for _name, (_res, _args) in _SIGNATURES.items():
+    _f = getattr(lib, _name)
+    _f.restype = _res
+    _f.argtypes = _args
+
+
+def check(code: int) -> None:
+    if code != 0:
+        raise B200feError(code, lib.b200fe_last_error().decode())

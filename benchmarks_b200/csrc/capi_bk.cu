@@ -1,0 +1,132 @@
+// capi_bk.cu -- C ABI: element-vector bake-off kernels, checksum, error reporting.
+#include <cstring>
+
+#include "common.h"
+#include "kernels.h"
+
+namespace b200fe {
+
+char *error_buffer()
+{
+    static thread_local char buf[512] = "";
+    return buf;
+}
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    std::vsnprintf(error_buffer(), 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int fail_cuda(cudaError_t e, const char *what)
+{
+    // cudaErrorInvalidValue from the dispatcher means "variant not built"
+    std::snprintf(error_buffer(), 512, "CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    (void)cudaGetLastError();  // clear sticky-less error state
+    return B200FE_ERR_CUDA;
+}
+
+namespace {
+int check_degree(int p, int nq, bool collocated)
+{
+    if (p < 1 || p > 8) return fail(B200FE_ERR_UNSUPPORTED, "degree p=%d outside 1..8", p);
+    if (collocated ? nq != p + 1 : nq != p + 2)
+        return fail(B200FE_ERR_UNSUPPORTED, "nq=%d not supported for p=%d (E-vector kernels: BK1/BK3 nq=p+2, BK5 nq=p+1)", nq, p);
+    return B200FE_OK;
+}
+
+__global__ void sum_squares_kernel(uint64_t n, const double *__restrict__ x, double *__restrict__ result)
+{
+    double s = 0.0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double v = x[i];
+        s = fma(v, v, s);
+    }
+    __shared__ double red[32];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) atomicAdd(result, s);
+    }
+}
+}  // namespace
+}  // namespace b200fe
+
+using namespace b200fe;
+
+extern "C" {
+
+int b200fe_version(void) { return B200FE_VERSION; }
+
+const char *b200fe_last_error(void) { return error_buffer(); }
+
+int b200fe_bk1_apply(int p, int nq, uint32_t nelmt, const double *h_basis, const double *d_JxW,
+                     const double *d_in, double *d_out, void *stream)
+{
+    if (int rc = check_degree(p, nq, false)) return rc;
+    B200FE_REQUIRE(h_basis && (nelmt == 0 || (d_JxW && d_in && d_out)), "b200fe_bk1_apply: null pointer");
+    KArgs a{nelmt, nullptr, d_JxW, d_in, d_out, nullptr, nullptr};
+    B200FE_CUDA_TRY(launch_sumfact(p + 1, nq, false, QOP_MASS, false, h_basis, nullptr, a, (cudaStream_t)stream, nullptr, false));
+    return B200FE_OK;
+}
+
+int b200fe_bk3_apply(int p, int nq, uint32_t nelmt, const double *h_basis, const double *h_dbasis,
+                     const double *d_G, const double *d_in, double *d_out, void *stream)
+{
+    if (int rc = check_degree(p, nq, false)) return rc;
+    B200FE_REQUIRE(h_basis && h_dbasis && (nelmt == 0 || (d_G && d_in && d_out)), "b200fe_bk3_apply: null pointer");
+    KArgs a{nelmt, d_G, nullptr, d_in, d_out, nullptr, nullptr};
+    B200FE_CUDA_TRY(launch_sumfact(p + 1, nq, false, QOP_LAPLACE, false, h_basis, h_dbasis, a, (cudaStream_t)stream, nullptr, false));
+    return B200FE_OK;
+}
+
+int b200fe_bk5_apply(int p, uint32_t nelmt, const double *h_dbasis, const double *d_G,
+                     const double *d_in, double *d_out, void *stream)
+{
+    if (int rc = check_degree(p, p + 1, true)) return rc;
+    B200FE_REQUIRE(h_dbasis && (nelmt == 0 || (d_G && d_in && d_out)), "b200fe_bk5_apply: null pointer");
+    KArgs a{nelmt, d_G, nullptr, d_in, d_out, nullptr, nullptr};
+    B200FE_CUDA_TRY(launch_sumfact(p + 1, p + 1, true, QOP_LAPLACE, false, nullptr, h_dbasis, a, (cudaStream_t)stream, nullptr, false));
+    return B200FE_OK;
+}
+
+int b200fe_sum_squares(uint64_t n, const double *d_x, double *d_result, void *stream)
+{
+    B200FE_REQUIRE(d_result && (n == 0 || d_x), "b200fe_sum_squares: null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    B200FE_CUDA_TRY(cudaMemsetAsync(d_result, 0, sizeof(double), s));
+    if (n == 0) return B200FE_OK;
+    int dev = 0, sms = 0;
+    B200FE_CUDA_TRY(cudaGetDevice(&dev));
+    B200FE_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    uint64_t blocks = (n + 1023) / 1024;
+    if (blocks > (uint64_t)sms * 8) blocks = (uint64_t)sms * 8;
+    sum_squares_kernel<<<(unsigned)blocks, 256, 0, s>>>(n, d_x, d_result);
+    B200FE_CUDA_TRY(cudaGetLastError());
+    return B200FE_OK;
+}
+
+int b200fe_bk_launch_info(int kind, int p, int nq, uint32_t nelmt, int *elems_per_block,
+                          int *num_blocks, int *threads_per_block, int *smem_bytes)
+{
+    B200FE_REQUIRE(kind == 1 || kind == 3 || kind == 5, "b200fe_bk_launch_info: kind must be 1, 3 or 5");
+    const bool coll = kind == 5;
+    if (int rc = check_degree(p, nq, coll)) return rc;
+    KArgs a{nelmt, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    LaunchInfo li{};
+    B200FE_CUDA_TRY(launch_sumfact(p + 1, nq, coll, kind == 1 ? QOP_MASS : QOP_LAPLACE, false, nullptr, nullptr, a, nullptr, &li, true));
+    if (elems_per_block) *elems_per_block = li.elems_per_block;
+    if (num_blocks) *num_blocks = li.num_blocks;
+    if (threads_per_block) *threads_per_block = li.threads_per_block;
+    if (smem_bytes) *smem_bytes = li.smem_bytes;
+    return B200FE_OK;
+}
+
+}  // extern "C"

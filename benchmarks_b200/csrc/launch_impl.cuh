@@ -1,0 +1,64 @@
+// launch_impl.cuh -- launcher template body; included only by inst.cu.
+#pragma once
+#include <cstdlib>
+#include <cstring>
+
+#include "kernels.h"
+
+namespace b200fe {
+
+// elements per CTA: fill ~256 threads with whole quadrature planes
+constexpr int epb_for(int nq)
+{
+    const int n2 = nq * nq;
+    int e = 256 / n2;
+    return e < 1 ? 1 : e;
+}
+
+template <int NM, int NQ, bool COLL, int QOP, bool LVEC>
+cudaError_t launch_t(const double *hB, const double *hD, const KArgs &a, cudaStream_t s,
+                     LaunchInfo *info, bool dry_run)
+{
+    constexpr int EPB = epb_for(NQ);
+    constexpr int T = EPB * NQ * NQ;
+    using L = Layout<NM, NQ, COLL>;
+    auto kern = sumfact_kernel<NM, NQ, COLL, QOP, LVEC, EPB, 1>;
+    const size_t smem = L::smem_bytes(EPB);
+
+    struct Cfg {
+        bool ready = false;
+        int blocks_per_sm = 0, sms = 0, regs = 0;
+    };
+    static Cfg cfg[64];  // per device
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return err;
+    Cfg &c = cfg[dev & 63];
+    if (!c.ready) {
+        err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.blocks_per_sm, kern, T, smem);
+        if (err != cudaSuccess) return err;
+        err = cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, dev);
+        if (err != cudaSuccess) return err;
+        cudaFuncAttributes fa;
+        err = cudaFuncGetAttributes(&fa, kern);
+        if (err != cudaSuccess) return err;
+        c.regs = fa.numRegs;
+        if (c.blocks_per_sm < 1) return cudaErrorLaunchOutOfResources;
+        c.ready = true;
+    }
+    const uint32_t n_batches = (a.n_elems + EPB - 1) / EPB;
+    long long resident = (long long)c.sms * c.blocks_per_sm * grid_multiplier();
+    const int grid = (int)(n_batches < (uint32_t)resident ? n_batches : resident);
+    if (info) *info = LaunchInfo{EPB, grid, T, (int)smem, c.blocks_per_sm, c.regs};
+    if (dry_run || a.n_elems == 0) return cudaSuccess;
+
+    Mats<NM, NQ> m;
+    if (hB) std::memcpy(m.B, hB, sizeof(m.B)); else std::memset(m.B, 0, sizeof(m.B));
+    if (hD) std::memcpy(m.D, hD, sizeof(m.D)); else std::memset(m.D, 0, sizeof(m.D));
+    kern<<<grid, T, smem, s>>>(m, a);
+    return cudaGetLastError();
+}
+
+}  // namespace b200fe
