@@ -6,6 +6,7 @@ memory, streams and torch.distributed plumbing.  There is no CPU fallback: impor
 package without the built library raises, and every compute call needs a CUDA device.
 """
 from ._lib import lib, LIB_PATH, B200feError, check  # noqa: F401
+from .mesh import BoxMesh, basis_1d, QUAD_GAUSS, QUAD_GLL, PARTITION_P4EST, PARTITION_BLOCKS, GHOSTS_MINIMAL, GHOSTS_RELEVANT  # noqa: F401
 from .bk import bk1_apply, bk3_apply, bk5_apply, sum_squares, bk_launch_info  # noqa: F401
 
 __all__ = ["lib", "LIB_PATH", "B200feError", "check", "bk1_apply", "bk3_apply", "bk5_apply",

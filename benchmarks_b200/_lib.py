@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200fe.so")
+LIB_PATH = os.environ.get("B200FE_LIB") or os.path.join(_HERE, "libb200fe.so")  # env override: tuning variants only
 
 
 class B200feError(RuntimeError):
@@ -33,6 +33,11 @@ _SIGNATURES = {
     "b200fe_bk5_apply": (_i, [_i, _u32, _vp, _vp, _vp, _vp, _vp]),
     "b200fe_sum_squares": (_i, [_u64, _vp, _vp, _vp]),
     "b200fe_bk_launch_info": (_i, [_i, _i, _i, _u32, _pi, _pi, _pi, _pi]),
+    "b200fe_basis_1d": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "b200fe_boxmesh_create": (_i, [_vp, C.POINTER(_vp)]),
+    "b200fe_boxmesh_destroy": (None, [_vp]),
+    "b200fe_boxmesh_info": (_i, [_vp, _vp]),
+    "b200fe_boxmesh_fill": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 for _name, (_res, _args) in _SIGNATURES.items():
     _f = getattr(lib, _name)

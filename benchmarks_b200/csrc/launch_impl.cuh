@@ -7,11 +7,31 @@
 
 namespace b200fe {
 
-// elements per CTA: fill ~256 threads with whole quadrature planes
+// Launch-shape heuristics (round-1 ncu sweep, profiles/r01_bk_variants.md): small planes want
+// ~128-thread CTAs, large planes want two CTAs per SM (register cap 128).  -D overrides are
+// tuning knobs for tools/gpu_run*.sh only.
+constexpr int tpb_for(int nq)
+{
+#ifdef B200FE_TPB
+    return B200FE_TPB;
+#else
+    return nq <= 6 ? 128 : 256;
+#endif
+}
+constexpr int minb_for(int nq)
+{
+#ifdef B200FE_MINB
+    return B200FE_MINB;
+#else
+    return nq >= 6 ? 2 : 1;
+#endif
+}
+
+// elements per CTA: fill ~tpb_for(nq) threads with whole quadrature planes
 constexpr int epb_for(int nq)
 {
     const int n2 = nq * nq;
-    int e = 256 / n2;
+    int e = tpb_for(nq) / n2;
     return e < 1 ? 1 : e;
 }
 
@@ -22,7 +42,7 @@ cudaError_t launch_t(const double *hB, const double *hD, const KArgs &a, cudaStr
     constexpr int EPB = epb_for(NQ);
     constexpr int T = EPB * NQ * NQ;
     using L = Layout<NM, NQ, COLL>;
-    auto kern = sumfact_kernel<NM, NQ, COLL, QOP, LVEC, EPB, 1>;
+    auto kern = sumfact_kernel<NM, NQ, COLL, QOP, LVEC, EPB, minb_for(NQ)>;
     const size_t smem = L::smem_bytes(EPB);
 
     struct Cfg {

@@ -1,0 +1,402 @@
+// mesh.cc -- box mesh, FE_Q DoF numbering, partition, ghost lists (host only, OpenMP).
+//
+// The reference takes all of this from deal.II (un-vendored): GridGenerator::subdivided_hyper_rectangle
+// + refine_global (CEED_bp/src/bp3.cc:452-488), DoFHandler::distribute_dofs (bp3.cc:135-136),
+// Dirichlet constraints on boundary id 0 (bp3.cc:147-151), the per-cell lexicographic index table
+// with invalid_unsigned_int on constrained DoFs (CEED_bp/include/portable_laplace_operator.h:304-394)
+// and the Partitioner's owned/ghost layout.  Here the same objects
+// are produced in closed form for structured boxes -- no cell-by-cell "first touch" sweep:
+//
+//   * active-cell order  = coarse cell (lexicographic, x fastest) * 8^n + Morton(local x,y,z)
+//   * owner of a mesh entity (vertex/line/quad/hex) = lowest rank among the cells sharing it
+//   * within its owner, an entity is numbered by the first (lowest active index) cell sharing it,
+//     in the order vertices, lines, quads, interior of that cell
+//   => global index = prefix[first cell] + (new entities of that cell before it) + index in entity,
+//      with one prefix sum over all cells in active order (ranks own contiguous cell ranges).
+//
+// The result is bit-identical to the literal first-touch simulation in oracle/fe_oracle.py
+// (tests/test_mesh.py).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <numeric>
+#include <vector>
+
+#include "common.h"
+
+namespace b200fe {
+
+namespace {
+
+// hierarchical entity order of a hex: 8 vertices, 12 lines, 6 quads, 1 interior.
+// code per axis: 0 = low plane, 1 = interior, 2 = high plane  (x, y, z)
+struct EntityTable {
+    int code[27][3];
+    int dim[27];  // number of interior axes
+    int id_of_code[3][3][3];
+    EntityTable()
+    {
+        int n = 0;
+        auto add = [&](int x, int y, int z) {
+            code[n][0] = x; code[n][1] = y; code[n][2] = z;
+            dim[n] = (x == 1) + (y == 1) + (z == 1);
+            id_of_code[x][y][z] = n++;
+        };
+        for (int v = 0; v < 8; ++v) add((v & 1) ? 2 : 0, (v & 2) ? 2 : 0, (v & 4) ? 2 : 0);
+        for (int z = 0; z <= 2; z += 2) {  // lines 0-3 (z low), 4-7 (z high)
+            add(0, 1, z); add(2, 1, z); add(1, 0, z); add(1, 2, z);
+        }
+        add(0, 0, 1); add(2, 0, 1); add(0, 2, 1); add(2, 2, 1);  // lines 8-11
+        add(0, 1, 1); add(2, 1, 1); add(1, 0, 1); add(1, 2, 1); add(1, 1, 0); add(1, 1, 2);  // quads
+        add(1, 1, 1);
+    }
+};
+const EntityTable kEnt;
+
+inline uint64_t morton3(uint32_t x, uint32_t y, uint32_t z, int nbits)
+{
+    uint64_t c = 0;
+    for (int b = 0; b < nbits; ++b)
+        c |= (uint64_t)((x >> b) & 1) << (3 * b) | (uint64_t)((y >> b) & 1) << (3 * b + 1) |
+             (uint64_t)((z >> b) & 1) << (3 * b + 2);
+    return c;
+}
+
+}  // namespace
+
+struct BoxMesh {
+    int sub[3], nref, p, nranks, rank, scheme, ghost_mode, dirichlet;
+    int64_t cells[3];
+    double p1[3], p2[3], h[3];
+    int64_t n_cells_global = 0;
+    uint64_t n_dofs_global = 0;
+    std::vector<uint32_t> newmask;   // by active index: which of the 27 entities the cell numbers
+    std::vector<uint64_t> gprefix;   // by active index: first global DoF numbered by the cell
+    std::vector<int64_t> rank_cell_begin;
+    std::vector<uint64_t> rank_dof_begin;
+    // local data of `rank`
+    int64_t cell_begin = 0, cell_end = 0;
+    uint64_t owned_begin = 0, owned_end = 0;
+    std::vector<uint32_t> dof_indices;   // [n_local_cells][nm^3] lexicographic, local numbering
+    std::vector<uint64_t> ghost_global;  // sorted
+    std::vector<int32_t> ghost_owner;
+    std::vector<uint32_t> constrained;   // owned local indices on the Dirichlet boundary
+    std::vector<int32_t> cell_xyz;       // [n_local_cells][3]
+    // lexicographic local dof -> (entity, index in entity)
+    std::vector<int> l_ent, l_idx;
+    int ent_size[27];
+
+    int64_t n_local_cells() const { return cell_end - cell_begin; }
+
+    uint64_t pos_of(int64_t x, int64_t y, int64_t z) const
+    {
+        const uint32_t f = (1u << nref) - 1;
+        const uint64_t coarse = (uint64_t)(x >> nref) + (uint64_t)sub[0] * ((uint64_t)(y >> nref) + (uint64_t)sub[1] * (uint64_t)(z >> nref));
+        return (coarse << (3 * nref)) | morton3((uint32_t)x & f, (uint32_t)y & f, (uint32_t)z & f, nref);
+    }
+    void xyz_of(uint64_t pos, int64_t &x, int64_t &y, int64_t &z) const
+    {
+        const uint64_t per = 1ull << (3 * nref);
+        const uint64_t coarse = pos >> (3 * nref), loc = pos & (per - 1);
+        uint32_t lx = 0, ly = 0, lz = 0;
+        for (int b = 0; b < nref; ++b) {
+            lx |= (uint32_t)((loc >> (3 * b)) & 1) << b;
+            ly |= (uint32_t)((loc >> (3 * b + 1)) & 1) << b;
+            lz |= (uint32_t)((loc >> (3 * b + 2)) & 1) << b;
+        }
+        const int64_t X = coarse % sub[0], Y = (coarse / sub[0]) % sub[1], Z = coarse / ((uint64_t)sub[0] * sub[1]);
+        x = (X << nref) | lx; y = (Y << nref) | ly; z = (Z << nref) | lz;
+    }
+    int rank_of_pos(uint64_t pos) const
+    {
+        const uint64_t N = (uint64_t)n_cells_global, P = (uint64_t)nranks;
+        if (scheme == B200FE_PARTITION_P4EST) return (int)(((pos + 1) * P - 1) / N);
+        const uint64_t per = (N + P - 1) / P;  // create_triangulation.h:44-51
+        return (int)(pos / per);
+    }
+
+    // owner rank and first-touch cell of entity `e` of cell (x,y,z); returns the entity's id
+    // relative to that first cell in *ef.
+    void entity_owner(const int64_t c[3], int e, int &owner, uint64_t &first, int *ef) const
+    {
+        int64_t lo[3], hi[3];
+        for (int d = 0; d < 3; ++d) {
+            const int t = kEnt.code[e][d];
+            lo[d] = t == 0 ? c[d] - 1 : c[d];
+            hi[d] = t == 2 ? c[d] + 1 : c[d];
+            lo[d] = std::max<int64_t>(lo[d], 0);
+            hi[d] = std::min<int64_t>(hi[d], cells[d] - 1);
+        }
+        owner = nranks;
+        first = ~0ull;
+        int64_t fx = 0, fy = 0, fz = 0;
+        for (int64_t z = lo[2]; z <= hi[2]; ++z)
+            for (int64_t y = lo[1]; y <= hi[1]; ++y)
+                for (int64_t x = lo[0]; x <= hi[0]; ++x) {
+                    const uint64_t ps = pos_of(x, y, z);
+                    const int r = rank_of_pos(ps);
+                    if (r < owner || (r == owner && ps < first)) {
+                        owner = r; first = ps; fx = x; fy = y; fz = z;
+                    }
+                }
+        if (ef) {
+            const int64_t f[3] = {fx, fy, fz};
+            int rc[3];
+            for (int d = 0; d < 3; ++d) {
+                const int t = kEnt.code[e][d];
+                if (t == 1) rc[d] = 1;
+                else {
+                    const int64_t plane = c[d] + (t == 2 ? 1 : 0);
+                    rc[d] = plane == f[d] ? 0 : 2;
+                }
+            }
+            *ef = kEnt.id_of_code[rc[0]][rc[1]][rc[2]];
+        }
+    }
+
+    uint64_t within_prefix(uint32_t mask, int e) const
+    {
+        uint64_t s = 0;
+        for (int k = 0; k < e; ++k)
+            if (mask >> k & 1) s += ent_size[k];
+        return s;
+    }
+
+    int build();
+};
+
+int BoxMesh::build()
+{
+    const int nm = p + 1, m = p - 1, nm3 = nm * nm * nm;
+    for (int e = 0; e < 27; ++e) ent_size[e] = kEnt.dim[e] == 0 ? 1 : kEnt.dim[e] == 1 ? m : kEnt.dim[e] == 2 ? m * m : m * m * m;
+    for (int d = 0; d < 3; ++d) {
+        cells[d] = (int64_t)sub[d] << nref;
+        h[d] = (p2[d] - p1[d]) / (double)cells[d];
+    }
+    n_cells_global = cells[0] * cells[1] * cells[2];
+    n_dofs_global = (uint64_t)(cells[0] * p + 1) * (uint64_t)(cells[1] * p + 1) * (uint64_t)(cells[2] * p + 1);
+    if (n_cells_global < nranks) return fail(B200FE_ERR_INVALID_ARG, "box mesh: fewer cells (%lld) than ranks (%d)", (long long)n_cells_global, nranks);
+
+    // lexicographic local dof -> entity and index in entity
+    l_ent.resize(nm3); l_idx.resize(nm3);
+    for (int c = 0; c < nm; ++c)
+        for (int b = 0; b < nm; ++b)
+            for (int a = 0; a < nm; ++a) {
+                const int t[3] = {a == 0 ? 0 : a == p ? 2 : 1, b == 0 ? 0 : b == p ? 2 : 1, c == 0 ? 0 : c == p ? 2 : 1};
+                const int e = kEnt.id_of_code[t[0]][t[1]][t[2]];
+                int idx = 0;
+                const int ia = a - 1, ib = b - 1, ic = c - 1;
+                switch (kEnt.dim[e]) {
+                    case 0: idx = 0; break;
+                    case 1: idx = t[0] == 1 ? ia : t[1] == 1 ? ib : ic; break;
+                    case 2:
+                        if (t[0] != 1) idx = ib + m * ic;        // x-face: (y fastest, z)
+                        else if (t[1] != 1) idx = ic + m * ia;   // y-face: (z fastest, x)
+                        else idx = ia + m * ib;                  // z-face: (x fastest, y)
+                        break;
+                    default: idx = ia + m * (ib + m * ic);
+                }
+                const int l = a + nm * (b + nm * c);
+                l_ent[l] = e; l_idx[l] = idx;
+            }
+
+    // pass 1 over ALL cells: which entities does each cell number, and how many DoFs
+    newmask.assign(n_cells_global, 0);
+    gprefix.assign(n_cells_global + 1, 0);
+#pragma omp parallel for schedule(static)
+    for (int64_t ps = 0; ps < n_cells_global; ++ps) {
+        int64_t c[3];
+        xyz_of((uint64_t)ps, c[0], c[1], c[2]);
+        uint32_t mask = 0;
+        uint64_t cnt = 0;
+        for (int e = 0; e < 27; ++e) {
+            if (ent_size[e] == 0) continue;
+            int owner; uint64_t first;
+            entity_owner(c, e, owner, first, nullptr);
+            if (first == (uint64_t)ps) { mask |= 1u << e; cnt += ent_size[e]; }
+        }
+        newmask[ps] = mask;
+        gprefix[ps + 1] = cnt;
+    }
+    for (int64_t ps = 0; ps < n_cells_global; ++ps) gprefix[ps + 1] += gprefix[ps];
+    if (gprefix[n_cells_global] != n_dofs_global)
+        return fail(B200FE_ERR_INVALID_ARG, "box mesh: internal numbering error (%llu != %llu)",
+                    (unsigned long long)gprefix[n_cells_global], (unsigned long long)n_dofs_global);
+
+    rank_cell_begin.resize(nranks + 1);
+    rank_dof_begin.resize(nranks + 1);
+    {
+        int64_t ps = 0;
+        for (int r = 0; r <= nranks; ++r) {
+            while (ps < n_cells_global && rank_of_pos((uint64_t)ps) < r) ++ps;  // monotone
+            rank_cell_begin[r] = r == nranks ? n_cells_global : ps;
+        }
+        // ranks own contiguous cell ranges => binary search instead of the linear scan
+        for (int r = 0; r <= nranks; ++r) rank_dof_begin[r] = gprefix[rank_cell_begin[r]];
+    }
+    cell_begin = rank_cell_begin[rank];
+    cell_end = rank_cell_begin[rank + 1];
+    owned_begin = rank_dof_begin[rank];
+    owned_end = rank_dof_begin[rank + 1];
+    const int64_t nloc = n_local_cells();
+    if (owned_end - owned_begin >= 0xFFFFFFFFull) return fail(B200FE_ERR_UNSUPPORTED, "box mesh: more than 2^32-2 owned DoFs on one rank");
+
+    // pass 2 over own cells: global index of every local DoF
+    std::vector<uint64_t> gidx((size_t)nloc * nm3);
+    cell_xyz.resize((size_t)nloc * 3);
+    const int64_t dimsL[3] = {cells[0] * p, cells[1] * p, cells[2] * p};
+    std::vector<uint8_t> on_boundary((size_t)nloc * nm3);
+#pragma omp parallel for schedule(static)
+    for (int64_t ci = 0; ci < nloc; ++ci) {
+        int64_t c[3];
+        xyz_of((uint64_t)(cell_begin + ci), c[0], c[1], c[2]);
+        for (int d = 0; d < 3; ++d) cell_xyz[ci * 3 + d] = (int32_t)c[d];
+        uint64_t base[27];
+        for (int e = 0; e < 27; ++e) {
+            if (ent_size[e] == 0) { base[e] = 0; continue; }
+            int owner, ef; uint64_t first;
+            entity_owner(c, e, owner, first, &ef);
+            base[e] = gprefix[first] + within_prefix(newmask[first], ef);
+        }
+        for (int l = 0; l < nm3; ++l) {
+            gidx[ci * nm3 + l] = base[l_ent[l]] + (uint64_t)l_idx[l];
+            const int a = l % nm, b = (l / nm) % nm, cc = l / (nm * nm);
+            const int64_t X = c[0] * p + a, Y = c[1] * p + b, Z = c[2] * p + cc;
+            on_boundary[ci * nm3 + l] = dirichlet && (X == 0 || Y == 0 || Z == 0 || X == dimsL[0] || Y == dimsL[1] || Z == dimsL[2]);
+        }
+    }
+
+    // ghost set: DoFs on own cells (minimal) or on own + vertex-neighbour cells (deal.II "relevant")
+    std::vector<uint64_t> cand;
+    for (size_t i = 0; i < gidx.size(); ++i)
+        if (gidx[i] < owned_begin || gidx[i] >= owned_end) cand.push_back(gidx[i]);
+    if (ghost_mode == B200FE_GHOSTS_RELEVANT && nranks > 1) {
+        std::vector<uint64_t> layer;
+        for (int64_t ci = 0; ci < nloc; ++ci) {
+            const int32_t *c = &cell_xyz[ci * 3];
+            for (int dz = -1; dz <= 1; ++dz)
+                for (int dy = -1; dy <= 1; ++dy)
+                    for (int dx = -1; dx <= 1; ++dx) {
+                        const int64_t x = c[0] + dx, y = c[1] + dy, z = c[2] + dz;
+                        if (x < 0 || y < 0 || z < 0 || x >= cells[0] || y >= cells[1] || z >= cells[2]) continue;
+                        const uint64_t ps = pos_of(x, y, z);
+                        if ((int64_t)ps < cell_begin || (int64_t)ps >= cell_end) layer.push_back(ps);
+                    }
+        }
+        std::sort(layer.begin(), layer.end());
+        layer.erase(std::unique(layer.begin(), layer.end()), layer.end());
+        for (uint64_t ps : layer) {
+            int64_t c[3];
+            xyz_of(ps, c[0], c[1], c[2]);
+            for (int e = 0; e < 27; ++e) {
+                if (ent_size[e] == 0) continue;
+                int owner, ef; uint64_t first;
+                entity_owner(c, e, owner, first, &ef);
+                if (owner == rank) continue;
+                const uint64_t b0 = gprefix[first] + within_prefix(newmask[first], ef);
+                for (int k = 0; k < ent_size[e]; ++k) cand.push_back(b0 + k);
+            }
+        }
+    }
+    std::sort(cand.begin(), cand.end());
+    cand.erase(std::unique(cand.begin(), cand.end()), cand.end());
+    ghost_global.swap(cand);
+    ghost_owner.resize(ghost_global.size());
+    for (size_t i = 0; i < ghost_global.size(); ++i)
+        ghost_owner[i] = (int32_t)(std::upper_bound(rank_dof_begin.begin(), rank_dof_begin.end(), ghost_global[i]) - rank_dof_begin.begin() - 1);
+    const uint64_t n_owned = owned_end - owned_begin;
+    if (n_owned + ghost_global.size() >= 0xFFFFFFFFull) return fail(B200FE_ERR_UNSUPPORTED, "box mesh: local vector too long for 32-bit indices");
+
+    // local index table with the Dirichlet mask, and the owned constrained list
+    dof_indices.resize(gidx.size());
+    std::vector<uint32_t> cons;
+#pragma omp parallel
+    {
+        std::vector<uint32_t> mine;
+#pragma omp for schedule(static) nowait
+        for (int64_t i = 0; i < (int64_t)gidx.size(); ++i) {
+            const uint64_t g = gidx[i];
+            uint32_t loc;
+            if (g >= owned_begin && g < owned_end) loc = (uint32_t)(g - owned_begin);
+            else loc = (uint32_t)(n_owned + (std::lower_bound(ghost_global.begin(), ghost_global.end(), g) - ghost_global.begin()));
+            if (on_boundary[i]) {
+                if (loc < n_owned) mine.push_back(loc);
+                dof_indices[i] = B200FE_INVALID_INDEX;
+            } else
+                dof_indices[i] = loc;
+        }
+#pragma omp critical
+        cons.insert(cons.end(), mine.begin(), mine.end());
+    }
+    std::sort(cons.begin(), cons.end());
+    cons.erase(std::unique(cons.begin(), cons.end()), cons.end());
+    constrained.swap(cons);
+    // owned boundary DoFs that only OTHER ranks' cells touch cannot exist: the owner is the lowest
+    // rank among the cells sharing the entity, so it has a cell there.
+    return B200FE_OK;
+}
+
+}  // namespace b200fe
+
+using namespace b200fe;
+
+extern "C" {
+
+int b200fe_boxmesh_create(const b200fe_boxmesh_desc *d, b200fe_boxmesh **out)
+{
+    B200FE_REQUIRE(d && out, "b200fe_boxmesh_create: null pointer");
+    if (d->p < 1 || d->p > 8) return fail(B200FE_ERR_UNSUPPORTED, "box mesh: degree p=%d outside 1..8", d->p);
+    B200FE_REQUIRE(d->n_refine >= 0 && d->n_refine <= 10, "box mesh: n_refine out of range");
+    B200FE_REQUIRE(d->n_ranks >= 1 && d->rank >= 0 && d->rank < d->n_ranks, "box mesh: bad rank %d of %d", d->rank, d->n_ranks);
+    B200FE_REQUIRE(d->partition == B200FE_PARTITION_P4EST || d->partition == B200FE_PARTITION_BLOCKS, "box mesh: bad partition scheme");
+    B200FE_REQUIRE(d->ghosts == B200FE_GHOSTS_MINIMAL || d->ghosts == B200FE_GHOSTS_RELEVANT, "box mesh: bad ghost mode");
+    auto m = std::make_unique<BoxMesh>();
+    for (int k = 0; k < 3; ++k) {
+        B200FE_REQUIRE(d->subdivisions[k] >= 1, "box mesh: subdivisions must be >= 1");
+        B200FE_REQUIRE(d->p2[k] > d->p1[k], "box mesh: p2 must exceed p1");
+        m->sub[k] = d->subdivisions[k];
+        m->p1[k] = d->p1[k];
+        m->p2[k] = d->p2[k];
+    }
+    m->nref = d->n_refine; m->p = d->p; m->nranks = d->n_ranks; m->rank = d->rank;
+    m->scheme = d->partition; m->ghost_mode = d->ghosts; m->dirichlet = d->dirichlet;
+    if (int rc = m->build()) return rc;
+    *out = reinterpret_cast<b200fe_boxmesh *>(m.release());
+    return B200FE_OK;
+}
+
+void b200fe_boxmesh_destroy(b200fe_boxmesh *mesh) { delete reinterpret_cast<BoxMesh *>(mesh); }
+
+int b200fe_boxmesh_info(const b200fe_boxmesh *mesh, b200fe_boxmesh_info_t *info)
+{
+    B200FE_REQUIRE(mesh && info, "b200fe_boxmesh_info: null pointer");
+    const BoxMesh *m = reinterpret_cast<const BoxMesh *>(mesh);
+    info->n_cells_global = (uint64_t)m->n_cells_global;
+    info->n_dofs_global = m->n_dofs_global;
+    info->n_cells_local = (uint32_t)m->n_local_cells();
+    info->first_cell = (uint64_t)m->cell_begin;
+    info->owned_begin = m->owned_begin;
+    info->n_owned = (uint32_t)(m->owned_end - m->owned_begin);
+    info->n_ghost = (uint32_t)m->ghost_global.size();
+    info->n_constrained = (uint32_t)m->constrained.size();
+    for (int d = 0; d < 3; ++d) { info->cells[d] = (uint32_t)m->cells[d]; info->h[d] = m->h[d]; }
+    return B200FE_OK;
+}
+
+int b200fe_boxmesh_fill(const b200fe_boxmesh *mesh, uint32_t *h_dof_indices, uint32_t *h_constrained,
+                        uint64_t *h_ghost_global, int32_t *h_ghost_owner, int32_t *h_cell_xyz,
+                        uint64_t *h_rank_dof_begin)
+{
+    B200FE_REQUIRE(mesh, "b200fe_boxmesh_fill: null mesh");
+    const BoxMesh *m = reinterpret_cast<const BoxMesh *>(mesh);
+    if (h_dof_indices) std::memcpy(h_dof_indices, m->dof_indices.data(), m->dof_indices.size() * sizeof(uint32_t));
+    if (h_constrained) std::memcpy(h_constrained, m->constrained.data(), m->constrained.size() * sizeof(uint32_t));
+    if (h_ghost_global) std::memcpy(h_ghost_global, m->ghost_global.data(), m->ghost_global.size() * sizeof(uint64_t));
+    if (h_ghost_owner) std::memcpy(h_ghost_owner, m->ghost_owner.data(), m->ghost_owner.size() * sizeof(int32_t));
+    if (h_cell_xyz) std::memcpy(h_cell_xyz, m->cell_xyz.data(), m->cell_xyz.size() * sizeof(int32_t));
+    if (h_rank_dof_begin) std::memcpy(h_rank_dof_begin, m->rank_dof_begin.data(), m->rank_dof_begin.size() * sizeof(uint64_t));
+    return B200FE_OK;
+}
+
+}  // extern "C"

@@ -73,6 +73,11 @@ __global__ void __launch_bounds__(EPB *NQ *NQ, MINB)
     constexpr int N2 = L::N2, N3 = L::N3, M3 = L::M3, RU = L::RU, RA = L::RA;
     constexpr int T = EPB * N2;
     constexpr bool LAP = (QOP & QOP_LAPLACE) != 0, MASS = (QOP & QOP_MASS) != 0;
+#ifdef B200FE_ROLL_P1
+    constexpr bool ROLL_P1 = B200FE_ROLL_P1 != 0;
+#else
+    constexpr bool ROLL_P1 = NQ >= 7;  // rolled flux loop: ~120 registers instead of 220+ (2 CTAs/SM)
+#endif
     static_assert(!COLL || NM == NQ, "collocated operators need nm == nq");
 
     extern __shared__ double smem[];
@@ -202,7 +207,7 @@ __global__ void __launch_bounds__(EPB *NQ *NQ, MINB)
                 dr[n] = sD[r * NQ + n];
             }
             __syncthreads();
-#pragma unroll
+#pragma unroll(ROLL_P1 ? 1 : NQ)
             for (int p = 0; p < NQ; ++p) {
                 double gn[6];
                 if (p + 1 < NQ) {

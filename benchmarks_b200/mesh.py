@@ -1,0 +1,90 @@
+"""Host-side mesh / basis objects over the C ABI (sections 2 and 3 of include/b200fe.h).
+
+Stands in for the deal.II objects the reference drivers build before they construct the operator
+(CEED_bp/src/bp3.cc:129-182, 452-488): Triangulation + DoFHandler + AffineConstraints + Partitioner.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._lib import check, lib
+
+QUAD_GAUSS, QUAD_GLL = 0, 1
+PARTITION_P4EST, PARTITION_BLOCKS = 0, 1
+GHOSTS_MINIMAL, GHOSTS_RELEVANT = 0, 1
+
+
+class _Desc(C.Structure):
+    _fields_ = [("subdivisions", C.c_int * 3), ("n_refine", C.c_int), ("p1", C.c_double * 3), ("p2", C.c_double * 3),
+                ("p", C.c_int), ("n_ranks", C.c_int), ("rank", C.c_int), ("partition", C.c_int), ("ghosts", C.c_int),
+                ("dirichlet", C.c_int)]
+
+
+class _Info(C.Structure):
+    _fields_ = [("n_cells_global", C.c_uint64), ("n_dofs_global", C.c_uint64), ("first_cell", C.c_uint64),
+                ("owned_begin", C.c_uint64), ("n_cells_local", C.c_uint32), ("n_owned", C.c_uint32),
+                ("n_ghost", C.c_uint32), ("n_constrained", C.c_uint32), ("cells", C.c_uint32 * 3), ("h", C.c_double * 3)]
+
+
+def basis_1d(p: int, nq: int, quad: int = QUAD_GAUSS):
+    """deal.II-layout 1-D arrays: shape_values[i*nq+q], co_shape_gradients[n*nq+q], shape_gradients[i*nq+q]."""
+    nm = p + 1
+    sv, cg, sg = np.empty(nm * nq), np.empty(nq * nq), np.empty(nm * nq)
+    x, w = np.empty(nq), np.empty(nq)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    check(lib.b200fe_basis_1d(p, nq, quad, ptr(sv), ptr(cg), ptr(sg), ptr(x), ptr(w)))
+    return dict(p=p, nq=nq, quad=quad, shape_values=sv, co_shape_gradients=cg, shape_gradients=sg, points=x, weights=w)
+
+
+class BoxMesh:
+    """subdivided_hyper_rectangle(subdivisions, p1, p2) + refine_global(n_refine), FE_Q(p) DoFs,
+    Dirichlet constraints on the whole boundary, this rank's partition of it."""
+
+    def __init__(self, subdivisions, n_refine, p, *, p1=(-1.0, -1.0, -1.0), p2=None, n_ranks=1, rank=0,
+                 partition=PARTITION_P4EST, ghosts=GHOSTS_MINIMAL, dirichlet=True):
+        if p2 is None:  # bp3.cc:452-463: coarse cells of side 1.9
+            p2 = [a + 1.9 * s for a, s in zip(p1, subdivisions)]
+        d = _Desc()
+        d.subdivisions[:] = list(subdivisions)
+        d.n_refine = n_refine
+        d.p1[:] = list(p1)
+        d.p2[:] = list(p2)
+        d.p, d.n_ranks, d.rank, d.partition, d.ghosts, d.dirichlet = p, n_ranks, rank, partition, ghosts, int(dirichlet)
+        self._h = C.c_void_p()
+        check(lib.b200fe_boxmesh_create(C.byref(d), C.byref(self._h)))
+        info = _Info()
+        check(lib.b200fe_boxmesh_info(self._h, C.byref(info)))
+        self.p, self.n_ranks, self.rank = p, n_ranks, rank
+        self.p1, self.p2 = np.array(p1, float), np.array(p2, float)
+        self.n_cells_global, self.n_dofs_global = info.n_cells_global, info.n_dofs_global
+        self.first_cell, self.owned_begin = info.first_cell, info.owned_begin
+        self.n_cells, self.n_owned, self.n_ghost = info.n_cells_local, info.n_owned, info.n_ghost
+        self.cells, self.h = tuple(info.cells), np.array(list(info.h))
+        nm3 = (p + 1) ** 3
+        self.dof_indices = np.empty((self.n_cells, nm3), dtype=np.uint32)
+        self.constrained = np.empty(info.n_constrained, dtype=np.uint32)
+        self.ghost_global = np.empty(self.n_ghost, dtype=np.uint64)
+        self.ghost_owner = np.empty(self.n_ghost, dtype=np.int32)
+        self.cell_xyz = np.empty((self.n_cells, 3), dtype=np.int32)
+        self.rank_dof_begin = np.empty(n_ranks + 1, dtype=np.uint64)
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+        check(lib.b200fe_boxmesh_fill(self._h, ptr(self.dof_indices), ptr(self.constrained), ptr(self.ghost_global),
+                                      ptr(self.ghost_owner), ptr(self.cell_xyz), ptr(self.rank_dof_begin)))
+
+    @classmethod
+    def bp3_cycle(cls, cycle: int, p: int, **kw):
+        """Mesh number `cycle` of the reference's sweep (CEED_bp/src/bp3.cc:443-473)."""
+        n_refine, rem = cycle // 3, cycle % 3
+        return cls([2 if d < rem else 1 for d in range(3)], n_refine, p, **kw)
+
+    @property
+    def n_local(self):
+        return self.n_owned + self.n_ghost
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            lib.b200fe_boxmesh_destroy(h)
+            self._h = None

@@ -53,7 +53,7 @@ const char *b200fe_last_error(void);
 
 /* out_e = B^T (JxW .* (B in_e)).  Replaces BK1::Parallel::MassOperator<T,nq><<<>>>
  * (CEED_BK/include/kernels/BK1/templated_cuda_kernels.cuh:10-195; launch at
- *  CEED_BK/src/BK1/templated_cuda_benchmark.cc:84).  nq may be p+1 or p+2. */
+ *  CEED_BK/src/BK1/templated_cuda_benchmark.cc:84).  nq = p+2 (the reference fixes nm = nq-1). */
 int b200fe_bk1_apply(int p, int nq, uint32_t nelmt, const double *h_basis, const double *d_JxW,
                      const double *d_in, double *d_out, void *stream);
 
@@ -77,6 +77,70 @@ int b200fe_sum_squares(uint64_t n, const double *d_x, double *d_result, void *st
  * kind: 1 = BK1, 3 = BK3, 5 = BK5. */
 int b200fe_bk_launch_info(int kind, int p, int nq, uint32_t nelmt, int *elems_per_block,
                           int *num_blocks, int *threads_per_block, int *smem_bytes);
+
+/* ------------------------------------------------------------------------------------------
+ * 2. 1-D bases (what deal.II's QGauss<1>/FE_Q/MatrixFree::ShapeInfo hand to the reference operator;
+ *    SURVEY.md appendix A7).  All arrays are HOST arrays, any output pointer may be NULL.
+ *      h_shape_values       [nm*nq]  shape_values[i*nq+q]        (bk3_kokkos_kernel.h:161)
+ *      h_co_shape_gradients [nq*nq]  co_shape_gradients[n*nq+q]  (bk3_kokkos_kernel.h:243)
+ *      h_shape_gradients    [nm*nq]  d/dx of shape i at point q
+ *      h_points, h_weights  [nq]     on [0,1], ascending, weights sum to 1
+ *    quad_kind GLL with nq = p+1 is the collocated BP5 setting: shape_values is the identity.
+ * ------------------------------------------------------------------------------------------ */
+enum { B200FE_QUAD_GAUSS = 0, B200FE_QUAD_GLL = 1 };
+
+int b200fe_basis_1d(int p, int nq, int quad_kind, double *h_shape_values,
+                    double *h_co_shape_gradients, double *h_shape_gradients, double *h_points,
+                    double *h_weights);
+
+/* ------------------------------------------------------------------------------------------
+ * 3. Box mesh + FE_Q(p) DoF numbering + partition (host).  Stands in for what the reference
+ *    drivers obtain from deal.II: subdivided_hyper_rectangle + refine_global
+ *    (CEED_bp/src/bp3.cc:452-488; bp5_kokkos/create_triangulation.h:17-29), distribute_dofs,
+ *    Dirichlet constraints on the whole boundary (bp3.cc:147-151) and the per-cell index table
+ *    of setup_dirichlet_boundary_dofs_masks (CEED_bp/include/portable_laplace_operator.h:304-394).
+ *    Every rank builds its own view; no communication.
+ * ------------------------------------------------------------------------------------------ */
+enum { B200FE_PARTITION_P4EST = 0, /* first cell of rank r = floor(N r / P) on the z-order curve */
+       B200FE_PARTITION_BLOCKS = 1 /* active_cell_index / ceil(N/P), create_triangulation.h:44-51 */ };
+enum { B200FE_GHOSTS_MINIMAL = 0,  /* DoFs of owned cells that another rank owns */
+       B200FE_GHOSTS_RELEVANT = 1  /* every DoF of the one-cell ghost layer (deal.II locally relevant set) */ };
+
+typedef struct {
+    int subdivisions[3]; /* coarse cells per axis */
+    int n_refine;        /* refine_global(n_refine) */
+    double p1[3], p2[3]; /* box corners */
+    int p;               /* FE_Q degree 1..8 */
+    int n_ranks, rank;
+    int partition;       /* B200FE_PARTITION_* */
+    int ghosts;          /* B200FE_GHOSTS_* */
+    int dirichlet;       /* 1: constrain every boundary DoF (boundary id 0), 0: no constraints */
+} b200fe_boxmesh_desc;
+
+typedef struct {
+    uint64_t n_cells_global, n_dofs_global;
+    uint64_t first_cell;  /* active index of the first owned cell */
+    uint64_t owned_begin; /* first owned global DoF */
+    uint32_t n_cells_local, n_owned, n_ghost, n_constrained;
+    uint32_t cells[3];
+    double h[3];
+} b200fe_boxmesh_info_t;
+
+typedef struct b200fe_boxmesh b200fe_boxmesh;
+
+int b200fe_boxmesh_create(const b200fe_boxmesh_desc *desc, b200fe_boxmesh **out);
+void b200fe_boxmesh_destroy(b200fe_boxmesh *mesh);
+int b200fe_boxmesh_info(const b200fe_boxmesh *mesh, b200fe_boxmesh_info_t *info);
+/* Copies out (any pointer may be NULL):
+ *   h_dof_indices   [n_cells_local][nm^3] partitioner-local index or B200FE_INVALID_INDEX
+ *   h_constrained   [n_constrained]       owned local indices with Dirichlet constraints (sorted)
+ *   h_ghost_global  [n_ghost]             global index of each ghost (sorted => grouped by owner)
+ *   h_ghost_owner   [n_ghost]             owning rank of each ghost
+ *   h_cell_xyz      [n_cells_local][3]    integer cell coordinates in iterator (z-order) order
+ *   h_rank_dof_begin[n_ranks+1]           owned ranges of all ranks */
+int b200fe_boxmesh_fill(const b200fe_boxmesh *mesh, uint32_t *h_dof_indices, uint32_t *h_constrained,
+                        uint64_t *h_ghost_global, int32_t *h_ghost_owner, int32_t *h_cell_xyz,
+                        uint64_t *h_rank_dof_begin);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,69 @@
+"""Host logic (no GPU): the product's closed-form box-mesh numbering / partition / ghost lists and
+its 1-D bases against the oracle's literal simulation of deal.II (oracle/fe_oracle.py).
+Bar: integer data bit-exact; 1-D matrices to 1e-13."""
+import numpy as np
+import pytest
+
+import benchmarks_b200 as b
+
+
+@pytest.mark.parametrize("p", range(1, 9))
+def test_basis_matches_oracle(oracle_mod, p):
+    fe = oracle_mod.fe
+    for nq, quad, kind in ((p + 2, "gauss", b.QUAD_GAUSS), (p + 1, "gauss", b.QUAD_GAUSS), (p + 1, "gll", b.QUAD_GLL)):
+        o = fe.basis_1d(p, nq, quad)
+        m = b.basis_1d(p, nq, kind)
+        assert np.abs(m["points"] - o["xq"]).max() < 1e-15
+        assert np.abs(m["weights"] - o["wq"]).max() < 1e-15
+        assert np.abs(m["shape_values"].reshape(p + 1, nq) - o["B"].T).max() < 1e-13
+        assert np.abs(m["co_shape_gradients"].reshape(nq, nq) - o["D"].T).max() < 1e-11 * np.abs(o["D"]).max()
+        assert np.abs(m["shape_gradients"].reshape(p + 1, nq) - o["Bg"].T).max() < 1e-11 * np.abs(o["Bg"]).max()
+
+
+CASES = [  # subdivisions, n_refine, p, n_ranks, partition
+    ((1, 1, 1), 0, 1, 1, "p4est"), ((1, 1, 1), 1, 2, 1, "p4est"), ((2, 2, 1), 1, 3, 1, "p4est"),
+    ((2, 1, 1), 2, 2, 1, "p4est"), ((1, 1, 1), 2, 4, 2, "p4est"), ((2, 2, 1), 1, 2, 3, "p4est"),
+    ((1, 1, 1), 2, 1, 8, "p4est"), ((2, 2, 2), 1, 3, 8, "p4est"), ((2, 1, 1), 1, 5, 4, "p4est"),
+    ((1, 1, 5), 1, 2, 4, "blocks"), ((2, 2, 7), 0, 3, 3, "blocks"), ((1, 1, 1), 1, 8, 2, "p4est"),
+]
+
+
+@pytest.mark.parametrize("sub,nref,p,nranks,scheme", CASES)
+@pytest.mark.parametrize("ghosts", ["minimal", "relevant"])
+def test_numbering_partition_ghosts_bitexact(oracle_mod, sub, nref, p, nranks, scheme, ghosts):
+    fe = oracle_mod.fe
+    omesh = fe.BoxMesh(sub, nref)
+    odofs = fe.distribute_dofs(omesh, p, nranks, scheme)
+    for rank in range(nranks):
+        ord_ = fe.rank_data(omesh, odofs, rank, ghost_set=ghosts)
+        m = b.BoxMesh(sub, nref, p, n_ranks=nranks, rank=rank,
+                      partition=b.PARTITION_P4EST if scheme == "p4est" else b.PARTITION_BLOCKS,
+                      ghosts=b.GHOSTS_MINIMAL if ghosts == "minimal" else b.GHOSTS_RELEVANT)
+        assert m.n_cells_global == omesh.n_cells
+        assert m.n_dofs_global == len(odofs["lattice_of_global"])
+        assert (m.owned_begin, m.owned_begin + m.n_owned) == odofs["owned_range"][rank]
+        assert m.first_cell == (ord_["cells"][0] if len(ord_["cells"]) else m.first_cell)
+        assert np.array_equal(m.cell_xyz, omesh.cell_xyz[ord_["cells"]])
+        assert np.array_equal(m.ghost_global.astype(np.int64), ord_["ghost_global"])
+        assert np.array_equal(m.ghost_owner, ord_["ghost_owner"])
+        assert np.array_equal(m.dof_indices, ord_["dof_indices"])
+        assert np.array_equal(m.constrained, ord_["constrained"])
+        assert [int(x) for x in m.rank_dof_begin] == [r[0] for r in odofs["owned_range"]] + [odofs["owned_range"][-1][1]]
+
+
+def test_bp3_sweep_dof_counts():
+    """Global DoF counts of the reference's p=4 sweep (CEED_bp/results/1xGH200_P4.txt:636-642)."""
+    expect = {8: (256, 18513), 9: (512, 35937), 10: (1024, 70785), 11: (2048, 139425), 12: (4096, 274625), 14: (16384, 1081665)}
+    for cycle, (cells, dofs) in expect.items():
+        m = b.BoxMesh.bp3_cycle(cycle, 4)
+        assert (m.n_cells_global, m.n_dofs_global) == (cells, dofs)
+        assert m.n_ghost == 0 and m.n_owned == dofs
+
+
+def test_mesh_argument_errors():
+    with pytest.raises(b.B200feError):
+        b.BoxMesh((1, 1, 1), 0, 9)
+    with pytest.raises(b.B200feError):
+        b.BoxMesh((1, 1, 1), 0, 2, n_ranks=2, rank=0)  # fewer cells than ranks
+    with pytest.raises(b.B200feError):
+        b.BoxMesh((1, 0, 1), 0, 2)
