@@ -4,6 +4,8 @@ from __future__ import annotations
 import ctypes as C
 import os
 
+import torch  # noqa: F401  (first: so that libnccl.so.2 resolves to the build torch ships)
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200FE_LIB") or os.path.join(_HERE, "libb200fe.so")  # env override: tuning variants only
 
@@ -38,6 +40,28 @@ _SIGNATURES = {
     "b200fe_boxmesh_destroy": (None, [_vp]),
     "b200fe_boxmesh_info": (_i, [_vp, _vp]),
     "b200fe_boxmesh_fill": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200fe_boxmesh_nodes": (_i, [_vp, _i, _i, C.c_double, C.c_double, _vp, _vp]),
+    "b200fe_geometry_from_nodes": (_i, [_i, _i, _i, _u32, _vp, _vp, _vp, _vp]),
+    "b200fe_op_create": (_i, [_vp, C.POINTER(_vp)]),
+    "b200fe_op_destroy": (None, [_vp]),
+    "b200fe_op_set_halo": (_i, [_vp, _vp]),
+    "b200fe_op_vmult": (_i, [_vp, _vp, _vp, _vp]),
+    "b200fe_op_vmult_dot": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "b200fe_op_vmult_dummy": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "b200fe_op_vmult_host": (_i, [_vp, _vp, _vp, _vp]),
+    "b200fe_op_diagonal": (_i, [_vp, _vp, _vp]),
+    "b200fe_op_rhs_one": (_i, [_vp, _vp, _vp]),
+    "b200fe_op_launch_info": (_i, [_vp, _pi, _pi, _pi, _pi, _pi, _pi]),
+    "b200fe_cg_solve": (_i, [_vp, _vp, _vp, _vp, C.c_double, C.c_double, _i, _i, _vp, _vp]),
+    "b200fe_cg_solve_host": (_i, [_vp, _vp, _vp, _vp, C.c_double, C.c_double, _i, _i, _vp, _vp]),
+    "b200fe_comm_available": (_i, []),
+    "b200fe_comm_unique_id": (_i, [_vp]),
+    "b200fe_halo_create": (_i, [_vp, C.POINTER(_vp)]),
+    "b200fe_halo_destroy": (None, [_vp]),
+    "b200fe_halo_update_ghosts": (_i, [_vp, _vp, _vp]),
+    "b200fe_halo_compress_add": (_i, [_vp, _vp, _vp]),
+    "b200fe_halo_zero_ghosts": (_i, [_vp, _vp, _vp]),
+    "b200fe_halo_allreduce_sum": (_i, [_vp, _vp, _i, _vp]),
 }
 for _name, (_res, _args) in _SIGNATURES.items():
     _f = getattr(lib, _name)

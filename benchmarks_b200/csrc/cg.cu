@@ -1,0 +1,268 @@
+// cg.cu -- C ABI section 5: conjugate gradients with fused vector updates and device-side control.
+//
+// Mirrors dealii::SolverCG + ReductionControl as the reference drivers use them
+// (CEED_bp/src/bp3.cc:266-285: PreconditionIdentity, ReductionControl(1e9, 1e-16, 1e-9);
+//  bp5_kokkos/benchmark.cc:355-378: Jacobi, ReductionControl(100, 1e-15, 1e-8), NoConvergence
+//  swallowed); loop restated from SURVEY.md appendix A9:
+//     r = b (x0 = 0); res0 = |r|
+//     it = 1..: rho_old = rho; rho = r.z (z = P^-1 r); p = z + (rho/rho_old) p (first: p = z)
+//               v = A p; alpha = rho / (p.v); x += alpha p; r -= alpha v; res = |r|
+//     stop when res <= abs_tol or res <= rel_tol * res0; last_step() = it
+//
+// B200 design: per iteration three kernels instead of deal.II's five vector sweeps + two host-synchronous
+// reductions:   [scalar step]  ->  [p = z + beta p]  ->  [v = A p with p.v fused into the cell kernel]
+//               ->  [x += alpha p; r -= alpha v; r.r and r.z fused]
+// alpha/beta/convergence live in device memory; the host only polls a flag every `check_every`
+// iterations, and iterations queued after convergence are no-ops, so x is exactly the iterate at
+// which ReductionControl would have stopped.
+#include <cmath>
+#include <cstring>
+#include <memory>
+
+#include "halo.h"
+#include "operator.h"
+
+namespace b200fe {
+
+namespace {
+
+struct CgScalars {      // device-resident
+    double rho, rho_old;
+    double acc[3];      // [0] p.Ap  [1] r.r  [2] r.z   (summed over ranks in place)
+    double res0, res;
+    int it;             // iterations started
+    int done, converged, its;
+};
+
+__global__ void cg_init_kernel(uint32_t n, const double *__restrict__ b, double *__restrict__ x, double *__restrict__ r,
+                               const double *__restrict__ inv_diag, CgScalars *sc)
+{
+    double rr = 0.0, rz = 0.0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double bi = b[i];
+        x[i] = 0.0;
+        r[i] = bi;
+        rr = fma(bi, bi, rr);
+        if (inv_diag) rz = fma(bi * inv_diag[i], bi, rz);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        rr += __shfl_xor_sync(0xffffffffu, rr, o);
+        rz += __shfl_xor_sync(0xffffffffu, rz, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&sc->acc[1], rr);
+        if (inv_diag) atomicAdd(&sc->acc[2], rz);
+    }
+}
+
+// ReductionControl check for the iterate just finished, then set up rho for the next iteration
+__global__ void cg_scalar_kernel(CgScalars *sc, int jacobi, int max_it, double abs_tol, double rel_tol)
+{
+    if (sc->done) return;
+    const double res = sqrt(fabs(sc->acc[1]));
+    sc->res = res;
+    if (sc->it == 0) sc->res0 = res;
+    if (res <= abs_tol || res <= rel_tol * sc->res0) {
+        sc->done = 1; sc->converged = 1; sc->its = sc->it;
+        return;
+    }
+    if (sc->it >= max_it) {
+        sc->done = 1; sc->converged = 0; sc->its = sc->it;
+        return;
+    }
+    sc->rho_old = sc->rho;
+    sc->rho = jacobi ? sc->acc[2] : sc->acc[1];
+    sc->acc[0] = sc->acc[1] = sc->acc[2] = 0.0;
+    sc->it += 1;
+}
+
+__global__ void cg_update_p_kernel(uint32_t n, const double *__restrict__ r, const double *__restrict__ inv_diag,
+                                   double *__restrict__ p, const CgScalars *sc)
+{
+    if (sc->done) return;
+    const bool first = sc->it == 1;
+    const double beta = first ? 0.0 : sc->rho / sc->rho_old;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double z = inv_diag ? inv_diag[i] * r[i] : r[i];
+        p[i] = first ? z : fma(beta, p[i], z);
+    }
+}
+
+__global__ void cg_update_xr_kernel(uint32_t n, const double *__restrict__ p, const double *__restrict__ v,
+                                    const double *__restrict__ inv_diag, double *__restrict__ x, double *__restrict__ r,
+                                    CgScalars *sc)
+{
+    if (sc->done) return;
+    const double alpha = sc->rho / sc->acc[0];
+    double rr = 0.0, rz = 0.0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        x[i] = fma(alpha, p[i], x[i]);
+        const double ri = fma(-alpha, v[i], r[i]);
+        r[i] = ri;
+        rr = fma(ri, ri, rr);
+        if (inv_diag) rz = fma(ri * inv_diag[i], ri, rz);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        rr += __shfl_xor_sync(0xffffffffu, rr, o);
+        rz += __shfl_xor_sync(0xffffffffu, rz, o);
+    }
+    __shared__ double s_rr[32], s_rz[32];
+    if ((threadIdx.x & 31) == 0) { s_rr[threadIdx.x >> 5] = rr; s_rz[threadIdx.x >> 5] = rz; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        rr = threadIdx.x < (blockDim.x >> 5) ? s_rr[threadIdx.x] : 0.0;
+        rz = threadIdx.x < (blockDim.x >> 5) ? s_rz[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) {
+            rr += __shfl_xor_sync(0xffffffffu, rr, o);
+            rz += __shfl_xor_sync(0xffffffffu, rz, o);
+        }
+        if (threadIdx.x == 0) {
+            // NB: acc[1]/acc[2] were zeroed by the scalar step; acc[0] is consumed above by every block
+            atomicAdd(&sc->acc[1], rr);
+            if (inv_diag) atomicAdd(&sc->acc[2], rz);
+        }
+    }
+}
+
+}  // namespace
+
+struct CgWork {
+    uint32_t n_local = 0;
+    double *r = nullptr, *p = nullptr, *v = nullptr, *xb = nullptr;  // xb: x and b for the host-buffer entry point
+    CgScalars *sc = nullptr;
+    CgScalars *h_sc = nullptr;  // pinned
+    ~CgWork()
+    {
+        cudaFree(r); cudaFree(p); cudaFree(v); cudaFree(xb); cudaFree(sc);
+        if (h_sc) cudaFreeHost(h_sc);
+    }
+};
+
+static int ensure_work(std::unique_ptr<CgWork> &w, uint32_t n_local, bool need_xb)
+{
+    if (!w || w->n_local != n_local) {
+        w = std::make_unique<CgWork>();
+        w->n_local = n_local;
+        const size_t bytes = sizeof(double) * std::max<uint32_t>(n_local, 1);
+        B200FE_CUDA_TRY(cudaMalloc(&w->r, bytes));
+        B200FE_CUDA_TRY(cudaMalloc(&w->p, bytes));
+        B200FE_CUDA_TRY(cudaMalloc(&w->v, bytes));
+        B200FE_CUDA_TRY(cudaMalloc(&w->sc, sizeof(CgScalars)));
+        B200FE_CUDA_TRY(cudaMallocHost(&w->h_sc, sizeof(CgScalars)));
+    }
+    if (need_xb && !w->xb) B200FE_CUDA_TRY(cudaMalloc(&w->xb, 2 * sizeof(double) * std::max<uint32_t>(n_local, 1)));
+    return B200FE_OK;
+}
+
+// one workspace per operator, keyed by the operator pointer (small map; operators are few)
+static std::unique_ptr<CgWork> &work_of(Operator *op)
+{
+    static std::vector<std::pair<Operator *, std::unique_ptr<CgWork>>> table;
+    for (auto &e : table)
+        if (e.first == op) return e.second;
+    table.emplace_back(op, nullptr);
+    return table.back().second;
+}
+
+void cg_release_work(Operator *op)
+{
+    auto &w = work_of(op);
+    w.reset();
+}
+
+static int cg_run(Operator &op, CgWork &w, double *d_x, const double *d_b, const double *d_inv_diag, double abs_tol,
+                  double rel_tol, int max_it, int check_every, b200fe_cg_result *res, cudaStream_t s)
+{
+    const uint32_t n = op.n_owned;
+    const unsigned blocks = n == 0 ? 1u : std::min<unsigned>((n + 1023) / 1024, 148u * 8u);
+    const int jacobi = d_inv_diag != nullptr;
+    if (check_every < 1) check_every = 1;
+    B200FE_CUDA_TRY(cudaMemsetAsync(w.sc, 0, sizeof(CgScalars), s));
+    // p and v carry ghost entries: start from a clean ghost segment
+    B200FE_CUDA_TRY(cudaMemsetAsync(w.p, 0, sizeof(double) * op.n_local(), s));
+    cg_init_kernel<<<blocks, 256, 0, s>>>(n, d_b, d_x, w.r, d_inv_diag, w.sc);
+    B200FE_CUDA_TRY(cudaGetLastError());
+    if (op.halo)
+        if (int rc = halo_allreduce_sum(*op.halo, w.sc->acc + 1, 2, s)) return rc;
+    int launched = 0;
+    for (;;) {
+        cg_scalar_kernel<<<1, 1, 0, s>>>(w.sc, jacobi, max_it, abs_tol, rel_tol);
+        B200FE_CUDA_TRY(cudaGetLastError());
+        if (launched % check_every == 0 || launched >= max_it) {
+            B200FE_CUDA_TRY(cudaMemcpyAsync(w.h_sc, w.sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, s));
+            B200FE_CUDA_TRY(cudaStreamSynchronize(s));
+            if (w.h_sc->done) break;
+        }
+        cg_update_p_kernel<<<blocks, 256, 0, s>>>(n, w.r, d_inv_diag, w.p, w.sc);
+        B200FE_CUDA_TRY(cudaGetLastError());
+        if (int rc = op_vmult(op, w.v, w.p, &w.sc->acc[0], true, true, s)) return rc;
+        if (op.halo)
+            if (int rc = halo_allreduce_sum(*op.halo, w.sc->acc, 1, s)) return rc;
+        cg_update_xr_kernel<<<blocks, 256, 0, s>>>(n, w.p, w.v, d_inv_diag, d_x, w.r, w.sc);
+        B200FE_CUDA_TRY(cudaGetLastError());
+        if (op.halo)
+            if (int rc = halo_allreduce_sum(*op.halo, w.sc->acc + 1, 2, s)) return rc;
+        ++launched;
+    }
+    if (res) {
+        res->iterations = w.h_sc->its;
+        res->converged = w.h_sc->converged;
+        res->initial_residual = w.h_sc->res0;
+        res->final_residual = w.h_sc->res;
+    }
+    return w.h_sc->converged ? B200FE_OK : B200FE_ERR_NO_CONVERGENCE;
+}
+
+}  // namespace b200fe
+
+using namespace b200fe;
+
+extern "C" {
+
+int b200fe_cg_solve(b200fe_op *o, double *d_x, const double *d_b, const double *d_inv_diag, double abs_tol,
+                    double rel_tol, int max_it, int check_every, b200fe_cg_result *result, void *stream)
+{
+    B200FE_REQUIRE(o && d_x && d_b, "b200fe_cg_solve: null pointer");
+    B200FE_REQUIRE(max_it >= 0, "b200fe_cg_solve: max_it < 0");
+    Operator &op = *reinterpret_cast<Operator *>(o);
+    auto &w = work_of(&op);
+    if (int rc = ensure_work(w, op.n_local(), false)) return rc;
+    int rc = cg_run(op, *w, d_x, d_b, d_inv_diag, abs_tol, rel_tol, max_it, check_every, result, (cudaStream_t)stream);
+    if (rc == B200FE_ERR_NO_CONVERGENCE) fail(rc, "CG did not converge in %d iterations", max_it);
+    return rc;
+}
+
+int b200fe_cg_solve_host(b200fe_op *o, double *h_x, const double *h_b, const double *d_inv_diag, double abs_tol,
+                         double rel_tol, int max_it, int check_every, b200fe_cg_result *result, void *stream)
+{
+    B200FE_REQUIRE(o && h_x && h_b, "b200fe_cg_solve_host: null pointer");
+    Operator &op = *reinterpret_cast<Operator *>(o);
+    auto &w = work_of(&op);
+    if (int rc = ensure_work(w, op.n_local(), true)) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    double *d_x = w->xb, *d_b = w->xb + std::max<uint32_t>(op.n_local(), 1);
+    B200FE_CUDA_TRY(cudaMemcpyAsync(d_b, h_b, sizeof(double) * op.n_owned, cudaMemcpyHostToDevice, s));
+    int rc = cg_run(op, *w, d_x, d_b, d_inv_diag, abs_tol, rel_tol, max_it, check_every, result, s);
+    if (rc != B200FE_OK && rc != B200FE_ERR_NO_CONVERGENCE) return rc;
+    B200FE_CUDA_TRY(cudaMemcpyAsync(h_x, d_x, sizeof(double) * op.n_owned, cudaMemcpyDeviceToHost, s));
+    B200FE_CUDA_TRY(cudaStreamSynchronize(s));
+    if (rc == B200FE_ERR_NO_CONVERGENCE) fail(rc, "CG did not converge in %d iterations", max_it);
+    return rc;
+}
+
+int b200fe_op_vmult_host(b200fe_op *o, double *h_dst, const double *h_src, void *stream)
+{
+    B200FE_REQUIRE(o && h_dst && h_src, "b200fe_op_vmult_host: null pointer");
+    Operator &op = *reinterpret_cast<Operator *>(o);
+    auto &w = work_of(&op);
+    if (int rc = ensure_work(w, op.n_local(), false)) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    B200FE_CUDA_TRY(cudaMemsetAsync(w->p, 0, sizeof(double) * op.n_local(), s));
+    B200FE_CUDA_TRY(cudaMemcpyAsync(w->p, h_src, sizeof(double) * op.n_owned, cudaMemcpyHostToDevice, s));
+    if (int rc = op_vmult(op, w->v, w->p, nullptr, true, true, s)) return rc;
+    B200FE_CUDA_TRY(cudaMemcpyAsync(h_dst, w->v, sizeof(double) * op.n_owned, cudaMemcpyDeviceToHost, s));
+    B200FE_CUDA_TRY(cudaStreamSynchronize(s));
+    return B200FE_OK;
+}
+
+}  // extern "C"

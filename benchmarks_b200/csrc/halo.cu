@@ -1,0 +1,283 @@
+// halo.cu -- C ABI section 6: ghost-DoF exchange and scalar all-reduce over NCCL (NVLink 5 / NVSwitch).
+//
+// One process per GPU.  NCCL is bound lazily with dlopen("libnccl.so.2") so that the library (and
+// its symbol table) loads on machines without NCCL; inside a PyTorch process this resolves to the
+// NCCL build torch already loaded.  Exchange pattern = deal.II Partitioner:
+//   update_ghosts : owners pack import_indices, peers receive straight into their ghost segment
+//   compress_add  : ghost segments travel back, owners add them into import_indices, ghosts zeroed
+// which is also p-halox's Irecv/Isend/Waitall round (p-halox/phalox.cc:104-126) with NCCL grouping.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstring>
+#include <memory>
+
+#include "common.h"
+#include "halo.h"
+
+namespace b200fe {
+
+namespace {
+
+struct Nccl {
+    void *h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    ncclResult_t (*GetVersion)(int *) = nullptr;
+    bool ok = false;
+};
+
+Nccl &nccl()
+{
+    static Nccl n = [] {
+        Nccl x;
+        x.h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!x.h) x.h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!x.h) return x;
+        auto sym = [&](const char *name) { return dlsym(x.h, name); };
+        x.GetUniqueId = (decltype(x.GetUniqueId))sym("ncclGetUniqueId");
+        x.CommInitRank = (decltype(x.CommInitRank))sym("ncclCommInitRank");
+        x.CommDestroy = (decltype(x.CommDestroy))sym("ncclCommDestroy");
+        x.Send = (decltype(x.Send))sym("ncclSend");
+        x.Recv = (decltype(x.Recv))sym("ncclRecv");
+        x.AllReduce = (decltype(x.AllReduce))sym("ncclAllReduce");
+        x.GroupStart = (decltype(x.GroupStart))sym("ncclGroupStart");
+        x.GroupEnd = (decltype(x.GroupEnd))sym("ncclGroupEnd");
+        x.GetErrorString = (decltype(x.GetErrorString))sym("ncclGetErrorString");
+        x.GetVersion = (decltype(x.GetVersion))sym("ncclGetVersion");
+        x.ok = x.GetUniqueId && x.CommInitRank && x.CommDestroy && x.Send && x.Recv && x.AllReduce && x.GroupStart &&
+               x.GroupEnd && x.GetErrorString;
+        return x;
+    }();
+    return n;
+}
+
+int fail_nccl(ncclResult_t r, const char *what)
+{
+    return fail(B200FE_ERR_COMM, "NCCL error %d (%s) in %s", (int)r, nccl().GetErrorString ? nccl().GetErrorString(r) : "?", what);
+}
+
+#define B200FE_NCCL_TRY(expr)                                  \
+    do {                                                       \
+        ncclResult_t _r = (expr);                              \
+        if (_r != ncclSuccess) return fail_nccl(_r, #expr);    \
+    } while (0)
+
+__global__ void pack_kernel(uint32_t n, const uint32_t *__restrict__ idx, const double *__restrict__ v,
+                            double *__restrict__ buf)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) buf[i] = v[idx[i]];
+}
+
+// the same owned DoF may be ghosted by several peers -> atomic accumulate
+__global__ void unpack_add_kernel(uint32_t n, const uint32_t *__restrict__ idx, const double *__restrict__ buf,
+                                  double *__restrict__ v)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) atomicAdd(v + idx[i], buf[i]);
+}
+
+inline unsigned blocks_for(uint32_t n) { return n == 0 ? 1u : std::min<unsigned>((n + 255) / 256, 148u * 8u); }
+
+int exchange_update(Halo &h, double *v, cudaStream_t s)
+{
+    Nccl &n = nccl();
+    if (h.n_send) {
+        pack_kernel<<<blocks_for(h.n_send), 256, 0, s>>>(h.n_send, h.d_send_idx, v, h.d_pack);
+        B200FE_CUDA_TRY(cudaGetLastError());
+    }
+    B200FE_NCCL_TRY(n.GroupStart());
+    for (size_t k = 0; k < h.peers.size(); ++k) {
+        if (h.recv_cnt[k]) B200FE_NCCL_TRY(n.Recv(v + h.n_owned + h.recv_off[k], h.recv_cnt[k], ncclDouble, h.peers[k], (ncclComm_t)h.comm, s));
+        if (h.send_cnt[k]) B200FE_NCCL_TRY(n.Send(h.d_pack + h.send_off[k], h.send_cnt[k], ncclDouble, h.peers[k], (ncclComm_t)h.comm, s));
+    }
+    B200FE_NCCL_TRY(n.GroupEnd());
+    return B200FE_OK;
+}
+
+int exchange_compress(Halo &h, double *v, cudaStream_t s)
+{
+    Nccl &n = nccl();
+    B200FE_NCCL_TRY(n.GroupStart());
+    for (size_t k = 0; k < h.peers.size(); ++k) {
+        if (h.send_cnt[k]) B200FE_NCCL_TRY(n.Recv(h.d_pack + h.send_off[k], h.send_cnt[k], ncclDouble, h.peers[k], (ncclComm_t)h.comm, s));
+        if (h.recv_cnt[k]) B200FE_NCCL_TRY(n.Send(v + h.n_owned + h.recv_off[k], h.recv_cnt[k], ncclDouble, h.peers[k], (ncclComm_t)h.comm, s));
+    }
+    B200FE_NCCL_TRY(n.GroupEnd());
+    return B200FE_OK;
+}
+
+int unpack_and_zero(Halo &h, double *v, cudaStream_t s)
+{
+    if (h.n_send) {
+        unpack_add_kernel<<<blocks_for(h.n_send), 256, 0, s>>>(h.n_send, h.d_send_idx, h.d_pack, v);
+        B200FE_CUDA_TRY(cudaGetLastError());
+    }
+    return halo_zero_ghosts(h, v, s);
+}
+
+}  // namespace
+
+int halo_zero_ghosts(Halo &h, double *v, cudaStream_t s)
+{
+    if (h.n_ghost) B200FE_CUDA_TRY(cudaMemsetAsync(v + h.n_owned, 0, sizeof(double) * h.n_ghost, s));
+    return B200FE_OK;
+}
+
+int halo_update_ghosts(Halo &h, double *v, cudaStream_t s)
+{
+    if (h.n_ranks == 1) return B200FE_OK;
+    return exchange_update(h, v, s);
+}
+
+int halo_compress_add(Halo &h, double *v, cudaStream_t s)
+{
+    if (h.n_ranks == 1) return B200FE_OK;
+    if (int rc = exchange_compress(h, v, s)) return rc;
+    return unpack_and_zero(h, v, s);
+}
+
+int halo_update_ghosts_start(Halo &h, double *v, cudaStream_t s)
+{
+    if (h.n_ranks == 1) return B200FE_OK;
+    B200FE_CUDA_TRY(cudaEventRecord(h.ev_ready, s));
+    B200FE_CUDA_TRY(cudaStreamWaitEvent(h.comm_stream, h.ev_ready, 0));
+    if (int rc = exchange_update(h, v, h.comm_stream)) return rc;
+    B200FE_CUDA_TRY(cudaEventRecord(h.ev_done, h.comm_stream));
+    return B200FE_OK;
+}
+
+int halo_update_ghosts_finish(Halo &h, cudaStream_t s)
+{
+    if (h.n_ranks == 1) return B200FE_OK;
+    B200FE_CUDA_TRY(cudaStreamWaitEvent(s, h.ev_done, 0));
+    return B200FE_OK;
+}
+
+int halo_compress_start(Halo &h, double *v, cudaStream_t s)
+{
+    if (h.n_ranks == 1) return B200FE_OK;
+    B200FE_CUDA_TRY(cudaEventRecord(h.ev_ready, s));
+    B200FE_CUDA_TRY(cudaStreamWaitEvent(h.comm_stream, h.ev_ready, 0));
+    if (int rc = exchange_compress(h, v, h.comm_stream)) return rc;
+    B200FE_CUDA_TRY(cudaEventRecord(h.ev_done, h.comm_stream));
+    return B200FE_OK;
+}
+
+int halo_compress_finish(Halo &h, double *v, cudaStream_t s)
+{
+    if (h.n_ranks == 1) return B200FE_OK;
+    B200FE_CUDA_TRY(cudaStreamWaitEvent(s, h.ev_done, 0));
+    return unpack_and_zero(h, v, s);
+}
+
+int halo_allreduce_sum(Halo &h, double *d_vals, int count, cudaStream_t s)
+{
+    if (h.n_ranks == 1) return B200FE_OK;
+    B200FE_NCCL_TRY(nccl().AllReduce(d_vals, d_vals, count, ncclDouble, ncclSum, (ncclComm_t)h.comm, s));
+    return B200FE_OK;
+}
+
+}  // namespace b200fe
+
+using namespace b200fe;
+
+extern "C" {
+
+int b200fe_comm_available(void) { return nccl().ok ? 1 : 0; }
+
+int b200fe_comm_unique_id(char *id128)
+{
+    B200FE_REQUIRE(id128, "b200fe_comm_unique_id: null pointer");
+    if (!nccl().ok) return fail(B200FE_ERR_COMM, "libnccl.so.2 not found");
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    B200FE_NCCL_TRY(nccl().GetUniqueId(&id));
+    std::memcpy(id128, &id, 128);
+    return B200FE_OK;
+}
+
+int b200fe_halo_create(const b200fe_halo_desc *d, b200fe_halo **out)
+{
+    B200FE_REQUIRE(d && out, "b200fe_halo_create: null pointer");
+    B200FE_REQUIRE(d->n_ranks >= 1 && d->rank >= 0 && d->rank < d->n_ranks, "b200fe_halo_create: bad rank %d of %d", d->rank, d->n_ranks);
+    B200FE_REQUIRE(d->n_peers >= 0 && (d->n_peers == 0 || (d->peers && d->recv_offset && d->recv_count && d->send_offset && d->send_count)),
+                   "b200fe_halo_create: peer tables missing");
+    auto h = std::make_unique<Halo>();
+    h->rank = d->rank; h->n_ranks = d->n_ranks; h->n_owned = d->n_owned; h->n_ghost = d->n_ghost; h->n_send = d->n_send;
+    for (int k = 0; k < d->n_peers; ++k) {
+        B200FE_REQUIRE(d->peers[k] >= 0 && d->peers[k] < d->n_ranks && d->peers[k] != d->rank, "b200fe_halo_create: bad peer %d", d->peers[k]);
+        B200FE_REQUIRE((uint64_t)d->recv_offset[k] + d->recv_count[k] <= d->n_ghost, "b200fe_halo_create: recv slice of peer %d exceeds the ghost segment", d->peers[k]);
+        B200FE_REQUIRE((uint64_t)d->send_offset[k] + d->send_count[k] <= d->n_send, "b200fe_halo_create: send slice of peer %d exceeds the send list", d->peers[k]);
+        h->peers.push_back(d->peers[k]);
+        h->recv_off.push_back(d->recv_offset[k]); h->recv_cnt.push_back(d->recv_count[k]);
+        h->send_off.push_back(d->send_offset[k]); h->send_cnt.push_back(d->send_count[k]);
+    }
+    B200FE_REQUIRE(d->n_send == 0 || d->h_send_indices, "b200fe_halo_create: send indices missing");
+    for (uint32_t i = 0; i < d->n_send; ++i)
+        B200FE_REQUIRE(d->h_send_indices[i] < d->n_owned, "b200fe_halo_create: send index %u is not an owned DoF", d->h_send_indices[i]);
+    if (d->n_ranks > 1) {
+        B200FE_REQUIRE(d->nccl_unique_id, "b200fe_halo_create: nccl_unique_id missing");
+        if (!nccl().ok) return fail(B200FE_ERR_COMM, "libnccl.so.2 not found");
+        ncclUniqueId id;
+        std::memcpy(&id, d->nccl_unique_id, 128);
+        ncclComm_t comm;
+        B200FE_NCCL_TRY(nccl().CommInitRank(&comm, d->n_ranks, id, d->rank));
+        h->comm = comm; h->owns_comm = true;
+        if (d->n_send) {
+            B200FE_CUDA_TRY(cudaMalloc(&h->d_send_idx, d->n_send * sizeof(uint32_t)));
+            B200FE_CUDA_TRY(cudaMemcpy(h->d_send_idx, d->h_send_indices, d->n_send * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            B200FE_CUDA_TRY(cudaMalloc(&h->d_pack, d->n_send * sizeof(double)));
+        }
+        B200FE_CUDA_TRY(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+        B200FE_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
+        B200FE_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
+    }
+    *out = reinterpret_cast<b200fe_halo *>(h.release());
+    return B200FE_OK;
+}
+
+void b200fe_halo_destroy(b200fe_halo *halo)
+{
+    Halo *h = reinterpret_cast<Halo *>(halo);
+    if (!h) return;
+    if (h->comm && h->owns_comm) nccl().CommDestroy((ncclComm_t)h->comm);
+    cudaFree(h->d_send_idx);
+    cudaFree(h->d_pack);
+    if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+    if (h->ev_ready) cudaEventDestroy(h->ev_ready);
+    if (h->ev_done) cudaEventDestroy(h->ev_done);
+    delete h;
+}
+
+int b200fe_halo_update_ghosts(b200fe_halo *halo, double *d_v, void *stream)
+{
+    B200FE_REQUIRE(halo && d_v, "b200fe_halo_update_ghosts: null pointer");
+    return halo_update_ghosts(*reinterpret_cast<Halo *>(halo), d_v, (cudaStream_t)stream);
+}
+
+int b200fe_halo_compress_add(b200fe_halo *halo, double *d_v, void *stream)
+{
+    B200FE_REQUIRE(halo && d_v, "b200fe_halo_compress_add: null pointer");
+    return halo_compress_add(*reinterpret_cast<Halo *>(halo), d_v, (cudaStream_t)stream);
+}
+
+int b200fe_halo_zero_ghosts(b200fe_halo *halo, double *d_v, void *stream)
+{
+    B200FE_REQUIRE(halo && d_v, "b200fe_halo_zero_ghosts: null pointer");
+    return halo_zero_ghosts(*reinterpret_cast<Halo *>(halo), d_v, (cudaStream_t)stream);
+}
+
+int b200fe_halo_allreduce_sum(b200fe_halo *halo, double *d_vals, int count, void *stream)
+{
+    B200FE_REQUIRE(halo && d_vals && count >= 0, "b200fe_halo_allreduce_sum: bad arguments");
+    return halo_allreduce_sum(*reinterpret_cast<Halo *>(halo), d_vals, count, (cudaStream_t)stream);
+}
+
+}  // extern "C"

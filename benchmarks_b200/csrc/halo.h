@@ -1,0 +1,44 @@
+// halo.h -- ghost-DoF exchange between the ranks of one NVSwitch domain (NCCL send/recv).
+//
+// Replaces deal.II's LinearAlgebra::distributed::Vector::update_ghost_values / compress(add) /
+// zero_out_ghost_values as used by CEED_bp/include/portable_laplace_operator.h:133,169,170 and the
+// split-phase variants of bakeoff_problems_dealii/include/portable_laplace_operator.h:669-695,
+// and the raw MPI_Isend/Irecv exchange of p-halox/phalox.cc:104-126.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <vector>
+
+namespace b200fe {
+
+struct Halo {
+    void *comm = nullptr;  // ncclComm_t (owned when created from a unique id)
+    bool owns_comm = false;
+    int rank = 0, n_ranks = 1;
+    uint32_t n_owned = 0, n_ghost = 0;
+    std::vector<int> peers;
+    std::vector<uint32_t> recv_off, recv_cnt;  // slices of the ghost segment (offset relative to n_owned)
+    std::vector<uint32_t> send_off, send_cnt;  // slices of the packed send list
+    uint32_t n_send = 0;
+    uint32_t *d_send_idx = nullptr;  // owned local indices to pack, grouped by peer
+    double *d_pack = nullptr;        // [n_send] packed owner values (update) / incoming contributions (compress)
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
+};
+
+// owner -> ghost copy of v (all on stream s)
+int halo_update_ghosts(Halo &h, double *d_v, cudaStream_t s);
+// ghost -> owner additive reduction of v, ghosts zeroed afterwards
+int halo_compress_add(Halo &h, double *d_v, cudaStream_t s);
+// split-phase versions for the 3-phase overlap schedule: work is issued on h.comm_stream after
+// everything already queued on s; *_finish makes s wait for it.
+int halo_update_ghosts_start(Halo &h, double *d_v, cudaStream_t s);
+int halo_update_ghosts_finish(Halo &h, cudaStream_t s);
+int halo_compress_start(Halo &h, double *d_v, cudaStream_t s);
+int halo_compress_finish(Halo &h, double *d_v, cudaStream_t s);
+int halo_zero_ghosts(Halo &h, double *d_v, cudaStream_t s);
+// sum over ranks of n doubles in place (CG inner products)
+int halo_allreduce_sum(Halo &h, double *d_vals, int n, cudaStream_t s);
+
+}  // namespace b200fe

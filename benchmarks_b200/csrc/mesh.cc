@@ -380,7 +380,7 @@ int b200fe_boxmesh_info(const b200fe_boxmesh *mesh, b200fe_boxmesh_info_t *info)
     info->n_owned = (uint32_t)(m->owned_end - m->owned_begin);
     info->n_ghost = (uint32_t)m->ghost_global.size();
     info->n_constrained = (uint32_t)m->constrained.size();
-    for (int d = 0; d < 3; ++d) { info->cells[d] = (uint32_t)m->cells[d]; info->h[d] = m->h[d]; }
+    for (int d = 0; d < 3; ++d) { info->cells[d] = (uint32_t)m->cells[d]; info->h[d] = m->h[d]; info->origin[d] = m->p1[d]; }
     return B200FE_OK;
 }
 

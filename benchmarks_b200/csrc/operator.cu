@@ -1,0 +1,482 @@
+// operator.cu -- C ABI section 4: geometry, the L-vector operator object (vmult & friends).
+//
+// Host-side mirror of Portable::LaplaceOperator (CEED_bp/include/portable_laplace_operator.h:17-96):
+//   ctor            -> b200fe_op_create           (:98-122)
+//   vmult           -> b200fe_op_vmult            (:124-172)
+//   vmult_dummy     -> b200fe_op_vmult_dummy      (:175-235)
+//   compute_G_tensors -> b200fe_geometry_from_nodes (:239-302, math of
+//                        bakeoff_problems_dealii/include/portable_laplace_operator.h:227-258)
+//   compute_diagonal  -> b200fe_op_diagonal       (bp5_kokkos/benchmark.cc:218-251)
+//   compute_rhs       -> b200fe_op_rhs_one        (CEED_bp/src/bp3.cc:184-239)
+#include <cstring>
+#include <memory>
+
+#include "halo.h"
+#include "operator.h"
+
+namespace b200fe {
+
+// ---------------------------------------------------------------------------------------------
+// setup kernels (not on the timed path): simple, runtime-sized
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct GeoMats {          // geometry basis at the quadrature points, ng <= 9, nq <= 10
+    double V[10 * 9];     // V[q*ng+a]
+    double dV[10 * 9];
+    double w[10];
+};
+
+// mapping support points of a (possibly smoothly deformed) box mesh: nodes[cell][d][c][b][a]
+__global__ void box_nodes_kernel(uint32_t n_cells, int ng, const int32_t *__restrict__ cell_xyz,
+                                 double p1x, double p1y, double p1z, double hx, double hy, double hz,
+                                 const double *__restrict__ t /*[ng] GLL on [0,1]*/, int deform_kind,
+                                 double amp, double freq, double *__restrict__ nodes)
+{
+    const int ng3 = ng * ng * ng;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (uint64_t)n_cells * ng3) return;
+    const uint32_t cell = (uint32_t)(i / ng3);
+    const int n = (int)(i % ng3), a = n % ng, b = (n / ng) % ng, c = n / (ng * ng);
+    double x = p1x + (cell_xyz[cell * 3 + 0] + t[a]) * hx;
+    double y = p1y + (cell_xyz[cell * 3 + 1] + t[b]) * hy;
+    double z = p1z + (cell_xyz[cell * 3 + 2] + t[c]) * hz;
+    if (deform_kind == 1) {  // smooth volume-preserving-ish perturbation, same family as bk3_dealii/check_bk3.cc:50-52
+        const double dx = amp * sin(freq * y), dy = amp * sin(freq * z), dz = amp * sin(freq * x);
+        x += dx; y += dy; z += dz;
+    }
+    double *o = nodes + (size_t)cell * 3 * ng3 + n;
+    o[0] = x; o[ng3] = y; o[2 * ng3] = z;
+}
+
+// one CTA per cell, one thread per quadrature point (looping): J = sum_nodes x_node grad phi_node
+__global__ void geometry_kernel(const __grid_constant__ GeoMats gm, uint32_t n_cells, int ng, int nq,
+                                const double *__restrict__ nodes, double *__restrict__ G,
+                                double *__restrict__ JxW)
+{
+    extern __shared__ double sn[];  // 3*ng^3
+    const int ng3 = ng * ng * ng, nq3 = nq * nq * nq;
+    for (uint32_t cell = blockIdx.x; cell < n_cells; cell += gridDim.x) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 3 * ng3; i += blockDim.x) sn[i] = nodes[(size_t)cell * 3 * ng3 + i];
+        __syncthreads();
+        for (int pt = threadIdx.x; pt < nq3; pt += blockDim.x) {
+            const int qx = pt % nq, qy = (pt / nq) % nq, qz = pt / (nq * nq);  // point index p*nq^2+q*nq+r, p<->z
+            double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};  // J[a][b] = d x_a / d xi_b, xi = (x^,y^,z^)
+            for (int c = 0; c < ng; ++c)
+                for (int b = 0; b < ng; ++b) {
+                    const double vz = gm.V[qz * ng + c], dz = gm.dV[qz * ng + c];
+                    const double vy = gm.V[qy * ng + b], dy = gm.dV[qy * ng + b];
+                    for (int a = 0; a < ng; ++a) {
+                        const double vx = gm.V[qx * ng + a], dx = gm.dV[qx * ng + a];
+                        const double g0 = dx * vy * vz, g1 = vx * dy * vz, g2 = vx * vy * dz;
+                        const int n = a + ng * (b + ng * c);
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) {
+                            const double xn = sn[d * ng3 + n];
+                            J[d][0] = fma(xn, g0, J[d][0]);
+                            J[d][1] = fma(xn, g1, J[d][1]);
+                            J[d][2] = fma(xn, g2, J[d][2]);
+                        }
+                    }
+                }
+            const double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) -
+                               J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+                               J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+            const double id = 1.0 / det;
+            double K[3][3];  // K[b][a] = d xi_b / d x_a
+            K[0][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) * id;
+            K[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * id;
+            K[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * id;
+            K[1][0] = (J[1][2] * J[2][0] - J[1][0] * J[2][2]) * id;
+            K[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * id;
+            K[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * id;
+            K[2][0] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) * id;
+            K[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * id;
+            K[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * id;
+            const double jxw = det * gm.w[qx] * gm.w[qy] * gm.w[qz];
+            if (JxW) JxW[(size_t)cell * nq3 + pt] = jxw;
+            if (G) {
+                // kernel directions (r,s,t) = (z^, y^, x^): rows of K in the order 2,1,0
+                const int perm[3] = {2, 1, 0};
+                int ci = 0;
+                for (int a = 0; a < 3; ++a)
+                    for (int b = a; b < 3; ++b, ++ci) {
+                        const double *ka = K[perm[a]], *kb = K[perm[b]];
+                        G[((size_t)cell * 6 + ci) * nq3 + pt] = jxw * (ka[0] * kb[0] + ka[1] * kb[1] + ka[2] * kb[2]);
+                    }
+            }
+        }
+    }
+}
+
+__global__ void copy_constrained_kernel(uint32_t n, const uint32_t *__restrict__ list,
+                                        const double *__restrict__ src, double *__restrict__ dst,
+                                        double *__restrict__ dot)
+{
+    double s = 0.0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t c = list[i];
+        const double v = src[c];
+        dst[c] = v;
+        s = fma(v, v, s);
+    }
+    if (dot != nullptr) {
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if ((threadIdx.x & 31) == 0 && s != 0.0) atomicAdd(dot, s);
+    }
+}
+
+// mats = shape_values[nm*nq] | co_shape_gradients[nq*nq] | shape_gradients[nm*nq]   (deal.II layouts)
+// diag_local[l] = sum_q sum_ab G_ab d_a phi_l d_b phi_l (+ JxW phi_l^2), scattered with atomics
+__global__ void diagonal_kernel(uint32_t n_cells, int nm, int nq, int qop, const double *__restrict__ mats,
+                                const double *__restrict__ G, const double *__restrict__ JxW,
+                                const uint32_t *__restrict__ idx, double *__restrict__ diag)
+{
+    const int nm3 = nm * nm * nm, nq3 = nq * nq * nq;
+    const double *S = mats, *Sg = mats + nm * nq + nq * nq;
+    for (uint32_t cell = blockIdx.x; cell < n_cells; cell += gridDim.x)
+        for (int l = threadIdx.x; l < nm3; l += blockDim.x) {
+            const uint32_t id = idx[(size_t)cell * nm3 + l];
+            if (id == kInvalidIndex) continue;
+            const int k = l % nm, j = (l / nm) % nm, i = l / (nm * nm);
+            double s = 0.0;
+            for (int p = 0; p < nq; ++p)
+                for (int q = 0; q < nq; ++q)
+                    for (int r = 0; r < nq; ++r) {
+                        const int pt = (p * nq + q) * nq + r;
+                        const double bi = S[i * nq + p], bj = S[j * nq + q], bk = S[k * nq + r];
+                        if (qop & QOP_LAPLACE) {
+                            const double gr = Sg[i * nq + p] * bj * bk, gs = bi * Sg[j * nq + q] * bk, gt = bi * bj * Sg[k * nq + r];
+                            const double *g = G + (size_t)cell * 6 * nq3 + pt;
+                            s += g[0] * gr * gr + g[3 * nq3] * gs * gs + g[5 * nq3] * gt * gt +
+                                 2.0 * (g[nq3] * gr * gs + g[2 * nq3] * gr * gt + g[4 * nq3] * gs * gt);
+                        }
+                        if (qop & QOP_MASS) {
+                            const double v = bi * bj * bk;
+                            s += JxW[(size_t)cell * nq3 + pt] * v * v;
+                        }
+                    }
+            atomicAdd(diag + id, s);
+        }
+}
+
+// b[l] += sum_q JxW(q) phi_l(q)    (bp3.cc:208-224: f = 1, constrained rows dropped)
+__global__ void rhs_one_kernel(uint32_t n_cells, int nm, int nq, const double *__restrict__ mats,
+                               const double *__restrict__ JxW, const uint32_t *__restrict__ idx,
+                               double *__restrict__ b)
+{
+    const int nm3 = nm * nm * nm, nq3 = nq * nq * nq;
+    const double *S = mats;
+    for (uint32_t cell = blockIdx.x; cell < n_cells; cell += gridDim.x)
+        for (int l = threadIdx.x; l < nm3; l += blockDim.x) {
+            const uint32_t id = idx[(size_t)cell * nm3 + l];
+            if (id == kInvalidIndex) continue;
+            const int k = l % nm, j = (l / nm) % nm, i = l / (nm * nm);
+            double s = 0.0;
+            for (int p = 0; p < nq; ++p)
+                for (int q = 0; q < nq; ++q) {
+                    const double bij = S[i * nq + p] * S[j * nq + q];
+                    for (int r = 0; r < nq; ++r)
+                        s = fma(JxW[(size_t)cell * nq3 + (p * nq + q) * nq + r], bij * S[k * nq + r], s);
+                }
+            atomicAdd(b + id, s);
+        }
+}
+
+__global__ void set_constrained_kernel(uint32_t n, const uint32_t *__restrict__ list, double value, double *__restrict__ v)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v[list[i]] = value;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// operator pieces
+// ---------------------------------------------------------------------------------------------
+int op_apply_cells(Operator &op, double *d_dst, const double *d_src, uint32_t cb, uint32_t ce,
+                   double *d_dot, cudaStream_t s)
+{
+    if (ce <= cb) return B200FE_OK;
+    const size_t nm3 = (size_t)op.nm * op.nm * op.nm, nq3 = (size_t)op.nq * op.nq * op.nq;
+    KArgs a{ce - cb, op.d_G ? op.d_G + cb * 6 * nq3 : nullptr, op.d_JxW ? op.d_JxW + cb * nq3 : nullptr,
+            d_src, d_dst, op.d_idx + cb * nm3, d_dot};
+    B200FE_CUDA_TRY(launch_sumfact(op.nm, op.nq, op.collocated, op.qop, true, op.B.data(), op.D.data(), a, s,
+                                   &op.last_launch, false));
+    return B200FE_OK;
+}
+
+int op_copy_constrained(Operator &op, double *d_dst, const double *d_src, double *d_dot, cudaStream_t s)
+{
+    if (op.n_constrained == 0) return B200FE_OK;
+    const unsigned blocks = std::min<unsigned>((op.n_constrained + 255) / 256, 1184);
+    copy_constrained_kernel<<<blocks, 256, 0, s>>>(op.n_constrained, op.d_constrained, d_src, d_dst, d_dot);
+    B200FE_CUDA_TRY(cudaGetLastError());
+    return B200FE_OK;
+}
+
+int op_vmult(Operator &op, double *d_dst, const double *d_src, double *d_dot, bool ghost_on, bool compute_on,
+             cudaStream_t s)
+{
+    Halo *h = op.halo;
+    double *src_mut = const_cast<double *>(d_src);  // ghost entries of src are scratch, as in deal.II
+    const bool split = h && ghost_on && compute_on && (op.n_phase0 + op.n_phase1 > 0);
+    if (compute_on) B200FE_CUDA_TRY(cudaMemsetAsync(d_dst, 0, sizeof(double) * op.n_local(), s));
+    if (split) {
+        // 3-phase overlap (bakeoff_problems_dealii/include/portable_laplace_operator.h:643-696)
+        if (int rc = halo_update_ghosts_start(*h, src_mut, s)) return rc;
+        if (int rc = op_apply_cells(op, d_dst, d_src, 0, op.n_phase0, d_dot, s)) return rc;
+        if (int rc = halo_update_ghosts_finish(*h, s)) return rc;
+        if (int rc = op_apply_cells(op, d_dst, d_src, op.n_phase0, op.n_phase0 + op.n_phase1, d_dot, s)) return rc;
+        if (int rc = halo_compress_start(*h, d_dst, s)) return rc;
+        if (int rc = op_apply_cells(op, d_dst, d_src, op.n_phase0 + op.n_phase1, op.n_cells, d_dot, s)) return rc;
+        if (int rc = halo_compress_finish(*h, d_dst, s)) return rc;
+        if (int rc = halo_zero_ghosts(*h, src_mut, s)) return rc;
+        return op_copy_constrained(op, d_dst, d_src, d_dot, s);
+    }
+    if (h && ghost_on)
+        if (int rc = halo_update_ghosts(*h, src_mut, s)) return rc;
+    if (compute_on)
+        if (int rc = op_apply_cells(op, d_dst, d_src, 0, op.n_cells, d_dot, s)) return rc;
+    if (h && ghost_on) {
+        if (int rc = halo_compress_add(*h, d_dst, s)) return rc;
+        if (int rc = halo_zero_ghosts(*h, src_mut, s)) return rc;
+    }
+    if (ghost_on)  // reference: copy_constrained_values sits inside the ghost_exchange_on branch (:229-234)
+        if (int rc = op_copy_constrained(op, d_dst, d_src, d_dot, s)) return rc;
+    return B200FE_OK;
+}
+
+}  // namespace b200fe
+
+using namespace b200fe;
+
+extern "C" {
+
+int b200fe_boxmesh_nodes(const b200fe_boxmesh *mesh, int p_geo, int deform_kind, double amplitude,
+                         double frequency, double *d_nodes, void *stream)
+{
+    B200FE_REQUIRE(mesh && d_nodes, "b200fe_boxmesh_nodes: null pointer");
+    B200FE_REQUIRE(p_geo >= 1 && p_geo <= 8, "b200fe_boxmesh_nodes: p_geo outside 1..8");
+    B200FE_REQUIRE(deform_kind == 0 || deform_kind == 1, "b200fe_boxmesh_nodes: unknown deformation");
+    b200fe_boxmesh_info_t info;
+    if (int rc = b200fe_boxmesh_info(mesh, &info)) return rc;
+    if (info.n_cells_local == 0) return B200FE_OK;
+    const int ng = p_geo + 1;
+    std::vector<int32_t> xyz((size_t)info.n_cells_local * 3);
+    if (int rc = b200fe_boxmesh_fill(mesh, nullptr, nullptr, nullptr, nullptr, xyz.data(), nullptr)) return rc;
+    std::vector<double> t(ng), w(ng);
+    if (int rc = b200fe_basis_1d(p_geo, ng, B200FE_QUAD_GLL, nullptr, nullptr, nullptr, t.data(), w.data())) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    int32_t *d_xyz = nullptr;
+    double *d_t = nullptr;
+    B200FE_CUDA_TRY(cudaMalloc(&d_xyz, xyz.size() * sizeof(int32_t)));
+    B200FE_CUDA_TRY(cudaMalloc(&d_t, ng * sizeof(double)));
+    B200FE_CUDA_TRY(cudaMemcpyAsync(d_xyz, xyz.data(), xyz.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    B200FE_CUDA_TRY(cudaMemcpyAsync(d_t, t.data(), ng * sizeof(double), cudaMemcpyHostToDevice, s));
+    // box corner and cell size from the mesh description
+    double p1[3], hh[3];
+    for (int d = 0; d < 3; ++d) { hh[d] = info.h[d]; p1[d] = info.origin[d]; }
+    const uint64_t total = (uint64_t)info.n_cells_local * ng * ng * ng;
+    box_nodes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(info.n_cells_local, ng, d_xyz, p1[0], p1[1], p1[2], hh[0],
+                                                                     hh[1], hh[2], d_t, deform_kind, amplitude, frequency, d_nodes);
+    cudaError_t e = cudaGetLastError();
+    cudaStreamSynchronize(s);  // setup call: the temporaries are freed right away
+    cudaFree(d_xyz);
+    cudaFree(d_t);
+    if (e != cudaSuccess) return fail_cuda(e, "box_nodes_kernel");
+    return B200FE_OK;
+}
+
+int b200fe_geometry_from_nodes(int p_geo, int nq, int quad_kind, uint32_t n_cells, const double *d_nodes,
+                               double *d_G, double *d_JxW, void *stream)
+{
+    B200FE_REQUIRE(p_geo >= 1 && p_geo <= 8, "b200fe_geometry_from_nodes: p_geo outside 1..8");
+    B200FE_REQUIRE(nq >= 2 && nq <= 10, "b200fe_geometry_from_nodes: nq outside 2..10");
+    B200FE_REQUIRE(n_cells == 0 || (d_nodes && (d_G || d_JxW)), "b200fe_geometry_from_nodes: null pointer");
+    if (n_cells == 0) return B200FE_OK;
+    const int ng = p_geo + 1;
+    // geometry basis (degree p_geo on GLL nodes) at the operator's quadrature points
+    std::vector<double> sv(ng * nq), sg(ng * nq), w(nq);
+    if (int rc = b200fe_basis_1d(p_geo, nq, quad_kind, nullptr, nullptr, sg.data(), nullptr, w.data())) return rc;
+    {   // values: always the true interpolation matrix (not the collocation identity shortcut)
+        std::vector<double> xq(nq), nodes(ng), wn(ng), V(nq * ng);
+        b200fe_basis_1d(p_geo, nq, quad_kind, nullptr, nullptr, nullptr, xq.data(), nullptr);
+        b200fe_basis_1d(p_geo, ng, B200FE_QUAD_GLL, nullptr, nullptr, nullptr, nodes.data(), wn.data());
+        for (int q = 0; q < nq; ++q)
+            for (int a = 0; a < ng; ++a) {
+                double v = 1.0;
+                for (int m = 0; m < ng; ++m)
+                    if (m != a) v *= (xq[q] - nodes[m]) / (nodes[a] - nodes[m]);
+                sv[a * nq + q] = v;
+            }
+    }
+    GeoMats gm;
+    std::memset(&gm, 0, sizeof(gm));
+    for (int q = 0; q < nq; ++q) {
+        gm.w[q] = w[q];
+        for (int a = 0; a < ng; ++a) {
+            gm.V[q * ng + a] = sv[a * nq + q];
+            gm.dV[q * ng + a] = sg[a * nq + q];
+        }
+    }
+    const int threads = std::min(256, ((nq * nq * nq + 31) / 32) * 32);
+    const unsigned blocks = std::min<uint32_t>(n_cells, 148u * 16u);
+    geometry_kernel<<<blocks, threads, 3 * ng * ng * ng * sizeof(double), (cudaStream_t)stream>>>(gm, n_cells, ng, nq, d_nodes, d_G, d_JxW);
+    B200FE_CUDA_TRY(cudaGetLastError());
+    return B200FE_OK;
+}
+
+int b200fe_op_create(const b200fe_op_desc *d, b200fe_op **out)
+{
+    B200FE_REQUIRE(d && out, "b200fe_op_create: null pointer");
+    if (d->p < 1 || d->p > 8) return fail(B200FE_ERR_UNSUPPORTED, "b200fe_op_create: degree p=%d outside 1..8", d->p);
+    const int nm = d->p + 1;
+    B200FE_REQUIRE(d->op_kind >= 1 && d->op_kind <= 3, "b200fe_op_create: op_kind must be LAPLACE, MASS or HELMHOLTZ");
+    const bool coll = d->collocated != 0;
+    // built variants (inst.cu): Laplace nq=p+2 | p+1 | collocated, mass nq=p+2, Helmholtz nq=p+1
+    bool ok = false;
+    if (d->op_kind == B200FE_OP_LAPLACE) ok = coll ? d->nq == nm : (d->nq == nm || d->nq == nm + 1);
+    if (d->op_kind == B200FE_OP_MASS) ok = !coll && d->nq == nm + 1;
+    if (d->op_kind == B200FE_OP_HELMHOLTZ) ok = !coll && d->nq == nm;
+    if (!ok) return fail(B200FE_ERR_UNSUPPORTED, "b200fe_op_create: no kernel for op_kind=%d p=%d nq=%d collocated=%d", d->op_kind, d->p, d->nq, (int)coll);
+    B200FE_REQUIRE(d->h_co_shape_gradients && (coll || d->h_shape_values), "b200fe_op_create: 1-D matrices missing");
+    B200FE_REQUIRE(d->n_cells == 0 || d->d_dof_indices, "b200fe_op_create: dof_indices missing");
+    B200FE_REQUIRE(!(d->op_kind & B200FE_OP_LAPLACE) || d->n_cells == 0 || d->d_G, "b200fe_op_create: G missing");
+    B200FE_REQUIRE(!(d->op_kind & B200FE_OP_MASS) || d->n_cells == 0 || d->d_JxW, "b200fe_op_create: JxW missing");
+    B200FE_REQUIRE(d->n_constrained == 0 || d->h_constrained, "b200fe_op_create: constrained list missing");
+    B200FE_REQUIRE((uint64_t)d->n_phase0 + d->n_phase1 <= d->n_cells, "b200fe_op_create: phase split exceeds n_cells");
+
+    auto op = std::make_unique<Operator>();
+    op->p = d->p; op->nm = nm; op->nq = d->nq; op->qop = d->op_kind; op->collocated = coll;
+    op->n_cells = d->n_cells; op->n_owned = d->n_owned; op->n_ghost = d->n_ghost; op->n_constrained = d->n_constrained;
+    op->n_phase0 = d->n_phase0; op->n_phase1 = d->n_phase1;
+    op->d_idx = d->d_dof_indices; op->d_G = d->d_G; op->d_JxW = d->d_JxW;
+    const int nq = d->nq;
+    op->shape_values.assign(nm * nq, 0.0);
+    if (coll) for (int i = 0; i < nm; ++i) op->shape_values[i * nq + i] = 1.0;
+    else op->shape_values.assign(d->h_shape_values, d->h_shape_values + nm * nq);
+    op->co_shape_gradients.assign(d->h_co_shape_gradients, d->h_co_shape_gradients + nq * nq);
+    // kernel (BK) layouts: B[q*nm+i] = shape_values[i*nq+q]; D[p*nq+n] = co_shape_gradients[n*nq+p]
+    op->B.resize(nq * nm); op->D.resize(nq * nq);
+    for (int q = 0; q < nq; ++q) {
+        for (int i = 0; i < nm; ++i) op->B[q * nm + i] = op->shape_values[i * nq + q];
+        for (int n = 0; n < nq; ++n) op->D[q * nq + n] = op->co_shape_gradients[n * nq + q];
+    }
+    // setup-kernel matrices on the device; shape gradients = D * B exactly (degree p <= nq-1)
+    std::vector<double> mats(nm * nq + nq * nq + nm * nq);
+    std::memcpy(mats.data(), op->shape_values.data(), sizeof(double) * nm * nq);
+    std::memcpy(mats.data() + nm * nq, op->co_shape_gradients.data(), sizeof(double) * nq * nq);
+    for (int i = 0; i < nm; ++i)
+        for (int q = 0; q < nq; ++q) {
+            double s = 0.0;
+            for (int n = 0; n < nq; ++n) s += op->D[q * nq + n] * op->shape_values[i * nq + n];
+            mats[nm * nq + nq * nq + i * nq + q] = s;
+        }
+    B200FE_CUDA_TRY(cudaMalloc(&op->d_mats, mats.size() * sizeof(double)));
+    B200FE_CUDA_TRY(cudaMemcpy(op->d_mats, mats.data(), mats.size() * sizeof(double), cudaMemcpyHostToDevice));
+    if (d->n_constrained) {
+        B200FE_CUDA_TRY(cudaMalloc(&op->d_constrained, d->n_constrained * sizeof(uint32_t)));
+        B200FE_CUDA_TRY(cudaMemcpy(op->d_constrained, d->h_constrained, d->n_constrained * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
+    *out = reinterpret_cast<b200fe_op *>(op.release());
+    return B200FE_OK;
+}
+
+void b200fe_op_destroy(b200fe_op *o)
+{
+    Operator *op = reinterpret_cast<Operator *>(o);
+    if (!op) return;
+    cg_release_work(op);
+    cudaFree(op->d_constrained);
+    cudaFree(op->d_mats);
+    delete op;
+}
+
+int b200fe_op_set_halo(b200fe_op *o, b200fe_halo *halo)
+{
+    B200FE_REQUIRE(o, "b200fe_op_set_halo: null operator");
+    reinterpret_cast<Operator *>(o)->halo = reinterpret_cast<Halo *>(halo);
+    return B200FE_OK;
+}
+
+int b200fe_op_vmult(b200fe_op *o, double *d_dst, const double *d_src, void *stream)
+{
+    B200FE_REQUIRE(o && d_dst && d_src, "b200fe_op_vmult: null pointer");
+    B200FE_REQUIRE(d_dst != d_src, "b200fe_op_vmult: dst and src must not alias");
+    return op_vmult(*reinterpret_cast<Operator *>(o), d_dst, d_src, nullptr, true, true, (cudaStream_t)stream);
+}
+
+int b200fe_op_vmult_dot(b200fe_op *o, double *d_dst, const double *d_src, double *d_dot, void *stream)
+{
+    B200FE_REQUIRE(o && d_dst && d_src && d_dot, "b200fe_op_vmult_dot: null pointer");
+    B200FE_REQUIRE(d_dst != d_src, "b200fe_op_vmult_dot: dst and src must not alias");
+    Operator &op = *reinterpret_cast<Operator *>(o);
+    cudaStream_t s = (cudaStream_t)stream;
+    B200FE_CUDA_TRY(cudaMemsetAsync(d_dot, 0, sizeof(double), s));
+    if (int rc = op_vmult(op, d_dst, d_src, d_dot, true, true, s)) return rc;
+    if (op.halo) return halo_allreduce_sum(*op.halo, d_dot, 1, s);
+    return B200FE_OK;
+}
+
+int b200fe_op_vmult_dummy(b200fe_op *o, double *d_dst, const double *d_src, int ghost_exchange_on,
+                          int computation_on, void *stream)
+{
+    B200FE_REQUIRE(o && d_dst && d_src, "b200fe_op_vmult_dummy: null pointer");
+    return op_vmult(*reinterpret_cast<Operator *>(o), d_dst, d_src, nullptr, ghost_exchange_on != 0, computation_on != 0,
+                    (cudaStream_t)stream);
+}
+
+int b200fe_op_diagonal(b200fe_op *o, double *d_diag, void *stream)
+{
+    B200FE_REQUIRE(o && d_diag, "b200fe_op_diagonal: null pointer");
+    Operator &op = *reinterpret_cast<Operator *>(o);
+    cudaStream_t s = (cudaStream_t)stream;
+    B200FE_CUDA_TRY(cudaMemsetAsync(d_diag, 0, sizeof(double) * op.n_local(), s));
+    if (op.n_cells) {
+        diagonal_kernel<<<std::min<uint32_t>(op.n_cells, 148u * 8u), 128, 0, s>>>(op.n_cells, op.nm, op.nq, op.qop, op.d_mats, op.d_G, op.d_JxW, op.d_idx, d_diag);
+        B200FE_CUDA_TRY(cudaGetLastError());
+    }
+    if (op.halo)
+        if (int rc = halo_compress_add(*op.halo, d_diag, s)) return rc;
+    if (op.n_constrained) {
+        set_constrained_kernel<<<std::min<unsigned>((op.n_constrained + 255) / 256, 1184), 256, 0, s>>>(op.n_constrained, op.d_constrained, 1.0, d_diag);
+        B200FE_CUDA_TRY(cudaGetLastError());
+    }
+    return B200FE_OK;
+}
+
+int b200fe_op_rhs_one(b200fe_op *o, double *d_b, void *stream)
+{
+    B200FE_REQUIRE(o && d_b, "b200fe_op_rhs_one: null pointer");
+    Operator &op = *reinterpret_cast<Operator *>(o);
+    B200FE_REQUIRE(op.d_JxW || op.n_cells == 0, "b200fe_op_rhs_one: the operator was created without JxW");
+    cudaStream_t s = (cudaStream_t)stream;
+    B200FE_CUDA_TRY(cudaMemsetAsync(d_b, 0, sizeof(double) * op.n_local(), s));
+    if (op.n_cells) {
+        rhs_one_kernel<<<std::min<uint32_t>(op.n_cells, 148u * 8u), 128, 0, s>>>(op.n_cells, op.nm, op.nq, op.d_mats, op.d_JxW, op.d_idx, d_b);
+        B200FE_CUDA_TRY(cudaGetLastError());
+    }
+    if (op.halo)
+        if (int rc = halo_compress_add(*op.halo, d_b, s)) return rc;
+    return B200FE_OK;
+}
+
+int b200fe_op_launch_info(b200fe_op *o, int *elems_per_block, int *num_blocks, int *threads_per_block,
+                          int *smem_bytes, int *blocks_per_sm, int *regs_per_thread)
+{
+    B200FE_REQUIRE(o, "b200fe_op_launch_info: null operator");
+    Operator &op = *reinterpret_cast<Operator *>(o);
+    KArgs a{op.n_cells, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    LaunchInfo li{};
+    B200FE_CUDA_TRY(launch_sumfact(op.nm, op.nq, op.collocated, op.qop, true, nullptr, nullptr, a, nullptr, &li, true));
+    if (elems_per_block) *elems_per_block = li.elems_per_block;
+    if (num_blocks) *num_blocks = li.num_blocks;
+    if (threads_per_block) *threads_per_block = li.threads_per_block;
+    if (smem_bytes) *smem_bytes = li.smem_bytes;
+    if (blocks_per_sm) *blocks_per_sm = li.blocks_per_sm;
+    if (regs_per_thread) *regs_per_thread = li.regs_per_thread;
+    return B200FE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,43 @@
+// operator.h -- internal view of the L-vector operator object behind b200fe_op.
+#pragma once
+#include <vector>
+
+#include "common.h"
+#include "kernels.h"
+
+namespace b200fe {
+
+struct Halo;  // halo.cu
+
+struct Operator {
+    int p = 0, nm = 0, nq = 0, qop = 0;
+    bool collocated = false;
+    uint32_t n_cells = 0, n_owned = 0, n_ghost = 0, n_constrained = 0;
+    // 1-D matrices in the kernel (BK) layout: B[q*nm+i], D[p*nq+n]; deal.II-layout copies for setup kernels
+    std::vector<double> B, D, shape_values, co_shape_gradients;
+    const uint32_t *d_idx = nullptr;  // borrowed
+    const double *d_G = nullptr;      // borrowed
+    const double *d_JxW = nullptr;    // borrowed
+    uint32_t *d_constrained = nullptr;  // owned
+    double *d_mats = nullptr;           // owned: shape_values | co_shape_gradients | shape_gradients (setup kernels)
+    Halo *halo = nullptr;               // borrowed, optional
+    // overlap split: cells [0, n_phase0) and [n_phase0+n_phase1, n_cells) touch no ghost DoF
+    uint32_t n_phase0 = 0, n_phase1 = 0;
+    LaunchInfo last_launch{};
+
+    uint32_t n_local() const { return n_owned + n_ghost; }
+};
+
+// dst = 0 on the local vector, cell kernel over cells [cell_begin, cell_end), optional fused dot.
+int op_apply_cells(Operator &op, double *d_dst, const double *d_src, uint32_t cell_begin, uint32_t cell_end,
+                   double *d_dot, cudaStream_t s);
+// dst[c] = src[c] on owned constrained DoFs; optional dot += sum src[c]^2
+int op_copy_constrained(Operator &op, double *d_dst, const double *d_src, double *d_dot, cudaStream_t s);
+// full local vmult: zero, cells, constrained rows (+ halo exchange when attached)
+int op_vmult(Operator &op, double *d_dst, const double *d_src, double *d_dot, bool ghost_on, bool compute_on,
+             cudaStream_t s);
+
+// cg.cu: frees the CG workspace cached for this operator
+void cg_release_work(Operator *op);
+
+}  // namespace b200fe

@@ -25,7 +25,8 @@ class _Desc(C.Structure):
 class _Info(C.Structure):
     _fields_ = [("n_cells_global", C.c_uint64), ("n_dofs_global", C.c_uint64), ("first_cell", C.c_uint64),
                 ("owned_begin", C.c_uint64), ("n_cells_local", C.c_uint32), ("n_owned", C.c_uint32),
-                ("n_ghost", C.c_uint32), ("n_constrained", C.c_uint32), ("cells", C.c_uint32 * 3), ("h", C.c_double * 3)]
+                ("n_ghost", C.c_uint32), ("n_constrained", C.c_uint32), ("cells", C.c_uint32 * 3), ("h", C.c_double * 3),
+                ("origin", C.c_double * 3)]
 
 
 def basis_1d(p: int, nq: int, quad: int = QUAD_GAUSS):

@@ -1,0 +1,259 @@
+"""Host-side mirror of the reference's operator / solver interface over the C ABI.
+
+  LaplaceOperator   <-> Portable::LaplaceOperator<dim,fe_degree,nq,double>
+                        (CEED_bp/include/portable_laplace_operator.h:17-96): vmult, Tvmult, vmult_dummy,
+                        initialize_dof_vector, m, n, compute_diagonal, get_matrix_diagonal_inverse
+                        (bp5_kokkos/benchmark.cc:157-168, 218-251), compute_rhs (bp3.cc:184-239)
+  ReductionControl, SolverCG <-> dealii::ReductionControl / SolverCG as called at bp3.cc:266-285
+Vectors are float64 CUDA tensors of n_owned + n_ghost entries (owned first, then ghosts), the
+layout of LinearAlgebra::distributed::Vector.  torch is only the allocator / stream provider.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from ._lib import B200feError, check, lib
+from .mesh import QUAD_GAUSS, QUAD_GLL, BoxMesh, basis_1d
+
+OP_LAPLACE, OP_MASS, OP_HELMHOLTZ = 1, 2, 3
+INVALID = 0xFFFFFFFF
+
+
+class _OpDesc(C.Structure):
+    _fields_ = [("p", C.c_int), ("nq", C.c_int), ("op_kind", C.c_int), ("collocated", C.c_int),
+                ("n_cells", C.c_uint32), ("n_owned", C.c_uint32), ("n_ghost", C.c_uint32),
+                ("h_shape_values", C.c_void_p), ("h_co_shape_gradients", C.c_void_p),
+                ("d_dof_indices", C.c_void_p), ("d_G", C.c_void_p), ("d_JxW", C.c_void_p),
+                ("h_constrained", C.c_void_p), ("n_constrained", C.c_uint32),
+                ("n_phase0", C.c_uint32), ("n_phase1", C.c_uint32)]
+
+
+class _CgResult(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("converged", C.c_int), ("initial_residual", C.c_double),
+                ("final_residual", C.c_double)]
+
+
+def _sp(stream=None):
+    s = torch.cuda.current_stream() if stream is None else stream
+    return C.c_void_p(s.cuda_stream)
+
+
+def _dp(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def overlap_permutation(dof_indices: np.ndarray, n_owned: int):
+    """Cell order [interior half | cells touching a ghost DoF | interior half] and the two sizes
+    (deal.II's three colours with overlap_communication_computation)."""
+    touches = ((dof_indices >= n_owned) & (dof_indices != INVALID)).any(axis=1)
+    interior = np.nonzero(~touches)[0]
+    boundary = np.nonzero(touches)[0]
+    half = len(interior) // 2
+    perm = np.concatenate([interior[:half], boundary, interior[half:]])
+    return perm, half, len(boundary)
+
+
+class LaplaceOperator:
+    """Matrix-free operator on one rank's partition of a BoxMesh.
+
+    kind 'laplace' with nq = p+2 is BP3 (the reference's bp3), nq = p+1 Gauss is "bp35",
+    quad='gll' (nq = p+1) is the collocated CEED BP5; 'mass' is BP1; 'helmholtz' is bp5_kokkos' operator.
+    """
+
+    def __init__(self, mesh: BoxMesh, nq: int | None = None, quad: str = "gauss", kind: str = "laplace",
+                 p_geo: int = 1, deform=None, overlap: bool = False, halo=None, with_jxw: bool = True,
+                 device=None):
+        self.mesh = mesh
+        p = mesh.p
+        self.p, self.nm = p, p + 1
+        self.quad = QUAD_GLL if quad == "gll" else QUAD_GAUSS
+        self.nq = nq if nq is not None else (p + 1 if quad == "gll" else p + 2)
+        self.collocated = quad == "gll" and self.nq == p + 1
+        self.kind = {"laplace": OP_LAPLACE, "mass": OP_MASS, "helmholtz": OP_HELMHOLTZ}[kind]
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        self.basis = basis_1d(p, self.nq, self.quad)
+        idx = mesh.dof_indices
+        self.perm = None
+        n_phase0 = n_phase1 = 0
+        if overlap and mesh.n_ranks > 1:
+            self.perm, n_phase0, n_phase1 = overlap_permutation(idx, mesh.n_owned)
+            idx = idx[self.perm]
+        self.dof_indices = torch.from_numpy(np.ascontiguousarray(idx)).to(self.device)
+        # geometry: mapping support points -> G, JxW on the device
+        ng3 = (p_geo + 1) ** 3
+        nodes = torch.empty(mesh.n_cells * 3 * ng3, dtype=torch.float64, device=self.device)
+        kind_d, amp, freq = (0, 0.0, 0.0) if deform is None else (1, float(deform[0]), float(deform[1]))
+        check(lib.b200fe_boxmesh_nodes(mesh._h, p_geo, kind_d, amp, freq, _dp(nodes), _sp()))
+        if self.perm is not None:
+            nodes = nodes.view(mesh.n_cells, 3 * ng3)[torch.from_numpy(self.perm).to(self.device)].contiguous().view(-1)
+        nq3 = self.nq ** 3
+        need_G = bool(self.kind & OP_LAPLACE)
+        need_J = bool(self.kind & OP_MASS) or with_jxw
+        self.G = torch.empty(mesh.n_cells * 6 * nq3, dtype=torch.float64, device=self.device) if need_G else None
+        self.JxW = torch.empty(mesh.n_cells * nq3, dtype=torch.float64, device=self.device) if need_J else None
+        check(lib.b200fe_geometry_from_nodes(p_geo, self.nq, self.quad, mesh.n_cells, _dp(nodes), _dp(self.G), _dp(self.JxW), _sp()))
+        torch.cuda.current_stream().synchronize()
+        del nodes
+        d = _OpDesc()
+        d.p, d.nq, d.op_kind, d.collocated = p, self.nq, self.kind, int(self.collocated)
+        d.n_cells, d.n_owned, d.n_ghost = mesh.n_cells, mesh.n_owned, mesh.n_ghost
+        self._sv = np.ascontiguousarray(self.basis["shape_values"])
+        self._cg = np.ascontiguousarray(self.basis["co_shape_gradients"])
+        self._con = np.ascontiguousarray(mesh.constrained)
+        d.h_shape_values = self._sv.ctypes.data
+        d.h_co_shape_gradients = self._cg.ctypes.data
+        d.d_dof_indices = self.dof_indices.data_ptr()
+        d.d_G = self.G.data_ptr() if self.G is not None else None
+        d.d_JxW = self.JxW.data_ptr() if self.JxW is not None else None
+        d.h_constrained = self._con.ctypes.data if len(self._con) else None
+        d.n_constrained = len(self._con)
+        d.n_phase0, d.n_phase1 = n_phase0, n_phase1
+        self._h = C.c_void_p()
+        check(lib.b200fe_op_create(C.byref(d), C.byref(self._h)))
+        self.halo = halo
+        if halo is not None:
+            check(lib.b200fe_op_set_halo(self._h, halo._h))
+        self._inv_diag = None
+
+    # --- the reference operator's interface ------------------------------------------------
+    def initialize_dof_vector(self) -> torch.Tensor:
+        return torch.zeros(self.mesh.n_owned + self.mesh.n_ghost, dtype=torch.float64, device=self.device)
+
+    def m(self) -> int:
+        return int(self.mesh.n_dofs_global)
+
+    n = m
+
+    def vmult(self, dst: torch.Tensor, src: torch.Tensor, stream=None) -> None:
+        check(lib.b200fe_op_vmult(self._h, _dp(dst), _dp(src), _sp(stream)))
+
+    Tvmult = vmult  # symmetric operator (portable_laplace_operator.h:396-409)
+
+    def vmult_dummy(self, dst, src, ghost_exchange_on: bool, computation_on: bool, stream=None) -> None:
+        check(lib.b200fe_op_vmult_dummy(self._h, _dp(dst), _dp(src), int(ghost_exchange_on), int(computation_on), _sp(stream)))
+
+    def vmult_dot(self, dst, src, stream=None) -> torch.Tensor:
+        dot = torch.empty(1, dtype=torch.float64, device=self.device)
+        check(lib.b200fe_op_vmult_dot(self._h, _dp(dst), _dp(src), _dp(dot), _sp(stream)))
+        return dot
+
+    def vmult_host(self, h_dst: torch.Tensor, h_src: torch.Tensor, stream=None) -> None:
+        """HOST tensors of n_owned doubles (pinned for full PCIe speed)."""
+        check(lib.b200fe_op_vmult_host(self._h, _dp(h_dst), _dp(h_src), _sp(stream)))
+
+    def compute_diagonal(self) -> torch.Tensor:
+        diag = self.initialize_dof_vector()
+        check(lib.b200fe_op_diagonal(self._h, _dp(diag), _sp()))
+        # reciprocal as in bp5_kokkos/benchmark.cc:240-250
+        d = diag[: self.mesh.n_owned]
+        self._inv_diag = torch.where(d > 0, 1.0 / d, torch.ones_like(d))
+        return diag
+
+    def get_matrix_diagonal_inverse(self) -> torch.Tensor:
+        if self._inv_diag is None:
+            self.compute_diagonal()
+        return self._inv_diag
+
+    def compute_rhs(self) -> torch.Tensor:
+        """b_i = int phi_i * 1 (bp3.cc:184-239)."""
+        b = self.initialize_dof_vector()
+        check(lib.b200fe_op_rhs_one(self._h, _dp(b), _sp()))
+        return b
+
+    def launch_info(self):
+        v = [C.c_int() for _ in range(6)]
+        check(lib.b200fe_op_launch_info(self._h, *[C.byref(x) for x in v]))
+        keys = ("elems_per_block", "num_blocks", "threads_per_block", "smem_bytes", "blocks_per_sm", "regs_per_thread")
+        return dict(zip(keys, [x.value for x in v]))
+
+    # algorithmic bytes of one apply: G + indices per cell, 32 B per local DoF
+    def algorithmic_bytes(self) -> int:
+        nq3, nm3 = self.nq ** 3, self.nm ** 3
+        per_cell = 4 * nm3 + (48 * nq3 if self.kind & OP_LAPLACE else 0) + (8 * nq3 if self.kind & OP_MASS else 0)
+        return self.mesh.n_cells * per_cell + 32 * self.mesh.n_owned
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            lib.b200fe_op_destroy(h)
+            self._h = None
+
+
+class ReductionControl:
+    """dealii::ReductionControl(max_steps, tolerance, reduction)."""
+
+    def __init__(self, max_steps: int = 100, tolerance: float = 1e-10, reduction: float = 1e-2):
+        self.max_steps, self.tolerance, self.reduction = max_steps, tolerance, reduction
+        self._res = None
+
+    def last_step(self) -> int:
+        return self._res.iterations
+
+    def last_value(self) -> float:
+        return self._res.final_residual
+
+    def initial_value(self) -> float:
+        return self._res.initial_residual
+
+
+class NoConvergence(RuntimeError):
+    """dealii::SolverControl::NoConvergence."""
+
+
+class SolverCG:
+    """dealii::SolverCG: solve(A, x, b, preconditioner); preconditioner None = PreconditionIdentity,
+    or a tensor holding the inverse diagonal (DiagonalMatrix)."""
+
+    def __init__(self, control: ReductionControl, check_every: int = 8):
+        self.control = control
+        self.check_every = check_every
+
+    def solve(self, A: LaplaceOperator, x: torch.Tensor, b: torch.Tensor, preconditioner=None, stream=None):
+        res = _CgResult()
+        rc = lib.b200fe_cg_solve(A._h, _dp(x), _dp(b), _dp(preconditioner), self.control.tolerance, self.control.reduction,
+                                 self.control.max_steps, self.check_every, C.byref(res), _sp(stream))
+        self.control._res = res
+        if rc == 5:
+            raise NoConvergence(f"CG: {res.iterations} iterations, residual {res.final_residual:g}")
+        check(rc)
+        return res
+
+    def solve_host(self, A: LaplaceOperator, h_x: torch.Tensor, h_b: torch.Tensor, preconditioner=None, stream=None):
+        res = _CgResult()
+        rc = lib.b200fe_cg_solve_host(A._h, _dp(h_x), _dp(h_b), _dp(preconditioner), self.control.tolerance,
+                                      self.control.reduction, self.control.max_steps, self.check_every, C.byref(res), _sp(stream))
+        self.control._res = res
+        if rc == 5:
+            raise NoConvergence(f"CG: {res.iterations} iterations, residual {res.final_residual:g}")
+        check(rc)
+        return res
+
+
+def smoke_operator() -> None:
+    """One small BP5 apply + CG on cuda:0 against the CPU oracle (used by __graft_entry__.smoke)."""
+    import oracle
+    fe = oracle.fe
+    p = 3
+    mesh = BoxMesh((2, 1, 1), 1, p)
+    A = LaplaceOperator(mesh, quad="gll")
+    om = fe.BoxMesh((2, 1, 1), 1)
+    od = fe.distribute_dofs(om, p, 1)
+    rd = fe.rank_data(om, od, 0)
+    bas = fe.basis_1d(p, p + 1, "gll")
+    G, JxW = fe.geometric_factors(fe.cell_nodes(om, rd["cells"], 1), 1, bas)
+    rng = np.random.default_rng(0)
+    src = rng.standard_normal(mesh.n_owned)
+    ref = fe.op_apply(src, rd, bas, G)
+    dst = A.initialize_dof_vector()
+    A.vmult(dst, torch.from_numpy(src).to(A.device))
+    err = np.abs(dst.cpu().numpy() - ref).max() / np.abs(ref).max()
+    b = A.compute_rhs()
+    x = A.initialize_dof_vector()
+    ctl = ReductionControl(1000, 1e-16, 1e-9)
+    SolverCG(ctl).solve(A, x, b)
+    _, its, _, _, _ = fe.solver_cg(lambda v: fe.op_apply(v, rd, bas, G), fe.rhs_one(rd, bas, JxW), 1000, 1e-16, 1e-9)
+    print(f"smoke: BP5 p={p} vmult rel err {err:.2e}; CG its {ctl.last_step()} (oracle {its})")
+    assert err <= 1e-12 and abs(ctl.last_step() - its) <= 1

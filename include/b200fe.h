@@ -123,7 +123,8 @@ typedef struct {
     uint64_t owned_begin; /* first owned global DoF */
     uint32_t n_cells_local, n_owned, n_ghost, n_constrained;
     uint32_t cells[3];
-    double h[3];
+    double h[3];      /* cell size per axis */
+    double origin[3]; /* p1 */
 } b200fe_boxmesh_info_t;
 
 typedef struct b200fe_boxmesh b200fe_boxmesh;
@@ -141,6 +142,127 @@ int b200fe_boxmesh_info(const b200fe_boxmesh *mesh, b200fe_boxmesh_info_t *info)
 int b200fe_boxmesh_fill(const b200fe_boxmesh *mesh, uint32_t *h_dof_indices, uint32_t *h_constrained,
                         uint64_t *h_ghost_global, int32_t *h_ghost_owner, int32_t *h_cell_xyz,
                         uint64_t *h_rank_dof_begin);
+
+/* Mapping support points of the owned cells on the DEVICE, d_nodes[cell][3][(p_geo+1)^3]
+ * (node index c*ng^2 + b*ng + a, a <-> x), Gauss-Lobatto lattice of MappingQ(p_geo).
+ * deform_kind 0: the box itself; 1: x += A sin(f y), y += A sin(f z), z += A sin(f x)
+ * (smooth deformed mesh in the spirit of bk3_dealii/check_bk3.cc:50-52).  Synchronises `stream`. */
+int b200fe_boxmesh_nodes(const b200fe_boxmesh *mesh, int p_geo, int deform_kind, double amplitude,
+                         double frequency, double *d_nodes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * 4. Geometry and the L-vector operator (drop-in for Portable::LaplaceOperator,
+ *    CEED_bp/include/portable_laplace_operator.h:17-96, and for bp5_kokkos' HelmholtzOperator,
+ *    bp5_kokkos/benchmark.cc:141-292).
+ * ------------------------------------------------------------------------------------------ */
+
+/* compute_G_tensors (CEED_bp/include/portable_laplace_operator.h:239-302) from mapping support
+ * points: d_G[cell][6][nq^3] = JxW * K K^T with K = J^-1 and the reference directions ordered
+ * (r,s,t) = (z^,y^,x^) as the cell kernel pairs them, i.e. the mathematically consistent form
+ * of bakeoff_problems_dealii/include/portable_laplace_operator.h:227-258 (on the reference's cube
+ * cells both coincide: G = diag(h w_q)).  d_JxW[cell][nq^3] = det J * w.  Either output may be NULL. */
+int b200fe_geometry_from_nodes(int p_geo, int nq, int quad_kind, uint32_t n_cells, const double *d_nodes,
+                               double *d_G, double *d_JxW, void *stream);
+
+enum { B200FE_OP_LAPLACE = 1, B200FE_OP_MASS = 2, B200FE_OP_HELMHOLTZ = 3 };
+
+typedef struct {
+    int p;          /* fe_degree 1..8 */
+    int nq;         /* 1-D quadrature points: p+2 (BP1/BP3), p+1 ("bp35", bp5_kokkos, BP5) */
+    int op_kind;    /* B200FE_OP_* */
+    int collocated; /* 1: quadrature points are the GLL nodes (CEED BP5); shape_values ignored */
+    uint32_t n_cells, n_owned, n_ghost;
+    const double *h_shape_values;       /* [nm*nq] shape_values[i*nq+q]       (MatrixFree data) */
+    const double *h_co_shape_gradients; /* [nq*nq] co_shape_gradients[n*nq+q] (MatrixFree data) */
+    const uint32_t *d_dof_indices; /* DEVICE [n_cells][nm^3], B200FE_INVALID_INDEX = constrained; BORROWED */
+    const double *d_G;             /* DEVICE [n_cells][6][nq^3]; BORROWED (may be NULL for MASS) */
+    const double *d_JxW;           /* DEVICE [n_cells][nq^3]; BORROWED (MASS/HELMHOLTZ, rhs_one) */
+    const uint32_t *h_constrained; /* HOST owned local indices of constrained DoFs; copied */
+    uint32_t n_constrained;
+    /* overlap split (deal.II colours with overlap_communication_computation = true): cells
+     * [0,n_phase0) and [n_phase0+n_phase1, n_cells) touch no ghost DoF, cells of phase 1 may.
+     * 0,0 = single colour, no overlap (the reference drivers' setting, bp3.cc:103). */
+    uint32_t n_phase0, n_phase1;
+} b200fe_op_desc;
+
+typedef struct b200fe_op b200fe_op;
+typedef struct b200fe_halo b200fe_halo;
+
+/* Borrowed device arrays must outlive the operator (the reference operator owns G and the masks;
+ * here the caller's vectors are used in place so a 4 GB G is never duplicated). */
+int b200fe_op_create(const b200fe_op_desc *desc, b200fe_op **out);
+void b200fe_op_destroy(b200fe_op *op);
+/* Attach the ghost exchange (NULL detaches).  Borrowed. */
+int b200fe_op_set_halo(b200fe_op *op, b200fe_halo *halo);
+
+/* LaplaceOperator::vmult (portable_laplace_operator.h:124-172): dst = 0; update ghosts of src;
+ * cell kernel (gather / sum factorisation / atomic scatter); compress(add); zero ghosts of src;
+ * dst[c] = src[c] on constrained DoFs.  Vectors hold n_owned + n_ghost doubles; the ghost entries
+ * of src are scratch (as with deal.II's mutable ghost section). */
+int b200fe_op_vmult(b200fe_op *op, double *d_dst, const double *d_src, void *stream);
+/* vmult with the inner product src . dst (summed over ranks) fused into the kernel -> *d_dot. */
+int b200fe_op_vmult_dot(b200fe_op *op, double *d_dst, const double *d_src, double *d_dot, void *stream);
+/* LaplaceOperator::vmult_dummy (portable_laplace_operator.h:175-235). */
+int b200fe_op_vmult_dummy(b200fe_op *op, double *d_dst, const double *d_src, int ghost_exchange_on,
+                          int computation_on, void *stream);
+/* vmult with HOST vectors of n_owned doubles (H2D, apply, D2H; synchronises the stream). */
+int b200fe_op_vmult_host(b200fe_op *op, double *h_dst, const double *h_src, void *stream);
+/* HelmholtzOperator::compute_diagonal (bp5_kokkos/benchmark.cc:218-251): matrix diagonal, 1 on
+ * constrained rows.  (The reciprocal of :240-250 is one elementwise op on the caller's side.) */
+int b200fe_op_diagonal(b200fe_op *op, double *d_diag, void *stream);
+/* compute_rhs of the BP drivers (CEED_bp/src/bp3.cc:184-239): b_i = int phi_i * 1, constrained rows 0. */
+int b200fe_op_rhs_one(b200fe_op *op, double *d_b, void *stream);
+int b200fe_op_launch_info(b200fe_op *op, int *elems_per_block, int *num_blocks, int *threads_per_block,
+                          int *smem_bytes, int *blocks_per_sm, int *regs_per_thread);
+
+/* ------------------------------------------------------------------------------------------
+ * 5. Conjugate gradients (dealii::SolverCG + ReductionControl as called at CEED_bp/src/bp3.cc:266-285
+ *    and bp5_kokkos/benchmark.cc:355-378).  x0 = 0.  d_inv_diag = NULL: PreconditionIdentity,
+ *    else Jacobi with the given inverse diagonal.  Convergence is tested on the device every
+ *    iteration; the host polls it every `check_every` iterations (iterations queued after
+ *    convergence are no-ops, so the result and the iteration count are those of deal.II's loop).
+ *    Returns B200FE_ERR_NO_CONVERGENCE (result still filled) when max_it is reached.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int iterations; /* ReductionControl::last_step() */
+    int converged;
+    double initial_residual, final_residual; /* initial_value(), last_value() */
+} b200fe_cg_result;
+
+int b200fe_cg_solve(b200fe_op *op, double *d_x, const double *d_b, const double *d_inv_diag, double abs_tol,
+                    double rel_tol, int max_it, int check_every, b200fe_cg_result *result, void *stream);
+/* Same with HOST x and b (n_owned doubles): H2D of b, solve, D2H of x, synchronises. */
+int b200fe_cg_solve_host(b200fe_op *op, double *h_x, const double *h_b, const double *d_inv_diag, double abs_tol,
+                         double rel_tol, int max_it, int check_every, b200fe_cg_result *result, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * 6. Ghost exchange between the GPUs of one node (NCCL over NVLink/NVSwitch; one process per GPU).
+ *    Replaces update_ghost_values / compress(add) / zero_out_ghost_values
+ *    (portable_laplace_operator.h:133,169,170) and p-halox's exchange round (p-halox/phalox.cc:104-126).
+ *    Lists follow deal.II's Partitioner: the ghost segment is grouped by owner rank; the send list
+ *    holds, per peer, the owned local indices that peer ghosts, in the peer's ghost order.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int rank, n_ranks;
+    const char *nccl_unique_id; /* 128 bytes from b200fe_comm_unique_id on rank 0, broadcast by the caller */
+    uint32_t n_owned, n_ghost;
+    int n_peers;
+    const int *peers;
+    const uint32_t *recv_offset, *recv_count; /* per peer: slice of the ghost segment (relative to n_owned) */
+    const uint32_t *send_offset, *send_count; /* per peer: slice of h_send_indices */
+    const uint32_t *h_send_indices;           /* owned local indices to pack */
+    uint32_t n_send;
+} b200fe_halo_desc;
+
+int b200fe_comm_available(void); /* 1 if libnccl.so.2 could be bound */
+int b200fe_comm_unique_id(char *id128);
+/* Collective over all ranks (ncclCommInitRank). */
+int b200fe_halo_create(const b200fe_halo_desc *desc, b200fe_halo **out);
+void b200fe_halo_destroy(b200fe_halo *halo);
+int b200fe_halo_update_ghosts(b200fe_halo *halo, double *d_v, void *stream);
+int b200fe_halo_compress_add(b200fe_halo *halo, double *d_v, void *stream);
+int b200fe_halo_zero_ghosts(b200fe_halo *halo, double *d_v, void *stream);
+int b200fe_halo_allreduce_sum(b200fe_halo *halo, double *d_vals, int count, void *stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,127 @@
+"""N>1 host logic on CPU: world_size-2 (and 3) gloo processes build their mesh partitions and the
+exchange lists; checked against the oracle's single-process construction, and a gloo emulation of
+update_ghost_values / compress(add) reproduces the single-rank operator result."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, sub, nref, p, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import benchmarks_b200 as b
+        from benchmarks_b200.dist import exchange_lists
+        import oracle
+        fe = oracle.fe
+        mesh = b.BoxMesh(sub, nref, p, n_ranks=world, rank=rank)
+        L = exchange_lists(mesh)
+        # oracle view of the same partition
+        om = fe.BoxMesh(sub, nref)
+        od = fe.distribute_dofs(om, p, world)
+        rds = [fe.rank_data(om, od, r) for r in range(world)]
+        ex = fe.exchange_lists(rds)[rank]
+        ok = sorted(ex["recv"]) == [t for t, c in zip(L["peers"], L["recv_count"]) if c]
+        for t, off, cnt, soff, scnt in zip(L["peers"], L["recv_offset"], L["recv_count"], L["send_offset"], L["send_count"]):
+            if cnt:
+                ok &= ex["recv"][int(t)] == (int(off), int(off + cnt))
+            if scnt:
+                ok &= np.array_equal(ex["send"][int(t)], L["send_indices"][soff:soff + scnt])
+            else:
+                ok &= int(t) not in ex["send"]
+        # distributed apply with gloo standing in for NCCL: update ghosts, local oracle apply, compress(add)
+        bas = fe.basis_1d(p, p + 2)
+        rd = rds[rank]
+        G, _ = fe.geometric_factors(fe.cell_nodes(om, rd["cells"], 1), 1, bas)
+        rng = np.random.default_rng(7)
+        u_global = rng.standard_normal(len(od["lattice_of_global"]))
+        v = np.zeros(mesh.n_owned + mesh.n_ghost)
+        v[:mesh.n_owned] = u_global[mesh.owned_begin:mesh.owned_begin + mesh.n_owned]
+
+        def exchange(send_bufs):
+            out = {}
+            reqs = []
+            for t in L["peers"]:
+                t = int(t)
+                if t in send_bufs:
+                    reqs.append(dist.isend(torch.from_numpy(send_bufs[t].copy()), t))
+            for t, n in recv_sizes.items():
+                out[t] = torch.empty(n, dtype=torch.float64)
+                reqs.append(dist.irecv(out[t], t))
+            for r in reqs:
+                r.wait()
+            return {t: o.numpy() for t, o in out.items()}
+
+        # update_ghost_values
+        send = {int(t): v[L["send_indices"][so:so + sc]] for t, so, sc in zip(L["peers"], L["send_offset"], L["send_count"]) if sc}
+        recv_sizes = {int(t): int(c) for t, c in zip(L["peers"], L["recv_count"]) if c}
+        got = exchange(send)
+        for t, off, cnt in zip(L["peers"], L["recv_offset"], L["recv_count"]):
+            if cnt:
+                v[mesh.n_owned + off:mesh.n_owned + off + cnt] = got[int(t)]
+        ok &= np.array_equal(v[mesh.n_owned:], u_global[mesh.ghost_global.astype(np.int64)])
+        y = fe.op_apply(v, rd, bas, G, constrained=np.zeros(0, np.uint32))
+        # compress(add): ghost contributions travel back
+        send = {int(t): y[mesh.n_owned + off:mesh.n_owned + off + cnt] for t, off, cnt in zip(L["peers"], L["recv_offset"], L["recv_count"]) if cnt}
+        recv_sizes = {int(t): int(c) for t, c in zip(L["peers"], L["send_count"]) if c}
+        got = exchange(send)
+        for t, so, sc in zip(L["peers"], L["send_offset"], L["send_count"]):
+            if sc:
+                np.add.at(y, L["send_indices"][so:so + sc], got[int(t)])
+        y = y[:mesh.n_owned]
+        y[mesh.constrained] = v[mesh.constrained]
+        # single-rank reference
+        od1 = fe.distribute_dofs(om, p, 1)
+        rd1 = fe.rank_data(om, od1, 0)
+        G1, _ = fe.geometric_factors(fe.cell_nodes(om, rd1["cells"], 1), 1, bas)
+        # map the distributed numbering onto the serial one through lattice coordinates
+        lat = od["lattice_of_global"]
+        ser_of_dist = od1["global_of_lattice"][lat[:, 0], lat[:, 1], lat[:, 2]]
+        u1 = np.empty_like(u_global)
+        u1[ser_of_dist] = u_global
+        y1 = fe.op_apply(u1, rd1, bas, G1)
+        mine = np.arange(mesh.owned_begin, mesh.owned_begin + mesh.n_owned)
+        err = np.abs(y - y1[ser_of_dist[mine]]).max() / np.abs(y1).max()
+        q.put((rank, bool(ok), float(err)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,sub,nref,p", [(2, (1, 1, 1), 1, 2), (2, (2, 1, 1), 1, 3), (3, (2, 2, 1), 1, 2)])
+def test_exchange_lists_and_distributed_apply_gloo(world, sub, nref, p):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, sub, nref, p, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    results = [q.get(timeout=240) for _ in range(world)]
+    for pr in procs:
+        pr.join(timeout=60)
+    assert len(results) == world
+    for rank, ok, err in results:
+        assert ok, f"rank {rank}: exchange lists differ from the oracle"
+        assert err <= 1e-13, f"rank {rank}: distributed apply differs ({err})"
+
+
+def test_overlap_permutation_splits_cells():
+    import benchmarks_b200 as b
+    mesh = b.BoxMesh((1, 1, 1), 2, 2, n_ranks=2, rank=1)
+    perm, n0, n1 = b.overlap_permutation(mesh.dof_indices, mesh.n_owned)
+    assert sorted(perm.tolist()) == list(range(mesh.n_cells))
+    idx = mesh.dof_indices[perm]
+    touches = ((idx >= mesh.n_owned) & (idx != 0xFFFFFFFF)).any(axis=1)
+    assert not touches[:n0].any() and touches[n0:n0 + n1].all() and not touches[n0 + n1:].any()
+    assert n1 > 0

@@ -1,0 +1,223 @@
+"""GPU parity of the L-vector operator path (gather -> sum factorisation -> atomic scatter, constrained
+rows, diagonal, right-hand side) and of CG, through the C ABI, against the CPU oracle.
+
+Tolerances (north star): one FP64 operator application <= 1e-12 relative max-norm; CG iteration
+counts within +-1 of the oracle and, for p=4 on the reference's box meshes, equal +-1 to the goldens of
+CEED_bp/results/1xGH200_P4.txt.  Atomics make the summation order nondeterministic, hence never bitwise.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+VARIANTS = [  # (name, nq offset from p, quad, kind)
+    ("bp3", 2, "gauss", "laplace"), ("bp35", 1, "gauss", "laplace"), ("bp5", 1, "gll", "laplace"),
+    ("bp1", 2, "gauss", "mass"), ("helmholtz", 1, "gauss", "helmholtz"),
+]
+DEFORM = (0.05, 2.0)
+
+
+def _oracle_setup(fe, sub, nref, p, nq, quad, p_geo, deform):
+    om = fe.BoxMesh(sub, nref)
+    od = fe.distribute_dofs(om, p, 1)
+    rd = fe.rank_data(om, od, 0)
+    bas = fe.basis_1d(p, nq, quad)
+    dfm = None if deform is None else (lambda P: P + deform[0] * np.sin(deform[1] * P[..., [1, 2, 0]]))
+    G, JxW = fe.geometric_factors(fe.cell_nodes(om, rd["cells"], p_geo, dfm), p_geo, bas)
+    return om, od, rd, bas, G, JxW
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.mark.parametrize("p", range(1, 9))
+@pytest.mark.parametrize("name,dq,quad,kind", VARIANTS)
+def test_vmult_matches_oracle_on_deformed_mesh(oracle_mod, p, name, dq, quad, kind):
+    import benchmarks_b200 as b
+    fe = oracle_mod.fe
+    sub, nref = ((2, 1, 1), 1) if p <= 5 else ((2, 1, 1), 0)
+    nq = p + dq
+    p_geo = min(p, 2)
+    om, od, rd, bas, G, JxW = _oracle_setup(fe, sub, nref, p, nq, quad, p_geo, DEFORM)
+    mesh = b.BoxMesh(sub, nref, p)
+    A = b.LaplaceOperator(mesh, nq=nq, quad=quad, kind=kind, p_geo=p_geo, deform=DEFORM)
+    # geometry (compute_G_tensors) parity
+    if A.G is not None:
+        assert rel(A.G.cpu().numpy().reshape(G.shape), G) <= TOL
+    assert rel(A.JxW.cpu().numpy().reshape(JxW.shape), JxW) <= TOL
+    rng = np.random.default_rng(p)
+    src = rng.standard_normal(mesh.n_owned)
+    ref = fe.op_apply(src, rd, bas, G, JxW, laplace=kind != "mass", mass=kind != "laplace")
+    dst = torch.full((mesh.n_owned,), 7.0, dtype=torch.float64, device="cuda")  # vmult must overwrite dst
+    A.vmult(dst, torch.from_numpy(src).cuda())
+    assert rel(dst.cpu().numpy(), ref) <= TOL, name
+    # fused inner product
+    dst2 = A.initialize_dof_vector()
+    dot = A.vmult_dot(dst2, torch.from_numpy(src).cuda())
+    assert abs(dot.item() - float(src @ ref)) <= 1e-11 * np.abs(src).dot(np.abs(ref))
+
+
+@pytest.mark.parametrize("p", [1, 2, 4, 7])
+def test_diagonal_rhs_and_dummy(oracle_mod, p):
+    import benchmarks_b200 as b
+    fe = oracle_mod.fe
+    sub, nref = (1, 1, 2), 1
+    for name, dq, quad, kind in (VARIANTS[0], VARIANTS[2], VARIANTS[4]):
+        nq = p + dq
+        om, od, rd, bas, G, JxW = _oracle_setup(fe, sub, nref, p, nq, quad, 1, None)
+        mesh = b.BoxMesh(sub, nref, p)
+        A = b.LaplaceOperator(mesh, nq=nq, quad=quad, kind=kind)
+        diag = A.compute_diagonal().cpu().numpy()
+        ref = fe.op_diagonal(rd, bas, G, JxW, laplace=kind != "mass", mass=kind != "laplace")
+        assert rel(diag, ref) <= 1e-11
+        assert rel(A.compute_rhs().cpu().numpy(), fe.rhs_one(rd, bas, JxW)) <= TOL
+    # vmult_dummy(ghost_exchange_on, computation_on) of portable_laplace_operator.h:175-235
+    src = torch.randn(mesh.n_owned, dtype=torch.float64, device="cuda")
+    full, comp_only, ghost_only = (torch.full_like(src, 3.0) for _ in range(3))
+    A.vmult(full, src)
+    A.vmult_dummy(comp_only, src, False, True)
+    A.vmult_dummy(ghost_only, src, True, False)
+    con = torch.from_numpy(mesh.constrained.astype(np.int64)).cuda()
+    free = torch.ones_like(src, dtype=torch.bool)
+    free[con] = False
+    assert torch.equal(comp_only[free], full[free]) or (comp_only[free] - full[free]).abs().max() <= 1e-12 * full.abs().max()
+    assert (comp_only[con] == 0).all()                  # computation only: constrained rows are not copied
+    assert torch.equal(ghost_only[con], src[con]) and (ghost_only[free] == 3.0).all()  # no dst = 0 without computation
+
+
+@pytest.fixture(scope="module")
+def cg_golden(golden_dir):
+    with open(os.path.join(golden_dir, "bp3_cg_p4.json")) as f:
+        return json.load(f)["rows"]
+
+
+@pytest.mark.parametrize("row", range(0, 7))
+@pytest.mark.parametrize("nq", [6, 5])
+def test_cg_reference_goldens_p4(cg_golden, row, nq):
+    """bp3 protocol: rhs = int phi, x0 = 0, ReductionControl(1e9, 1e-16, 1e-9) (bp3.cc:266-285)."""
+    import benchmarks_b200 as b
+    cycle, cells, ndofs, its_g, red_g = cg_golden[row]
+    mesh = b.BoxMesh.bp3_cycle(cycle, 4)
+    assert (mesh.n_cells_global, mesh.n_dofs_global) == (cells, ndofs)
+    A = b.LaplaceOperator(mesh, nq=nq)
+    rhs = A.compute_rhs()
+    x = A.initialize_dof_vector()
+    ctl = b.ReductionControl(10 ** 9, 1e-16, 1e-9)
+    b.SolverCG(ctl).solve(A, x, rhs)
+    assert abs(ctl.last_step() - its_g) <= 1
+    red = (ctl.last_value() / ctl.initial_value()) ** (1.0 / ctl.last_step())
+    assert red == pytest.approx(red_g, abs=2e-3)
+    # the solve really solved: ||b - A x|| <= 1e-9 ||b|| (recomputed residual)
+    r = A.initialize_dof_vector()
+    A.vmult(r, x)
+    assert (rhs - r).norm().item() <= 2e-9 * rhs.norm().item()
+
+
+@pytest.mark.parametrize("p,name,dq,quad,kind,jacobi", [
+    (2, "bp3", 2, "gauss", "laplace", False), (6, "bp5", 1, "gll", "laplace", False), (3, "helmholtz", 1, "gauss", "helmholtz", True),
+    (5, "bp1", 2, "gauss", "mass", False), (8, "bp35", 1, "gauss", "laplace", True)])
+def test_cg_matches_c_oracle(oracle_mod, p, name, dq, quad, kind, jacobi):
+    import benchmarks_b200 as b
+    fe = oracle_mod.fe
+    sub, nref = ((2, 2, 1), 1) if p <= 6 else ((2, 1, 1), 1)
+    nq = p + dq
+    om, od, rd, bas, G, JxW = _oracle_setup(fe, sub, nref, p, nq, quad, 1, None)
+    mesh = b.BoxMesh(sub, nref, p)
+    A = b.LaplaceOperator(mesh, nq=nq, quad=quad, kind=kind)
+    # bp5_kokkos right-hand side: b[i] = i % 8 on unconstrained owned DoFs (benchmark.cc:341-347)
+    rhs = np.arange(mesh.n_owned, dtype=np.float64) % 8
+    rhs[mesh.constrained] = 0.0
+    flags = {"laplace": 1, "mass": 2, "helmholtz": 3}[kind]
+    inv_diag = None
+    pre = None
+    if jacobi:
+        pre = A.get_matrix_diagonal_inverse()
+        inv_diag = pre.cpu().numpy()
+    xo, its_o, r0_o, rn_o, ok_o = oracle_mod.port.cg_solve(
+        rhs, nm=p + 1, nq=nq, collocated=(quad == "gll"), flags=flags, shape_values=bas["B"].T.copy(),
+        co_shape_gradients=bas["D"].T.copy(), G=G, JxW=JxW, dof_indices=rd["dof_indices"], constrained=rd["constrained"],
+        inv_diag=inv_diag, max_it=5000, abs_tol=1e-15, rel_tol=1e-8)
+    x = A.initialize_dof_vector()
+    ctl = b.ReductionControl(5000, 1e-15, 1e-8)
+    b.SolverCG(ctl).solve(A, x, torch.from_numpy(rhs).cuda(), pre)
+    assert ok_o and abs(ctl.last_step() - its_o) <= 1
+    assert ctl.initial_value() == pytest.approx(r0_o, rel=1e-13)
+    assert rel(x.cpu().numpy(), xo) <= 1e-6  # both stop at 1e-8 relative residual
+
+
+def test_cg_no_convergence_is_reported_like_dealii():
+    import benchmarks_b200 as b
+    mesh = b.BoxMesh.bp3_cycle(8, 4)
+    A = b.LaplaceOperator(mesh, nq=5)
+    rhs = A.compute_rhs()
+    x = A.initialize_dof_vector()
+    ctl = b.ReductionControl(10, 1e-16, 1e-12)  # bp5_kokkos caps its at 100 and swallows NoConvergence
+    with pytest.raises(b.NoConvergence):
+        b.SolverCG(ctl).solve(A, x, rhs)
+    assert ctl.last_step() == 10
+    # host-buffer entry point gives the same iterate
+    hx = torch.empty(mesh.n_owned, dtype=torch.float64).pin_memory()
+    hb = rhs.cpu().pin_memory()
+    with pytest.raises(b.NoConvergence):
+        b.SolverCG(ctl).solve_host(A, hx, hb)
+    assert (hx - x.cpu()).abs().max().item() <= 1e-12 * x.abs().max().item()
+
+
+def _kron_full(fe, mesh, A, bas, u):
+    """Element-free operator on a uniform box: (Kx x My x Mz + ...) u evaluated with torch matmuls."""
+    import benchmarks_b200 as b
+    p = mesh.p
+    dev = u.device
+    n = [c * p + 1 for c in mesh.cells]
+    idx = A.dof_indices.view(mesh.n_cells, -1).to(torch.int64)
+    xyz = torch.from_numpy(mesh.cell_xyz if A.perm is None else mesh.cell_xyz[A.perm]).to(dev).to(torch.int64)
+    nm = p + 1
+    l = torch.arange(nm ** 3, device=dev)
+    a, bb, c = l % nm, (l // nm) % nm, l // (nm * nm)
+    X = xyz[:, 0:1] * p + a[None]
+    Y = xyz[:, 1:2] * p + bb[None]
+    Z = xyz[:, 2:3] * p + c[None]
+    valid = idx != 0xFFFFFFFF
+    lin = (Z * n[1] + Y) * n[0] + X
+    U = torch.zeros(n[2] * n[1] * n[0], dtype=torch.float64, device=dev)
+    U[lin[valid]] = u[idx[valid]]
+    U = U.view(n[2], n[1], n[0])[1:-1, 1:-1, 1:-1]
+    mats = [[torch.from_numpy(m).to(dev) for m in fe.kron_1d(mesh.cells[d], mesh.h[d], bas)[:2]] for d in range(3)]
+    (Kx, Mx), (Ky, My), (Kz, Mz) = mats
+    t = lambda Az, Ay, Ax: torch.einsum("ai,ijk->ajk", Az, torch.einsum("bj,ijk->ibk", Ay, torch.einsum("ck,ijk->ijc", Ax, U)))
+    Yk = t(Mz, My, Kx) + t(Mz, Ky, Mx) + t(Kz, My, Mx)
+    return Yk, lin, valid, idx, n
+
+
+@pytest.mark.parametrize("cells_log2,p,quad,dq", [(5, 4, "gauss", 2), (6, 6, "gll", 1)])
+def test_full_size_apply_against_kronecker_form(oracle_mod, cells_log2, p, quad, dq):
+    """BASELINE configs C4 per-GPU size (p=4 at 32^3 here, 64^3 in bench) and C3 (64^3 cells, p=6,
+    57,066,625 DoFs): the whole vmult against the element-free Kronecker operator,
+    an oracle that shares no gather/scatter or sum-factorisation code with the kernel."""
+    import benchmarks_b200 as b
+    fe = oracle_mod.fe
+    mesh = b.BoxMesh((1, 1, 1), cells_log2, p)
+    nq = p + dq
+    A = b.LaplaceOperator(mesh, nq=nq, quad=quad, with_jxw=False)
+    bas = fe.basis_1d(p, nq, quad)
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    u = torch.randn(mesh.n_owned, dtype=torch.float64, device="cuda", generator=gen)
+    u[torch.from_numpy(mesh.constrained.astype(np.int64)).cuda()] = 0.0
+    y = A.initialize_dof_vector()
+    A.vmult(y, u)
+    Yk, lin, valid, idx, n = _kron_full(fe, mesh, A, bas, u)
+    Yp = torch.zeros(n[2] * n[1] * n[0], dtype=torch.float64, device="cuda")
+    Yp[lin[valid]] = y[idx[valid]]
+    Yp = Yp.view(n[2], n[1], n[0])[1:-1, 1:-1, 1:-1]
+    assert ((Yp - Yk).abs().max() / Yk.abs().max()).item() <= TOL
+    # symmetry and linearity at full size
+    v = torch.randn(mesh.n_owned, dtype=torch.float64, device="cuda", generator=gen)
+    Av = A.initialize_dof_vector()
+    A.vmult(Av, v)
+    assert abs(torch.dot(y, v).item() - torch.dot(u, Av).item()) <= 1e-12 * (y.norm() * v.norm()).item()
