@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the b200fe hot path.
+
+Workload (BASELINE.json configs[2], the single-GPU configuration the metric is quoted on):
+  CEED BP5 -- collocated GLL Laplacian, p = 6, 64^3 cells per GPU (57,066,625 DoFs on one GPU),
+  conjugate gradients from x0 = 0 on rhs = int phi (bp3.cc:184-239), a fixed number of iterations per
+  solve (bp5_kokkos/benchmark.cc:355 caps CG at 100 iterations the same way).
+  One *step* = one CG solve of `--its` iterations.  metric = GDoF/s = global DoFs * iterations / time
+  (bp5_kokkos/benchmark.cc:406).  Weak scaling: 64^3 cells per GPU, box of 2x1x1 / 2x2x1 / 2x2x2 blocks.
+
+Contract keys: value (device-resident vectors, CUDA events, max over ranks), e2e (same solve through
+the host-buffer C-ABI entry point b200fe_cg_solve_host: H2D of b and D2H of x inside the timed
+region), roofline (the sum-factorised cell kernel, timed per launch with CUDA events inside the
+library during the timed region), cpu_baseline (the oracle's C+OpenMP port on the host cores, on a
+bounded sample), clocks, gpu_launches.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  torchrun --nproc-per-node N ... bench.py --gpus N ...
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+P_DEGREE = 6
+CELLS_LOG2 = 6          # 64^3 cells per GPU
+CPU_SAMPLE_LOG2 = 5     # CPU arm: 32^3 cells (7,189,057 DoFs), same operator and solver
+BLOCKS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        pw = [float(r[3]) for r in self.rows if len(r) >= 9 and r[3].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def colors_of(cell_xyz):
+    col = (cell_xyz[:, 0] & 1) + 2 * (cell_xyz[:, 1] & 1) + 4 * (cell_xyz[:, 2] & 1)
+    order = np.argsort(col, kind="stable")
+    off = np.concatenate([[0], np.cumsum(np.bincount(col, minlength=8))])
+    return off.astype(np.uint32), order.astype(np.uint32)
+
+
+def cpu_cg_arm(p, cells_log2, its, repeats=1):
+    """The oracle's C + OpenMP restatement of the same operator + CG on the host cores (kind 'port':
+    the reference's own CPU path, bk3_dealii / deal.II, cannot be built here -- DESIGN.md)."""
+    import benchmarks_b200 as b
+    import oracle
+    fe = oracle.fe
+    mesh = b.BoxMesh((1, 1, 1), cells_log2, p)           # index tables: host data, no GPU involved
+    bas = fe.basis_1d(p, p + 1, "gll")
+    h = mesh.h[0]
+    w = bas["wq"]
+    nq = p + 1
+    W3 = np.einsum("r,q,p->rqp", w, w, w).ravel()
+    G = np.zeros((mesh.n_cells, 6, nq ** 3))
+    G[:, 0] = G[:, 3] = G[:, 5] = h * W3                 # cube cells: G = diag(h w_q)
+    rhs = np.arange(mesh.n_owned, dtype=np.float64) % 8  # bp5_kokkos/benchmark.cc:341-347 (cost is rhs-independent)
+    rhs[mesh.constrained] = 0.0
+    kw = dict(nm=p + 1, nq=nq, collocated=True, flags=1, shape_values=bas["B"].T.copy(), co_shape_gradients=bas["D"].T.copy(),
+              G=G, JxW=None, dof_indices=mesh.dof_indices, colors=colors_of(mesh.cell_xyz), constrained=mesh.constrained,
+              max_it=its, abs_tol=0.0, rel_tol=0.0)
+    times = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        _, n_it, _, _, _ = oracle.port.cg_solve(rhs, **kw)
+        times.append(time.perf_counter() - t0)
+        assert n_it == its
+    return dict(n_dofs=int(mesh.n_dofs_global), its=its, times=times, cores=oracle.port.num_threads())
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    its = args.cpu_its
+    r = cpu_cg_arm(P_DEGREE, CPU_SAMPLE_LOG2, its, repeats=args.warmup + args.steps)
+    t = float(np.mean(r["times"][args.warmup:]))
+    val = 1e-9 * r["n_dofs"] * its / t
+    sample = f"BP5 p={P_DEGREE} CG, {2**CPU_SAMPLE_LOG2}^3 cells ({r['n_dofs']} DoFs), {its} iterations per step"
+    print(json.dumps({
+        "impl": "reference", "metric": "BP5 CG GDoF/s (DoFs x iterations / s)", "value": val, "unit": "GDoF/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"CEED BP5 collocated GLL Laplacian CG, p={P_DEGREE}, 64^3 cells/GPU; CPU arm on a bounded sample", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "GDoF/s", "cores": r["cores"], "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "GDoF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--its", type=int, default=100, help="CG iterations per step")
+    ap.add_argument("--cpu-its", type=int, default=20, help="CG iterations per step of the CPU arm")
+    ap.add_argument("--p", type=int, default=P_DEGREE)
+    ap.add_argument("--cells-log2", type=int, default=CELLS_LOG2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--overlap", type=int, default=1)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import benchmarks_b200 as b
+    from benchmarks_b200._lib import lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    setup_group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        setup_group = dist.new_group(backend="gloo")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    p, its = args.p, args.its
+    if world not in BLOCKS:
+        raise SystemExit(f"--gpus must be one of {sorted(BLOCKS)}")
+    t_setup = time.perf_counter()
+    mesh = b.BoxMesh(BLOCKS[world], args.cells_log2, p, n_ranks=world, rank=rank)
+    halo = None
+    if world > 1:
+        from benchmarks_b200.dist import Halo
+        halo = Halo(mesh, group=setup_group)
+    A = b.LaplaceOperator(mesh, quad="gll", halo=halo, overlap=bool(args.overlap))
+    rhs = A.compute_rhs()
+    x = A.initialize_dof_vector()
+    t_setup = time.perf_counter() - t_setup
+    n_dofs = int(mesh.n_dofs_global)
+    ctl = b.ReductionControl(its, 0.0, 0.0)      # fixed iteration count: tolerances unreachable
+    solver = b.SolverCG(ctl, check_every=1 << 30)
+
+    def solve_device():
+        try:
+            solver.solve(A, x, rhs)
+        except b.NoConvergence:
+            pass  # expected: the step is `its` iterations (bp5_kokkos/benchmark.cc:370-374)
+
+    h_b = rhs[: mesh.n_owned].cpu().pin_memory()
+    h_x = torch.empty(mesh.n_owned, dtype=torch.float64).pin_memory()
+
+    def solve_host():
+        try:
+            solver.solve_host(A, h_x, h_b)
+        except b.NoConvergence:
+            pass
+
+    # ---- device-resident arm ------------------------------------------------------------------
+    for _ in range(args.warmup):
+        solve_device()
+    assert ctl.last_step() == its
+    A.timing_enable(args.steps * its * 3 + 16)
+    launches0 = lib.b200fe_launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        solve_device()
+    e1.record()
+    barrier()
+    t_dev = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None
+    gpu_launches = int(lib.b200fe_launch_count() - launches0)
+    k_ms, k_n = A.timing_read()
+    A.timing_enable(0)
+    res_final = ctl.last_value() / ctl.initial_value()
+
+    # ---- end-to-end arm: host buffers through b200fe_cg_solve_host ----------------------------
+    for _ in range(2):
+        solve_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        solve_host()
+    barrier()
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------
+    peaks, peak_kind = measured_peaks()
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    alg_bytes = A.algorithmic_bytes()          # per launch over all local cells (single phase)
+    launches_per_apply = 3 if (world > 1 and args.overlap) else 1
+    k_avg_s = 1e-3 * k_ms / max(k_n, 1) * launches_per_apply   # per apply
+    achieved = 1e-9 * alg_bytes / k_avg_s if k_n else 0.0
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"bp5_p{p}_bytes_per_launch")
+    except Exception:
+        pass
+
+    # ---- apply-only number and degree sweep (explains the headline; not the headline) ---------
+    def time_apply(op, reps=20):
+        src = op.compute_rhs()
+        dst = op.initialize_dof_vector()
+        for _ in range(3):
+            op.vmult(dst, src)
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(reps):
+            op.vmult(dst, src)
+        a1.record()
+        barrier()
+        return max_over_ranks(a0.elapsed_time(a1) * 1e-3 / reps)
+
+    t_apply = time_apply(A)
+    apply_info = {"gdofs": 1e-9 * n_dofs / t_apply, "ms": 1e3 * t_apply,
+                  "frac_of_hbm_roofline": 1e-9 * alg_bytes / t_apply / peak}
+    sweep = None
+    if world == 1 and not args.no_sweep:
+        sweep = []
+        del A, rhs, x
+        torch.cuda.empty_cache()
+        for pp in range(1, 9):
+            # ~1e7 DoFs: cells per axis ~ (1e7^(1/3))/p, rounded to the reference's mesh family
+            def ndofs(c):  # bp3.cc:443-468
+                n, rem = c // 3, c % 3
+                return float(np.prod([((2 if d < rem else 1) << n) * pp + 1 for d in range(3)]))
+            best = min(range(0, 27), key=lambda c: abs(np.log(ndofs(c) / 1.2e7)))
+            m2 = b.BoxMesh.bp3_cycle(best, pp)
+            for name, kw in (("bp5", dict(quad="gll")), ("bp3", dict(quad="gauss", nq=pp + 2))):
+                op = b.LaplaceOperator(m2, **kw)
+                t = time_apply(op, reps=10)
+                sweep.append({"op": name, "p": pp, "n_dofs": int(m2.n_dofs_global), "gdofs": 1e-9 * m2.n_dofs_global / t,
+                              "frac_of_hbm_roofline": 1e-9 * op.algorithmic_bytes() / t / peak})
+                del op
+                torch.cuda.empty_cache()
+
+    # ---- CPU baseline (rank 0, N = 1 only) ----------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_cg_arm(p, CPU_SAMPLE_LOG2, args.cpu_its, repeats=1)
+        cpu = {"value": 1e-9 * r["n_dofs"] * r["its"] / r["times"][0], "unit": "GDoF/s", "cores": r["cores"], "kind": "port",
+               "sample": f"BP5 p={p} CG, {2**CPU_SAMPLE_LOG2}^3 cells ({r['n_dofs']} DoFs), {r['its']} iterations, oracle/fe_oracle.c (C + OpenMP)"}
+
+    if rank == 0:
+        value = 1e-9 * n_dofs * its * args.steps / t_dev
+        out = {
+            "metric": "BP5 CG GDoF/s (DoFs x iterations / s)", "value": value, "unit": "GDoF/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"CEED BP5 collocated GLL Laplacian CG, p={p}, {2**args.cells_log2}^3 cells per GPU "
+                                   f"({n_dofs} DoFs global), {its} CG iterations per step, rhs = int phi, x0 = 0",
+                       "mesh_blocks": list(BLOCKS[world]), "n_dofs": n_dofs, "cg_iterations_per_step": its,
+                       "l2_policy": "working set (G 4.3 GB + vectors) >> 126 MB L2; no flush needed",
+                       "overlap_halo_with_interior_cells": bool(args.overlap) and world > 1,
+                       "relative_residual_after_step": res_final, "setup_s": t_setup},
+            "e2e": {"value": 1e-9 * n_dofs * its * args.steps / t_e2e, "unit": "GDoF/s",
+                    "h2d_bytes_per_step": int(mesh.n_owned) * 8 * world, "d2h_bytes_per_step": int(mesh.n_owned) * 8 * world,
+                    "api": "b200fe_cg_solve_host (pinned host b -> device, CG, device x -> pinned host)"},
+            "gpu_launches": gpu_launches,
+            "roofline": {"bound": "hbm", "kernel": f"sumfact_kernel<{p+1},{p+1},collocated,laplace,lvec> (BP5 cell kernel: gather + D^T G D + atomic scatter + fused p.Ap)",
+                         "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak if peak else None,
+                         "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": 1e3 * k_avg_s,
+                         "launches_timed": k_n, "kernel_share_of_step": (1e-3 * k_ms) / t_dev if t_dev else None},
+            "apply_only": apply_info,
+            "clocks": clocks,
+        }
+        if cpu:
+            out["cpu_baseline"] = cpu
+        if sweep:
+            out["degree_sweep_apply"] = sweep
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -182,12 +182,14 @@ static int cg_run(Operator &op, CgWork &w, double *d_x, const double *d_b, const
     B200FE_CUDA_TRY(cudaMemsetAsync(w.p, 0, sizeof(double) * op.n_local(), s));
     cg_init_kernel<<<blocks, 256, 0, s>>>(n, d_b, d_x, w.r, d_inv_diag, w.sc);
     B200FE_CUDA_TRY(cudaGetLastError());
+    ++g_launch_count;
     if (op.halo)
         if (int rc = halo_allreduce_sum(*op.halo, w.sc->acc + 1, 2, s)) return rc;
     int launched = 0;
     for (;;) {
         cg_scalar_kernel<<<1, 1, 0, s>>>(w.sc, jacobi, max_it, abs_tol, rel_tol);
         B200FE_CUDA_TRY(cudaGetLastError());
+        ++g_launch_count;
         if (launched % check_every == 0 || launched >= max_it) {
             B200FE_CUDA_TRY(cudaMemcpyAsync(w.h_sc, w.sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, s));
             B200FE_CUDA_TRY(cudaStreamSynchronize(s));
@@ -195,11 +197,13 @@ static int cg_run(Operator &op, CgWork &w, double *d_x, const double *d_b, const
         }
         cg_update_p_kernel<<<blocks, 256, 0, s>>>(n, w.r, d_inv_diag, w.p, w.sc);
         B200FE_CUDA_TRY(cudaGetLastError());
+        ++g_launch_count;
         if (int rc = op_vmult(op, w.v, w.p, &w.sc->acc[0], true, true, s)) return rc;
         if (op.halo)
             if (int rc = halo_allreduce_sum(*op.halo, w.sc->acc, 1, s)) return rc;
         cg_update_xr_kernel<<<blocks, 256, 0, s>>>(n, w.p, w.v, d_inv_diag, d_x, w.r, w.sc);
         B200FE_CUDA_TRY(cudaGetLastError());
+        ++g_launch_count;
         if (op.halo)
             if (int rc = halo_allreduce_sum(*op.halo, w.sc->acc + 1, 2, s)) return rc;
         ++launched;

@@ -16,6 +16,8 @@
 
 namespace b200fe {
 
+unsigned long long g_launch_count = 0;
+
 // ---------------------------------------------------------------------------------------------
 // setup kernels (not on the timed path): simple, runtime-sized
 // ---------------------------------------------------------------------------------------------
@@ -201,8 +203,15 @@ int op_apply_cells(Operator &op, double *d_dst, const double *d_src, uint32_t cb
     const size_t nm3 = (size_t)op.nm * op.nm * op.nm, nq3 = (size_t)op.nq * op.nq * op.nq;
     KArgs a{ce - cb, op.d_G ? op.d_G + cb * 6 * nq3 : nullptr, op.d_JxW ? op.d_JxW + cb * nq3 : nullptr,
             d_src, d_dst, op.d_idx + cb * nm3, d_dot};
+    const bool timed = op.timing && op.ev_used + 2 <= op.ev.size();
+    if (timed) B200FE_CUDA_TRY(cudaEventRecord(op.ev[op.ev_used], s));
     B200FE_CUDA_TRY(launch_sumfact(op.nm, op.nq, op.collocated, op.qop, true, op.B.data(), op.D.data(), a, s,
                                    &op.last_launch, false));
+    if (timed) {
+        B200FE_CUDA_TRY(cudaEventRecord(op.ev[op.ev_used + 1], s));
+        op.ev_used += 2;
+    }
+    ++g_launch_count;
     return B200FE_OK;
 }
 
@@ -212,6 +221,7 @@ int op_copy_constrained(Operator &op, double *d_dst, const double *d_src, double
     const unsigned blocks = std::min<unsigned>((op.n_constrained + 255) / 256, 1184);
     copy_constrained_kernel<<<blocks, 256, 0, s>>>(op.n_constrained, op.d_constrained, d_src, d_dst, d_dot);
     B200FE_CUDA_TRY(cudaGetLastError());
+    ++g_launch_count;
     return B200FE_OK;
 }
 
@@ -388,6 +398,7 @@ void b200fe_op_destroy(b200fe_op *o)
     Operator *op = reinterpret_cast<Operator *>(o);
     if (!op) return;
     cg_release_work(op);
+    for (cudaEvent_t e : op->ev) cudaEventDestroy(e);
     cudaFree(op->d_constrained);
     cudaFree(op->d_mats);
     delete op;
@@ -461,6 +472,41 @@ int b200fe_op_rhs_one(b200fe_op *o, double *d_b, void *stream)
         if (int rc = halo_compress_add(*op.halo, d_b, s)) return rc;
     return B200FE_OK;
 }
+
+int b200fe_op_timing_enable(b200fe_op *o, int max_launches)
+{
+    B200FE_REQUIRE(o && max_launches >= 0, "b200fe_op_timing_enable: bad arguments");
+    Operator &op = *reinterpret_cast<Operator *>(o);
+    for (cudaEvent_t e : op.ev) cudaEventDestroy(e);
+    op.ev.clear();
+    op.ev_used = 0;
+    op.timing = max_launches > 0;
+    for (int i = 0; i < 2 * max_launches; ++i) {
+        cudaEvent_t e;
+        B200FE_CUDA_TRY(cudaEventCreate(&e));
+        op.ev.push_back(e);
+    }
+    return B200FE_OK;
+}
+
+int b200fe_op_timing_read(b200fe_op *o, double *total_ms, int *launches)
+{
+    B200FE_REQUIRE(o && total_ms && launches, "b200fe_op_timing_read: null pointer");
+    Operator &op = *reinterpret_cast<Operator *>(o);
+    double sum = 0.0;
+    for (size_t i = 0; i + 1 < op.ev_used; i += 2) {
+        B200FE_CUDA_TRY(cudaEventSynchronize(op.ev[i + 1]));
+        float ms = 0.f;
+        B200FE_CUDA_TRY(cudaEventElapsedTime(&ms, op.ev[i], op.ev[i + 1]));
+        sum += ms;
+    }
+    *total_ms = sum;
+    *launches = (int)(op.ev_used / 2);
+    op.ev_used = 0;
+    return B200FE_OK;
+}
+
+unsigned long long b200fe_launch_count(void) { return g_launch_count; }
 
 int b200fe_op_launch_info(b200fe_op *o, int *elems_per_block, int *num_blocks, int *threads_per_block,
                           int *smem_bytes, int *blocks_per_sm, int *regs_per_thread)

@@ -24,6 +24,10 @@ struct Operator {
     // overlap split: cells [0, n_phase0) and [n_phase0+n_phase1, n_cells) touch no ghost DoF
     uint32_t n_phase0 = 0, n_phase1 = 0;
     LaunchInfo last_launch{};
+    // optional per-launch timing of the cell kernel (bench.py roofline): ring of event pairs
+    bool timing = false;
+    std::vector<cudaEvent_t> ev;   // 2 per launch
+    size_t ev_used = 0;
 
     uint32_t n_local() const { return n_owned + n_ghost; }
 };
@@ -36,6 +40,9 @@ int op_copy_constrained(Operator &op, double *d_dst, const double *d_src, double
 // full local vmult: zero, cells, constrained rows (+ halo exchange when attached)
 int op_vmult(Operator &op, double *d_dst, const double *d_src, double *d_dot, bool ghost_on, bool compute_on,
              cudaStream_t s);
+
+// number of kernels this library has launched so far (all kinds)
+extern unsigned long long g_launch_count;
 
 // cg.cu: frees the CG workspace cached for this operator
 void cg_release_work(Operator *op);

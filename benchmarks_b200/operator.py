@@ -163,6 +163,15 @@ class LaplaceOperator:
         check(lib.b200fe_op_rhs_one(self._h, _dp(b), _sp()))
         return b
 
+    def timing_enable(self, max_launches: int) -> None:
+        check(lib.b200fe_op_timing_enable(self._h, max_launches))
+
+    def timing_read(self):
+        """(total kernel ms, launches) of the cell kernel since the last read (CUDA events in the library)."""
+        ms, n = C.c_double(), C.c_int()
+        check(lib.b200fe_op_timing_read(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def launch_info(self):
         v = [C.c_int() for _ in range(6)]
         check(lib.b200fe_op_launch_info(self._h, *[C.byref(x) for x in v]))

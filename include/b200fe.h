@@ -212,6 +212,13 @@ int b200fe_op_vmult_host(b200fe_op *op, double *h_dst, const double *h_src, void
 int b200fe_op_diagonal(b200fe_op *op, double *d_diag, void *stream);
 /* compute_rhs of the BP drivers (CEED_bp/src/bp3.cc:184-239): b_i = int phi_i * 1, constrained rows 0. */
 int b200fe_op_rhs_one(b200fe_op *op, double *d_b, void *stream);
+/* Per-launch CUDA-event timing of the cell kernel (what bench.py's roofline reads): enable with room
+ * for max_launches launches (0 disables); read returns the summed kernel time and the number of
+ * launches recorded since the last read (waits for them to finish). */
+int b200fe_op_timing_enable(b200fe_op *op, int max_launches);
+int b200fe_op_timing_read(b200fe_op *op, double *total_ms, int *launches);
+/* Number of kernels this library has launched in this process (cell kernels, CG vector kernels, ...). */
+unsigned long long b200fe_launch_count(void);
 int b200fe_op_launch_info(b200fe_op *op, int *elems_per_block, int *num_blocks, int *threads_per_block,
                           int *smem_bytes, int *blocks_per_sm, int *regs_per_thread);
 
