@@ -4,6 +4,7 @@
 #include <cstring>
 
 #include "kernels.h"
+#include "sumfact2.cuh"
 
 namespace b200fe {
 
@@ -35,15 +36,61 @@ constexpr int epb_for(int nq)
     return e < 1 ? 1 : e;
 }
 
+// v2 kernel: target threads per CTA.  r01 sweeps (profiles/r01_v2_variants.txt): small planes want
+// several elements per CTA (~160 threads), nq >= 7 wants one element per CTA.
+#ifdef B200FE_V2_TPB
+#define B200FE_V2_TPB_FOR(nq) (B200FE_V2_TPB)
+#else
+#define B200FE_V2_TPB_FOR(nq) ((nq) <= 6 ? 160 : 96)
+#endif
+// v2 kernel: registers per thread the occupancy target must leave (tuning knob)
+#ifdef B200FE_V2_RMIN_FIXED
+#define B200FE_V2_RMIN(nq) (B200FE_V2_RMIN_FIXED)
+#else
+#ifndef B200FE_V2_RMIN_HI
+#define B200FE_V2_RMIN_HI 160
+#endif
+#define B200FE_V2_RMIN(nq) (((QOP) & QOP_LAPLACE) ? ((nq) >= 7 ? B200FE_V2_RMIN_HI : 96) : 64 + 12 * (nq))
+#endif
+
+template <int NM, int NQ, bool COLL, int QOP>
+struct V2Cfg {
+    using L = v2::Layout2<NM, NQ, COLL, QOP>;
+    static constexpr int EPB = (B200FE_V2_TPB_FOR(NQ) / (NQ * NQ)) < 1 ? 1 : (B200FE_V2_TPB_FOR(NQ) / (NQ * NQ));
+    static constexpr int T = EPB * NQ * NQ;
+    static constexpr int T32 = (T + 31) / 32 * 32;
+    static constexpr size_t SMEM = L::smem_bytes(EPB);
+    static constexpr int BY_SMEM = (int)((227 * 1024) / (SMEM + 1024));
+    static constexpr int BY_REGS = 65536 / (B200FE_V2_RMIN(NQ) * T32);
+    static constexpr int BY_THREADS = 2048 / T32;
+    static constexpr int M0 = BY_SMEM < BY_REGS ? BY_SMEM : BY_REGS;
+    static constexpr int M1 = M0 < BY_THREADS ? M0 : BY_THREADS;
+#ifdef B200FE_MINB
+    static constexpr int MINB = B200FE_MINB;
+#else
+    static constexpr int MINB = M1 < 1 ? 1 : (M1 > 16 ? 16 : M1);
+#endif
+};
+
 template <int NM, int NQ, bool COLL, int QOP, bool LVEC>
 cudaError_t launch_t(const double *hB, const double *hD, const KArgs &a, cudaStream_t s,
                      LaunchInfo *info, bool dry_run)
 {
+#ifdef B200FE_KERNEL_V1
     constexpr int EPB = epb_for(NQ);
     constexpr int T = EPB * NQ * NQ;
     using L = Layout<NM, NQ, COLL>;
     auto kern = sumfact_kernel<NM, NQ, COLL, QOP, LVEC, EPB, minb_for(NQ)>;
     const size_t smem = L::smem_bytes(EPB);
+#else
+    using C = V2Cfg<NM, NQ, COLL, QOP>;
+    constexpr int EPB = C::EPB;
+    constexpr int T = C::T;
+    auto kern = sumfact2_kernel<NM, NQ, COLL, QOP, LVEC, EPB, C::MINB>;
+    const size_t smem = C::SMEM;
+    // TMA bulk copies need a 16-byte aligned source (the batch block offset is a multiple of 48 nq^3 bytes)
+    if ((QOP & QOP_LAPLACE) && !dry_run && (reinterpret_cast<uintptr_t>(a.G) & 15u) != 0) return cudaErrorMisalignedAddress;
+#endif
 
     struct Cfg {
         bool ready = false;
@@ -56,6 +103,8 @@ cudaError_t launch_t(const double *hB, const double *hD, const KArgs &a, cudaStr
     Cfg &c = cfg[dev & 63];
     if (!c.ready) {
         err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+        err = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (err != cudaSuccess) return err;
         err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.blocks_per_sm, kern, T, smem);
         if (err != cudaSuccess) return err;

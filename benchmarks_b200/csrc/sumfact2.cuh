@@ -1,0 +1,418 @@
+// sumfact2.cuh -- second-generation cell kernel for sm_100a (FP64): TMA-staged geometric factors +
+// register-column contractions in all three directions.
+//
+// Why (ncu, profiles/r01a_bp5_p6_kernel_summary.txt): the first kernel (sumfact.cuh) was bound by
+// exposed HBM latency (stall long_scoreboard 10.6 per issue at 25 % occupancy) and by shared-memory
+// wavefronts (881 per element at nq = 7, equal to the whole HBM-roofline cycle budget).  Changes:
+//
+//  * G (6 nq^3 doubles per element = 75 % of all traffic) no longer goes through registers: the
+//    CTA's whole element batch is one contiguous 16-byte-aligned block of the reference layout
+//    [e][6][nq^3], fetched by ONE cp.async.bulk (TMA, SASS UBLKCP) into shared memory, completion
+//    on an mbarrier.  The copy for batch b+1 is issued as soon as the flux loop of batch b has
+//    drained the buffer; 3-6 resident CTAs per SM keep > 100 KB in flight per SM with zero
+//    registers spent on it.
+//  * every contraction is "register column x constant-bank matrix": besides layout P (thread =
+//    (q,r), column over p) the threads of an element also act in layout Q (thread = (p,r), column
+//    over q) and layout R (thread = (p,q), column over r).  A layout change costs one shared-memory
+//    store + one load per point instead of nq loads per point: 22 accesses per point instead of
+//    4 nq + 9.  Two staging arrays with different paddings make every access conflict-free:
+//      RQ[p][q][r] plane stride = nq^2 padded to == nq (mod 16)   (column reads with r across lanes)
+//      RR[p][q][r] row stride odd                                  (row reads with q across lanes)
+//  * results (flux, transposed derivative) are written back in place, so two arrays per element
+//    suffice (three with interpolation).
+//
+// Same template signature, arguments and numerics contract as sumfact.cuh (<= 1e-12 vs the oracle).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "sumfact.cuh"
+
+namespace b200fe {
+
+namespace v2 {
+
+constexpr __host__ __device__ int pad_plane_q(int nq)
+{
+    // smallest PS >= nq^2 with PS == nq (mod 16)
+    int ps = nq * nq;
+    while ((ps - nq) % 16 != 0) ++ps;
+    return ps;
+}
+
+template <int NM, int NQ, bool COLL, int QOP>
+struct Layout2 {
+    static constexpr int N2 = NQ * NQ, N3 = N2 * NQ, M3 = NM * NM * NM;
+    static constexpr bool LAP = (QOP & QOP_LAPLACE) != 0;
+    static constexpr int PSQ = pad_plane_q(NQ);       // RQ plane stride
+    static constexpr int RSR = odd(NQ);               // RR row stride
+    static constexpr int PSR = NQ * RSR;              // RR plane stride
+    static constexpr int RU = odd(NM), RA = odd(NQ);  // interpolation staging (as in sumfact.cuh)
+    static constexpr int SZ_FLUX = cmax(NQ * PSQ, NQ * PSR);
+    static constexpr int SZ_INTERP = cmax(cmax(NM * NM * RU, NM * NM * RA), N3);
+    static constexpr int REGION = (COLL ? SZ_FLUX : cmax(SZ_FLUX, SZ_INTERP) + 1) & ~1;  // even: keeps 16 B alignment
+    static constexpr int N_REGIONS = COLL ? (LAP ? 2 : 0) : 3;
+    // element stride == nq^2 (mod 16): a warp that spans two elements keeps hitting distinct banks
+    static constexpr int pad_elem(int w) { while ((w - N2) % 16 != 0) ++w; return w; }
+    static constexpr int WORK_PER_ELEM = N_REGIONS == 0 ? 0 : pad_elem(N_REGIONS * REGION);
+    static constexpr int G_PER_ELEM = LAP ? 6 * N3 : 0;
+    static constexpr size_t smem_bytes(int epb)
+    {
+        return 16 /* mbarrier */ + sizeof(double) * (size_t)epb * (G_PER_ELEM + WORK_PER_ELEM);
+    }
+};
+
+// ---- PTX helpers (mbarrier + bulk async copy) -------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// out[m] = sum_n M(m,n) in[n] with M(m,n) = mat[m*RS + n*CS] (compile-time indices -> constant bank)
+template <int NOUT, int NIN, int RS, int CS, typename MatT>
+__device__ __forceinline__ void col_mul(const MatT &mat, const double (&in)[NIN], double (&out)[NOUT])
+{
+#pragma unroll
+    for (int m = 0; m < NOUT; ++m) {
+        double s = 0.0;
+#pragma unroll
+        for (int n = 0; n < NIN; ++n) s = fma(mat[m * RS + n * CS], in[n], s);
+        out[m] = s;
+    }
+}
+
+}  // namespace v2
+
+// ---------------------------------------------------------------------------------------------
+template <int NM, int NQ, bool COLL, int QOP, bool LVEC, int EPB, int MINB>
+__global__ void __launch_bounds__(EPB *NQ *NQ, MINB)
+    sumfact2_kernel(const __grid_constant__ Mats<NM, NQ> m, const KArgs a)
+{
+    using L = v2::Layout2<NM, NQ, COLL, QOP>;
+    constexpr int N2 = L::N2, N3 = L::N3, M3 = L::M3, RA = L::RA;
+    constexpr int PSQ = L::PSQ, RSR = L::RSR, PSR = L::PSR;
+    constexpr bool LAP = L::LAP, MASS = (QOP & QOP_MASS) != 0;
+    static_assert(!COLL || NM == NQ, "collocated operators need nm == nq");
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    double *Gs = reinterpret_cast<double *>(smem_raw + 16);      // [EPB][6][N3]
+    double *work = Gs + EPB * L::G_PER_ELEM;
+    const int tid = threadIdx.x;
+    const int el = tid / N2;
+    const int t2 = tid - el * N2;
+    const int ta = t2 / NQ, tb = t2 - ta * NQ;  // (q,r) in layout P; (p,r) in layout Q; (p,q) in layout R
+    double *R0 = work + el * L::WORK_PER_ELEM;
+    [[maybe_unused]] double *R1 = R0 + L::REGION;
+    [[maybe_unused]] double *R2 = R1 + L::REGION;
+    double *RQ = R0, *RR = R1;
+    const double *Ge = Gs + el * L::G_PER_ELEM + t2;
+
+    const uint32_t n_batches = (a.n_elems + EPB - 1) / EPB;
+    auto issue_g = [&](uint32_t eb) {  // one elected thread: fetch the batch's G block
+        const uint32_t first = eb * EPB;
+        const uint32_t cnt = (a.n_elems - first) < (uint32_t)EPB ? (a.n_elems - first) : (uint32_t)EPB;
+        const uint32_t bytes = cnt * (uint32_t)(L::G_PER_ELEM * sizeof(double));
+        v2::mbar_expect_tx(bar, bytes);
+        v2::bulk_g2s(Gs, a.G + (size_t)first * L::G_PER_ELEM, bytes, bar);
+    };
+    if constexpr (LAP) {
+        if (tid == 0) {
+            v2::mbar_init(bar, 1);
+            v2::fence_mbar_init();
+        }
+        __syncthreads();
+        if (tid == 0 && blockIdx.x < n_batches) issue_g(blockIdx.x);
+    }
+    uint32_t parity = 0;
+
+    // Inputs are software-pipelined one batch ahead (ncu: the exposed in/idx -> src[idx] latency at the top
+    // of a batch was the largest stall once G moved to TMA).  Collocated: a column over p per thread;
+    // interpolated: a row over k for the threads (i,j) = t2 < NM^2, which feed the first sweep directly
+    // from registers (no staging of U / Z in shared memory).
+    constexpr int NIN = COLL ? NQ : NM;
+#ifndef B200FE_V2_PREFETCH_MAXNQ
+#define B200FE_V2_PREFETCH_MAXNQ 10  // software-pipelined inputs for every degree (r01 sweep: needs >= 160 registers at nq >= 7)
+#endif
+    constexpr bool PREFETCH = NQ <= B200FE_V2_PREFETCH_MAXNQ;
+    const bool loader = COLL ? true : (t2 < NM * NM);
+    double cur_val[NIN];
+    [[maybe_unused]] uint32_t cur_idx[NIN];
+    [[maybe_unused]] double nxt_val[NIN];
+    [[maybe_unused]] uint32_t nxt_idx[NIN];
+    auto in_offset = [&](uint32_t e_, int n) -> size_t {
+        return COLL ? (size_t)e_ * N3 + n * N2 + t2 : (size_t)e_ * M3 + t2 * NM + n;
+    };
+    auto load_idx = [&](uint32_t eb_, uint32_t (&ix)[NIN]) {
+        const uint32_t e_ = eb_ * EPB + el;
+        const bool ok = loader && eb_ < n_batches && e_ < a.n_elems;
+#pragma unroll
+        for (int n = 0; n < NIN; ++n) ix[n] = ok ? __ldg(a.idx + in_offset(e_, n)) : kInvalidIndex;
+    };
+    auto load_val = [&](uint32_t eb_, const uint32_t (&ix)[NIN], double (&val)[NIN]) {
+        if constexpr (LVEC) {
+#pragma unroll
+            for (int n = 0; n < NIN; ++n) val[n] = ix[n] == kInvalidIndex ? 0.0 : __ldg(a.in + ix[n]);
+        } else {
+            const uint32_t e_ = eb_ * EPB + el;
+            const bool ok = loader && eb_ < n_batches && e_ < a.n_elems;
+#pragma unroll
+            for (int n = 0; n < NIN; ++n) val[n] = ok ? __ldg(a.in + in_offset(e_, n)) : 0.0;
+        }
+    };
+    if constexpr (LVEC) load_idx(blockIdx.x, cur_idx);
+    load_val(blockIdx.x, cur_idx, cur_val);
+
+    double dot_acc = 0.0;
+    for (uint32_t eb = blockIdx.x; eb < n_batches; eb += gridDim.x) {
+        const uint32_t e = eb * EPB + el;
+        const bool active = e < a.n_elems;
+        const uint32_t nb = eb + gridDim.x;
+        // prefetch: next batch's indices (L-vector) or values (E-vector)
+        if constexpr (PREFETCH) {
+            if constexpr (LVEC) load_idx(nb, nxt_idx);
+            else load_val(nb, nxt_idx, nxt_val);
+        }
+        [[maybe_unused]] double jw[NQ];
+        if constexpr (MASS) {  // JxW column early: its latency hides behind the interpolation sweeps
+            const double *Je = a.JxW + (size_t)(active ? e : 0) * N3 + t2;
+#pragma unroll
+            for (int p = 0; p < NQ; ++p) jw[p] = active ? __ldg(Je + p * N2) : 0.0;
+        }
+        double v[NQ];
+        // ------------------------------------------------------------------ load (+ interpolation)
+        if constexpr (COLL) {
+#pragma unroll
+            for (int p = 0; p < NQ; ++p) v[p] = cur_val[p];
+        } else {
+            if (t2 < NM * NM) {  // k -> r straight from the register row -> A[i][j][r] in R1
+                double o[NQ];
+                v2::col_mul<NQ, NM, NM, 1>(m.B, cur_val, o);
+#pragma unroll
+                for (int r = 0; r < NQ; ++r) R1[t2 * RA + r] = o[r];
+            }
+            __syncthreads();
+            if (t2 < NM * NQ) {  // j -> q : columns of A -> B~[i][q][r] in R2
+                const int i = t2 / NQ, r2 = t2 - i * NQ;
+                double u[NM], o[NQ];
+#pragma unroll
+                for (int j = 0; j < NM; ++j) u[j] = R1[(i * NM + j) * RA + r2];
+                v2::col_mul<NQ, NM, NM, 1>(m.B, u, o);
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) R2[(i * NQ + q) * NQ + r2] = o[q];
+            }
+            __syncthreads();
+            {  // i -> p into the register column
+                double u[NM];
+#pragma unroll
+                for (int i = 0; i < NM; ++i) u[i] = R2[i * N2 + t2];
+                v2::col_mul<NQ, NM, NM, 1>(m.B, u, v);
+            }
+        }
+
+        // ------------------------------------------------------------------ operator at the points
+        double w[NQ];
+        if constexpr (LAP) {
+            double gr[NQ];  // d/dr (along p) from the register column; later the r-flux
+            v2::col_mul<NQ, NQ, NQ, 1>(m.D, v, gr);
+#pragma unroll
+            for (int p = 0; p < NQ; ++p) {
+                RQ[p * PSQ + t2] = v[p];
+                RR[p * PSR + ta * RSR + tb] = v[p];
+            }
+            __syncthreads();
+            {   // layout Q: thread (p,r) = (ta,tb), column over q, in place
+                double c[NQ], o[NQ];
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) c[q] = RQ[ta * PSQ + q * NQ + tb];
+                v2::col_mul<NQ, NQ, NQ, 1>(m.D, c, o);
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) RQ[ta * PSQ + q * NQ + tb] = o[q];
+            }
+            {   // layout R: thread (p,q) = (ta,tb), row over r, in place
+                double c[NQ], o[NQ];
+#pragma unroll
+                for (int r = 0; r < NQ; ++r) c[r] = RR[ta * PSR + tb * RSR + r];
+                v2::col_mul<NQ, NQ, NQ, 1>(m.D, c, o);
+#pragma unroll
+                for (int r = 0; r < NQ; ++r) RR[ta * PSR + tb * RSR + r] = o[r];
+            }
+            __syncthreads();
+            v2::mbar_wait(bar, parity);  // G of this batch has landed
+            parity ^= 1u;
+#pragma unroll
+            for (int p = 0; p < NQ; ++p) {
+                const double qr = gr[p];
+                const double qs = RQ[p * PSQ + t2];
+                const double qt = RR[p * PSR + ta * RSR + tb];
+                const double g0 = Ge[0 * N3 + p * N2], g1 = Ge[1 * N3 + p * N2], g2 = Ge[2 * N3 + p * N2];
+                const double g3 = Ge[3 * N3 + p * N2], g4 = Ge[4 * N3 + p * N2], g5 = Ge[5 * N3 + p * N2];
+                const double fr = g0 * qr + g1 * qs + g2 * qt;
+                const double fs = g1 * qr + g3 * qs + g4 * qt;
+                const double ft = g2 * qr + g4 * qs + g5 * qt;
+                gr[p] = fr;
+                RQ[p * PSQ + t2] = fs;
+                RR[p * PSR + ta * RSR + tb] = ft;
+                // u.(A u) = sum over points of grad(u)^T G grad(u): the CG inner product comes for free here,
+                // no need to keep the gathered values alive until the scatter
+                if constexpr (LVEC) dot_acc = fma(qr, fr, fma(qs, fs, fma(qt, ft, dot_acc)));
+            }
+            __syncthreads();
+            if (tid == 0) {  // the G buffer is drained: fetch the next batch's block behind the rest of this one
+                const uint32_t nb = eb + gridDim.x;
+                if (nb < n_batches) {
+                    v2::fence_proxy_async();
+                    issue_g(nb);
+                }
+            }
+            if constexpr (LVEC && PREFETCH) load_val(nb, nxt_idx, nxt_val);  // next batch's gathers (indices arrived long ago)
+            v2::col_mul<NQ, NQ, 1, NQ>(m.D, gr, w);  // w[p'] = sum_p D[p][p'] f_r[p]
+            {   // layout Q, transposed derivative along q, in place
+                double c[NQ], o[NQ];
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) c[q] = RQ[ta * PSQ + q * NQ + tb];
+                v2::col_mul<NQ, NQ, 1, NQ>(m.D, c, o);
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) RQ[ta * PSQ + q * NQ + tb] = o[q];
+            }
+            {   // layout R, transposed derivative along r, in place
+                double c[NQ], o[NQ];
+#pragma unroll
+                for (int r = 0; r < NQ; ++r) c[r] = RR[ta * PSR + tb * RSR + r];
+                v2::col_mul<NQ, NQ, 1, NQ>(m.D, c, o);
+#pragma unroll
+                for (int r = 0; r < NQ; ++r) RR[ta * PSR + tb * RSR + r] = o[r];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int p = 0; p < NQ; ++p) w[p] += RQ[p * PSQ + t2] + RR[p * PSR + ta * RSR + tb];
+        } else {
+#pragma unroll
+            for (int p = 0; p < NQ; ++p) w[p] = 0.0;
+        }
+        if constexpr (MASS) {
+#pragma unroll
+            for (int p = 0; p < NQ; ++p) {
+                const double mv = jw[p] * v[p];
+                w[p] += mv;
+                if constexpr (LVEC) dot_acc = fma(mv, v[p], dot_acc);  // + u^T M u at the points
+            }
+        }
+        if constexpr (LVEC && !LAP && PREFETCH) load_val(nb, nxt_idx, nxt_val);
+
+        // ------------------------------------------------------------------ (interpolation +) store
+        if constexpr (COLL) {
+            if constexpr (LVEC) {
+#pragma unroll
+                for (int p = 0; p < NQ; ++p) {
+                    if (cur_idx[p] != kInvalidIndex) atomicAdd(a.out + cur_idx[p], w[p]);
+                }
+            } else {
+                if (active) {
+#pragma unroll
+                    for (int p = 0; p < NQ; ++p) a.out[(size_t)e * N3 + p * N2 + t2] = w[p];
+                }
+            }
+        } else {
+            {   // p -> i in registers; X[i][q][r] -> R2 (dense)
+                double x[NM];
+                v2::col_mul<NM, NQ, 1, NM>(m.B, w, x);
+#pragma unroll
+                for (int i = 0; i < NM; ++i) R2[i * N2 + t2] = x[i];
+            }
+            __syncthreads();
+            if (t2 < NM * NQ) {  // q -> j : columns of X -> Y[i][j][r] in R0
+                const int i = t2 / NQ, r2 = t2 - i * NQ;
+                double x[NQ], o[NM];
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) x[q] = R2[(i * NQ + q) * NQ + r2];
+                v2::col_mul<NM, NQ, 1, NM>(m.B, x, o);
+#pragma unroll
+                for (int j = 0; j < NM; ++j) R0[(i * NM + j) * RA + r2] = o[j];
+            }
+            __syncthreads();
+            if (t2 < NM * NM) {  // r -> k : rows of Y -> the output row of thread (i,j), straight to memory
+                double x[NQ], z[NM];
+#pragma unroll
+                for (int r = 0; r < NQ; ++r) x[r] = R0[t2 * RA + r];
+                v2::col_mul<NM, NQ, 1, NM>(m.B, x, z);
+                if constexpr (LVEC) {
+#pragma unroll
+                    for (int k = 0; k < NM; ++k) {
+                        if (cur_idx[k] != kInvalidIndex) atomicAdd(a.out + cur_idx[k], z[k]);
+                    }
+                } else {
+                    if (active) {
+#pragma unroll
+                        for (int k = 0; k < NM; ++k) a.out[(size_t)e * M3 + t2 * NM + k] = z[k];
+                    }
+                }
+            }
+            // next batch writes R1 first: its last readers (flux loop, own points) left two barriers ago
+        }
+        // rotate the software pipeline (or load the next batch's inputs now)
+        if constexpr (PREFETCH) {
+#pragma unroll
+            for (int n = 0; n < NIN; ++n) {
+                cur_val[n] = nxt_val[n];
+                if constexpr (LVEC) cur_idx[n] = nxt_idx[n];
+            }
+        } else {
+            if constexpr (LVEC) load_idx(nb, cur_idx);
+            load_val(nb, cur_idx, cur_val);
+        }
+    }
+
+    if constexpr (LVEC) {
+        if (a.dot != nullptr) {
+            __shared__ double red[32];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) dot_acc += __shfl_xor_sync(0xffffffffu, dot_acc, o);
+            __syncthreads();
+            if ((tid & 31) == 0) red[tid >> 5] = dot_acc;
+            __syncthreads();
+            if (tid < 32) {
+                double s = tid < (EPB * N2 + 31) / 32 ? red[tid] : 0.0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (tid == 0) atomicAdd(a.dot, s);
+            }
+        }
+    }
+}
+
+}  // namespace b200fe

@@ -5,7 +5,7 @@ txt = sys.stdin.read()
 cur = None
 rows = []
 for line in txt.splitlines():
-    m = re.search(r"sumfact_kernelILi(\d+)ELi(\d+)ELb([01])ELi(\d)ELb([01])ELi(\d+)ELi(\d+)E", line)
+    m = re.search(r"sumfact2?_kernelILi(\d+)ELi(\d+)ELb([01])ELi(\d)ELb([01])ELi(\d+)ELi(\d+)E", line)
     if m and "Compiling" in line:
         cur = dict(nm=int(m[1]), nq=int(m[2]), coll=int(m[3]), qop=int(m[4]), lvec=int(m[5]), epb=int(m[6]), minb=int(m[7]))
         continue
