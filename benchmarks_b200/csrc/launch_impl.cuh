@@ -43,15 +43,25 @@ constexpr int epb_for(int nq)
 #else
 #define B200FE_V2_TPB_FOR(nq) ((nq) <= 6 ? 160 : 96)
 #endif
-// v2 kernel: registers per thread the occupancy target must leave (tuning knob)
+// v2 kernel: registers per thread that the occupancy target (MINB) must leave.  Data-driven
+// (profiles/r01_v2_variants.txt): with the software-pipelined inputs the large planes need 160-240
+// registers to stay spill-free; below nq = 7 a 96-register floor (more CTAs per SM) wins.
+constexpr int v2_rmin(int nq, bool coll, int qop)
+{
 #ifdef B200FE_V2_RMIN_FIXED
-#define B200FE_V2_RMIN(nq) (B200FE_V2_RMIN_FIXED)
+    return B200FE_V2_RMIN_FIXED;
 #else
-#ifndef B200FE_V2_RMIN_HI
-#define B200FE_V2_RMIN_HI 160
+    if (!(qop & QOP_LAPLACE)) return 64 + 12 * nq;  // mass only: no G buffer, registers are the limit
+    if (nq <= 6) return 96;
+#ifdef B200FE_V2_RMIN_HI
+    return B200FE_V2_RMIN_HI;
+#else
+    if (nq == 7) return coll ? 160 : 240;
+    if (nq == 8) return coll ? 208 : 240;
+    return coll ? 208 : 160;
 #endif
-#define B200FE_V2_RMIN(nq) (((QOP) & QOP_LAPLACE) ? ((nq) >= 7 ? B200FE_V2_RMIN_HI : 96) : 64 + 12 * (nq))
 #endif
+}
 
 template <int NM, int NQ, bool COLL, int QOP>
 struct V2Cfg {
@@ -61,7 +71,7 @@ struct V2Cfg {
     static constexpr int T32 = (T + 31) / 32 * 32;
     static constexpr size_t SMEM = L::smem_bytes(EPB);
     static constexpr int BY_SMEM = (int)((227 * 1024) / (SMEM + 1024));
-    static constexpr int BY_REGS = 65536 / (B200FE_V2_RMIN(NQ) * T32);
+    static constexpr int BY_REGS = 65536 / (v2_rmin(NQ, COLL, QOP) * T32);
     static constexpr int BY_THREADS = 2048 / T32;
     static constexpr int M0 = BY_SMEM < BY_REGS ? BY_SMEM : BY_REGS;
     static constexpr int M1 = M0 < BY_THREADS ? M0 : BY_THREADS;
