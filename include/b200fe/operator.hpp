@@ -1,0 +1,280 @@
+// b200fe/operator.hpp -- header-only C++ host layer over the C ABI (include/b200fe.h).
+//
+// Same class / method names as the reference so that its drivers port by changing only the types:
+//   b200fe::LaplaceOperator<dim, fe_degree, nq, number>   <-> Portable::LaplaceOperator
+//        (CEED_bp/include/portable_laplace_operator.h:17-96): vmult, Tvmult, vmult_dummy,
+//        initialize_dof_vector, m, n; compute_diagonal / get_matrix_diagonal_inverse
+//        (bp5_kokkos/benchmark.cc:157-168, 218-251)
+//   b200fe::Vector            <-> LinearAlgebra::distributed::Vector<double, MemorySpace::Default>
+//   b200fe::ReductionControl  <-> dealii::ReductionControl        (bp3.cc:268)
+//   b200fe::SolverCG          <-> dealii::SolverCG                (bp3.cc:269-278)
+//   b200fe::BoxMesh           <-> Triangulation + DoFHandler + AffineConstraints of the drivers
+//        (GridGenerator::subdivided_hyper_rectangle + refine_global + distribute_dofs, bp3.cc:452-488)
+// Needs the CUDA runtime only for device allocations (cudaMalloc / cudaMemcpy).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../b200fe.h"
+
+namespace b200fe {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+struct NoConvergence : Error {  // SolverControl::NoConvergence
+    using Error::Error;
+};
+
+inline void check(int rc)
+{
+    if (rc != B200FE_OK) throw Error(rc, std::string("b200fe: ") + b200fe_last_error());
+}
+inline void check_cuda(cudaError_t e, const char *what)
+{
+    if (e != cudaSuccess) throw Error(B200FE_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+template <typename T>
+class DeviceArray {
+  public:
+    DeviceArray() = default;
+    explicit DeviceArray(size_t n) { resize(n); }
+    DeviceArray(const DeviceArray &) = delete;
+    DeviceArray &operator=(const DeviceArray &) = delete;
+    DeviceArray(DeviceArray &&o) noexcept : p_(o.p_), n_(o.n_) { o.p_ = nullptr; o.n_ = 0; }
+    DeviceArray &operator=(DeviceArray &&o) noexcept
+    {
+        if (this != &o) { release(); p_ = o.p_; n_ = o.n_; o.p_ = nullptr; o.n_ = 0; }
+        return *this;
+    }
+    ~DeviceArray() { release(); }
+    void resize(size_t n)
+    {
+        release();
+        n_ = n;
+        if (n) check_cuda(cudaMalloc(&p_, n * sizeof(T)), "cudaMalloc");
+    }
+    void upload(const T *h, size_t n)
+    {
+        if (n_ != n) resize(n);
+        if (n) check_cuda(cudaMemcpy(p_, h, n * sizeof(T), cudaMemcpyHostToDevice), "cudaMemcpy H2D");
+    }
+    void download(T *h) const
+    {
+        if (n_) check_cuda(cudaMemcpy(h, p_, n_ * sizeof(T), cudaMemcpyDeviceToHost), "cudaMemcpy D2H");
+    }
+    T *data() { return p_; }
+    const T *data() const { return p_; }
+    size_t size() const { return n_; }
+
+  private:
+    void release() { if (p_) cudaFree(p_); p_ = nullptr; n_ = 0; }
+    T *p_ = nullptr;
+    size_t n_ = 0;
+};
+
+// owned DoFs followed by ghosts, like LinearAlgebra::distributed::Vector
+class Vector {
+  public:
+    Vector() = default;
+    void reinit(size_t n_owned, size_t n_ghost)
+    {
+        n_owned_ = n_owned; n_ghost_ = n_ghost;
+        d_.resize(n_owned + n_ghost);
+        *this = 0.0;
+    }
+    void reinit(const Vector &o) { reinit(o.n_owned_, o.n_ghost_); }
+    Vector &operator=(double v)
+    {
+        if (v != 0.0) throw Error(B200FE_ERR_INVALID_ARG, "Vector = s only implemented for s = 0");
+        if (d_.size()) check_cuda(cudaMemset(d_.data(), 0, d_.size() * sizeof(double)), "cudaMemset");
+        return *this;
+    }
+    double *get_values() { return d_.data(); }
+    const double *get_values() const { return d_.data(); }
+    size_t locally_owned_size() const { return n_owned_; }
+    size_t size_with_ghosts() const { return n_owned_ + n_ghost_; }
+    std::vector<double> to_host() const
+    {
+        std::vector<double> h(d_.size());
+        d_.download(h.data());
+        h.resize(n_owned_);
+        return h;
+    }
+    void from_host(const std::vector<double> &h)
+    {
+        check_cuda(cudaMemcpy(d_.data(), h.data(), std::min(h.size(), d_.size()) * sizeof(double), cudaMemcpyHostToDevice), "cudaMemcpy H2D");
+    }
+    double l2_norm() const
+    {
+        DeviceArray<double> s(1);
+        check(b200fe_sum_squares(n_owned_, d_.data(), s.data(), nullptr));
+        double h = 0;
+        s.download(&h);
+        return std::sqrt(h);
+    }
+
+  private:
+    DeviceArray<double> d_;
+    size_t n_owned_ = 0, n_ghost_ = 0;
+};
+
+class BoxMesh {
+  public:
+    BoxMesh(const int (&subdivisions)[3], int n_refine, int p, const double (&p1)[3], const double (&p2)[3],
+            int n_ranks = 1, int rank = 0, int partition = B200FE_PARTITION_P4EST, int ghosts = B200FE_GHOSTS_MINIMAL,
+            bool dirichlet = true)
+    {
+        b200fe_boxmesh_desc d{};
+        for (int k = 0; k < 3; ++k) { d.subdivisions[k] = subdivisions[k]; d.p1[k] = p1[k]; d.p2[k] = p2[k]; }
+        d.n_refine = n_refine; d.p = p; d.n_ranks = n_ranks; d.rank = rank; d.partition = partition; d.ghosts = ghosts;
+        d.dirichlet = dirichlet ? 1 : 0;
+        check(b200fe_boxmesh_create(&d, &h_));
+        check(b200fe_boxmesh_info(h_, &info));
+        degree = p;
+    }
+    // mesh number `cycle` of the reference sweep (CEED_bp/src/bp3.cc:443-473)
+    static BoxMesh bp3_cycle(unsigned cycle, int p, int n_ranks = 1, int rank = 0)
+    {
+        const int n_refine = cycle / 3, rem = cycle % 3;
+        int sub[3];
+        double p1[3] = {-1, -1, -1}, p2[3];
+        for (int d = 0; d < 3; ++d) { sub[d] = d < rem ? 2 : 1; p2[d] = d < rem ? 2.8 : 0.9; }
+        return BoxMesh(sub, n_refine, p, p1, p2, n_ranks, rank);
+    }
+    static unsigned long long bp3_projected_size(unsigned cycle, int p)
+    {
+        const unsigned n_refine = cycle / 3, rem = cycle % 3;
+        unsigned long long s = 1;
+        for (unsigned d = 0; d < 3; ++d) s *= (unsigned long long)((1u << n_refine) * (d < rem ? 2 : 1) * p + 1);
+        return s;
+    }
+    BoxMesh(BoxMesh &&o) noexcept : info(o.info), degree(o.degree), h_(o.h_) { o.h_ = nullptr; }
+    BoxMesh(const BoxMesh &) = delete;
+    ~BoxMesh() { if (h_) b200fe_boxmesh_destroy(h_); }
+    const b200fe_boxmesh *handle() const { return h_; }
+    unsigned long long n_dofs() const { return info.n_dofs_global; }
+    unsigned long long n_global_active_cells() const { return info.n_cells_global; }
+    b200fe_boxmesh_info_t info{};
+    int degree = 0;
+
+  private:
+    b200fe_boxmesh *h_ = nullptr;
+};
+
+enum class Quadrature { Gauss, GaussLobatto };
+
+template <int dim, int fe_degree, int nq, typename number = double>
+class LaplaceOperator {
+    static_assert(dim == 3, "the bake-off operators are three-dimensional");
+    static_assert(std::is_same<number, double>::value, "FP64 only");
+
+  public:
+    // p_geo: degree of the mapping (MappingQ(p_geo)); op_kind: B200FE_OP_*
+    LaplaceOperator(const BoxMesh &mesh, Quadrature quad = Quadrature::Gauss, int op_kind = B200FE_OP_LAPLACE, int p_geo = 1)
+        : n_dofs_global_(mesh.n_dofs()), n_owned_(mesh.info.n_owned), n_ghost_(mesh.info.n_ghost)
+    {
+        if (mesh.degree != fe_degree) throw Error(B200FE_ERR_INVALID_ARG, "mesh degree != fe_degree");
+        const int nm = fe_degree + 1, qk = quad == Quadrature::Gauss ? B200FE_QUAD_GAUSS : B200FE_QUAD_GLL;
+        const bool collocated = quad == Quadrature::GaussLobatto && nq == nm;
+        const uint32_t nc = mesh.info.n_cells_local;
+        std::vector<double> sv(nm * nq), cg(nq * nq);
+        check(b200fe_basis_1d(fe_degree, nq, qk, sv.data(), cg.data(), nullptr, nullptr, nullptr));
+        std::vector<uint32_t> idx((size_t)nc * nm * nm * nm), con(mesh.info.n_constrained);
+        check(b200fe_boxmesh_fill(mesh.handle(), idx.data(), con.data(), nullptr, nullptr, nullptr, nullptr));
+        idx_.upload(idx.data(), idx.size());
+        const size_t ng3 = (size_t)(p_geo + 1) * (p_geo + 1) * (p_geo + 1), nq3 = (size_t)nq * nq * nq;
+        DeviceArray<double> nodes((size_t)nc * 3 * ng3);
+        check(b200fe_boxmesh_nodes(mesh.handle(), p_geo, 0, 0.0, 0.0, nodes.data(), nullptr));
+        if (op_kind & B200FE_OP_LAPLACE) G_.resize((size_t)nc * 6 * nq3);
+        JxW_.resize((size_t)nc * nq3);
+        check(b200fe_geometry_from_nodes(p_geo, nq, qk, nc, nodes.data(), G_.data(), JxW_.data(), nullptr));
+        check_cuda(cudaDeviceSynchronize(), "geometry");
+        b200fe_op_desc d{};
+        d.p = fe_degree; d.nq = nq; d.op_kind = op_kind; d.collocated = collocated;
+        d.n_cells = nc; d.n_owned = n_owned_; d.n_ghost = n_ghost_;
+        d.h_shape_values = sv.data(); d.h_co_shape_gradients = cg.data();
+        d.d_dof_indices = idx_.data(); d.d_G = G_.data(); d.d_JxW = JxW_.data();
+        d.h_constrained = con.data(); d.n_constrained = (uint32_t)con.size();
+        check(b200fe_op_create(&d, &op_));
+    }
+    LaplaceOperator(const LaplaceOperator &) = delete;
+    ~LaplaceOperator() { if (op_) b200fe_op_destroy(op_); }
+
+    void vmult(Vector &dst, const Vector &src) const { check(b200fe_op_vmult(op_, dst.get_values(), src.get_values(), nullptr)); }
+    void Tvmult(Vector &dst, const Vector &src) const { vmult(dst, src); }
+    void vmult_dummy(Vector &dst, const Vector &src, const bool ghost_exchange_on, const bool computation_on) const
+    {
+        check(b200fe_op_vmult_dummy(op_, dst.get_values(), src.get_values(), ghost_exchange_on, computation_on, nullptr));
+    }
+    void initialize_dof_vector(Vector &vec) const { vec.reinit(n_owned_, n_ghost_); }
+    unsigned long long m() const { return n_dofs_global_; }
+    unsigned long long n() const { return n_dofs_global_; }
+    void compute_rhs(Vector &b) const { check(b200fe_op_rhs_one(op_, b.get_values(), nullptr)); }  // bp3.cc:184-239
+    void compute_diagonal()                                                                      // benchmark.cc:218-251
+    {
+        Vector d;
+        initialize_dof_vector(d);
+        check(b200fe_op_diagonal(op_, d.get_values(), nullptr));
+        std::vector<double> h = d.to_host();
+        for (double &x : h) x = x > 0 ? 1.0 / x : 1.0;
+        inv_diag_.upload(h.data(), h.size());
+    }
+    const double *get_matrix_diagonal_inverse()
+    {
+        if (!inv_diag_.size()) compute_diagonal();
+        return inv_diag_.data();
+    }
+    b200fe_op *handle() const { return op_; }
+
+  private:
+    b200fe_op *op_ = nullptr;
+    unsigned long long n_dofs_global_;
+    uint32_t n_owned_, n_ghost_;
+    DeviceArray<uint32_t> idx_;
+    DeviceArray<double> G_, JxW_, inv_diag_;
+};
+
+class ReductionControl {
+  public:
+    ReductionControl(unsigned max_steps = 100, double tolerance = 1e-10, double reduction = 1e-2)
+        : max_steps_(max_steps), tol_(tolerance), red_(reduction) {}
+    unsigned last_step() const { return (unsigned)res_.iterations; }
+    double last_value() const { return res_.final_residual; }
+    double initial_value() const { return res_.initial_residual; }
+    unsigned max_steps_;
+    double tol_, red_;
+    b200fe_cg_result res_{};
+};
+
+struct PreconditionIdentity {};
+
+class SolverCG {
+  public:
+    explicit SolverCG(ReductionControl &c, int check_every = 8) : control_(c), check_every_(check_every) {}
+    template <class Operator>
+    void solve(const Operator &A, Vector &x, const Vector &b, const PreconditionIdentity &) { run(A.handle(), x, b, nullptr); }
+    template <class Operator>
+    void solve(const Operator &A, Vector &x, const Vector &b, const double *d_inverse_diagonal) { run(A.handle(), x, b, d_inverse_diagonal); }
+
+  private:
+    void run(b200fe_op *op, Vector &x, const Vector &b, const double *inv_diag)
+    {
+        const int max_it = control_.max_steps_ > 2000000000u ? 2000000000 : (int)control_.max_steps_;
+        const int rc = b200fe_cg_solve(op, x.get_values(), b.get_values(), inv_diag, control_.tol_, control_.red_, max_it,
+                                       check_every_, &control_.res_, nullptr);
+        if (rc == B200FE_ERR_NO_CONVERGENCE) throw NoConvergence(rc, b200fe_last_error());
+        check(rc);
+    }
+    ReductionControl &control_;
+    int check_every_;
+};
+
+}  // namespace b200fe

@@ -1,0 +1,53 @@
+"""The C++ host layer (include/b200fe/operator.hpp) through the ported reference drivers:
+benchmarks_b200/drivers/bk_benchmark (CEED_BK/src/BK*/templated_cuda_benchmark.cc protocol) must print the
+reference's known-answer norms, benchmarks_b200/drivers/bp3 (CEED_bp/src/bp3.cc protocol) the reference's
+golden CG iteration counts for p = 4."""
+import json
+import os
+import re
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DRV = os.path.join(ROOT, "benchmarks_b200", "drivers")
+
+
+def _run(args, timeout=600):
+    exe = os.path.join(DRV, args[0])
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", DRV], check=True)
+    r = subprocess.run([exe] + [str(a) for a in args[1:]], capture_output=True, text=True, timeout=timeout)
+    assert r.returncode == 0, r.stderr
+    return r.stdout
+
+
+@pytest.mark.parametrize("kind,p", [("bk1", 2), ("bk3", 2), ("bk5", 4), ("bk3", 8), ("bk1", 7), ("bk5", 1)])
+def test_bk_benchmark_prints_reference_norms(golden_dir, kind, p):
+    gold = json.load(open(os.path.join(golden_dir, "bk_norms.json")))["kat_norms_nelmt64"][str(p)][kind]
+    out = _run(["bk_benchmark", kind, p, 64, 2])
+    last = out.strip().splitlines()[-1].split()
+    assert last[0] == kind.upper() and int(last[1]) == p and int(last[2]) == 64
+    assert float(last[-1]) == pytest.approx(gold, rel=1e-7)  # printed with 8 significant digits
+
+
+def test_bp3_driver_reproduces_reference_table(golden_dir):
+    rows = json.load(open(os.path.join(golden_dir, "bp3_cg_p4.json")))["rows"]
+    out = _run(["bp3", 4, 10000, 300000])
+    # last printed convergence table
+    block = out[out.rindex(" cells    dofs    matvec"):]
+    table = [l.split() for l in block.splitlines()[1:] if re.match(r"^\s*\d+\s+\d+\s+\d\.\d+e", l)]
+    assert len(table) >= 5
+    for got, want in zip(table, rows):
+        assert int(got[0]) == want[1] and int(got[1]) == want[2]
+        assert abs(int(got[5]) - want[3]) <= 1
+        assert float(got[6]) == pytest.approx(want[4], abs=2e-3)
+
+
+def test_bp3_driver_reports_errors_like_the_reference():
+    exe = os.path.join(DRV, "bp3")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", DRV], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 1 and "Expected at least one argument" in r.stdout
