@@ -65,6 +65,7 @@ _SIGNATURES = {
     "b200fe_halo_compress_add": (_i, [_vp, _vp, _vp]),
     "b200fe_halo_zero_ghosts": (_i, [_vp, _vp, _vp]),
     "b200fe_halo_allreduce_sum": (_i, [_vp, _vp, _i, _vp]),
+    "b200fe_halo_exchange_raw": (_i, [_vp, _vp, _vp, _vp]),
 }
 for _name, (_res, _args) in _SIGNATURES.items():
     _f = getattr(lib, _name)

@@ -133,12 +133,14 @@ int halo_zero_ghosts(Halo &h, double *v, cudaStream_t s)
 int halo_update_ghosts(Halo &h, double *v, cudaStream_t s)
 {
     if (h.n_ranks == 1) return B200FE_OK;
+    if (h.n_send && !h.d_send_idx) return fail(B200FE_ERR_INVALID_ARG, "halo was created in raw mode (no send indices)");
     return exchange_update(h, v, s);
 }
 
 int halo_compress_add(Halo &h, double *v, cudaStream_t s)
 {
     if (h.n_ranks == 1) return B200FE_OK;
+    if (h.n_send && !h.d_send_idx) return fail(B200FE_ERR_INVALID_ARG, "halo was created in raw mode (no send indices)");
     if (int rc = exchange_compress(h, v, s)) return rc;
     return unpack_and_zero(h, v, s);
 }
@@ -219,9 +221,10 @@ int b200fe_halo_create(const b200fe_halo_desc *d, b200fe_halo **out)
         h->recv_off.push_back(d->recv_offset[k]); h->recv_cnt.push_back(d->recv_count[k]);
         h->send_off.push_back(d->send_offset[k]); h->send_cnt.push_back(d->send_count[k]);
     }
-    B200FE_REQUIRE(d->n_send == 0 || d->h_send_indices, "b200fe_halo_create: send indices missing");
-    for (uint32_t i = 0; i < d->n_send; ++i)
-        B200FE_REQUIRE(d->h_send_indices[i] < d->n_owned, "b200fe_halo_create: send index %u is not an owned DoF", d->h_send_indices[i]);
+    // h_send_indices == NULL with n_send > 0: raw mode (b200fe_halo_exchange_raw only, no pack list)
+    if (d->h_send_indices)
+        for (uint32_t i = 0; i < d->n_send; ++i)
+            B200FE_REQUIRE(d->h_send_indices[i] < d->n_owned, "b200fe_halo_create: send index %u is not an owned DoF", d->h_send_indices[i]);
     if (d->n_ranks > 1) {
         B200FE_REQUIRE(d->nccl_unique_id, "b200fe_halo_create: nccl_unique_id missing");
         if (!nccl().ok) return fail(B200FE_ERR_COMM, "libnccl.so.2 not found");
@@ -230,7 +233,7 @@ int b200fe_halo_create(const b200fe_halo_desc *d, b200fe_halo **out)
         ncclComm_t comm;
         B200FE_NCCL_TRY(nccl().CommInitRank(&comm, d->n_ranks, id, d->rank));
         h->comm = comm; h->owns_comm = true;
-        if (d->n_send) {
+        if (d->n_send && d->h_send_indices) {
             B200FE_CUDA_TRY(cudaMalloc(&h->d_send_idx, d->n_send * sizeof(uint32_t)));
             B200FE_CUDA_TRY(cudaMemcpy(h->d_send_idx, d->h_send_indices, d->n_send * sizeof(uint32_t), cudaMemcpyHostToDevice));
             B200FE_CUDA_TRY(cudaMalloc(&h->d_pack, d->n_send * sizeof(double)));
@@ -272,6 +275,23 @@ int b200fe_halo_zero_ghosts(b200fe_halo *halo, double *d_v, void *stream)
 {
     B200FE_REQUIRE(halo && d_v, "b200fe_halo_zero_ghosts: null pointer");
     return halo_zero_ghosts(*reinterpret_cast<Halo *>(halo), d_v, (cudaStream_t)stream);
+}
+
+int b200fe_halo_exchange_raw(b200fe_halo *halo, const double *d_send, double *d_recv, void *stream)
+{
+    B200FE_REQUIRE(halo && d_send && d_recv, "b200fe_halo_exchange_raw: null pointer");
+    Halo &h = *reinterpret_cast<Halo *>(halo);
+    if (h.n_ranks == 1) return B200FE_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    Nccl &n = nccl();
+    // one round of p-halox: post all receives, all sends, complete together (phalox.cc:111-125)
+    B200FE_NCCL_TRY(n.GroupStart());
+    for (size_t k = 0; k < h.peers.size(); ++k)
+        if (h.recv_cnt[k]) B200FE_NCCL_TRY(n.Recv(d_recv + h.recv_off[k], h.recv_cnt[k], ncclDouble, h.peers[k], (ncclComm_t)h.comm, s));
+    for (size_t k = 0; k < h.peers.size(); ++k)
+        if (h.send_cnt[k]) B200FE_NCCL_TRY(n.Send(d_send + h.send_off[k], h.send_cnt[k], ncclDouble, h.peers[k], (ncclComm_t)h.comm, s));
+    B200FE_NCCL_TRY(n.GroupEnd());
+    return B200FE_OK;
 }
 
 int b200fe_halo_allreduce_sum(b200fe_halo *halo, double *d_vals, int count, void *stream)

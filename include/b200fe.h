@@ -270,6 +270,11 @@ int b200fe_halo_update_ghosts(b200fe_halo *halo, double *d_v, void *stream);
 int b200fe_halo_compress_add(b200fe_halo *halo, double *d_v, void *stream);
 int b200fe_halo_zero_ghosts(b200fe_halo *halo, double *d_v, void *stream);
 int b200fe_halo_allreduce_sum(b200fe_halo *halo, double *d_vals, int count, void *stream);
+/* One exchange round of p-halox (p-halox/phalox.cc:111-125: Irecv all, Isend all, Waitall) without
+ * pack lists: per peer k, d_send[send_offset[k] .. +send_count[k]) goes to peers[k] and
+ * d_recv[recv_offset[k] .. +recv_count[k]) is filled from it.  A halo created with
+ * h_send_indices = NULL ("raw mode") supports only this call; the same peer may appear twice. */
+int b200fe_halo_exchange_raw(b200fe_halo *halo, const double *d_send, double *d_recv, void *stream);
 
 #ifdef __cplusplus
 }
