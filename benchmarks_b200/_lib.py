@@ -35,6 +35,7 @@ _SIGNATURES = {
     "b200fe_bk5_apply": (_i, [_i, _u32, _vp, _vp, _vp, _vp, _vp]),
     "b200fe_sum_squares": (_i, [_u64, _vp, _vp, _vp]),
     "b200fe_bk_launch_info": (_i, [_i, _i, _i, _u32, _pi, _pi, _pi, _pi]),
+    "b200fe_debug_poison_smem": (_i, [_vp]),
     "b200fe_basis_1d": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "b200fe_boxmesh_create": (_i, [_vp, C.POINTER(_vp)]),
     "b200fe_boxmesh_destroy": (None, [_vp]),

@@ -56,6 +56,14 @@ __global__ void sum_squares_kernel(uint64_t n, const double *__restrict__ x, dou
         if (threadIdx.x == 0) atomicAdd(result, s);
     }
 }
+// debugging aid: fill the whole shared-memory carve-out of every SM with signalling garbage (NaN)
+__global__ void poison_smem_kernel(int n_doubles)
+{
+    extern __shared__ double sm[];
+    for (int i = threadIdx.x; i < n_doubles; i += blockDim.x) sm[i] = __longlong_as_double(0x7ff8dead00000000ll + i);
+    __syncthreads();
+    if (sm[(threadIdx.x * 7) % n_doubles] == 0.0) printf("unreachable\n");
+}
 }  // namespace
 }  // namespace b200fe
 
@@ -109,6 +117,18 @@ int b200fe_sum_squares(uint64_t n, const double *d_x, double *d_result, void *st
     uint64_t blocks = (n + 1023) / 1024;
     if (blocks > (uint64_t)sms * 8) blocks = (uint64_t)sms * 8;
     sum_squares_kernel<<<(unsigned)blocks, 256, 0, s>>>(n, d_x, d_result);
+    B200FE_CUDA_TRY(cudaGetLastError());
+    return B200FE_OK;
+}
+
+int b200fe_debug_poison_smem(void *stream)
+{
+    int dev = 0, sms = 0, max_smem = 0;
+    B200FE_CUDA_TRY(cudaGetDevice(&dev));
+    B200FE_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    B200FE_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    B200FE_CUDA_TRY(cudaFuncSetAttribute(poison_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    poison_smem_kernel<<<sms * 2, 256, max_smem, (cudaStream_t)stream>>>(max_smem / 8);
     B200FE_CUDA_TRY(cudaGetLastError());
     return B200FE_OK;
 }

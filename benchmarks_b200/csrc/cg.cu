@@ -62,6 +62,10 @@ __global__ void cg_scalar_kernel(CgScalars *sc, int jacobi, int max_it, double a
     const double res = sqrt(fabs(sc->acc[1]));
     sc->res = res;
     if (sc->it == 0) sc->res0 = res;
+    if (!(res == res) || isinf(res)) {  // breakdown (NaN/Inf): stop like deal.II's is_finite assertion, not converged
+        sc->done = 1; sc->converged = 0; sc->its = sc->it;
+        return;
+    }
     if (res <= abs_tol || res <= rel_tol * sc->res0) {
         sc->done = 1; sc->converged = 1; sc->its = sc->it;
         return;

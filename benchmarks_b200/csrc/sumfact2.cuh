@@ -289,7 +289,10 @@ __global__ void __launch_bounds__(EPB *NQ *NQ, MINB)
                 RR[p * PSR + ta * RSR + tb] = ft;
                 // u.(A u) = sum over points of grad(u)^T G grad(u): the CG inner product comes for free here,
                 // no need to keep the gathered values alive until the scatter
-                if constexpr (LVEC) dot_acc = fma(qr, fr, fma(qs, fs, fma(qt, ft, dot_acc)));
+                // (inactive slots of a tail batch read a stale G buffer: keep their 0 * garbage out of the sum)
+                if constexpr (LVEC) {
+                    if (active) dot_acc = fma(qr, fr, fma(qs, fs, fma(qt, ft, dot_acc)));
+                }
             }
             __syncthreads();
             if (tid == 0) {  // the G buffer is drained: fetch the next batch's block behind the rest of this one
@@ -329,7 +332,9 @@ __global__ void __launch_bounds__(EPB *NQ *NQ, MINB)
             for (int p = 0; p < NQ; ++p) {
                 const double mv = jw[p] * v[p];
                 w[p] += mv;
-                if constexpr (LVEC) dot_acc = fma(mv, v[p], dot_acc);  // + u^T M u at the points
+                if constexpr (LVEC) {
+                    if (active) dot_acc = fma(mv, v[p], dot_acc);  // + u^T M u at the points
+                }
             }
         }
         if constexpr (LVEC && !LAP && PREFETCH) load_val(nb, nxt_idx, nxt_val);

@@ -78,6 +78,10 @@ int b200fe_sum_squares(uint64_t n, const double *d_x, double *d_result, void *st
 int b200fe_bk_launch_info(int kind, int p, int nq, uint32_t nelmt, int *elems_per_block,
                           int *num_blocks, int *threads_per_block, int *smem_bytes);
 
+/* Debugging aid for tests: overwrite the shared memory of every SM with NaN patterns, so that a kernel
+ * reading shared memory it did not write (e.g. the unused slots of a tail batch) shows up in results. */
+int b200fe_debug_poison_smem(void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * 2. 1-D bases (what deal.II's QGauss<1>/FE_Q/MatrixFree::ShapeInfo hand to the reference operator;
  *    SURVEY.md appendix A7).  All arrays are HOST arrays, any output pointer may be NULL.

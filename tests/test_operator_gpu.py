@@ -221,3 +221,40 @@ def test_full_size_apply_against_kronecker_form(oracle_mod, cells_log2, p, quad,
     Av = A.initialize_dof_vector()
     A.vmult(Av, v)
     assert abs(torch.dot(y, v).item() - torch.dot(u, Av).item()) <= 1e-12 * (y.norm() * v.norm()).item()
+
+
+@pytest.mark.parametrize("p,dq,quad,kind", [(3, 2, "gauss", "laplace"), (2, 1, "gll", "laplace"), (4, 1, "gauss", "helmholtz"), (6, 1, "gll", "laplace")])
+def test_tail_batches_do_not_leak_stale_shared_memory(oracle_mod, p, dq, quad, kind):
+    """Cell counts that are not a multiple of the CTA's element batch: the unused slots read a stale
+    (here NaN-poisoned) G buffer and must not reach dst or the fused inner product (round-1 bug found
+    by the 8-GPU run: 0 * NaN from a tail batch turned p.Ap into NaN)."""
+    import benchmarks_b200 as b
+    from benchmarks_b200._lib import check, lib
+    fe = oracle_mod.fe
+    sub, nref = (3, 1, 1), 0 if p >= 6 else 1   # 3 or 24 cells: never a multiple of the batch sizes in use
+    nq = p + dq
+    om, od, rd, bas, G, JxW = _oracle_setup(fe, sub, nref, p, nq, quad, 1, None)
+    mesh = b.BoxMesh(sub, nref, p)
+    A = b.LaplaceOperator(mesh, nq=nq, quad=quad, kind=kind)
+    src = np.random.default_rng(11).standard_normal(mesh.n_owned)
+    ref = fe.op_apply(src, rd, bas, G, JxW, laplace=kind != "mass", mass=kind != "laplace")
+    for _ in range(3):
+        check(lib.b200fe_debug_poison_smem(None))
+        dst = A.initialize_dof_vector()
+        dot = A.vmult_dot(dst, torch.from_numpy(src).cuda())
+        assert torch.isfinite(dst).all() and np.isfinite(dot.item())
+        assert rel(dst.cpu().numpy(), ref) <= TOL
+        assert abs(dot.item() - float(src @ ref)) <= 1e-11 * np.abs(src).dot(np.abs(ref))
+
+
+def test_cg_stops_on_nan_like_dealii():
+    import benchmarks_b200 as b
+    mesh = b.BoxMesh.bp3_cycle(6, 2)
+    A = b.LaplaceOperator(mesh)
+    rhs = A.compute_rhs()
+    rhs[5] = float("nan")
+    x = A.initialize_dof_vector()
+    ctl = b.ReductionControl(10 ** 9, 1e-16, 1e-9)
+    with pytest.raises(b.NoConvergence):
+        b.SolverCG(ctl).solve(A, x, rhs)
+    assert ctl.last_step() <= 1

@@ -66,10 +66,10 @@ def main():
         err = np.abs(mine[sel] - full[own[sel]]).max() / np.abs(full).max()
         # CG with the bp3 protocol: iteration counts must agree
         rhs, x = A.compute_rhs(), A.initialize_dof_vector()
-        ctl = b.ReductionControl(10 ** 6, 1e-16, 1e-9)
+        ctl = b.ReductionControl(20000, 1e-16, 1e-9)
         b.SolverCG(ctl).solve(A, x, rhs)
         rhs1, x1 = A1.compute_rhs(), A1.initialize_dof_vector()
-        ctl1 = b.ReductionControl(10 ** 6, 1e-16, 1e-9)
+        ctl1 = b.ReductionControl(20000, 1e-16, 1e-9)
         b.SolverCG(ctl1).solve(A1, x1, rhs1)
         xs = np.zeros(n_lat)
         xs[lat1[lat1 >= 0]] = x1.cpu().numpy()[lat1 >= 0]
