@@ -404,18 +404,16 @@ __global__ void __launch_bounds__(EPB *NQ *NQ, MINB)
 
     if constexpr (LVEC) {
         if (a.dot != nullptr) {
-            __shared__ double red[32];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) dot_acc += __shfl_xor_sync(0xffffffffu, dot_acc, o);
+            // block reduction of the fused inner product.  The CTA size is a multiple of the plane size,
+            // not of 32, so the last warp is partial: no full-mask shuffles here (they would read lanes
+            // that do not exist) -- shared-memory atomics instead, once per thread per launch.
+            __shared__ double red;
             __syncthreads();
-            if ((tid & 31) == 0) red[tid >> 5] = dot_acc;
+            if (tid == 0) red = 0.0;
             __syncthreads();
-            if (tid < 32) {
-                double s = tid < (EPB * N2 + 31) / 32 ? red[tid] : 0.0;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                if (tid == 0) atomicAdd(a.dot, s);
-            }
+            atomicAdd(&red, dot_acc);
+            __syncthreads();
+            if (tid == 0) atomicAdd(a.dot, red);
         }
     }
 }
