@@ -331,7 +331,7 @@ def main():
                     "h2d_bytes_per_step": int(mesh.n_owned) * 8 * world, "d2h_bytes_per_step": int(mesh.n_owned) * 8 * world,
                     "api": "b200fe_cg_solve_host (pinned host b -> device, CG, device x -> pinned host)"},
             "gpu_launches": gpu_launches,
-            "roofline": {"bound": "hbm", "kernel": f"sumfact_kernel<{p+1},{p+1},collocated,laplace,lvec> (BP5 cell kernel: gather + D^T G D + atomic scatter + fused p.Ap)",
+            "roofline": {"bound": "hbm", "kernel": f"sumfact2_kernel<{p+1},{p+1},collocated,laplace,lvec> (BP5 cell kernel: gather + D^T G D + atomic scatter + fused p.Ap)",
                          "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak if peak else None,
                          "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": 1e3 * k_avg_s,
                          "launches_timed": k_n, "kernel_share_of_step": (1e-3 * k_ms) / t_dev if t_dev else None},
