@@ -47,6 +47,7 @@ _SIGNATURES = {
     "b200fe_op_destroy": (None, [_vp]),
     "b200fe_op_set_halo": (_i, [_vp, _vp]),
     "b200fe_op_vmult": (_i, [_vp, _vp, _vp, _vp]),
+    "b200fe_op_vmult_components": (_i, [_vp, _i, _vp, _vp, _vp]),
     "b200fe_op_vmult_dot": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "b200fe_op_vmult_dummy": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "b200fe_op_vmult_host": (_i, [_vp, _vp, _vp, _vp]),

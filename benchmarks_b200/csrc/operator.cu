@@ -418,6 +418,17 @@ int b200fe_op_vmult(b200fe_op *o, double *d_dst, const double *d_src, void *stre
     return op_vmult(*reinterpret_cast<Operator *>(o), d_dst, d_src, nullptr, true, true, (cudaStream_t)stream);
 }
 
+int b200fe_op_vmult_components(b200fe_op *o, int n_components, double *d_dst, const double *d_src, void *stream)
+{
+    B200FE_REQUIRE(o && d_dst && d_src && n_components >= 1, "b200fe_op_vmult_components: bad arguments");
+    B200FE_REQUIRE(d_dst != d_src, "b200fe_op_vmult_components: dst and src must not alias");
+    Operator &op = *reinterpret_cast<Operator *>(o);
+    const size_t n = op.n_local();
+    for (int c = 0; c < n_components; ++c)
+        if (int rc = op_vmult(op, d_dst + c * n, d_src + c * n, nullptr, true, true, (cudaStream_t)stream)) return rc;
+    return B200FE_OK;
+}
+
 int b200fe_op_vmult_dot(b200fe_op *o, double *d_dst, const double *d_src, double *d_dot, void *stream)
 {
     B200FE_REQUIRE(o && d_dst && d_src && d_dot, "b200fe_op_vmult_dot: null pointer");

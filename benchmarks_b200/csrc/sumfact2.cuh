@@ -40,6 +40,42 @@ constexpr __host__ __device__ int pad_plane_q(int nq)
     return ps;
 }
 
+// ---- compile-time search of the [i][j][r] staging strides (interpolated operators) -------------
+// Two access patterns hit that array: rows (thread = (i,j), slot = i*PA + j*RA) and columns
+// (thread = (i,r), slot = i*PA + r).  A 64-bit shared-memory access is conflict-free when the 16
+// threads of a half-warp fall into 16 different 8-byte slots; cost = sum over half-warps of the
+// worst multiplicity.  (tools: /tmp-style python prototype reproduced these numbers.)
+constexpr int halfwarp_cost(int n_threads, int n_active, int div, int s_hi, int s_lo)
+{
+    int total = 0;
+    for (int h = 0; h < n_threads; h += 16) {
+        int cnt[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        int worst = 0;
+        for (int t = h; t < h + 16 && t < n_active; ++t) {
+            const int slot = ((t / div) * s_hi + (t % div) * s_lo) % 16;
+            if (++cnt[slot] > worst) worst = cnt[slot];
+        }
+        total += worst;
+    }
+    return total;
+}
+constexpr int stride_cost(int nm, int nq, int pa, int ra)
+{
+    return nq * halfwarp_cost(nq * nq, nm * nm, nm, pa, ra) + nm * halfwarp_cost(nq * nq, nm * nq, nq, pa, 1);
+}
+struct Strides { int ra, pa; };
+constexpr Strides best_strides(int nm, int nq)
+{
+    Strides best{odd(nq), nm * odd(nq)};
+    int best_cost = stride_cost(nm, nq, best.pa, best.ra);
+    for (int ra = nq; ra <= nq + 4; ++ra)
+        for (int pa = nm * ra; pa <= nm * ra + 16; ++pa) {
+            const int c = stride_cost(nm, nq, pa, ra);
+            if (c < best_cost || (c == best_cost && nm * pa < nm * best.pa)) { best_cost = c; best = Strides{ra, pa}; }
+        }
+    return best;
+}
+
 template <int NM, int NQ, bool COLL, int QOP>
 struct Layout2 {
     static constexpr int N2 = NQ * NQ, N3 = N2 * NQ, M3 = NM * NM * NM;
@@ -47,9 +83,11 @@ struct Layout2 {
     static constexpr int PSQ = pad_plane_q(NQ);       // RQ plane stride
     static constexpr int RSR = odd(NQ);               // RR row stride
     static constexpr int PSR = NQ * RSR;              // RR plane stride
-    static constexpr int RU = odd(NM), RA = odd(NQ);  // interpolation staging (as in sumfact.cuh)
+    static constexpr Strides SA = best_strides(NM, NQ);
+    static constexpr int RA = SA.ra, PA = SA.pa;      // A / Y staging [i][j][r]: row and plane stride
+    static constexpr int PB = PSQ;                    // B~ / X staging [i][q][r]: dense rows, padded planes
     static constexpr int SZ_FLUX = cmax(NQ * PSQ, NQ * PSR);
-    static constexpr int SZ_INTERP = cmax(cmax(NM * NM * RU, NM * NM * RA), N3);
+    static constexpr int SZ_INTERP = cmax(NM * PA, NM * PB);
     static constexpr int REGION = (COLL ? SZ_FLUX : cmax(SZ_FLUX, SZ_INTERP) + 1) & ~1;  // even: keeps 16 B alignment
     static constexpr int N_REGIONS = COLL ? (LAP ? 2 : 0) : 3;
     // element stride == nq^2 (mod 16): a warp that spans two elements keeps hitting distinct banks
@@ -123,7 +161,7 @@ __global__ void __launch_bounds__(EPB *NQ *NQ, MINB)
     sumfact2_kernel(const __grid_constant__ Mats<NM, NQ> m, const KArgs a)
 {
     using L = v2::Layout2<NM, NQ, COLL, QOP>;
-    constexpr int N2 = L::N2, N3 = L::N3, M3 = L::M3, RA = L::RA;
+    constexpr int N2 = L::N2, N3 = L::N3, M3 = L::M3, RA = L::RA, PA = L::PA, PB = L::PB;
     constexpr int PSQ = L::PSQ, RSR = L::RSR, PSR = L::PSR;
     constexpr bool LAP = L::LAP, MASS = (QOP & QOP_MASS) != 0;
     static_assert(!COLL || NM == NQ, "collocated operators need nm == nq");
@@ -223,23 +261,23 @@ __global__ void __launch_bounds__(EPB *NQ *NQ, MINB)
                 double o[NQ];
                 v2::col_mul<NQ, NM, NM, 1>(m.B, cur_val, o);
 #pragma unroll
-                for (int r = 0; r < NQ; ++r) R1[t2 * RA + r] = o[r];
+                for (int r = 0; r < NQ; ++r) R1[(t2 / NM) * PA + (t2 % NM) * RA + r] = o[r];
             }
             __syncthreads();
             if (t2 < NM * NQ) {  // j -> q : columns of A -> B~[i][q][r] in R2
                 const int i = t2 / NQ, r2 = t2 - i * NQ;
                 double u[NM], o[NQ];
 #pragma unroll
-                for (int j = 0; j < NM; ++j) u[j] = R1[(i * NM + j) * RA + r2];
+                for (int j = 0; j < NM; ++j) u[j] = R1[i * PA + j * RA + r2];
                 v2::col_mul<NQ, NM, NM, 1>(m.B, u, o);
 #pragma unroll
-                for (int q = 0; q < NQ; ++q) R2[(i * NQ + q) * NQ + r2] = o[q];
+                for (int q = 0; q < NQ; ++q) R2[i * PB + q * NQ + r2] = o[q];
             }
             __syncthreads();
             {  // i -> p into the register column
                 double u[NM];
 #pragma unroll
-                for (int i = 0; i < NM; ++i) u[i] = R2[i * N2 + t2];
+                for (int i = 0; i < NM; ++i) u[i] = R2[i * PB + t2];
                 v2::col_mul<NQ, NM, NM, 1>(m.B, u, v);
             }
         }
@@ -357,23 +395,23 @@ __global__ void __launch_bounds__(EPB *NQ *NQ, MINB)
                 double x[NM];
                 v2::col_mul<NM, NQ, 1, NM>(m.B, w, x);
 #pragma unroll
-                for (int i = 0; i < NM; ++i) R2[i * N2 + t2] = x[i];
+                for (int i = 0; i < NM; ++i) R2[i * PB + t2] = x[i];
             }
             __syncthreads();
             if (t2 < NM * NQ) {  // q -> j : columns of X -> Y[i][j][r] in R0
                 const int i = t2 / NQ, r2 = t2 - i * NQ;
                 double x[NQ], o[NM];
 #pragma unroll
-                for (int q = 0; q < NQ; ++q) x[q] = R2[(i * NQ + q) * NQ + r2];
+                for (int q = 0; q < NQ; ++q) x[q] = R2[i * PB + q * NQ + r2];
                 v2::col_mul<NM, NQ, 1, NM>(m.B, x, o);
 #pragma unroll
-                for (int j = 0; j < NM; ++j) R0[(i * NM + j) * RA + r2] = o[j];
+                for (int j = 0; j < NM; ++j) R0[i * PA + j * RA + r2] = o[j];
             }
             __syncthreads();
             if (t2 < NM * NM) {  // r -> k : rows of Y -> the output row of thread (i,j), straight to memory
                 double x[NQ], z[NM];
 #pragma unroll
-                for (int r = 0; r < NQ; ++r) x[r] = R0[t2 * RA + r];
+                for (int r = 0; r < NQ; ++r) x[r] = R0[(t2 / NM) * PA + (t2 % NM) * RA + r];
                 v2::col_mul<NM, NQ, 1, NM>(m.B, x, z);
                 if constexpr (LVEC) {
 #pragma unroll

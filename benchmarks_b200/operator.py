@@ -135,6 +135,10 @@ class LaplaceOperator:
     def vmult_dummy(self, dst, src, ghost_exchange_on: bool, computation_on: bool, stream=None) -> None:
         check(lib.b200fe_op_vmult_dummy(self._h, _dp(dst), _dp(src), int(ghost_exchange_on), int(computation_on), _sp(stream)))
 
+    def vmult_components(self, dst, src, n_components: int, stream=None) -> None:
+        """Vector-valued apply (BP2/BP4/BP6): component-blocked vectors [component][n_owned + n_ghost]."""
+        check(lib.b200fe_op_vmult_components(self._h, n_components, _dp(dst), _dp(src), _sp(stream)))
+
     def vmult_dot(self, dst, src, stream=None) -> torch.Tensor:
         dot = torch.empty(1, dtype=torch.float64, device=self.device)
         check(lib.b200fe_op_vmult_dot(self._h, _dp(dst), _dp(src), _dp(dot), _sp(stream)))

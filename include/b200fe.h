@@ -204,6 +204,10 @@ int b200fe_op_set_halo(b200fe_op *op, b200fe_halo *halo);
  * dst[c] = src[c] on constrained DoFs.  Vectors hold n_owned + n_ghost doubles; the ghost entries
  * of src are scratch (as with deal.II's mutable ghost section). */
 int b200fe_op_vmult(b200fe_op *op, double *d_dst, const double *d_src, void *stream);
+/* Vector-valued problems (CEED BP2/BP4/BP6: the scalar operator applied to each of n_components
+ * components): vectors are component-blocked, [component][n_owned + n_ghost].  One cell-kernel launch
+ * per component (a fused multi-component kernel that streams G once is the planned next step). */
+int b200fe_op_vmult_components(b200fe_op *op, int n_components, double *d_dst, const double *d_src, void *stream);
 /* vmult with the inner product src . dst (summed over ranks) fused into the kernel -> *d_dot. */
 int b200fe_op_vmult_dot(b200fe_op *op, double *d_dst, const double *d_src, double *d_dot, void *stream);
 /* LaplaceOperator::vmult_dummy (portable_laplace_operator.h:175-235). */

@@ -258,3 +258,21 @@ def test_cg_stops_on_nan_like_dealii():
     with pytest.raises(b.NoConvergence):
         b.SolverCG(ctl).solve(A, x, rhs)
     assert ctl.last_step() <= 1
+
+
+def test_vector_valued_apply_bp6_style(oracle_mod):
+    """CEED BP6-style vector Laplacian (3 components, GLL collocated): component-blocked apply equals the
+    scalar oracle applied per component (no reference implementation exists for BP2/4/6)."""
+    import benchmarks_b200 as b
+    fe = oracle_mod.fe
+    p, sub, nref = 4, (2, 1, 1), 1
+    om, od, rd, bas, G, JxW = _oracle_setup(fe, sub, nref, p, p + 1, "gll", 2, DEFORM)
+    mesh = b.BoxMesh(sub, nref, p)
+    A = b.LaplaceOperator(mesh, quad="gll", p_geo=2, deform=DEFORM)
+    rng = np.random.default_rng(2)
+    src = rng.standard_normal((3, mesh.n_owned))
+    dst = torch.empty(3 * mesh.n_owned, dtype=torch.float64, device="cuda")
+    A.vmult_components(dst, torch.from_numpy(src.ravel()).cuda(), 3)
+    out = dst.cpu().numpy().reshape(3, -1)
+    for c in range(3):
+        assert rel(out[c], fe.op_apply(src[c], rd, bas, G)) <= TOL
