@@ -66,8 +66,12 @@ constexpr int v2_rmin(int nq, bool coll, int qop)
 template <int NM, int NQ, bool COLL, int QOP>
 struct V2Cfg {
     using L = v2::Layout2<NM, NQ, COLL, QOP>;
-    static constexpr int EPB = (B200FE_V2_TPB_FOR(NQ) / (NQ * NQ)) < 1 ? 1 : (B200FE_V2_TPB_FOR(NQ) / (NQ * NQ));
-    static constexpr int T = EPB * NQ * NQ;
+#ifndef B200FE_V2_WL_WARPS
+#define B200FE_V2_WL_WARPS 4   // warp-local mode (nq <= 5): warps per CTA
+#endif
+    static constexpr int EPB_PLAIN = (B200FE_V2_TPB_FOR(NQ) / (NQ * NQ)) < 1 ? 1 : (B200FE_V2_TPB_FOR(NQ) / (NQ * NQ));
+    static constexpr int EPB = L::WARP_LOCAL ? B200FE_V2_WL_WARPS * L::EPW : EPB_PLAIN;
+    static constexpr int T = L::threads(EPB);
     static constexpr int T32 = (T + 31) / 32 * 32;
     static constexpr size_t SMEM = L::smem_bytes(EPB);
     static constexpr int BY_SMEM = (int)((227 * 1024) / (SMEM + 1024));

@@ -94,10 +94,17 @@ struct Layout2 {
     static constexpr int pad_elem(int w) { while ((w - N2) % 16 != 0) ++w; return w; }
     static constexpr int WORK_PER_ELEM = N_REGIONS == 0 ? 0 : pad_elem(N_REGIONS * REGION);
     static constexpr int G_PER_ELEM = LAP ? 6 * N3 : 0;
+    // warp-local mode (nq <= 5): an element's nq^2 threads sit inside one warp, EPW elements per warp;
+    // every intra-element barrier becomes __syncwarp().  Idle lanes of a warp work on a dummy slot.
+    // Measured (profiles/r01d_warp_local.txt): a win only when the planes tile the warp exactly (nq = 2, 4:
+    // bk3 p=2 72 -> 82 %, bk1 p=2 44 -> 58 %); with idle lanes (nq = 3, 5) the CTA-barrier version is faster.
+    static constexpr bool WARP_LOCAL = N2 <= 32 && 32 % N2 == 0 && WORK_PER_ELEM > 0;
+    static constexpr int EPW = WARP_LOCAL ? 32 / N2 : 0;
     static constexpr size_t smem_bytes(int epb)
     {
-        return 16 /* mbarrier */ + sizeof(double) * (size_t)epb * (G_PER_ELEM + WORK_PER_ELEM);
+        return 16 /* mbarrier */ + sizeof(double) * ((size_t)epb * G_PER_ELEM + (size_t)(epb + (WARP_LOCAL ? 1 : 0)) * WORK_PER_ELEM);
     }
+    static constexpr int threads(int epb) { return WARP_LOCAL ? (epb / EPW) * 32 : epb * N2; }
 };
 
 // ---- PTX helpers (mbarrier + bulk async copy) -------------------------------------------------
@@ -157,7 +164,7 @@ __device__ __forceinline__ void col_mul(const MatT &mat, const double (&in)[NIN]
 
 // ---------------------------------------------------------------------------------------------
 template <int NM, int NQ, bool COLL, int QOP, bool LVEC, int EPB, int MINB>
-__global__ void __launch_bounds__(EPB *NQ *NQ, MINB)
+__global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB)), MINB)
     sumfact2_kernel(const __grid_constant__ Mats<NM, NQ> m, const KArgs a)
 {
     using L = v2::Layout2<NM, NQ, COLL, QOP>;
@@ -171,14 +178,30 @@ __global__ void __launch_bounds__(EPB *NQ *NQ, MINB)
     double *Gs = reinterpret_cast<double *>(smem_raw + 16);      // [EPB][6][N3]
     double *work = Gs + EPB * L::G_PER_ELEM;
     const int tid = threadIdx.x;
-    const int el = tid / N2;
-    const int t2 = tid - el * N2;
+    constexpr bool WL = L::WARP_LOCAL;
+    // element slot and position in the plane; `lane_ok` is false only for the idle lanes of warp-local mode
+    int el, t2;
+    bool lane_ok = true;
+    if constexpr (WL) {
+        static_assert(!WL || EPB % (WL ? L::EPW : 1) == 0, "warp-local mode: EPB must be a multiple of EPW");
+        const int warp = tid >> 5, lane = tid & 31;
+        lane_ok = lane < L::EPW * N2;
+        el = lane_ok ? warp * L::EPW + lane / N2 : EPB;  // EPB = dummy slot
+        t2 = lane % N2;
+    } else {
+        el = tid / N2;
+        t2 = tid - el * N2;
+    }
+    auto sync_elem = [&]() {  // barrier among the threads of one element
+        if constexpr (WL) __syncwarp();
+        else __syncthreads();
+    };
     const int ta = t2 / NQ, tb = t2 - ta * NQ;  // (q,r) in layout P; (p,r) in layout Q; (p,q) in layout R
     double *R0 = work + el * L::WORK_PER_ELEM;
     [[maybe_unused]] double *R1 = R0 + L::REGION;
     [[maybe_unused]] double *R2 = R1 + L::REGION;
     double *RQ = R0, *RR = R1;
-    const double *Ge = Gs + el * L::G_PER_ELEM + t2;
+    const double *Ge = Gs + (lane_ok ? el : 0) * L::G_PER_ELEM + t2;
 
     const uint32_t n_batches = (a.n_elems + EPB - 1) / EPB;
     auto issue_g = [&](uint32_t eb) {  // one elected thread: fetch the batch's G block
@@ -217,7 +240,7 @@ __global__ void __launch_bounds__(EPB *NQ *NQ, MINB)
     };
     auto load_idx = [&](uint32_t eb_, uint32_t (&ix)[NIN]) {
         const uint32_t e_ = eb_ * EPB + el;
-        const bool ok = loader && eb_ < n_batches && e_ < a.n_elems;
+        const bool ok = lane_ok && loader && eb_ < n_batches && e_ < a.n_elems;
 #pragma unroll
         for (int n = 0; n < NIN; ++n) ix[n] = ok ? __ldg(a.idx + in_offset(e_, n)) : kInvalidIndex;
     };
@@ -227,18 +250,27 @@ __global__ void __launch_bounds__(EPB *NQ *NQ, MINB)
             for (int n = 0; n < NIN; ++n) val[n] = ix[n] == kInvalidIndex ? 0.0 : __ldg(a.in + ix[n]);
         } else {
             const uint32_t e_ = eb_ * EPB + el;
-            const bool ok = loader && eb_ < n_batches && e_ < a.n_elems;
+            const bool ok = lane_ok && loader && eb_ < n_batches && e_ < a.n_elems;
 #pragma unroll
             for (int n = 0; n < NIN; ++n) val[n] = ok ? __ldg(a.in + in_offset(e_, n)) : 0.0;
         }
     };
     if constexpr (LVEC) load_idx(blockIdx.x, cur_idx);
     load_val(blockIdx.x, cur_idx, cur_val);
+    constexpr bool JW_PIPE = MASS && !LAP && PREFETCH;
+    [[maybe_unused]] double jw_cur[NQ];
+    auto load_jw = [&](uint32_t eb_, double (&j)[NQ]) {
+        const uint32_t e_ = eb_ * EPB + el;
+        const bool ok = lane_ok && eb_ < n_batches && e_ < a.n_elems;
+#pragma unroll
+        for (int p = 0; p < NQ; ++p) j[p] = ok ? __ldg(a.JxW + (size_t)e_ * N3 + p * N2 + t2) : 0.0;
+    };
+    if constexpr (JW_PIPE) load_jw(blockIdx.x, jw_cur);
 
     double dot_acc = 0.0;
     for (uint32_t eb = blockIdx.x; eb < n_batches; eb += gridDim.x) {
         const uint32_t e = eb * EPB + el;
-        const bool active = e < a.n_elems;
+        const bool active = lane_ok && e < a.n_elems;
         const uint32_t nb = eb + gridDim.x;
         // prefetch: next batch's indices (L-vector) or values (E-vector)
         if constexpr (PREFETCH) {
@@ -246,7 +278,11 @@ __global__ void __launch_bounds__(EPB *NQ *NQ, MINB)
             else load_val(nb, nxt_idx, nxt_val);
         }
         [[maybe_unused]] double jw[NQ];
-        if constexpr (MASS) {  // JxW column early: its latency hides behind the interpolation sweeps
+        if constexpr (MASS && JW_PIPE) {  // pure mass operator: JxW is the dominant stream -> one batch ahead, like `in`
+#pragma unroll
+            for (int p = 0; p < NQ; ++p) jw[p] = jw_cur[p];
+            load_jw(nb, jw_cur);
+        } else if constexpr (MASS) {  // Helmholtz: JxW column early, its latency hides behind the interpolation sweeps
             const double *Je = a.JxW + (size_t)(active ? e : 0) * N3 + t2;
 #pragma unroll
             for (int p = 0; p < NQ; ++p) jw[p] = active ? __ldg(Je + p * N2) : 0.0;
@@ -263,7 +299,7 @@ __global__ void __launch_bounds__(EPB *NQ *NQ, MINB)
 #pragma unroll
                 for (int r = 0; r < NQ; ++r) R1[(t2 / NM) * PA + (t2 % NM) * RA + r] = o[r];
             }
-            __syncthreads();
+            sync_elem();
             if (t2 < NM * NQ) {  // j -> q : columns of A -> B~[i][q][r] in R2
                 const int i = t2 / NQ, r2 = t2 - i * NQ;
                 double u[NM], o[NQ];
@@ -273,7 +309,7 @@ __global__ void __launch_bounds__(EPB *NQ *NQ, MINB)
 #pragma unroll
                 for (int q = 0; q < NQ; ++q) R2[i * PB + q * NQ + r2] = o[q];
             }
-            __syncthreads();
+            sync_elem();
             {  // i -> p into the register column
                 double u[NM];
 #pragma unroll
@@ -292,7 +328,7 @@ __global__ void __launch_bounds__(EPB *NQ *NQ, MINB)
                 RQ[p * PSQ + t2] = v[p];
                 RR[p * PSR + ta * RSR + tb] = v[p];
             }
-            __syncthreads();
+            sync_elem();
             {   // layout Q: thread (p,r) = (ta,tb), column over q, in place
                 double c[NQ], o[NQ];
 #pragma unroll
@@ -309,7 +345,7 @@ __global__ void __launch_bounds__(EPB *NQ *NQ, MINB)
 #pragma unroll
                 for (int r = 0; r < NQ; ++r) RR[ta * PSR + tb * RSR + r] = o[r];
             }
-            __syncthreads();
+            sync_elem();
             v2::mbar_wait(bar, parity);  // G of this batch has landed
             parity ^= 1u;
 #pragma unroll
@@ -358,7 +394,7 @@ __global__ void __launch_bounds__(EPB *NQ *NQ, MINB)
 #pragma unroll
                 for (int r = 0; r < NQ; ++r) RR[ta * PSR + tb * RSR + r] = o[r];
             }
-            __syncthreads();
+            sync_elem();
 #pragma unroll
             for (int p = 0; p < NQ; ++p) w[p] += RQ[p * PSQ + t2] + RR[p * PSR + ta * RSR + tb];
         } else {
@@ -397,7 +433,7 @@ __global__ void __launch_bounds__(EPB *NQ *NQ, MINB)
 #pragma unroll
                 for (int i = 0; i < NM; ++i) R2[i * PB + t2] = x[i];
             }
-            __syncthreads();
+            sync_elem();
             if (t2 < NM * NQ) {  // q -> j : columns of X -> Y[i][j][r] in R0
                 const int i = t2 / NQ, r2 = t2 - i * NQ;
                 double x[NQ], o[NM];
@@ -407,7 +443,7 @@ __global__ void __launch_bounds__(EPB *NQ *NQ, MINB)
 #pragma unroll
                 for (int j = 0; j < NM; ++j) R0[i * PA + j * RA + r2] = o[j];
             }
-            __syncthreads();
+            sync_elem();
             if (t2 < NM * NM) {  // r -> k : rows of Y -> the output row of thread (i,j), straight to memory
                 double x[NQ], z[NM];
 #pragma unroll
