@@ -98,7 +98,8 @@ struct Layout2 {
     // every intra-element barrier becomes __syncwarp().  Idle lanes of a warp work on a dummy slot.
     // Measured (profiles/r01d_warp_local.txt): a win only when the planes tile the warp exactly (nq = 2, 4:
     // bk3 p=2 72 -> 82 %, bk1 p=2 44 -> 58 %); with idle lanes (nq = 3, 5) the CTA-barrier version is faster.
-    static constexpr bool WARP_LOCAL = N2 <= 32 && 32 % N2 == 0 && WORK_PER_ELEM > 0;
+    // Collocated kernels (4 barriers per batch) lose slightly (bk5 p=3 86 -> 82 %), so interpolated operators only.
+    static constexpr bool WARP_LOCAL = !COLL && N2 <= 32 && 32 % N2 == 0 && WORK_PER_ELEM > 0;
     static constexpr int EPW = WARP_LOCAL ? 32 / N2 : 0;
     static constexpr size_t smem_bytes(int epb)
     {
