@@ -217,6 +217,11 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
             v2::mbar_init(bar, 1);
             v2::fence_mbar_init();
         }
+        // The unused slots of a tail batch read whatever the G buffer holds.  Zero it once, so that it only
+        // ever contains zeros or earlier (finite) geometric factors: 0 * stale stays 0 in the fused inner
+        // product without a branch in the flux loop (round-1 bug: 0 * NaN from a poisoned buffer).
+        for (int i = tid; i < EPB * L::G_PER_ELEM; i += blockDim.x) Gs[i] = 0.0;
+        v2::fence_proxy_async();  // order the generic-proxy zeros before the async-proxy (TMA) writes
         __syncthreads();
         if (tid == 0 && blockIdx.x < n_batches) issue_g(blockIdx.x);
     }
@@ -364,10 +369,8 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
                 RR[p * PSR + ta * RSR + tb] = ft;
                 // u.(A u) = sum over points of grad(u)^T G grad(u): the CG inner product comes for free here,
                 // no need to keep the gathered values alive until the scatter
-                // (inactive slots of a tail batch read a stale G buffer: keep their 0 * garbage out of the sum)
-                if constexpr (LVEC) {
-                    if (active) dot_acc = fma(qr, fr, fma(qs, fs, fma(qt, ft, dot_acc)));
-                }
+                // (inactive slots contribute 0 * finite: the G buffer is zero-initialised, see above)
+                if constexpr (LVEC) dot_acc = fma(qr, fr, fma(qs, fs, fma(qt, ft, dot_acc)));
             }
             __syncthreads();
             if (tid == 0) {  // the G buffer is drained: fetch the next batch's block behind the rest of this one
@@ -407,9 +410,7 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
             for (int p = 0; p < NQ; ++p) {
                 const double mv = jw[p] * v[p];
                 w[p] += mv;
-                if constexpr (LVEC) {
-                    if (active) dot_acc = fma(mv, v[p], dot_acc);  // + u^T M u at the points
-                }
+                if constexpr (LVEC) dot_acc = fma(mv, v[p], dot_acc);  // + u^T M u at the points (jw = 0 on inactive slots)
             }
         }
         if constexpr (LVEC && !LAP && PREFETCH) load_val(nb, nxt_idx, nxt_val);
