@@ -1,6 +1,7 @@
 #!/bin/bash
-# compute-sanitizer on small parity cases: memcheck + racecheck (shared-memory hazards of the hand-placed barriers)
+# compute-sanitizer racecheck on small parity cases (shared-memory hazards of the hand-placed barriers)
 mkdir -p gpurun_out
-SEL='(random_inputs and 37) or (vmult_matches and (bp3 or bp5 or helmholtz) and (2- or 5- or 7-)) or tail_batches'
-timeout 280 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_bk_gpu.py tests/test_operator_gpu.py -m gpu -x -q -k "$SEL" > gpurun_out/sanitize_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -3 gpurun_out/sanitize_memcheck.log
-timeout 280 compute-sanitizer --tool racecheck --racecheck-report all --error-exitcode 9 python -m pytest tests/test_bk_gpu.py tests/test_operator_gpu.py -m gpu -x -q -k "$SEL" > gpurun_out/sanitize_racecheck.log 2>&1; echo "racecheck rc=$?"; grep -E "RACECHECK SUMMARY|hazard|passed|failed" gpurun_out/sanitize_racecheck.log | tail -5
+SEL='(random_inputs and 37) or (vmult_matches and (bp3 or bp5 or helmholtz or bp1) and (2- or 3- or 5- or 7-)) or tail_batches'
+timeout 400 compute-sanitizer --tool racecheck --racecheck-report all --print-limit 2000 python -m pytest tests/test_bk_gpu.py tests/test_operator_gpu.py -m gpu -x -q -k "$SEL" > gpurun_out/sanitize_racecheck.log 2>&1; echo "racecheck rc=$?"
+grep -E "RACECHECK SUMMARY|passed|failed" gpurun_out/sanitize_racecheck.log | tail -3
+grep -E "(Write|Read) Thread" gpurun_out/sanitize_racecheck.log | sed -E 's/Thread \([0-9]+,0,0\)/Thread/; s/\+0x[0-9a-f]+//; s/\(b200fe::Mats.*//' | sort | uniq -c | sort -rn | head -20
