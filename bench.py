@@ -308,6 +308,34 @@ def main():
                 del op
                 torch.cuda.empty_cache()
 
+    # ---- E-vector BK3 kernel vs degree (the other half of the metric "BK3/BP5 GDoF/s vs degree p") ----
+    bk3_sweep = None
+    if world == 1 and not args.no_sweep:
+        bk3_sweep = []
+        for pp in range(1, 9):
+            nm, nq = pp + 1, pp + 2
+            nelmt = 10_000_000 // nm ** 3               # BASELINE config C2 size
+            basis = np.cos(np.arange(nq * nm, dtype=np.float64))
+            dbasis = np.cos(np.arange(nq * nq, dtype=np.float64))
+            u = torch.rand(nelmt * nm ** 3, dtype=torch.float64, device=dev)
+            Gk = torch.rand(nelmt * 6 * nq ** 3, dtype=torch.float64, device=dev)
+            out_k = torch.empty_like(u)
+            for _ in range(3):
+                b.bk3_apply(pp, nq, basis, dbasis, Gk, u, out_k)
+            torch.cuda.synchronize()
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0.record()
+            for _ in range(10):
+                b.bk3_apply(pp, nq, basis, dbasis, Gk, u, out_k)
+            k1.record()
+            torch.cuda.synchronize()
+            t = k0.elapsed_time(k1) * 1e-4
+            nbytes = 8 * (2 * nelmt * nm ** 3 + 6 * nelmt * nq ** 3)   # CEED_BK/src/BK3/templated_cuda_benchmark.cc:113
+            bk3_sweep.append({"p": pp, "nelmt": nelmt, "gdofs": 1e-9 * nelmt * nm ** 3 / t, "gbs": 1e-9 * nbytes / t,
+                              "frac_of_hbm_roofline": 1e-9 * nbytes / t / peak})
+            del u, Gk, out_k
+            torch.cuda.empty_cache()
+
     # ---- CPU baseline (rank 0, N = 1 only) ----------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -342,6 +370,8 @@ def main():
             out["cpu_baseline"] = cpu
         if sweep:
             out["degree_sweep_apply"] = sweep
+        if bk3_sweep:
+            out["degree_sweep_bk3_evector"] = bk3_sweep
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -243,30 +243,3 @@ class SolverCG:
             raise NoConvergence(f"CG: {res.iterations} iterations, residual {res.final_residual:g}")
         check(rc)
         return res
-
-
-def smoke_operator() -> None:
-    """One small BP5 apply + CG on cuda:0 against the CPU oracle (used by __graft_entry__.smoke)."""
-    import oracle
-    fe = oracle.fe
-    p = 3
-    mesh = BoxMesh((2, 1, 1), 1, p)
-    A = LaplaceOperator(mesh, quad="gll")
-    om = fe.BoxMesh((2, 1, 1), 1)
-    od = fe.distribute_dofs(om, p, 1)
-    rd = fe.rank_data(om, od, 0)
-    bas = fe.basis_1d(p, p + 1, "gll")
-    G, JxW = fe.geometric_factors(fe.cell_nodes(om, rd["cells"], 1), 1, bas)
-    rng = np.random.default_rng(0)
-    src = rng.standard_normal(mesh.n_owned)
-    ref = fe.op_apply(src, rd, bas, G)
-    dst = A.initialize_dof_vector()
-    A.vmult(dst, torch.from_numpy(src).to(A.device))
-    err = np.abs(dst.cpu().numpy() - ref).max() / np.abs(ref).max()
-    b = A.compute_rhs()
-    x = A.initialize_dof_vector()
-    ctl = ReductionControl(1000, 1e-16, 1e-9)
-    SolverCG(ctl).solve(A, x, b)
-    _, its, _, _, _ = fe.solver_cg(lambda v: fe.op_apply(v, rd, bas, G), fe.rhs_one(rd, bas, JxW), 1000, 1e-16, 1e-9)
-    print(f"smoke: BP5 p={p} vmult rel err {err:.2e}; CG its {ctl.last_step()} (oracle {its})")
-    assert err <= 1e-12 and abs(ctl.last_step() - its) <= 1
