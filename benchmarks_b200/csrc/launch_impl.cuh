@@ -41,7 +41,7 @@ constexpr int epb_for(int nq)
 #ifdef B200FE_V2_TPB
 #define B200FE_V2_TPB_FOR(nq) (B200FE_V2_TPB)
 #else
-#define B200FE_V2_TPB_FOR(nq) ((nq) <= 6 ? 160 : 96)
+#define B200FE_V2_TPB_FOR(nq) ((nq) <= 6 ? (COLL ? 160 : 128) : 96)  // r01 sweep: bk3 p=3,4 71/70 % at 128 vs 68/67 % at 160
 #endif
 // v2 kernel: registers per thread that the occupancy target (MINB) must leave.  Data-driven
 // (profiles/r01_v2_variants.txt): with the software-pipelined inputs the large planes need 160-240
