@@ -97,3 +97,26 @@ def test_full_size_properties(kind, p):
     assert abs(lhs - rhs) <= 1e-12 * scale
     comb = A(0.5 * u - 1.25 * v)
     assert (comb - (0.5 * Au - 1.25 * Av)).abs().max().item() <= 1e-12 * Au.abs().max().item()
+
+
+@pytest.mark.parametrize("degree", [3, 4, 5])
+def test_check_bk3_deformed_strip_matches_oracle(oracle_mod, degree):
+    """The reference's CPU BK3 program (bk3_dealii/check_bk3.cc): deformed strip, MappingQ1, FE_DGQ element vectors,
+    QGauss(p+2), its input vector -- against the oracle (numpy geometry from the same vertices + serial BK3)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("check_bk3", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                                            "benchmarks_b200", "drivers", "check_bk3.py"))
+    drv = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(drv)
+    import benchmarks_b200 as b
+    fe = oracle_mod.fe
+    n = 24
+    basis, dbasis, nodes, G, u = drv.setup(degree, n)
+    out = b.bk3_apply(degree, degree + 2, basis, dbasis, G, u).cpu().numpy()
+    bas = fe.basis_1d(degree, degree + 2)
+    Go, _ = fe.geometric_factors(nodes.cpu().numpy(), 1, bas)
+    assert np.abs(G.cpu().numpy().reshape(Go.shape) - Go).max() <= TOL * np.abs(Go).max()
+    ref, _ = oracle_mod.port.bk3(degree + 1, degree + 2, bas["B"].ravel(), bas["D"].ravel(), Go.ravel(), u.cpu().numpy(), 1)
+    assert rel_max(out, ref) <= TOL
+    # the deformation is really there: first cell is not a cube (off-diagonal geometric factors present)
+    assert np.abs(Go[0, 1]).max() > 1e-3 * np.abs(Go[0, 0]).max()
