@@ -87,7 +87,7 @@ struct Layout2 {
     static constexpr int RA = SA.ra, PA = SA.pa;      // A / Y staging [i][j][r]: row and plane stride
     static constexpr int PB = PSQ;                    // B~ / X staging [i][q][r]: dense rows, padded planes
     static constexpr int SZ_FLUX = cmax(NQ * PSQ, NQ * PSR);
-    static constexpr int SZ_INTERP = cmax(NM * PA, NM * PB);
+    static constexpr int SZ_INTERP = cmax(cmax(NM * PA, NM * PB), NM * NM * odd(NM));  // A|Y, B~|X, U|Z
     static constexpr int REGION = (COLL ? SZ_FLUX : cmax(SZ_FLUX, SZ_INTERP) + 1) & ~1;  // even: keeps 16 B alignment
     static constexpr int N_REGIONS = COLL ? (LAP ? 2 : 0) : 3;
     // element stride == nq^2 (mod 16): a warp that spans two elements keeps hitting distinct banks
@@ -231,24 +231,30 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
     // of a batch was the largest stall once G moved to TMA).  Collocated: a column over p per thread;
     // interpolated: a row over k for the threads (i,j) = t2 < NM^2, which feed the first sweep directly
     // from registers (no staging of U / Z in shared memory).
-    constexpr int NIN = COLL ? NQ : NM;
+    // Interpolated operators: thread t2 of an element owns the nodal values l = t2 + c*nq^2 (c < NK), i.e. the
+    // CTA reads / writes / gathers element vectors and index tables with fully coalesced requests; they are
+    // re-shaped into rows through one shared-memory staging array.  (ncu, profiles/r01d_bk_l1tex.txt: per-thread
+    // row access cost 19-20 sectors per request and made L1TEX the bottleneck of BK1/BK3 at 87-89 %.)
+    constexpr int NK = (M3 + N2 - 1) / N2;
+    constexpr int NIN = COLL ? NQ : NK;
+    constexpr int RU = odd(NM);  // row stride of the nodal staging arrays U / Z
 #ifndef B200FE_V2_PREFETCH_MAXNQ
 #define B200FE_V2_PREFETCH_MAXNQ 10  // software-pipelined inputs for every degree (r01 sweep: needs >= 160 registers at nq >= 7)
 #endif
     constexpr bool PREFETCH = NQ <= B200FE_V2_PREFETCH_MAXNQ;
-    const bool loader = COLL ? true : (t2 < NM * NM);
     double cur_val[NIN];
     [[maybe_unused]] uint32_t cur_idx[NIN];
     [[maybe_unused]] double nxt_val[NIN];
     [[maybe_unused]] uint32_t nxt_idx[NIN];
-    auto in_offset = [&](uint32_t e_, int n) -> size_t {
-        return COLL ? (size_t)e_ * N3 + n * N2 + t2 : (size_t)e_ * M3 + t2 * NM + n;
+    auto in_offset = [&](uint32_t e_, int n) -> size_t {  // both are "plane n of the element, position t2"
+        return (size_t)e_ * (COLL ? N3 : M3) + n * N2 + t2;
     };
+    auto in_valid = [&](int n) { return COLL || (n * N2 + t2 < M3); };
     auto load_idx = [&](uint32_t eb_, uint32_t (&ix)[NIN]) {
         const uint32_t e_ = eb_ * EPB + el;
-        const bool ok = lane_ok && loader && eb_ < n_batches && e_ < a.n_elems;
+        const bool ok = lane_ok && eb_ < n_batches && e_ < a.n_elems;
 #pragma unroll
-        for (int n = 0; n < NIN; ++n) ix[n] = ok ? __ldg(a.idx + in_offset(e_, n)) : kInvalidIndex;
+        for (int n = 0; n < NIN; ++n) ix[n] = (ok && in_valid(n)) ? __ldg(a.idx + in_offset(e_, n)) : kInvalidIndex;
     };
     auto load_val = [&](uint32_t eb_, const uint32_t (&ix)[NIN], double (&val)[NIN]) {
         if constexpr (LVEC) {
@@ -256,9 +262,9 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
             for (int n = 0; n < NIN; ++n) val[n] = ix[n] == kInvalidIndex ? 0.0 : __ldg(a.in + ix[n]);
         } else {
             const uint32_t e_ = eb_ * EPB + el;
-            const bool ok = lane_ok && loader && eb_ < n_batches && e_ < a.n_elems;
+            const bool ok = lane_ok && eb_ < n_batches && e_ < a.n_elems;
 #pragma unroll
-            for (int n = 0; n < NIN; ++n) val[n] = ok ? __ldg(a.in + in_offset(e_, n)) : 0.0;
+            for (int n = 0; n < NIN; ++n) val[n] = (ok && in_valid(n)) ? __ldg(a.in + in_offset(e_, n)) : 0.0;
         }
     };
     if constexpr (LVEC) load_idx(blockIdx.x, cur_idx);
@@ -299,9 +305,17 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
 #pragma unroll
             for (int p = 0; p < NQ; ++p) v[p] = cur_val[p];
         } else {
-            if (t2 < NM * NM) {  // k -> r straight from the register row -> A[i][j][r] in R1
-                double o[NQ];
-                v2::col_mul<NQ, NM, NM, 1>(m.B, cur_val, o);
+#pragma unroll
+            for (int c = 0; c < NK; ++c) {  // U -> R0, rows [i][j][.] with odd stride
+                const int l = t2 + c * N2;
+                if (l < M3) R0[(l / NM) * RU + (l % NM)] = cur_val[c];
+            }
+            sync_elem();
+            if (t2 < NM * NM) {  // k -> r : rows of U -> A[i][j][r] in R1
+                double u[NM], o[NQ];
+#pragma unroll
+                for (int k = 0; k < NM; ++k) u[k] = R0[t2 * RU + k];
+                v2::col_mul<NQ, NM, NM, 1>(m.B, u, o);
 #pragma unroll
                 for (int r = 0; r < NQ; ++r) R1[(t2 / NM) * PA + (t2 % NM) * RA + r] = o[r];
             }
@@ -446,24 +460,29 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
                 for (int j = 0; j < NM; ++j) R0[i * PA + j * RA + r2] = o[j];
             }
             sync_elem();
-            if (t2 < NM * NM) {  // r -> k : rows of Y -> the output row of thread (i,j), straight to memory
+            if (t2 < NM * NM) {  // r -> k : rows of Y -> Z[i][j][k] in R1 (odd row stride)
                 double x[NQ], z[NM];
 #pragma unroll
                 for (int r = 0; r < NQ; ++r) x[r] = R0[(t2 / NM) * PA + (t2 % NM) * RA + r];
                 v2::col_mul<NM, NQ, 1, NM>(m.B, x, z);
-                if constexpr (LVEC) {
 #pragma unroll
-                    for (int k = 0; k < NM; ++k) {
-                        if (cur_idx[k] != kInvalidIndex) atomicAdd(a.out + cur_idx[k], z[k]);
-                    }
-                } else {
-                    if (active) {
+                for (int k = 0; k < NM; ++k) R1[t2 * RU + k] = z[k];
+            }
+            sync_elem();
 #pragma unroll
-                        for (int k = 0; k < NM; ++k) a.out[(size_t)e * M3 + t2 * NM + k] = z[k];
+            for (int c = 0; c < NK; ++c) {  // coalesced store / scatter of the nodal values this thread owns
+                const int l = t2 + c * N2;
+                if (l < M3) {
+                    const double z = R1[(l / NM) * RU + (l % NM)];
+                    if constexpr (LVEC) {
+                        if (cur_idx[c] != kInvalidIndex) atomicAdd(a.out + cur_idx[c], z);
+                    } else {
+                        if (active) a.out[(size_t)e * M3 + l] = z;
                     }
                 }
             }
-            // next batch writes R1 first: its last readers (flux loop, own points) left two barriers ago
+            // next batch: U -> R0 (last read by the r -> k sweep, fenced by the barrier above); its k-sweep
+            // writes R1 only after the barrier that follows the U staging, i.e. after these Z reads
         }
         // rotate the software pipeline (or load the next batch's inputs now)
         if constexpr (PREFETCH) {
