@@ -10,6 +10,11 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # a fresh checkout has no binaries: build the product library and the CPU checker once
+    if not (os.path.exists(os.path.join(ROOT, "benchmarks_b200", "libb200fe.so"))
+            and os.path.exists(os.path.join(ROOT, "oracle", "liboracle.so"))):
+        import __graft_entry__
+        __graft_entry__.build()
 
 
 def _cuda_available():
