@@ -52,3 +52,27 @@ def test_bp3_driver_reports_errors_like_the_reference():
         subprocess.run(["make", "-C", DRV], check=True)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 1 and "Expected at least one argument" in r.stdout
+
+
+def test_bp5_driver_helmholtz_jacobi_matches_c_oracle(oracle_mod):
+    """bp5_kokkos protocol (Helmholtz, QGauss(p+1), Jacobi CG capped at 100 iterations, rhs = i % 8): the C++ driver's
+    iteration count and DoF count against the C oracle on the same mesh (s = 3: 1 x 1 x 7 cells, p = 3)."""
+    import numpy as np
+    out = _run(["bp5", 3, 3, 1])
+    row = [x.strip() for x in out.strip().splitlines()[-1].split("|")]
+    p, q, n_el, n_dofs, its = int(row[0]), int(row[1]), int(row[2]), int(row[3]), int(row[6])
+    assert (p, q, n_el) == (3, 4, 7) and n_dofs == 4 * 4 * 22
+    fe = oracle_mod.fe
+    om = fe.BoxMesh((1, 1, 7), 0, p1=(0.0, 0.0, 0.0), p2=(1.0, 1.0, 7.0))
+    od = fe.distribute_dofs(om, 3, 1)
+    rd = fe.rank_data(om, od, 0)
+    bas = fe.basis_1d(3, 4)
+    G, JxW = fe.geometric_factors(fe.cell_nodes(om, rd["cells"], 1), 1, bas)
+    rhs = np.arange(rd["n_owned"], dtype=np.float64) % 8
+    rhs[rd["constrained"]] = 0.0
+    inv_diag = fe.op_diagonal(rd, bas, G, JxW, laplace=True, mass=True)
+    inv_diag = np.where(inv_diag > 0, 1.0 / inv_diag, 1.0)
+    _, its_o, _, _, _ = oracle_mod.port.cg_solve(rhs, nm=4, nq=4, collocated=False, flags=3, shape_values=bas["B"].T.copy(),
+                                                 co_shape_gradients=bas["D"].T.copy(), G=G, JxW=JxW, dof_indices=rd["dof_indices"],
+                                                 constrained=rd["constrained"], inv_diag=inv_diag, max_it=100, abs_tol=1e-15, rel_tol=1e-8)
+    assert abs(its - its_o) <= 1
