@@ -14,14 +14,15 @@ struct LaunchInfo {
 // Defined (explicitly instantiated) in inst.cu, one translation unit per degree.
 // hB: nq*nm doubles B[q*nm+i] (may be null when COLL), hD: nq*nq doubles D[p*nq+n] (may be null for mass).
 template <int NM, int NQ, bool COLL, int QOP, bool LVEC>
-cudaError_t launch_t(const double *hB, const double *hD, const KArgs &a, cudaStream_t s,
+cudaError_t launch_t(const double *hB, const double *hD, const double *hW, const KArgs &a, cudaStream_t s,
                      LaunchInfo *info, bool dry_run);
 
 // Runtime dispatch over the instantiated set.  Returns cudaErrorInvalidValue for a combination
 // that is not built (caller maps it to B200FE_ERR_UNSUPPORTED).
+// hW: nq quadrature weights, only read for qop & QOP_AFFINE.
 cudaError_t launch_sumfact(int nm, int nq, bool coll, int qop, bool lvec, const double *hB,
                            const double *hD, const KArgs &a, cudaStream_t s, LaunchInfo *info,
-                           bool dry_run);
+                           bool dry_run, const double *hW = nullptr);
 
 // grid multiplier for the persistent launches (env B200FE_GRID_MULT, default 1 = one resident wave)
 int grid_multiplier();

@@ -87,7 +87,7 @@ struct V2Cfg {
 };
 
 template <int NM, int NQ, bool COLL, int QOP, bool LVEC>
-cudaError_t launch_t(const double *hB, const double *hD, const KArgs &a, cudaStream_t s,
+cudaError_t launch_t(const double *hB, const double *hD, const double *hW, const KArgs &a, cudaStream_t s,
                      LaunchInfo *info, bool dry_run)
 {
 #ifdef B200FE_KERNEL_V1
@@ -103,7 +103,7 @@ cudaError_t launch_t(const double *hB, const double *hD, const KArgs &a, cudaStr
     auto kern = sumfact2_kernel<NM, NQ, COLL, QOP, LVEC, EPB, C::MINB>;
     const size_t smem = C::SMEM;
     // TMA bulk copies need a 16-byte aligned source (the batch block offset is a multiple of 48 nq^3 bytes)
-    if ((QOP & QOP_LAPLACE) && !dry_run && (reinterpret_cast<uintptr_t>(a.G) & 15u) != 0) return cudaErrorMisalignedAddress;
+    if ((QOP & QOP_LAPLACE) && !(QOP & QOP_AFFINE) && !dry_run && (reinterpret_cast<uintptr_t>(a.G) & 15u) != 0) return cudaErrorMisalignedAddress;
 #endif
 
     struct Cfg {
@@ -140,6 +140,7 @@ cudaError_t launch_t(const double *hB, const double *hD, const KArgs &a, cudaStr
     Mats<NM, NQ> m;
     if (hB) std::memcpy(m.B, hB, sizeof(m.B)); else std::memset(m.B, 0, sizeof(m.B));
     if (hD) std::memcpy(m.D, hD, sizeof(m.D)); else std::memset(m.D, 0, sizeof(m.D));
+    if (hW) std::memcpy(m.W, hW, sizeof(m.W)); else std::memset(m.W, 0, sizeof(m.W));
     kern<<<grid, T, smem, s>>>(m, a);
     return cudaGetLastError();
 }

@@ -112,6 +112,45 @@ __global__ void geometry_kernel(const __grid_constant__ GeoMats gm, uint32_t n_c
     }
 }
 
+// affine cells: J from the vertex differences of the trilinear map (columns v1-v0, v2-v0, v4-v0)
+__global__ void affine_geometry_kernel(uint32_t n_cells, const double *__restrict__ nodes /*[cell][3][2][2][2]*/,
+                                       double *__restrict__ cellG)
+{
+    const uint32_t cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= n_cells) return;
+    const double *x = nodes + (size_t)cell * 24;
+    double J[3][3];
+    for (int d = 0; d < 3; ++d) {
+        const double *xd = x + d * 8;  // node index c*4 + b*2 + a
+        J[d][0] = xd[1] - xd[0];
+        J[d][1] = xd[2] - xd[0];
+        J[d][2] = xd[4] - xd[0];
+    }
+    const double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+                       J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+    const double id = 1.0 / det;
+    double K[3][3];
+    K[0][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) * id;
+    K[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * id;
+    K[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * id;
+    K[1][0] = (J[1][2] * J[2][0] - J[1][0] * J[2][2]) * id;
+    K[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * id;
+    K[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * id;
+    K[2][0] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) * id;
+    K[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * id;
+    K[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * id;
+    const int perm[3] = {2, 1, 0};  // (r,s,t) = (z^, y^, x^), as in geometry_kernel
+    double *o = cellG + (size_t)cell * 8;
+    int ci = 0;
+    for (int a = 0; a < 3; ++a)
+        for (int b = a; b < 3; ++b, ++ci) {
+            const double *ka = K[perm[a]], *kb = K[perm[b]];
+            o[ci] = det * (ka[0] * kb[0] + ka[1] * kb[1] + ka[2] * kb[2]);
+        }
+    o[6] = det;
+    o[7] = 0.0;
+}
+
 __global__ void copy_constrained_kernel(uint32_t n, const uint32_t *__restrict__ list,
                                         const double *__restrict__ src, double *__restrict__ dst,
                                         double *__restrict__ dot)
@@ -201,12 +240,14 @@ int op_apply_cells(Operator &op, double *d_dst, const double *d_src, uint32_t cb
 {
     if (ce <= cb) return B200FE_OK;
     const size_t nm3 = (size_t)op.nm * op.nm * op.nm, nq3 = (size_t)op.nq * op.nq * op.nq;
-    KArgs a{ce - cb, op.d_G ? op.d_G + cb * 6 * nq3 : nullptr, op.d_JxW ? op.d_JxW + cb * nq3 : nullptr,
-            d_src, d_dst, op.d_idx + cb * nm3, d_dot};
+    const bool affine = op.d_cellG != nullptr;
+    KArgs a{ce - cb, (op.d_G && !affine) ? op.d_G + cb * 6 * nq3 : nullptr, op.d_JxW ? op.d_JxW + cb * nq3 : nullptr,
+            d_src, d_dst, op.d_idx + cb * nm3, d_dot, affine ? op.d_cellG + (size_t)cb * 8 : nullptr};
+    const int qop = op.qop | (affine ? QOP_AFFINE : 0);
     const bool timed = op.timing && op.ev_used + 2 <= op.ev.size();
     if (timed) B200FE_CUDA_TRY(cudaEventRecord(op.ev[op.ev_used], s));
-    B200FE_CUDA_TRY(launch_sumfact(op.nm, op.nq, op.collocated, op.qop, true, op.B.data(), op.D.data(), a, s,
-                                   &op.last_launch, false));
+    B200FE_CUDA_TRY(launch_sumfact(op.nm, op.nq, op.collocated, qop, true, op.B.data(), op.D.data(), a, s,
+                                   &op.last_launch, false, affine ? op.W.data() : nullptr));
     if (timed) {
         B200FE_CUDA_TRY(cudaEventRecord(op.ev[op.ev_used + 1], s));
         op.ev_used += 2;
@@ -337,6 +378,15 @@ int b200fe_geometry_from_nodes(int p_geo, int nq, int quad_kind, uint32_t n_cell
     return B200FE_OK;
 }
 
+int b200fe_geometry_affine_from_nodes(uint32_t n_cells, const double *d_nodes, double *d_cell_G, void *stream)
+{
+    B200FE_REQUIRE(n_cells == 0 || (d_nodes && d_cell_G), "b200fe_geometry_affine_from_nodes: null pointer");
+    if (n_cells == 0) return B200FE_OK;
+    affine_geometry_kernel<<<(n_cells + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n_cells, d_nodes, d_cell_G);
+    B200FE_CUDA_TRY(cudaGetLastError());
+    return B200FE_OK;
+}
+
 int b200fe_op_create(const b200fe_op_desc *d, b200fe_op **out)
 {
     B200FE_REQUIRE(d && out, "b200fe_op_create: null pointer");
@@ -352,7 +402,11 @@ int b200fe_op_create(const b200fe_op_desc *d, b200fe_op **out)
     if (!ok) return fail(B200FE_ERR_UNSUPPORTED, "b200fe_op_create: no kernel for op_kind=%d p=%d nq=%d collocated=%d", d->op_kind, d->p, d->nq, (int)coll);
     B200FE_REQUIRE(d->h_co_shape_gradients && (coll || d->h_shape_values), "b200fe_op_create: 1-D matrices missing");
     B200FE_REQUIRE(d->n_cells == 0 || d->d_dof_indices, "b200fe_op_create: dof_indices missing");
-    B200FE_REQUIRE(!(d->op_kind & B200FE_OP_LAPLACE) || d->n_cells == 0 || d->d_G, "b200fe_op_create: G missing");
+    const bool affine = d->d_cell_G != nullptr;
+    if (affine && d->op_kind != B200FE_OP_LAPLACE)
+        return fail(B200FE_ERR_UNSUPPORTED, "b200fe_op_create: on-the-fly (affine) geometry is built for the Laplace operators only");
+    B200FE_REQUIRE(!affine || d->h_weights, "b200fe_op_create: affine geometry needs the 1-D quadrature weights");
+    B200FE_REQUIRE(!(d->op_kind & B200FE_OP_LAPLACE) || d->n_cells == 0 || d->d_G || affine, "b200fe_op_create: G missing");
     B200FE_REQUIRE(!(d->op_kind & B200FE_OP_MASS) || d->n_cells == 0 || d->d_JxW, "b200fe_op_create: JxW missing");
     B200FE_REQUIRE(d->n_constrained == 0 || d->h_constrained, "b200fe_op_create: constrained list missing");
     B200FE_REQUIRE((uint64_t)d->n_phase0 + d->n_phase1 <= d->n_cells, "b200fe_op_create: phase split exceeds n_cells");
@@ -361,7 +415,8 @@ int b200fe_op_create(const b200fe_op_desc *d, b200fe_op **out)
     op->p = d->p; op->nm = nm; op->nq = d->nq; op->qop = d->op_kind; op->collocated = coll;
     op->n_cells = d->n_cells; op->n_owned = d->n_owned; op->n_ghost = d->n_ghost; op->n_constrained = d->n_constrained;
     op->n_phase0 = d->n_phase0; op->n_phase1 = d->n_phase1;
-    op->d_idx = d->d_dof_indices; op->d_G = d->d_G; op->d_JxW = d->d_JxW;
+    op->d_idx = d->d_dof_indices; op->d_G = d->d_G; op->d_JxW = d->d_JxW; op->d_cellG = d->d_cell_G;
+    if (affine) op->W.assign(d->h_weights, d->h_weights + d->nq);
     const int nq = d->nq;
     op->shape_values.assign(nm * nq, 0.0);
     if (coll) for (int i = 0; i < nm; ++i) op->shape_values[i * nq + i] = 1.0;
@@ -453,6 +508,7 @@ int b200fe_op_diagonal(b200fe_op *o, double *d_diag, void *stream)
 {
     B200FE_REQUIRE(o && d_diag, "b200fe_op_diagonal: null pointer");
     Operator &op = *reinterpret_cast<Operator *>(o);
+    B200FE_REQUIRE(!(op.qop & QOP_LAPLACE) || op.d_G, "b200fe_op_diagonal: needs the stored geometric factors (d_G)");
     cudaStream_t s = (cudaStream_t)stream;
     B200FE_CUDA_TRY(cudaMemsetAsync(d_diag, 0, sizeof(double) * op.n_local(), s));
     if (op.n_cells) {
@@ -524,9 +580,9 @@ int b200fe_op_launch_info(b200fe_op *o, int *elems_per_block, int *num_blocks, i
 {
     B200FE_REQUIRE(o, "b200fe_op_launch_info: null operator");
     Operator &op = *reinterpret_cast<Operator *>(o);
-    KArgs a{op.n_cells, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    KArgs a{op.n_cells, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     LaunchInfo li{};
-    B200FE_CUDA_TRY(launch_sumfact(op.nm, op.nq, op.collocated, op.qop, true, nullptr, nullptr, a, nullptr, &li, true));
+    B200FE_CUDA_TRY(launch_sumfact(op.nm, op.nq, op.collocated, op.qop | (op.d_cellG ? QOP_AFFINE : 0), true, nullptr, nullptr, a, nullptr, &li, true));
     if (elems_per_block) *elems_per_block = li.elems_per_block;
     if (num_blocks) *num_blocks = li.num_blocks;
     if (threads_per_block) *threads_per_block = li.threads_per_block;

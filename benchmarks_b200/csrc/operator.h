@@ -18,6 +18,8 @@ struct Operator {
     const uint32_t *d_idx = nullptr;  // borrowed
     const double *d_G = nullptr;      // borrowed
     const double *d_JxW = nullptr;    // borrowed
+    const double *d_cellG = nullptr;  // borrowed; affine on-the-fly geometry: [cell][8]
+    std::vector<double> W;            // 1-D quadrature weights (affine geometry)
     uint32_t *d_constrained = nullptr;  // owned
     double *d_mats = nullptr;           // owned: shape_values | co_shape_gradients | shape_gradients (setup kernels)
     Halo *halo = nullptr;               // borrowed, optional

@@ -28,7 +28,10 @@ namespace b200fe {
 
 constexpr uint32_t kInvalidIndex = 0xFFFFFFFFu;  // numbers::invalid_unsigned_int
 
-enum : int { QOP_LAPLACE = 1, QOP_MASS = 2, QOP_HELMHOLTZ = 3 };
+enum : int { QOP_LAPLACE = 1, QOP_MASS = 2, QOP_HELMHOLTZ = 3,
+             // geometry evaluated on the fly for affine cells: G(q) = cellG * w_p w_q w_r with six
+             // per-cell constants instead of the streamed 6 nq^3 factors; sumfact2 kernel, L-vector operators only
+             QOP_AFFINE = 4 };
 
 // 1-D matrices in the BK layout: B[q*NM+i] (CEED_BK BK1 serial_kernels.hpp:39),
 // D[p*NQ+n] = derivative of collocation function n at point p (BK3 serial_kernels.hpp:98).
@@ -36,6 +39,7 @@ template <int NM, int NQ>
 struct Mats {
     double B[NQ * NM];
     double D[NQ * NQ];
+    double W[NQ];  // 1-D quadrature weights (affine on-the-fly geometry only)
 };
 
 struct KArgs {
@@ -46,6 +50,7 @@ struct KArgs {
     double *out;            // E-vector [e][NM^3]  | L-vector dst
     const uint32_t *idx;    // L-vector only: [e][NM^3], kInvalidIndex = constrained
     double *dot;            // L-vector only, optional: += sum_e u_e . (A_e u_e)
+    const double *cellG;    // affine geometry only: [e][8] = det J * K K^T (rr,rs,rt,ss,st,tt), det J, pad
 };
 
 constexpr __host__ __device__ int odd(int n) { return n | 1; }

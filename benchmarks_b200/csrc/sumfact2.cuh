@@ -93,7 +93,8 @@ struct Layout2 {
     // element stride == nq^2 (mod 16): a warp that spans two elements keeps hitting distinct banks
     static constexpr int pad_elem(int w) { while ((w - N2) % 16 != 0) ++w; return w; }
     static constexpr int WORK_PER_ELEM = N_REGIONS == 0 ? 0 : pad_elem(N_REGIONS * REGION);
-    static constexpr int G_PER_ELEM = LAP ? 6 * N3 : 0;
+    static constexpr bool AFFINE = (QOP & QOP_AFFINE) != 0;  // no streamed G: nothing to stage
+    static constexpr int G_PER_ELEM = (LAP && !AFFINE) ? 6 * N3 : 0;
     // warp-local mode (nq <= 5): an element's nq^2 threads sit inside one warp, EPW elements per warp;
     // every intra-element barrier becomes __syncwarp().  Idle lanes of a warp work on a dummy slot.
     // Measured (profiles/r01d_warp_local.txt): a win only when the planes tile the warp exactly (nq = 2, 4:
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
     using L = v2::Layout2<NM, NQ, COLL, QOP>;
     constexpr int N2 = L::N2, N3 = L::N3, M3 = L::M3, RA = L::RA, PA = L::PA, PB = L::PB;
     constexpr int PSQ = L::PSQ, RSR = L::RSR, PSR = L::PSR;
-    constexpr bool LAP = L::LAP, MASS = (QOP & QOP_MASS) != 0;
+    constexpr bool LAP = L::LAP, MASS = (QOP & QOP_MASS) != 0, AFFINE = L::AFFINE, STORED_G = LAP && !AFFINE;
     static_assert(!COLL || NM == NQ, "collocated operators need nm == nq");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
         v2::mbar_expect_tx(bar, bytes);
         v2::bulk_g2s(Gs, a.G + (size_t)first * L::G_PER_ELEM, bytes, bar);
     };
-    if constexpr (LAP) {
+    if constexpr (STORED_G) {
         if (tid == 0) {
             v2::mbar_init(bar, 1);
             v2::fence_mbar_init();
@@ -366,15 +367,31 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
                 for (int r = 0; r < NQ; ++r) RR[ta * PSR + tb * RSR + r] = o[r];
             }
             sync_elem();
-            v2::mbar_wait(bar, parity);  // G of this batch has landed
-            parity ^= 1u;
+            if constexpr (STORED_G) {
+                v2::mbar_wait(bar, parity);  // G of this batch has landed
+                parity ^= 1u;
+            }
+            [[maybe_unused]] double cg[6];
+            [[maybe_unused]] double wqr = 0.0;
+            if constexpr (AFFINE) {  // six constants per cell, scaled by the tensor-product quadrature weight
+                const double *c8 = a.cellG + (size_t)(active ? e : 0) * 8;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) cg[c] = active ? __ldg(c8 + c) : 0.0;
+                wqr = m.W[ta] * m.W[tb];
+            }
 #pragma unroll
             for (int p = 0; p < NQ; ++p) {
                 const double qr = gr[p];
                 const double qs = RQ[p * PSQ + t2];
                 const double qt = RR[p * PSR + ta * RSR + tb];
-                const double g0 = Ge[0 * N3 + p * N2], g1 = Ge[1 * N3 + p * N2], g2 = Ge[2 * N3 + p * N2];
-                const double g3 = Ge[3 * N3 + p * N2], g4 = Ge[4 * N3 + p * N2], g5 = Ge[5 * N3 + p * N2];
+                double g0, g1, g2, g3, g4, g5;
+                if constexpr (AFFINE) {
+                    const double wt = wqr * m.W[p];
+                    g0 = cg[0] * wt; g1 = cg[1] * wt; g2 = cg[2] * wt; g3 = cg[3] * wt; g4 = cg[4] * wt; g5 = cg[5] * wt;
+                } else {
+                    g0 = Ge[0 * N3 + p * N2]; g1 = Ge[1 * N3 + p * N2]; g2 = Ge[2 * N3 + p * N2];
+                    g3 = Ge[3 * N3 + p * N2]; g4 = Ge[4 * N3 + p * N2]; g5 = Ge[5 * N3 + p * N2];
+                }
                 const double fr = g0 * qr + g1 * qs + g2 * qt;
                 const double fs = g1 * qr + g3 * qs + g4 * qt;
                 const double ft = g2 * qr + g4 * qs + g5 * qt;
@@ -386,12 +403,14 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
                 // (inactive slots contribute 0 * finite: the G buffer is zero-initialised, see above)
                 if constexpr (LVEC) dot_acc = fma(qr, fr, fma(qs, fs, fma(qt, ft, dot_acc)));
             }
-            __syncthreads();
-            if (tid == 0) {  // the G buffer is drained: fetch the next batch's block behind the rest of this one
-                const uint32_t nb = eb + gridDim.x;
-                if (nb < n_batches) {
-                    v2::fence_proxy_async();
-                    issue_g(nb);
+            if constexpr (STORED_G) __syncthreads();  // CTA-wide: the shared G buffer is about to be refilled
+            else sync_elem();
+            if constexpr (STORED_G) {
+                if (tid == 0) {  // the G buffer is drained: fetch the next batch's block behind the rest of this one
+                    if (nb < n_batches) {
+                        v2::fence_proxy_async();
+                        issue_g(nb);
+                    }
                 }
             }
             if constexpr (LVEC && PREFETCH) load_val(nb, nxt_idx, nxt_val);  // next batch's gathers (indices arrived long ago)

@@ -28,7 +28,8 @@ class _OpDesc(C.Structure):
                 ("h_shape_values", C.c_void_p), ("h_co_shape_gradients", C.c_void_p),
                 ("d_dof_indices", C.c_void_p), ("d_G", C.c_void_p), ("d_JxW", C.c_void_p),
                 ("h_constrained", C.c_void_p), ("n_constrained", C.c_uint32),
-                ("n_phase0", C.c_uint32), ("n_phase1", C.c_uint32)]
+                ("n_phase0", C.c_uint32), ("n_phase1", C.c_uint32),
+                ("d_cell_G", C.c_void_p), ("h_weights", C.c_void_p)]
 
 
 class _CgResult(C.Structure):
@@ -65,7 +66,7 @@ class LaplaceOperator:
 
     def __init__(self, mesh: BoxMesh, nq: int | None = None, quad: str = "gauss", kind: str = "laplace",
                  p_geo: int = 1, deform=None, overlap: bool = False, halo=None, with_jxw: bool = True,
-                 device=None):
+                 device=None, geometry: str = "stored"):
         self.mesh = mesh
         p = mesh.p
         self.p, self.nm = p, p + 1
@@ -90,11 +91,21 @@ class LaplaceOperator:
         if self.perm is not None:
             nodes = nodes.view(mesh.n_cells, 3 * ng3)[torch.from_numpy(self.perm).to(self.device)].contiguous().view(-1)
         nq3 = self.nq ** 3
-        need_G = bool(self.kind & OP_LAPLACE)
+        self.geometry = geometry
+        self.cell_G = None
+        if geometry == "affine":  # on-the-fly geometric factors from six per-cell constants
+            if p_geo != 1 or deform is not None or self.kind != OP_LAPLACE:
+                raise ValueError("geometry='affine' needs p_geo=1, no deformation and the Laplace operator")
+            self.cell_G = torch.empty(mesh.n_cells * 8, dtype=torch.float64, device=self.device)
+            check(lib.b200fe_geometry_affine_from_nodes(mesh.n_cells, _dp(nodes), _dp(self.cell_G), _sp()))
+        elif geometry != "stored":
+            raise ValueError(geometry)
+        need_G = bool(self.kind & OP_LAPLACE) and geometry == "stored"
         need_J = bool(self.kind & OP_MASS) or with_jxw
         self.G = torch.empty(mesh.n_cells * 6 * nq3, dtype=torch.float64, device=self.device) if need_G else None
         self.JxW = torch.empty(mesh.n_cells * nq3, dtype=torch.float64, device=self.device) if need_J else None
-        check(lib.b200fe_geometry_from_nodes(p_geo, self.nq, self.quad, mesh.n_cells, _dp(nodes), _dp(self.G), _dp(self.JxW), _sp()))
+        if self.G is not None or self.JxW is not None:
+            check(lib.b200fe_geometry_from_nodes(p_geo, self.nq, self.quad, mesh.n_cells, _dp(nodes), _dp(self.G), _dp(self.JxW), _sp()))
         torch.cuda.current_stream().synchronize()
         del nodes
         d = _OpDesc()
@@ -111,6 +122,9 @@ class LaplaceOperator:
         d.h_constrained = self._con.ctypes.data if len(self._con) else None
         d.n_constrained = len(self._con)
         d.n_phase0, d.n_phase1 = n_phase0, n_phase1
+        self._w = np.ascontiguousarray(self.basis["weights"])
+        d.d_cell_G = self.cell_G.data_ptr() if self.cell_G is not None else None
+        d.h_weights = self._w.ctypes.data
         self._h = C.c_void_p()
         check(lib.b200fe_op_create(C.byref(d), C.byref(self._h)))
         self.halo = halo
@@ -185,7 +199,8 @@ class LaplaceOperator:
     # algorithmic bytes of one apply: G + indices per cell, 32 B per local DoF
     def algorithmic_bytes(self) -> int:
         nq3, nm3 = self.nq ** 3, self.nm ** 3
-        per_cell = 4 * nm3 + (48 * nq3 if self.kind & OP_LAPLACE else 0) + (8 * nq3 if self.kind & OP_MASS else 0)
+        g_bytes = 64 if self.geometry == "affine" else 48 * nq3
+        per_cell = 4 * nm3 + (g_bytes if self.kind & OP_LAPLACE else 0) + (8 * nq3 if self.kind & OP_MASS else 0)
         return self.mesh.n_cells * per_cell + 32 * self.mesh.n_owned
 
     def __del__(self):

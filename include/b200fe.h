@@ -168,6 +168,10 @@ int b200fe_boxmesh_nodes(const b200fe_boxmesh *mesh, int p_geo, int deform_kind,
 int b200fe_geometry_from_nodes(int p_geo, int nq, int quad_kind, uint32_t n_cells, const double *d_nodes,
                                double *d_G, double *d_JxW, void *stream);
 
+/* Per-cell constants for the on-the-fly geometry of affine (parallelepiped) cells from MappingQ1 support points
+ * d_nodes[cell][3][2][2][2] (b200fe_boxmesh_nodes with p_geo = 1): d_cell_G[cell][8], see b200fe_op_desc. */
+int b200fe_geometry_affine_from_nodes(uint32_t n_cells, const double *d_nodes, double *d_cell_G, void *stream);
+
 enum { B200FE_OP_LAPLACE = 1, B200FE_OP_MASS = 2, B200FE_OP_HELMHOLTZ = 3 };
 
 typedef struct {
@@ -187,6 +191,14 @@ typedef struct {
      * [0,n_phase0) and [n_phase0+n_phase1, n_cells) touch no ghost DoF, cells of phase 1 may.
      * 0,0 = single colour, no overlap (the reference drivers' setting, bp3.cc:103). */
     uint32_t n_phase0, n_phase1;
+    /* Optional: geometry evaluated on the fly for AFFINE cells ("next" row): when
+     * d_cell_G != NULL the Laplace kernels do not stream d_G (48 nq^3 bytes per cell) but use
+     * G(q) = cell_G * w_p w_q w_r with DEVICE d_cell_G[cell][8] = {det J * K K^T (rr,rs,rt,ss,st,tt), det J, 0}
+     * (b200fe_geometry_affine_from_nodes) and the HOST 1-D weights h_weights[nq].  Results equal the
+     * stored-G path to rounding on parallelepiped cells; algorithmic bytes drop to 4 nm^3 + 64 per cell.
+     * d_G may still be given (needed by b200fe_op_diagonal).  BORROWED. */
+    const double *d_cell_G;
+    const double *h_weights;
 } b200fe_op_desc;
 
 typedef struct b200fe_op b200fe_op;

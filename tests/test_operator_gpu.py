@@ -276,3 +276,40 @@ def test_vector_valued_apply_bp6_style(oracle_mod):
     out = dst.cpu().numpy().reshape(3, -1)
     for c in range(3):
         assert rel(out[c], fe.op_apply(src[c], rd, bas, G)) <= TOL
+
+
+@pytest.mark.parametrize("p", [1, 2, 3, 4, 6, 8])
+@pytest.mark.parametrize("dq,quad", [(2, "gauss"), (1, "gauss"), (1, "gll")])
+def test_on_the_fly_affine_geometry_matches_stored_G_and_oracle(oracle_mod, p, dq, quad):
+    """SURVEY section 8f.1 ("next"): geometric factors from six per-cell constants on affine (here anisotropic box)
+    cells.  Same operator as the stored-G path and as the oracle, to 1e-12; same CG iteration count."""
+    import benchmarks_b200 as b
+    fe = oracle_mod.fe
+    sub, nref = ((3, 2, 1), 1) if p <= 4 else ((3, 1, 1), 0)
+    p1, p2 = (0.0, -1.0, 0.5), (1.3, 0.2, 1.0)   # cells 0.217 x 0.3 x 0.25: anisotropic, off-origin
+    nq = p + dq
+    om = fe.BoxMesh(sub, nref, p1=p1, p2=p2)
+    od = fe.distribute_dofs(om, p, 1)
+    rd = fe.rank_data(om, od, 0)
+    bas = fe.basis_1d(p, nq, quad)
+    G, JxW = fe.geometric_factors(fe.cell_nodes(om, rd["cells"], 1), 1, bas)
+    mesh = b.BoxMesh(sub, nref, p, p1=p1, p2=p2)
+    A_st = b.LaplaceOperator(mesh, nq=nq, quad=quad)
+    A_af = b.LaplaceOperator(mesh, nq=nq, quad=quad, geometry="affine")
+    src = np.random.default_rng(p).standard_normal(mesh.n_owned)
+    ref = fe.op_apply(src, rd, bas, G)
+    d_src = torch.from_numpy(src).cuda()
+    y_st, y_af = A_st.initialize_dof_vector(), A_af.initialize_dof_vector()
+    A_st.vmult(y_st, d_src)
+    dot = A_af.vmult_dot(y_af, d_src)
+    assert rel(y_af.cpu().numpy(), ref) <= TOL
+    assert rel(y_af.cpu().numpy(), y_st.cpu().numpy()) <= TOL
+    assert abs(dot.item() - float(src @ ref)) <= 1e-11 * np.abs(src).dot(np.abs(ref))
+    rhs = A_af.compute_rhs()
+    its = []
+    for A in (A_st, A_af):
+        x = A.initialize_dof_vector()
+        ctl = b.ReductionControl(5000, 1e-16, 1e-9)
+        b.SolverCG(ctl).solve(A, x, rhs)
+        its.append(ctl.last_step())
+    assert abs(its[0] - its[1]) <= 1
