@@ -236,8 +236,12 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
     // CTA reads / writes / gathers element vectors and index tables with fully coalesced requests; they are
     // re-shaped into rows through one shared-memory staging array.  (ncu, profiles/r01d_bk_l1tex.txt: per-thread
     // row access cost 19-20 sectors per request and made L1TEX the bottleneck of BK1/BK3 at 87-89 %.)
+    // L-vector operators keep the register-row variant (thread (i,j) owns the row over k and feeds / drains the
+    // outer sweeps without staging): measured faster there (BP3 p=5 0.65 vs 0.57, p=8 0.34 vs 0.29 of the HBM
+    // roofline, profiles/r01f_*), while for element vectors both variants time the same.
+    constexpr bool ROW_IO = LVEC && !COLL;
     constexpr int NK = (M3 + N2 - 1) / N2;
-    constexpr int NIN = COLL ? NQ : NK;
+    constexpr int NIN = COLL ? NQ : (ROW_IO ? NM : NK);
     constexpr int RU = odd(NM);  // row stride of the nodal staging arrays U / Z
 #ifndef B200FE_V2_PREFETCH_MAXNQ
 #define B200FE_V2_PREFETCH_MAXNQ 10  // software-pipelined inputs for every degree (r01 sweep: needs >= 160 registers at nq >= 7)
@@ -247,10 +251,11 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
     [[maybe_unused]] uint32_t cur_idx[NIN];
     [[maybe_unused]] double nxt_val[NIN];
     [[maybe_unused]] uint32_t nxt_idx[NIN];
-    auto in_offset = [&](uint32_t e_, int n) -> size_t {  // both are "plane n of the element, position t2"
-        return (size_t)e_ * (COLL ? N3 : M3) + n * N2 + t2;
+    auto in_offset = [&](uint32_t e_, int n) -> size_t {
+        if constexpr (ROW_IO) return (size_t)e_ * M3 + t2 * NM + n;   // row (i,j) = t2, entry k = n
+        else return (size_t)e_ * (COLL ? N3 : M3) + n * N2 + t2;       // "plane n of the element, position t2"
     };
-    auto in_valid = [&](int n) { return COLL || (n * N2 + t2 < M3); };
+    auto in_valid = [&](int n) { return COLL || (ROW_IO ? t2 < NM * NM : n * N2 + t2 < M3); };
     auto load_idx = [&](uint32_t eb_, uint32_t (&ix)[NIN]) {
         const uint32_t e_ = eb_ * EPB + el;
         const bool ok = lane_ok && eb_ < n_batches && e_ < a.n_elems;
@@ -306,19 +311,30 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
 #pragma unroll
             for (int p = 0; p < NQ; ++p) v[p] = cur_val[p];
         } else {
+            if constexpr (ROW_IO) {
+                if (t2 < NM * NM) {  // k -> r straight from the register row -> A[i][j][r] in R1
+                    double u[NM], o[NQ];
 #pragma unroll
-            for (int c = 0; c < NK; ++c) {  // U -> R0, rows [i][j][.] with odd stride
-                const int l = t2 + c * N2;
-                if (l < M3) R0[(l / NM) * RU + (l % NM)] = cur_val[c];
-            }
-            sync_elem();
-            if (t2 < NM * NM) {  // k -> r : rows of U -> A[i][j][r] in R1
-                double u[NM], o[NQ];
+                    for (int k = 0; k < NM; ++k) u[k] = cur_val[k];
+                    v2::col_mul<NQ, NM, NM, 1>(m.B, u, o);
 #pragma unroll
-                for (int k = 0; k < NM; ++k) u[k] = R0[t2 * RU + k];
-                v2::col_mul<NQ, NM, NM, 1>(m.B, u, o);
+                    for (int r = 0; r < NQ; ++r) R1[(t2 / NM) * PA + (t2 % NM) * RA + r] = o[r];
+                }
+            } else {
 #pragma unroll
-                for (int r = 0; r < NQ; ++r) R1[(t2 / NM) * PA + (t2 % NM) * RA + r] = o[r];
+                for (int c = 0; c < NK; ++c) {  // U -> R0, rows [i][j][.] with odd stride
+                    const int l = t2 + c * N2;
+                    if (l < M3) R0[(l / NM) * RU + (l % NM)] = cur_val[c];
+                }
+                sync_elem();
+                if (t2 < NM * NM) {  // k -> r : rows of U -> A[i][j][r] in R1
+                    double u[NM], o[NQ];
+#pragma unroll
+                    for (int k = 0; k < NM; ++k) u[k] = R0[t2 * RU + k];
+                    v2::col_mul<NQ, NM, NM, 1>(m.B, u, o);
+#pragma unroll
+                    for (int r = 0; r < NQ; ++r) R1[(t2 / NM) * PA + (t2 % NM) * RA + r] = o[r];
+                }
             }
             sync_elem();
             if (t2 < NM * NQ) {  // j -> q : columns of A -> B~[i][q][r] in R2
@@ -479,17 +495,23 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
                 for (int j = 0; j < NM; ++j) R0[i * PA + j * RA + r2] = o[j];
             }
             sync_elem();
-            if (t2 < NM * NM) {  // r -> k : rows of Y -> Z[i][j][k] in R1 (odd row stride)
+            if (t2 < NM * NM) {  // r -> k : rows of Y -> Z[i][j][k]
                 double x[NQ], z[NM];
 #pragma unroll
                 for (int r = 0; r < NQ; ++r) x[r] = R0[(t2 / NM) * PA + (t2 % NM) * RA + r];
                 v2::col_mul<NM, NQ, 1, NM>(m.B, x, z);
+                if constexpr (ROW_IO) {  // scatter the row straight from registers
 #pragma unroll
-                for (int k = 0; k < NM; ++k) R1[t2 * RU + k] = z[k];
+                    for (int k = 0; k < NM; ++k)
+                        if (cur_idx[k] != kInvalidIndex) atomicAdd(a.out + cur_idx[k], z[k]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < NM; ++k) R1[t2 * RU + k] = z[k];  // odd row stride
+                }
             }
-            sync_elem();
+            if constexpr (!ROW_IO) sync_elem();
 #pragma unroll
-            for (int c = 0; c < NK; ++c) {  // coalesced store / scatter of the nodal values this thread owns
+            for (int c = 0; c < (ROW_IO ? 0 : NK); ++c) {  // coalesced store of the nodal values this thread owns
                 const int l = t2 + c * N2;
                 if (l < M3) {
                     const double z = R1[(l / NM) * RU + (l % NM)];
