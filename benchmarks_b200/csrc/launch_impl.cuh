@@ -52,7 +52,7 @@ constexpr int v2_rmin(int nq, bool coll, int qop)
     return B200FE_V2_RMIN_FIXED;
 #else
     if (!(qop & QOP_LAPLACE)) return 64 + 12 * nq;  // mass only: no G buffer, registers are the limit
-    if (nq <= 6) return 96;
+    if (nq <= 6) return (qop & QOP_AFFINE) ? 128 : 96;  // affine kernels keep six more constants + weights live
 #ifdef B200FE_V2_RMIN_HI
     return B200FE_V2_RMIN_HI;
 #else
