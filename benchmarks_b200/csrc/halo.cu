@@ -124,6 +124,16 @@ int unpack_and_zero(Halo &h, double *v, cudaStream_t s)
 
 }  // namespace
 
+Halo::~Halo()
+{
+    if (comm && owns_comm) nccl().CommDestroy((ncclComm_t)comm);
+    cudaFree(d_send_idx);
+    cudaFree(d_pack);
+    if (comm_stream) cudaStreamDestroy(comm_stream);
+    if (ev_ready) cudaEventDestroy(ev_ready);
+    if (ev_done) cudaEventDestroy(ev_done);
+}
+
 int halo_zero_ghosts(Halo &h, double *v, cudaStream_t s)
 {
     if (h.n_ghost) B200FE_CUDA_TRY(cudaMemsetAsync(v + h.n_owned, 0, sizeof(double) * h.n_ghost, s));
@@ -246,18 +256,7 @@ int b200fe_halo_create(const b200fe_halo_desc *d, b200fe_halo **out)
     return B200FE_OK;
 }
 
-void b200fe_halo_destroy(b200fe_halo *halo)
-{
-    Halo *h = reinterpret_cast<Halo *>(halo);
-    if (!h) return;
-    if (h->comm && h->owns_comm) nccl().CommDestroy((ncclComm_t)h->comm);
-    cudaFree(h->d_send_idx);
-    cudaFree(h->d_pack);
-    if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
-    if (h->ev_ready) cudaEventDestroy(h->ev_ready);
-    if (h->ev_done) cudaEventDestroy(h->ev_done);
-    delete h;
-}
+void b200fe_halo_destroy(b200fe_halo *halo) { delete reinterpret_cast<Halo *>(halo); }
 
 int b200fe_halo_update_ghosts(b200fe_halo *halo, double *d_v, void *stream)
 {

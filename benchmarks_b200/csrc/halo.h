@@ -25,6 +25,10 @@ struct Halo {
     double *d_pack = nullptr;        // [n_send] packed owner values (update) / incoming contributions (compress)
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
+    Halo() = default;
+    Halo(const Halo &) = delete;
+    Halo &operator=(const Halo &) = delete;
+    ~Halo();  // halo.cu: frees the communicator (if owned), pack lists, stream and events
 };
 
 // owner -> ghost copy of v (all on stream s)

@@ -453,10 +453,7 @@ void b200fe_op_destroy(b200fe_op *o)
     Operator *op = reinterpret_cast<Operator *>(o);
     if (!op) return;
     cg_release_work(op);
-    for (cudaEvent_t e : op->ev) cudaEventDestroy(e);
-    cudaFree(op->d_constrained);
-    cudaFree(op->d_mats);
-    delete op;
+    delete op;  // ~Operator frees the owned device arrays and events
 }
 
 int b200fe_op_set_halo(b200fe_op *o, b200fe_halo *halo)

@@ -32,6 +32,15 @@ struct Operator {
     size_t ev_used = 0;
 
     uint32_t n_local() const { return n_owned + n_ghost; }
+    Operator() = default;
+    Operator(const Operator &) = delete;
+    Operator &operator=(const Operator &) = delete;
+    ~Operator()
+    {   // owned device resources only; borrowed arrays stay with the caller
+        for (cudaEvent_t e : ev) cudaEventDestroy(e);
+        cudaFree(d_constrained);
+        cudaFree(d_mats);
+    }
 };
 
 // dst = 0 on the local vector, cell kernel over cells [cell_begin, cell_end), optional fused dot.
