@@ -80,7 +80,7 @@ int b200fe_bk1_apply(int p, int nq, uint32_t nelmt, const double *h_basis, const
 {
     if (int rc = check_degree(p, nq, false)) return rc;
     B200FE_REQUIRE(h_basis && (nelmt == 0 || (d_JxW && d_in && d_out)), "b200fe_bk1_apply: null pointer");
-    KArgs a{nelmt, nullptr, d_JxW, d_in, d_out, nullptr, nullptr, nullptr};
+    KArgs a{nelmt, nullptr, d_JxW, d_in, d_out, nullptr, nullptr, nullptr, nullptr};
     B200FE_CUDA_TRY(launch_sumfact(p + 1, nq, false, QOP_MASS, false, h_basis, nullptr, a, (cudaStream_t)stream, nullptr, false));
     return B200FE_OK;
 }
@@ -90,7 +90,7 @@ int b200fe_bk3_apply(int p, int nq, uint32_t nelmt, const double *h_basis, const
 {
     if (int rc = check_degree(p, nq, false)) return rc;
     B200FE_REQUIRE(h_basis && h_dbasis && (nelmt == 0 || (d_G && d_in && d_out)), "b200fe_bk3_apply: null pointer");
-    KArgs a{nelmt, d_G, nullptr, d_in, d_out, nullptr, nullptr, nullptr};
+    KArgs a{nelmt, d_G, nullptr, d_in, d_out, nullptr, nullptr, nullptr, nullptr};
     B200FE_CUDA_TRY(launch_sumfact(p + 1, nq, false, QOP_LAPLACE, false, h_basis, h_dbasis, a, (cudaStream_t)stream, nullptr, false));
     return B200FE_OK;
 }
@@ -100,7 +100,7 @@ int b200fe_bk5_apply(int p, uint32_t nelmt, const double *h_dbasis, const double
 {
     if (int rc = check_degree(p, p + 1, true)) return rc;
     B200FE_REQUIRE(h_dbasis && (nelmt == 0 || (d_G && d_in && d_out)), "b200fe_bk5_apply: null pointer");
-    KArgs a{nelmt, d_G, nullptr, d_in, d_out, nullptr, nullptr, nullptr};
+    KArgs a{nelmt, d_G, nullptr, d_in, d_out, nullptr, nullptr, nullptr, nullptr};
     B200FE_CUDA_TRY(launch_sumfact(p + 1, p + 1, true, QOP_LAPLACE, false, nullptr, h_dbasis, a, (cudaStream_t)stream, nullptr, false));
     return B200FE_OK;
 }
@@ -139,7 +139,7 @@ int b200fe_bk_launch_info(int kind, int p, int nq, uint32_t nelmt, int *elems_pe
     B200FE_REQUIRE(kind == 1 || kind == 3 || kind == 5, "b200fe_bk_launch_info: kind must be 1, 3 or 5");
     const bool coll = kind == 5;
     if (int rc = check_degree(p, nq, coll)) return rc;
-    KArgs a{nelmt, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    KArgs a{nelmt, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     LaunchInfo li{};
     B200FE_CUDA_TRY(launch_sumfact(p + 1, nq, coll, kind == 1 ? QOP_MASS : QOP_LAPLACE, false, nullptr, nullptr, a, nullptr, &li, true));
     if (elems_per_block) *elems_per_block = li.elems_per_block;

@@ -16,6 +16,7 @@
 // iterations, and iterations queued after convergence are no-ops, so x is exactly the iterate at
 // which ReductionControl would have stopped.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 
@@ -189,16 +190,21 @@ static int cg_run(Operator &op, CgWork &w, double *d_x, const double *d_b, const
     ++g_launch_count;
     if (op.halo)
         if (int rc = halo_allreduce_sum(*op.halo, w.sc->acc + 1, 2, s)) return rc;
-    int launched = 0;
-    for (;;) {
+    // Sequence: S [U V X S] [U V X S] ...  (S = ReductionControl check + rho bookkeeping, U = p update,
+    // V = operator apply with fused p.Ap, X = x/r update with fused r.r).  Once S has set `done`, U, V, X and S
+    // are no-ops (V through KArgs::skip), so a chunk of iterations can be replayed blindly.
+    auto poll = [&]() -> int {
+        B200FE_CUDA_TRY(cudaMemcpyAsync(w.h_sc, w.sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, s));
+        B200FE_CUDA_TRY(cudaStreamSynchronize(s));
+        return B200FE_OK;
+    };
+    auto scalar_step = [&]() -> int {
         cg_scalar_kernel<<<1, 1, 0, s>>>(w.sc, jacobi, max_it, abs_tol, rel_tol);
         B200FE_CUDA_TRY(cudaGetLastError());
         ++g_launch_count;
-        if (launched % check_every == 0 || launched >= max_it) {
-            B200FE_CUDA_TRY(cudaMemcpyAsync(w.h_sc, w.sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, s));
-            B200FE_CUDA_TRY(cudaStreamSynchronize(s));
-            if (w.h_sc->done) break;
-        }
+        return B200FE_OK;
+    };
+    auto iteration = [&]() -> int {
         cg_update_p_kernel<<<blocks, 256, 0, s>>>(n, w.r, d_inv_diag, w.p, w.sc);
         B200FE_CUDA_TRY(cudaGetLastError());
         ++g_launch_count;
@@ -210,8 +216,56 @@ static int cg_run(Operator &op, CgWork &w, double *d_x, const double *d_b, const
         ++g_launch_count;
         if (op.halo)
             if (int rc = halo_allreduce_sum(*op.halo, w.sc->acc + 1, 2, s)) return rc;
-        ++launched;
+        return scalar_step();
+    };
+    struct SkipGuard {  // the apply kernels watch sc->done only for the duration of this solve
+        Operator &op;
+        SkipGuard(Operator &o, const int *flag) : op(o) { op.d_skip = flag; }
+        ~SkipGuard() { op.d_skip = nullptr; }
+    } skip_guard(op, &w.sc->done);
+
+    if (int rc = scalar_step()) return rc;
+    if (int rc = poll()) return rc;
+    int launched = 0;
+    // CUDA-graph replay of `chunk` iterations at a time (single GPU, no per-launch event timing): the latency
+    // floor of small problems is launch overhead (SURVEY.md hard part 4 / appendix B); the first iteration runs
+    // directly so that every kernel is configured before capture.
+    static const bool graphs_on = [] { const char *e = std::getenv("B200FE_CG_GRAPH"); return !e || std::atoi(e) != 0; }();
+    const int chunk = check_every < 32 ? check_every : 32;
+    const bool use_graph = graphs_on && !op.halo && !op.timing && chunk >= 2 && max_it >= 2 * chunk;
+    cudaGraphExec_t exec = nullptr;
+    unsigned long long launches_per_chunk = 0;
+    int rc_loop = B200FE_OK;
+    while (!w.h_sc->done) {
+        if (use_graph && launched >= 1 && max_it - launched >= chunk) {
+            if (exec == nullptr) {
+                cudaGraph_t graph = nullptr;
+                const unsigned long long before = g_launch_count;
+                B200FE_CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+                for (int k = 0; k < chunk && rc_loop == B200FE_OK; ++k) rc_loop = iteration();
+                cudaError_t ce = cudaStreamEndCapture(s, &graph);
+                launches_per_chunk = g_launch_count - before;
+                g_launch_count = before;  // capture enqueued nothing; replays are counted below
+                if (rc_loop != B200FE_OK) { if (graph) cudaGraphDestroy(graph); break; }
+                if (ce != cudaSuccess) { rc_loop = fail_cuda(ce, "cudaStreamEndCapture"); break; }
+                ce = cudaGraphInstantiate(&exec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (ce != cudaSuccess) { rc_loop = fail_cuda(ce, "cudaGraphInstantiate"); break; }
+            }
+            cudaError_t ce = cudaGraphLaunch(exec, s);
+            if (ce != cudaSuccess) { rc_loop = fail_cuda(ce, "cudaGraphLaunch"); break; }
+            g_launch_count += launches_per_chunk;
+            launched += chunk;
+            if ((rc_loop = poll()) != B200FE_OK) break;
+        } else {
+            if ((rc_loop = iteration()) != B200FE_OK) break;
+            ++launched;
+            if (launched % check_every == 0 || launched >= max_it || (use_graph && launched == 1))
+                if ((rc_loop = poll()) != B200FE_OK) break;
+        }
     }
+    if (exec) cudaGraphExecDestroy(exec);
+    if (rc_loop != B200FE_OK) return rc_loop;
     if (res) {
         res->iterations = w.h_sc->its;
         res->converged = w.h_sc->converged;

@@ -153,8 +153,9 @@ __global__ void affine_geometry_kernel(uint32_t n_cells, const double *__restric
 
 __global__ void copy_constrained_kernel(uint32_t n, const uint32_t *__restrict__ list,
                                         const double *__restrict__ src, double *__restrict__ dst,
-                                        double *__restrict__ dot)
+                                        double *__restrict__ dot, const int *__restrict__ skip)
 {
+    if (skip != nullptr && *skip != 0) return;
     double s = 0.0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t c = list[i];
@@ -242,7 +243,7 @@ int op_apply_cells(Operator &op, double *d_dst, const double *d_src, uint32_t cb
     const size_t nm3 = (size_t)op.nm * op.nm * op.nm, nq3 = (size_t)op.nq * op.nq * op.nq;
     const bool affine = op.d_cellG != nullptr;
     KArgs a{ce - cb, (op.d_G && !affine) ? op.d_G + cb * 6 * nq3 : nullptr, op.d_JxW ? op.d_JxW + cb * nq3 : nullptr,
-            d_src, d_dst, op.d_idx + cb * nm3, d_dot, affine ? op.d_cellG + (size_t)cb * 8 : nullptr};
+            d_src, d_dst, op.d_idx + cb * nm3, d_dot, affine ? op.d_cellG + (size_t)cb * 8 : nullptr, op.d_skip};
     const int qop = op.qop | (affine ? QOP_AFFINE : 0);
     const bool timed = op.timing && op.ev_used + 2 <= op.ev.size();
     if (timed) B200FE_CUDA_TRY(cudaEventRecord(op.ev[op.ev_used], s));
@@ -260,7 +261,7 @@ int op_copy_constrained(Operator &op, double *d_dst, const double *d_src, double
 {
     if (op.n_constrained == 0) return B200FE_OK;
     const unsigned blocks = std::min<unsigned>((op.n_constrained + 255) / 256, 1184);
-    copy_constrained_kernel<<<blocks, 256, 0, s>>>(op.n_constrained, op.d_constrained, d_src, d_dst, d_dot);
+    copy_constrained_kernel<<<blocks, 256, 0, s>>>(op.n_constrained, op.d_constrained, d_src, d_dst, d_dot, op.d_skip);
     B200FE_CUDA_TRY(cudaGetLastError());
     ++g_launch_count;
     return B200FE_OK;
@@ -577,7 +578,7 @@ int b200fe_op_launch_info(b200fe_op *o, int *elems_per_block, int *num_blocks, i
 {
     B200FE_REQUIRE(o, "b200fe_op_launch_info: null operator");
     Operator &op = *reinterpret_cast<Operator *>(o);
-    KArgs a{op.n_cells, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    KArgs a{op.n_cells, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     LaunchInfo li{};
     B200FE_CUDA_TRY(launch_sumfact(op.nm, op.nq, op.collocated, op.qop | (op.d_cellG ? QOP_AFFINE : 0), true, nullptr, nullptr, a, nullptr, &li, true));
     if (elems_per_block) *elems_per_block = li.elems_per_block;

@@ -23,6 +23,7 @@ struct Operator {
     uint32_t *d_constrained = nullptr;  // owned
     double *d_mats = nullptr;           // owned: shape_values | co_shape_gradients | shape_gradients (setup kernels)
     Halo *halo = nullptr;               // borrowed, optional
+    const int *d_skip = nullptr;        // set by the CG driver for the duration of a solve (see KArgs::skip)
     // overlap split: cells [0, n_phase0) and [n_phase0+n_phase1, n_cells) touch no ghost DoF
     uint32_t n_phase0 = 0, n_phase1 = 0;
     LaunchInfo last_launch{};

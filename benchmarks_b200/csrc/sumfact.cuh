@@ -51,6 +51,7 @@ struct KArgs {
     const uint32_t *idx;    // L-vector only: [e][NM^3], kInvalidIndex = constrained
     double *dot;            // L-vector only, optional: += sum_e u_e . (A_e u_e)
     const double *cellG;    // affine geometry only: [e][8] = det J * K K^T (rr,rs,rt,ss,st,tt), det J, pad
+    const int *skip;        // optional: when *skip != 0 the launch is a no-op (CG iterations replayed after convergence)
 };
 
 constexpr __host__ __device__ int odd(int n) { return n | 1; }

@@ -175,6 +175,7 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
     constexpr bool LAP = L::LAP, MASS = (QOP & QOP_MASS) != 0, AFFINE = L::AFFINE, STORED_G = LAP && !AFFINE;
     static_assert(!COLL || NM == NQ, "collocated operators need nm == nq");
 
+    if (a.skip != nullptr && *a.skip != 0) return;  // uniform across the grid: decided before any barrier
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
     double *Gs = reinterpret_cast<double *>(smem_raw + 16);      // [EPB][6][N3]
