@@ -232,7 +232,9 @@ static int cg_run(Operator &op, CgWork &w, double *d_x, const double *d_b, const
     // directly so that every kernel is configured before capture.
     static const bool graphs_on = [] { const char *e = std::getenv("B200FE_CG_GRAPH"); return !e || std::atoi(e) != 0; }();
     const int chunk = check_every < 32 ? check_every : 32;
-    const bool use_graph = graphs_on && !op.halo && !op.timing && chunk >= 2 && max_it >= 2 * chunk;
+    // (stream capture is not permitted on the legacy / per-thread default streams: callers on those keep plain launches)
+    const bool capturable = s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread;
+    const bool use_graph = graphs_on && capturable && !op.halo && !op.timing && chunk >= 2 && max_it >= 2 * chunk;
     cudaGraphExec_t exec = nullptr;
     unsigned long long launches_per_chunk = 0;
     int rc_loop = B200FE_OK;

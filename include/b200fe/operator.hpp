@@ -259,6 +259,9 @@ struct PreconditionIdentity {};
 class SolverCG {
   public:
     explicit SolverCG(ReductionControl &c, int check_every = 8) : control_(c), check_every_(check_every) {}
+    // Run the solve on this (blocking) stream instead of the default stream; a non-default stream lets the
+    // library replay CG iterations as a CUDA graph (small-problem latency).
+    void set_stream(cudaStream_t s) { stream_ = s; }
     template <class Operator>
     void solve(const Operator &A, Vector &x, const Vector &b, const PreconditionIdentity &) { run(A.handle(), x, b, nullptr); }
     template <class Operator>
@@ -269,12 +272,13 @@ class SolverCG {
     {
         const int max_it = control_.max_steps_ > 2000000000u ? 2000000000 : (int)control_.max_steps_;
         const int rc = b200fe_cg_solve(op, x.get_values(), b.get_values(), inv_diag, control_.tol_, control_.red_, max_it,
-                                       check_every_, &control_.res_, nullptr);
+                                       check_every_, &control_.res_, stream_);
         if (rc == B200FE_ERR_NO_CONVERGENCE) throw NoConvergence(rc, b200fe_last_error());
         check(rc);
     }
     ReductionControl &control_;
     int check_every_;
+    cudaStream_t stream_ = nullptr;
 };
 
 }  // namespace b200fe

@@ -313,3 +313,30 @@ def test_on_the_fly_affine_geometry_matches_stored_G_and_oracle(oracle_mod, p, d
         b.SolverCG(ctl).solve(A, x, rhs)
         its.append(ctl.last_step())
     assert abs(its[0] - its[1]) <= 1
+
+
+@pytest.mark.parametrize("p,quad,dq", [(4, "gauss", 2), (6, "gll", 1)])
+def test_cg_graph_replay_on_explicit_stream_equals_plain_launches(p, quad, dq):
+    """On a non-default stream the library replays chunks of CG iterations as a CUDA graph; iterations queued after
+    convergence are no-ops.  Same iteration count, same iterate as the plain-launch path (default stream)."""
+    import benchmarks_b200 as b
+    mesh = b.BoxMesh.bp3_cycle(9, p)
+    A = b.LaplaceOperator(mesh, nq=p + dq, quad=quad)
+    rhs = A.compute_rhs()
+    x0, x1 = A.initialize_dof_vector(), A.initialize_dof_vector()
+    c0, c1 = b.ReductionControl(10 ** 6, 1e-16, 1e-9), b.ReductionControl(10 ** 6, 1e-16, 1e-9)
+    b.SolverCG(c0).solve(A, x0, rhs)                       # default stream: plain launches
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        b.SolverCG(c1).solve(A, x1, rhs, stream=side)      # explicit stream: graph replay
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    assert c1.last_step() == c0.last_step()
+    assert (x1 - x0).abs().max().item() <= 1e-9 * x0.abs().max().item()
+    # capped solve (bp5_kokkos style): the tail that does not fill a chunk runs un-graphed, the count is exact
+    c2 = b.ReductionControl(37, 0.0, 0.0)
+    with torch.cuda.stream(side):
+        with pytest.raises(b.NoConvergence):
+            b.SolverCG(c2).solve(A, x1, rhs, stream=side)
+    assert c2.last_step() == 37
