@@ -67,3 +67,30 @@ def test_mesh_argument_errors():
         b.BoxMesh((1, 1, 1), 0, 2, n_ranks=2, rank=0)  # fewer cells than ranks
     with pytest.raises(b.B200feError):
         b.BoxMesh((1, 0, 1), 0, 2)
+
+
+@pytest.mark.parametrize("n_ranks,sub", [(2, (2, 1, 1)), (4, (2, 2, 1)), (8, (2, 2, 2))])
+def test_bench_partitions_are_consistent(n_ranks, sub):
+    """The weak-scaling layouts bench.py uses (one coarse cell of 64^3 per GPU; here 8^3): owned ranges tile the global
+    numbering, every ghost lies in its owner's range, every rank owns a cube, and the overlap split is sane."""
+    p, nref = 3, 3
+    meshes = [b.BoxMesh(sub, nref, p, n_ranks=n_ranks, rank=r) for r in range(n_ranks)]
+    n_global = meshes[0].n_dofs_global
+    assert sum(m.n_owned for m in meshes) == n_global
+    begins = [int(x) for x in meshes[0].rank_dof_begin]
+    assert begins[0] == 0 and begins[-1] == n_global
+    for r, m in enumerate(meshes):
+        assert m.n_cells == 8 ** nref and (m.owned_begin, m.owned_begin + m.n_owned) == (begins[r], begins[r + 1])
+        # one coarse cell per rank: the owned cells form a cube
+        lo, hi = m.cell_xyz.min(axis=0), m.cell_xyz.max(axis=0)
+        assert ((hi - lo + 1) == 8).all()
+        own = m.ghost_owner
+        assert (own != r).all()
+        gg = m.ghost_global.astype(np.int64)
+        assert ((gg >= np.array(begins)[own]) & (gg < np.array(begins)[own + 1])).all()
+        assert (np.diff(gg) > 0).all()
+        if n_ranks > 1:
+            perm, n0, n1 = b.overlap_permutation(m.dof_indices, m.n_owned)
+            assert n1 < m.n_cells and n0 + n1 <= m.n_cells
+            # lower ranks own the interfaces: rank 0 never ghosts anything
+            assert (r > 0) or m.n_ghost == 0
