@@ -176,6 +176,9 @@ def main():
     dev = torch.device("cuda", local_rank)
     setup_group = None
     if world > 1:
+        # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
         setup_group = dist.new_group(backend="gloo")
 
@@ -261,8 +264,10 @@ def main():
     peaks, peak_kind = measured_peaks()
     peak = float(peaks.get("hbm_gbs", 6650.0))
     alg_bytes = A.algorithmic_bytes()          # per launch over all local cells (single phase)
-    launches_per_apply = 3 if (world > 1 and args.overlap) else 1
-    k_avg_s = 1e-3 * k_ms / max(k_n, 1) * launches_per_apply   # per apply
+    # cell-kernel time per operator application on this rank (1 launch, or up to 3 with the overlap split)
+    n_applies = args.steps * its
+    launches_per_apply = k_n / max(n_applies, 1)
+    k_avg_s = 1e-3 * k_ms / max(n_applies, 1)
     achieved = 1e-9 * alg_bytes / k_avg_s if k_n else 0.0
     traffic = None
     try:
@@ -373,7 +378,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": f"sumfact2_kernel<{p+1},{p+1},collocated,laplace,lvec> (BP5 cell kernel: gather + D^T G D + atomic scatter + fused p.Ap)",
                          "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak if peak else None,
                          "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": 1e3 * k_avg_s,
-                         "launches_timed": k_n, "kernel_share_of_step": (1e-3 * k_ms) / t_dev if t_dev else None},
+                         "launches_timed": k_n, "launches_per_apply": launches_per_apply, "kernel_share_of_step": (1e-3 * k_ms) / t_dev if t_dev else None},
             "apply_only": apply_info,
             "clocks": clocks,
         }
