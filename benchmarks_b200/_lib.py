@@ -42,11 +42,18 @@ _SIGNATURES = {
     "b200fe_boxmesh_info": (_i, [_vp, _vp]),
     "b200fe_boxmesh_fill": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200fe_boxmesh_nodes": (_i, [_vp, _i, _i, C.c_double, C.c_double, _vp, _vp]),
+    "b200fe_hangmesh_create": (_i, [_vp, C.POINTER(_vp)]),
+    "b200fe_hangmesh_destroy": (None, [_vp]),
+    "b200fe_hangmesh_info": (_i, [_vp, _vp]),
+    "b200fe_hangmesh_fill": (_i, [_vp] * 11),
+    "b200fe_hangmesh_nodes": (_i, [_vp, _i, _i, C.c_double, C.c_double, _vp, _vp]),
     "b200fe_geometry_from_nodes": (_i, [_i, _i, _i, _u32, _vp, _vp, _vp, _vp]),
     "b200fe_geometry_affine_from_nodes": (_i, [_u32, _vp, _vp, _vp]),
     "b200fe_op_create": (_i, [_vp, C.POINTER(_vp)]),
     "b200fe_op_destroy": (None, [_vp]),
     "b200fe_op_set_halo": (_i, [_vp, _vp]),
+    "b200fe_op_set_constraints": (_i, [_vp, _u32, _vp, _vp, _vp, _vp]),
+    "b200fe_op_distribute": (_i, [_vp, _vp, _vp]),
     "b200fe_op_vmult": (_i, [_vp, _vp, _vp, _vp]),
     "b200fe_op_vmult_components": (_i, [_vp, _i, _vp, _vp, _vp]),
     "b200fe_op_vmult_dot": (_i, [_vp, _vp, _vp, _vp, _vp]),

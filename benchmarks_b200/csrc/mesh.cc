@@ -24,46 +24,12 @@
 #include <vector>
 
 #include "common.h"
+#include "mesh_common.h"
 
 namespace b200fe {
 
-namespace {
-
-// hierarchical entity order of a hex: 8 vertices, 12 lines, 6 quads, 1 interior.
-// code per axis: 0 = low plane, 1 = interior, 2 = high plane  (x, y, z)
-struct EntityTable {
-    int code[27][3];
-    int dim[27];  // number of interior axes
-    int id_of_code[3][3][3];
-    EntityTable()
-    {
-        int n = 0;
-        auto add = [&](int x, int y, int z) {
-            code[n][0] = x; code[n][1] = y; code[n][2] = z;
-            dim[n] = (x == 1) + (y == 1) + (z == 1);
-            id_of_code[x][y][z] = n++;
-        };
-        for (int v = 0; v < 8; ++v) add((v & 1) ? 2 : 0, (v & 2) ? 2 : 0, (v & 4) ? 2 : 0);
-        for (int z = 0; z <= 2; z += 2) {  // lines 0-3 (z low), 4-7 (z high)
-            add(0, 1, z); add(2, 1, z); add(1, 0, z); add(1, 2, z);
-        }
-        add(0, 0, 1); add(2, 0, 1); add(0, 2, 1); add(2, 2, 1);  // lines 8-11
-        add(0, 1, 1); add(2, 1, 1); add(1, 0, 1); add(1, 2, 1); add(1, 1, 0); add(1, 1, 2);  // quads
-        add(1, 1, 1);
-    }
-};
-const EntityTable kEnt;
-
-inline uint64_t morton3(uint32_t x, uint32_t y, uint32_t z, int nbits)
-{
-    uint64_t c = 0;
-    for (int b = 0; b < nbits; ++b)
-        c |= (uint64_t)((x >> b) & 1) << (3 * b) | (uint64_t)((y >> b) & 1) << (3 * b + 1) |
-             (uint64_t)((z >> b) & 1) << (3 * b + 2);
-    return c;
-}
-
-}  // namespace
+using meshdetail::kEnt;
+using meshdetail::morton3;
 
 struct BoxMesh {
     int sub[3], nref, p, nranks, rank, scheme, ghost_mode, dirichlet;
@@ -168,8 +134,8 @@ struct BoxMesh {
 
 int BoxMesh::build()
 {
-    const int nm = p + 1, m = p - 1, nm3 = nm * nm * nm;
-    for (int e = 0; e < 27; ++e) ent_size[e] = kEnt.dim[e] == 0 ? 1 : kEnt.dim[e] == 1 ? m : kEnt.dim[e] == 2 ? m * m : m * m * m;
+    const int nm = p + 1, nm3 = nm * nm * nm;
+    for (int e = 0; e < 27; ++e) ent_size[e] = meshdetail::entity_size(p, e);
     for (int d = 0; d < 3; ++d) {
         cells[d] = (int64_t)sub[d] << nref;
         h[d] = (p2[d] - p1[d]) / (double)cells[d];
@@ -178,28 +144,7 @@ int BoxMesh::build()
     n_dofs_global = (uint64_t)(cells[0] * p + 1) * (uint64_t)(cells[1] * p + 1) * (uint64_t)(cells[2] * p + 1);
     if (n_cells_global < nranks) return fail(B200FE_ERR_INVALID_ARG, "box mesh: fewer cells (%lld) than ranks (%d)", (long long)n_cells_global, nranks);
 
-    // lexicographic local dof -> entity and index in entity
-    l_ent.resize(nm3); l_idx.resize(nm3);
-    for (int c = 0; c < nm; ++c)
-        for (int b = 0; b < nm; ++b)
-            for (int a = 0; a < nm; ++a) {
-                const int t[3] = {a == 0 ? 0 : a == p ? 2 : 1, b == 0 ? 0 : b == p ? 2 : 1, c == 0 ? 0 : c == p ? 2 : 1};
-                const int e = kEnt.id_of_code[t[0]][t[1]][t[2]];
-                int idx = 0;
-                const int ia = a - 1, ib = b - 1, ic = c - 1;
-                switch (kEnt.dim[e]) {
-                    case 0: idx = 0; break;
-                    case 1: idx = t[0] == 1 ? ia : t[1] == 1 ? ib : ic; break;
-                    case 2:
-                        if (t[0] != 1) idx = ib + m * ic;        // x-face: (y fastest, z)
-                        else if (t[1] != 1) idx = ic + m * ia;   // y-face: (z fastest, x)
-                        else idx = ia + m * ib;                  // z-face: (x fastest, y)
-                        break;
-                    default: idx = ia + m * (ib + m * ic);
-                }
-                const int l = a + nm * (b + nm * c);
-                l_ent[l] = e; l_idx[l] = idx;
-            }
+    meshdetail::lexicographic_entities(p, l_ent, l_idx);  // lexicographic local dof -> entity and index in entity
 
     // pass 1 over ALL cells: which entities does each cell number, and how many DoFs
     newmask.assign(n_cells_global, 0);

@@ -30,7 +30,8 @@ struct GeoMats {          // geometry basis at the quadrature points, ng <= 9, n
 };
 
 // mapping support points of a (possibly smoothly deformed) box mesh: nodes[cell][d][c][b][a]
-__global__ void box_nodes_kernel(uint32_t n_cells, int ng, const int32_t *__restrict__ cell_xyz,
+// cell_xyz[cell][stride]: stride 3 = (x,y,z) on the uniform mesh; stride 4 = (level,x,y,z), a level-1 cell is half the size
+__global__ void box_nodes_kernel(uint32_t n_cells, int ng, const int32_t *__restrict__ cell_xyz, int stride,
                                  double p1x, double p1y, double p1z, double hx, double hy, double hz,
                                  const double *__restrict__ t /*[ng] GLL on [0,1]*/, int deform_kind,
                                  double amp, double freq, double *__restrict__ nodes)
@@ -40,9 +41,11 @@ __global__ void box_nodes_kernel(uint32_t n_cells, int ng, const int32_t *__rest
     if (i >= (uint64_t)n_cells * ng3) return;
     const uint32_t cell = (uint32_t)(i / ng3);
     const int n = (int)(i % ng3), a = n % ng, b = (n / ng) % ng, c = n / (ng * ng);
-    double x = p1x + (cell_xyz[cell * 3 + 0] + t[a]) * hx;
-    double y = p1y + (cell_xyz[cell * 3 + 1] + t[b]) * hy;
-    double z = p1z + (cell_xyz[cell * 3 + 2] + t[c]) * hz;
+    const int32_t *cx = cell_xyz + (size_t)cell * stride + (stride - 3);
+    const double sc = (stride == 4 && cell_xyz[(size_t)cell * 4] == 1) ? 0.5 : 1.0;
+    double x = p1x + (cx[0] + t[a]) * (hx * sc);
+    double y = p1y + (cx[1] + t[b]) * (hy * sc);
+    double z = p1z + (cx[2] + t[c]) * (hz * sc);
     if (deform_kind == 1) {  // smooth volume-preserving-ish perturbation, same family as bk3_dealii/check_bk3.cc:50-52
         const double dx = amp * sin(freq * y), dy = amp * sin(freq * z), dz = amp * sin(freq * x);
         x += dx; y += dy; z += dz;
@@ -231,6 +234,47 @@ __global__ void set_constrained_kernel(uint32_t n, const uint32_t *__restrict__ 
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v[list[i]] = value;
 }
 
+// hanging-node rows, one warp per row (rows hold 2 ... (p+1)^2 parents): v[h] = sum_k w[k] v[col[k]]
+__global__ void distribute_kernel(uint32_t n_rows, const uint32_t *__restrict__ hdof, const uint32_t *__restrict__ ptr,
+                                  const uint32_t *__restrict__ col, const double *__restrict__ w, double *__restrict__ v,
+                                  double *__restrict__ save, const int *__restrict__ skip)
+{
+    if (skip != nullptr && *skip != 0) return;
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_rows; r += warps) {
+        const uint32_t b = ptr[r], e = ptr[r + 1];
+        double s = 0.0;
+        for (uint32_t k = b + lane; k < e; k += 32) s = fma(w[k], v[col[k]], s);
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) {
+            const uint32_t h = hdof[r];
+            if (save) save[r] = v[h];
+            v[h] = s;  // a hanging DoF is never a parent (chain-free rows): no other warp reads v[h]
+        }
+    }
+}
+
+// transpose: dst[col[k]] += w[k] dst[h]; dst[h] = 0; optionally src[h] = save[r]
+__global__ void condense_kernel(uint32_t n_rows, const uint32_t *__restrict__ hdof, const uint32_t *__restrict__ ptr,
+                                const uint32_t *__restrict__ col, const double *__restrict__ w, double *__restrict__ dst,
+                                double *__restrict__ src, const double *__restrict__ save, const int *__restrict__ skip)
+{
+    if (skip != nullptr && *skip != 0) return;
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_rows; r += warps) {
+        const uint32_t h = hdof[r], b = ptr[r], e = ptr[r + 1];
+        const double t = dst[h];
+        for (uint32_t k = b + lane; k < e; k += 32) atomicAdd(dst + col[k], w[k] * t);
+        __syncwarp();
+        if (lane == 0) {
+            dst[h] = 0.0;
+            if (src) src[h] = save[r];
+        }
+    }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -267,12 +311,35 @@ int op_copy_constrained(Operator &op, double *d_dst, const double *d_src, double
     return B200FE_OK;
 }
 
+int op_distribute(Operator &op, double *d_v, bool save, cudaStream_t s)
+{
+    if (op.n_hang == 0) return B200FE_OK;
+    const unsigned blocks = std::min<unsigned>((op.n_hang + 7) / 8, 148u * 8u);  // 8 warps (rows) per CTA
+    distribute_kernel<<<blocks, 256, 0, s>>>(op.n_hang, op.d_hang_dof, op.d_hang_ptr, op.d_hang_col, op.d_hang_w, d_v,
+                                             save ? op.d_hang_save : nullptr, op.d_skip);
+    B200FE_CUDA_TRY(cudaGetLastError());
+    ++g_launch_count;
+    return B200FE_OK;
+}
+
+int op_condense(Operator &op, double *d_dst, double *d_src_restore, cudaStream_t s)
+{
+    if (op.n_hang == 0) return B200FE_OK;
+    const unsigned blocks = std::min<unsigned>((op.n_hang + 7) / 8, 148u * 8u);
+    condense_kernel<<<blocks, 256, 0, s>>>(op.n_hang, op.d_hang_dof, op.d_hang_ptr, op.d_hang_col, op.d_hang_w, d_dst,
+                                           d_src_restore, op.d_hang_save, op.d_skip);
+    B200FE_CUDA_TRY(cudaGetLastError());
+    ++g_launch_count;
+    return B200FE_OK;
+}
+
 int op_vmult(Operator &op, double *d_dst, const double *d_src, double *d_dot, bool ghost_on, bool compute_on,
              cudaStream_t s)
 {
     Halo *h = op.halo;
-    double *src_mut = const_cast<double *>(d_src);  // ghost entries of src are scratch, as in deal.II
-    const bool split = h && ghost_on && compute_on && (op.n_phase0 + op.n_phase1 > 0);
+    double *src_mut = const_cast<double *>(d_src);  // ghost (and hanging) entries of src are scratch, as in deal.II
+    // hanging-node rows need the parents' ghost values before the first cell runs: no overlap split with constraints
+    const bool split = h && ghost_on && compute_on && (op.n_phase0 + op.n_phase1 > 0) && op.n_hang == 0;
     if (compute_on) B200FE_CUDA_TRY(cudaMemsetAsync(d_dst, 0, sizeof(double) * op.n_local(), s));
     if (split) {
         // 3-phase overlap (bakeoff_problems_dealii/include/portable_laplace_operator.h:643-696)
@@ -288,8 +355,11 @@ int op_vmult(Operator &op, double *d_dst, const double *d_src, double *d_dot, bo
     }
     if (h && ghost_on)
         if (int rc = halo_update_ghosts(*h, src_mut, s)) return rc;
-    if (compute_on)
+    if (compute_on) {
+        if (int rc = op_distribute(op, src_mut, true, s)) return rc;
         if (int rc = op_apply_cells(op, d_dst, d_src, 0, op.n_cells, d_dot, s)) return rc;
+        if (int rc = op_condense(op, d_dst, src_mut, s)) return rc;
+    }
     if (h && ghost_on) {
         if (int rc = halo_compress_add(*h, d_dst, s)) return rc;
         if (int rc = halo_zero_ghosts(*h, src_mut, s)) return rc;
@@ -305,6 +375,33 @@ using namespace b200fe;
 
 extern "C" {
 
+// shared body of b200fe_boxmesh_nodes / b200fe_hangmesh_nodes: cell table [n_cells][stride] -> mapping support points
+static int nodes_from_cell_table(const std::vector<int32_t> &cells, int stride, uint32_t n_cells, const double p1[3],
+                                 const double hh[3], int p_geo, int deform_kind, double amplitude, double frequency,
+                                 double *d_nodes, cudaStream_t s)
+{
+    const int ng = p_geo + 1;
+    std::vector<double> t(ng), w(ng);
+    if (int rc = b200fe_basis_1d(p_geo, ng, B200FE_QUAD_GLL, nullptr, nullptr, nullptr, t.data(), w.data())) return rc;
+    int32_t *d_xyz = nullptr;
+    double *d_t = nullptr;
+    B200FE_CUDA_TRY(cudaMalloc(&d_xyz, cells.size() * sizeof(int32_t)));
+    cudaError_t e = cudaMalloc(&d_t, ng * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_xyz, cells.data(), cells.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_t, t.data(), ng * sizeof(double), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) {
+        const uint64_t total = (uint64_t)n_cells * ng * ng * ng;
+        box_nodes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(n_cells, ng, d_xyz, stride, p1[0], p1[1], p1[2], hh[0], hh[1],
+                                                                         hh[2], d_t, deform_kind, amplitude, frequency, d_nodes);
+        e = cudaGetLastError();
+    }
+    cudaStreamSynchronize(s);  // setup call: the temporaries are freed right away
+    cudaFree(d_xyz);
+    cudaFree(d_t);
+    if (e != cudaSuccess) return fail_cuda(e, "box_nodes_kernel");
+    return B200FE_OK;
+}
+
 int b200fe_boxmesh_nodes(const b200fe_boxmesh *mesh, int p_geo, int deform_kind, double amplitude,
                          double frequency, double *d_nodes, void *stream)
 {
@@ -314,30 +411,25 @@ int b200fe_boxmesh_nodes(const b200fe_boxmesh *mesh, int p_geo, int deform_kind,
     b200fe_boxmesh_info_t info;
     if (int rc = b200fe_boxmesh_info(mesh, &info)) return rc;
     if (info.n_cells_local == 0) return B200FE_OK;
-    const int ng = p_geo + 1;
     std::vector<int32_t> xyz((size_t)info.n_cells_local * 3);
     if (int rc = b200fe_boxmesh_fill(mesh, nullptr, nullptr, nullptr, nullptr, xyz.data(), nullptr)) return rc;
-    std::vector<double> t(ng), w(ng);
-    if (int rc = b200fe_basis_1d(p_geo, ng, B200FE_QUAD_GLL, nullptr, nullptr, nullptr, t.data(), w.data())) return rc;
-    cudaStream_t s = (cudaStream_t)stream;
-    int32_t *d_xyz = nullptr;
-    double *d_t = nullptr;
-    B200FE_CUDA_TRY(cudaMalloc(&d_xyz, xyz.size() * sizeof(int32_t)));
-    B200FE_CUDA_TRY(cudaMalloc(&d_t, ng * sizeof(double)));
-    B200FE_CUDA_TRY(cudaMemcpyAsync(d_xyz, xyz.data(), xyz.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-    B200FE_CUDA_TRY(cudaMemcpyAsync(d_t, t.data(), ng * sizeof(double), cudaMemcpyHostToDevice, s));
-    // box corner and cell size from the mesh description
-    double p1[3], hh[3];
-    for (int d = 0; d < 3; ++d) { hh[d] = info.h[d]; p1[d] = info.origin[d]; }
-    const uint64_t total = (uint64_t)info.n_cells_local * ng * ng * ng;
-    box_nodes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(info.n_cells_local, ng, d_xyz, p1[0], p1[1], p1[2], hh[0],
-                                                                     hh[1], hh[2], d_t, deform_kind, amplitude, frequency, d_nodes);
-    cudaError_t e = cudaGetLastError();
-    cudaStreamSynchronize(s);  // setup call: the temporaries are freed right away
-    cudaFree(d_xyz);
-    cudaFree(d_t);
-    if (e != cudaSuccess) return fail_cuda(e, "box_nodes_kernel");
-    return B200FE_OK;
+    return nodes_from_cell_table(xyz, 3, info.n_cells_local, info.origin, info.h, p_geo, deform_kind, amplitude, frequency, d_nodes,
+                                 (cudaStream_t)stream);
+}
+
+int b200fe_hangmesh_nodes(const b200fe_hangmesh *mesh, int p_geo, int deform_kind, double amplitude,
+                          double frequency, double *d_nodes, void *stream)
+{
+    B200FE_REQUIRE(mesh && d_nodes, "b200fe_hangmesh_nodes: null pointer");
+    B200FE_REQUIRE(p_geo >= 1 && p_geo <= 8, "b200fe_hangmesh_nodes: p_geo outside 1..8");
+    B200FE_REQUIRE(deform_kind == 0 || deform_kind == 1, "b200fe_hangmesh_nodes: unknown deformation");
+    b200fe_hangmesh_info_t info;
+    if (int rc = b200fe_hangmesh_info(mesh, &info)) return rc;
+    if (info.n_cells_local == 0) return B200FE_OK;
+    std::vector<int32_t> lxyz((size_t)info.n_cells_local * 4);
+    if (int rc = b200fe_hangmesh_fill(mesh, nullptr, nullptr, nullptr, nullptr, lxyz.data(), nullptr, nullptr, nullptr, nullptr, nullptr)) return rc;
+    return nodes_from_cell_table(lxyz, 4, info.n_cells_local, info.origin, info.h, p_geo, deform_kind, amplitude, frequency, d_nodes,
+                                 (cudaStream_t)stream);
 }
 
 int b200fe_geometry_from_nodes(int p_geo, int nq, int quad_kind, uint32_t n_cells, const double *d_nodes,
@@ -464,6 +556,53 @@ int b200fe_op_set_halo(b200fe_op *o, b200fe_halo *halo)
     return B200FE_OK;
 }
 
+int b200fe_op_set_constraints(b200fe_op *o, uint32_t n_rows, const uint32_t *h_hang_dof, const uint32_t *h_hang_row_ptr,
+                              const uint32_t *h_hang_col, const double *h_hang_w)
+{
+    B200FE_REQUIRE(o, "b200fe_op_set_constraints: null operator");
+    Operator &op = *reinterpret_cast<Operator *>(o);
+    op.free_constraints();
+    if (n_rows == 0) return B200FE_OK;
+    B200FE_REQUIRE(h_hang_dof && h_hang_row_ptr, "b200fe_op_set_constraints: null pointer");
+    const uint32_t nnz = h_hang_row_ptr[n_rows];
+    B200FE_REQUIRE(h_hang_row_ptr[0] == 0, "b200fe_op_set_constraints: row_ptr[0] must be 0");
+    B200FE_REQUIRE(nnz == 0 || (h_hang_col && h_hang_w), "b200fe_op_set_constraints: null pointer");
+    // rows must be chain-free (a hanging DoF is never a parent) and inside the local vector
+    std::vector<uint8_t> is_hanging(op.n_local(), 0);
+    for (uint32_t r = 0; r < n_rows; ++r) {
+        B200FE_REQUIRE(h_hang_dof[r] < op.n_local(), "b200fe_op_set_constraints: row %u constrains index %u outside the local vector", r, h_hang_dof[r]);
+        B200FE_REQUIRE(h_hang_row_ptr[r] <= h_hang_row_ptr[r + 1], "b200fe_op_set_constraints: row_ptr not monotone at row %u", r);
+        B200FE_REQUIRE(!is_hanging[h_hang_dof[r]], "b200fe_op_set_constraints: index %u constrained twice", h_hang_dof[r]);
+        is_hanging[h_hang_dof[r]] = 1;
+    }
+    for (uint32_t k = 0; k < nnz; ++k) {
+        B200FE_REQUIRE(h_hang_col[k] < op.n_local(), "b200fe_op_set_constraints: parent index %u outside the local vector", h_hang_col[k]);
+        B200FE_REQUIRE(!is_hanging[h_hang_col[k]], "b200fe_op_set_constraints: constraint chain through index %u", h_hang_col[k]);
+    }
+    auto upload = [](auto **dst, const auto *src, size_t n) -> cudaError_t {
+        cudaError_t e = cudaMalloc(dst, std::max<size_t>(n, 1) * sizeof(**dst));
+        if (e == cudaSuccess && n) e = cudaMemcpy(*dst, src, n * sizeof(**dst), cudaMemcpyHostToDevice);
+        return e;
+    };
+    cudaError_t e = upload(&op.d_hang_dof, h_hang_dof, n_rows);
+    if (e == cudaSuccess) e = upload(&op.d_hang_ptr, h_hang_row_ptr, (size_t)n_rows + 1);
+    if (e == cudaSuccess) e = upload(&op.d_hang_col, h_hang_col, nnz);
+    if (e == cudaSuccess) e = upload(&op.d_hang_w, h_hang_w, nnz);
+    if (e == cudaSuccess) e = cudaMalloc(&op.d_hang_save, n_rows * sizeof(double));
+    if (e != cudaSuccess) {
+        op.free_constraints();
+        return fail_cuda(e, "b200fe_op_set_constraints");
+    }
+    op.n_hang = n_rows;
+    return B200FE_OK;
+}
+
+int b200fe_op_distribute(b200fe_op *o, double *d_x, void *stream)
+{
+    B200FE_REQUIRE(o && d_x, "b200fe_op_distribute: null pointer");
+    return op_distribute(*reinterpret_cast<Operator *>(o), d_x, false, (cudaStream_t)stream);
+}
+
 int b200fe_op_vmult(b200fe_op *o, double *d_dst, const double *d_src, void *stream)
 {
     B200FE_REQUIRE(o && d_dst && d_src, "b200fe_op_vmult: null pointer");
@@ -507,6 +646,7 @@ int b200fe_op_diagonal(b200fe_op *o, double *d_diag, void *stream)
     B200FE_REQUIRE(o && d_diag, "b200fe_op_diagonal: null pointer");
     Operator &op = *reinterpret_cast<Operator *>(o);
     B200FE_REQUIRE(!(op.qop & QOP_LAPLACE) || op.d_G, "b200fe_op_diagonal: needs the stored geometric factors (d_G)");
+    if (op.n_hang) return fail(B200FE_ERR_UNSUPPORTED, "b200fe_op_diagonal: not built for operators with hanging-node constraints");
     cudaStream_t s = (cudaStream_t)stream;
     B200FE_CUDA_TRY(cudaMemsetAsync(d_diag, 0, sizeof(double) * op.n_local(), s));
     if (op.n_cells) {
@@ -533,6 +673,7 @@ int b200fe_op_rhs_one(b200fe_op *o, double *d_b, void *stream)
         rhs_one_kernel<<<std::min<uint32_t>(op.n_cells, 148u * 8u), 128, 0, s>>>(op.n_cells, op.nm, op.nq, op.d_mats, op.d_JxW, op.d_idx, d_b);
         B200FE_CUDA_TRY(cudaGetLastError());
     }
+    if (int rc = op_condense(op, d_b, nullptr, s)) return rc;  // b = C^T b_hat, hanging rows 0
     if (op.halo)
         if (int rc = halo_compress_add(*op.halo, d_b, s)) return rc;
     return B200FE_OK;

@@ -23,6 +23,10 @@ struct Operator {
     uint32_t *d_constrained = nullptr;  // owned
     double *d_mats = nullptr;           // owned: shape_values | co_shape_gradients | shape_gradients (setup kernels)
     Halo *halo = nullptr;               // borrowed, optional
+    // hanging-node rows (b200fe_op_set_constraints), owned copies: u[hang_dof[r]] = sum_k w[k] u[col[k]]
+    uint32_t n_hang = 0;
+    uint32_t *d_hang_dof = nullptr, *d_hang_ptr = nullptr, *d_hang_col = nullptr;
+    double *d_hang_w = nullptr, *d_hang_save = nullptr;  // save: src values of the hanging entries during a vmult
     const int *d_skip = nullptr;        // set by the CG driver for the duration of a solve (see KArgs::skip)
     // overlap split: cells [0, n_phase0) and [n_phase0+n_phase1, n_cells) touch no ghost DoF
     uint32_t n_phase0 = 0, n_phase1 = 0;
@@ -41,6 +45,14 @@ struct Operator {
         for (cudaEvent_t e : ev) cudaEventDestroy(e);
         cudaFree(d_constrained);
         cudaFree(d_mats);
+        free_constraints();
+    }
+    void free_constraints()
+    {
+        cudaFree(d_hang_dof); cudaFree(d_hang_ptr); cudaFree(d_hang_col); cudaFree(d_hang_w); cudaFree(d_hang_save);
+        d_hang_dof = d_hang_ptr = d_hang_col = nullptr;
+        d_hang_w = d_hang_save = nullptr;
+        n_hang = 0;
     }
 };
 
@@ -49,6 +61,10 @@ int op_apply_cells(Operator &op, double *d_dst, const double *d_src, uint32_t ce
                    double *d_dot, cudaStream_t s);
 // dst[c] = src[c] on owned constrained DoFs; optional dot += sum src[c]^2
 int op_copy_constrained(Operator &op, double *d_dst, const double *d_src, double *d_dot, cudaStream_t s);
+// hanging-node rows: src[h] = sum w src[parents] (old values saved when `save`), and its transpose on dst
+// (dst[parents] += w dst[h]; dst[h] = 0; src[h] restored when `restore`)
+int op_distribute(Operator &op, double *d_v, bool save, cudaStream_t s);
+int op_condense(Operator &op, double *d_dst, double *d_src_restore, cudaStream_t s);
 // full local vmult: zero, cells, constrained rows (+ halo exchange when attached)
 int op_vmult(Operator &op, double *d_dst, const double *d_src, double *d_dot, bool ghost_on, bool compute_on,
              cudaStream_t s);

@@ -84,8 +84,82 @@ class BoxMesh:
     def n_local(self):
         return self.n_owned + self.n_ghost
 
+    def fill_nodes(self, p_geo, deform_kind, amplitude, frequency, d_nodes_ptr, stream_ptr):
+        """Mapping support points of the owned cells into a device array [cell][3][(p_geo+1)^3]."""
+        check(lib.b200fe_boxmesh_nodes(self._h, p_geo, deform_kind, amplitude, frequency, d_nodes_ptr, stream_ptr))
+
     def __del__(self):
         h = getattr(self, "_h", None)
         if h:
             lib.b200fe_boxmesh_destroy(h)
+            self._h = None
+
+
+class _HangDesc(C.Structure):
+    _fields_ = [("box", _Desc), ("refine_lo", C.c_int * 3), ("refine_hi", C.c_int * 3)]
+
+
+class _HangInfo(C.Structure):
+    _fields_ = [("n_cells_global", C.c_uint64), ("n_dofs_global", C.c_uint64), ("first_cell", C.c_uint64),
+                ("owned_begin", C.c_uint64), ("n_cells_local", C.c_uint32), ("n_owned", C.c_uint32),
+                ("n_ghost", C.c_uint32), ("n_constrained", C.c_uint32), ("n_hanging_rows", C.c_uint32),
+                ("n_hanging_entries", C.c_uint32), ("cells", C.c_uint32 * 3), ("h", C.c_double * 3), ("origin", C.c_double * 3)]
+
+
+class HangingBoxMesh:
+    """BoxMesh whose cells [refine_lo, refine_hi) are refined once more: two-level mesh with hanging nodes
+    (BASELINE config C5).  Same attributes as BoxMesh plus the hanging-node rows (CSR, local indices):
+    hang_dof, hang_row_ptr, hang_col, hang_w; `constrained` lists Dirichlet and hanging DoFs; cell_lxyz holds
+    (level, x, y, z) per owned cell."""
+
+    def __init__(self, subdivisions, n_refine, p, refine_lo, refine_hi, *, p1=(-1.0, -1.0, -1.0), p2=None, n_ranks=1,
+                 rank=0, dirichlet=True):
+        if p2 is None:
+            p2 = [a + 1.9 * s for a, s in zip(p1, subdivisions)]
+        d = _HangDesc()
+        d.box.subdivisions[:] = list(subdivisions)
+        d.box.n_refine = n_refine
+        d.box.p1[:] = list(p1)
+        d.box.p2[:] = list(p2)
+        d.box.p, d.box.n_ranks, d.box.rank = p, n_ranks, rank
+        d.box.partition, d.box.ghosts, d.box.dirichlet = PARTITION_P4EST, GHOSTS_MINIMAL, int(dirichlet)
+        d.refine_lo[:] = list(refine_lo)
+        d.refine_hi[:] = list(refine_hi)
+        self._h = C.c_void_p()
+        check(lib.b200fe_hangmesh_create(C.byref(d), C.byref(self._h)))
+        info = _HangInfo()
+        check(lib.b200fe_hangmesh_info(self._h, C.byref(info)))
+        self.p, self.n_ranks, self.rank = p, n_ranks, rank
+        self.p1, self.p2 = np.array(p1, float), np.array(p2, float)
+        self.n_cells_global, self.n_dofs_global = info.n_cells_global, info.n_dofs_global
+        self.first_cell, self.owned_begin = info.first_cell, info.owned_begin
+        self.n_cells, self.n_owned, self.n_ghost = info.n_cells_local, info.n_owned, info.n_ghost
+        self.cells, self.h = tuple(info.cells), np.array(list(info.h))
+        nm3 = (p + 1) ** 3
+        self.dof_indices = np.empty((self.n_cells, nm3), dtype=np.uint32)
+        self.constrained = np.empty(info.n_constrained, dtype=np.uint32)
+        self.ghost_global = np.empty(self.n_ghost, dtype=np.uint64)
+        self.ghost_owner = np.empty(self.n_ghost, dtype=np.int32)
+        self.cell_lxyz = np.empty((self.n_cells, 4), dtype=np.int32)
+        self.rank_dof_begin = np.empty(n_ranks + 1, dtype=np.uint64)
+        self.hang_dof = np.empty(info.n_hanging_rows, dtype=np.uint32)
+        self.hang_row_ptr = np.empty(info.n_hanging_rows + 1, dtype=np.uint32)
+        self.hang_col = np.empty(info.n_hanging_entries, dtype=np.uint32)
+        self.hang_w = np.empty(info.n_hanging_entries, dtype=np.float64)
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+        check(lib.b200fe_hangmesh_fill(self._h, ptr(self.dof_indices), ptr(self.constrained), ptr(self.ghost_global),
+                                       ptr(self.ghost_owner), ptr(self.cell_lxyz), ptr(self.rank_dof_begin), ptr(self.hang_dof),
+                                       ptr(self.hang_row_ptr), ptr(self.hang_col), ptr(self.hang_w)))
+
+    @property
+    def n_local(self):
+        return self.n_owned + self.n_ghost
+
+    def fill_nodes(self, p_geo, deform_kind, amplitude, frequency, d_nodes_ptr, stream_ptr):
+        check(lib.b200fe_hangmesh_nodes(self._h, p_geo, deform_kind, amplitude, frequency, d_nodes_ptr, stream_ptr))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            lib.b200fe_hangmesh_destroy(h)
             self._h = None

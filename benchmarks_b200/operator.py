@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from ._lib import B200feError, check, lib
-from .mesh import QUAD_GAUSS, QUAD_GLL, BoxMesh, basis_1d
+from .mesh import QUAD_GAUSS, QUAD_GLL, BoxMesh, basis_1d  # noqa: F401
 
 OP_LAPLACE, OP_MASS, OP_HELMHOLTZ = 1, 2, 3
 INVALID = 0xFFFFFFFF
@@ -79,7 +79,7 @@ class LaplaceOperator:
         idx = mesh.dof_indices
         self.perm = None
         n_phase0 = n_phase1 = 0
-        if overlap and mesh.n_ranks > 1:
+        if overlap and mesh.n_ranks > 1 and not len(getattr(mesh, "hang_dof", ())):  # no split with hanging rows
             self.perm, n_phase0, n_phase1 = overlap_permutation(idx, mesh.n_owned)
             idx = idx[self.perm]
         self.dof_indices = torch.from_numpy(np.ascontiguousarray(idx)).to(self.device)
@@ -87,7 +87,7 @@ class LaplaceOperator:
         ng3 = (p_geo + 1) ** 3
         nodes = torch.empty(mesh.n_cells * 3 * ng3, dtype=torch.float64, device=self.device)
         kind_d, amp, freq = (0, 0.0, 0.0) if deform is None else (1, float(deform[0]), float(deform[1]))
-        check(lib.b200fe_boxmesh_nodes(mesh._h, p_geo, kind_d, amp, freq, _dp(nodes), _sp()))
+        mesh.fill_nodes(p_geo, kind_d, amp, freq, _dp(nodes), _sp())
         if self.perm is not None:
             nodes = nodes.view(mesh.n_cells, 3 * ng3)[torch.from_numpy(self.perm).to(self.device)].contiguous().view(-1)
         nq3 = self.nq ** 3
@@ -130,6 +130,11 @@ class LaplaceOperator:
         self.halo = halo
         if halo is not None:
             check(lib.b200fe_op_set_halo(self._h, halo._h))
+        n_rows = len(getattr(mesh, "hang_dof", ()))
+        if n_rows:  # hanging-node rows of a HangingBoxMesh: the operator becomes C^T A C
+            ptr = lambda a: a.ctypes.data if a.size else None
+            check(lib.b200fe_op_set_constraints(self._h, n_rows, ptr(mesh.hang_dof), ptr(mesh.hang_row_ptr), ptr(mesh.hang_col),
+                                                ptr(mesh.hang_w)))
         self._inv_diag = None
 
     # --- the reference operator's interface ------------------------------------------------
@@ -180,6 +185,10 @@ class LaplaceOperator:
         b = self.initialize_dof_vector()
         check(lib.b200fe_op_rhs_one(self._h, _dp(b), _sp()))
         return b
+
+    def distribute(self, x: torch.Tensor, stream=None) -> None:
+        """AffineConstraints::distribute: hanging entries of x from their parents (after a solve)."""
+        check(lib.b200fe_op_distribute(self._h, _dp(x), _sp(stream)))
 
     def timing_enable(self, max_launches: int) -> None:
         check(lib.b200fe_op_timing_enable(self._h, max_launches))

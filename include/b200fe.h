@@ -155,6 +155,51 @@ int b200fe_boxmesh_nodes(const b200fe_boxmesh *mesh, int p_geo, int deform_kind,
                          double frequency, double *d_nodes, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * 3b. Box mesh with ONE extra level of local refinement (hanging nodes; BASELINE config C5).
+ *    The reference has no such mesh; a deal.II driver would get these objects from
+ *    Triangulation::execute_coarsening_and_refinement + DoFHandler::distribute_dofs +
+ *    DoFTools::make_hanging_node_constraints + AffineConstraints.  Conventions: csrc/hangmesh.cc (H1-H5).
+ *    The cells [refine_lo, refine_hi) of the box mesh (coordinates after refine_global) are refined once.
+ *    Only B200FE_PARTITION_P4EST and B200FE_GHOSTS_MINIMAL are built.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    b200fe_boxmesh_desc box;
+    int refine_lo[3], refine_hi[3];
+} b200fe_hangmesh_desc;
+
+typedef struct {
+    uint64_t n_cells_global, n_dofs_global;
+    uint64_t first_cell;  /* position of the first owned cell on the p4est curve */
+    uint64_t owned_begin;
+    uint32_t n_cells_local, n_owned, n_ghost, n_constrained;
+    uint32_t n_hanging_rows, n_hanging_entries;
+    uint32_t cells[3]; /* of the unrefined box mesh */
+    double h[3];       /* cell size of the unrefined box mesh */
+    double origin[3];
+} b200fe_hangmesh_info_t;
+
+typedef struct b200fe_hangmesh b200fe_hangmesh;
+
+int b200fe_hangmesh_create(const b200fe_hangmesh_desc *desc, b200fe_hangmesh **out);
+void b200fe_hangmesh_destroy(b200fe_hangmesh *mesh);
+int b200fe_hangmesh_info(const b200fe_hangmesh *mesh, b200fe_hangmesh_info_t *info);
+/* Copies out (any pointer may be NULL); the first six arrays as in b200fe_boxmesh_fill except
+ *   h_dof_indices   hanging DoFs are ordinary entries (their values come from b200fe_op_set_constraints)
+ *   h_constrained   owned Dirichlet AND owned hanging DoFs (rows that act as identity)
+ *   h_cell_lxyz     [n_cells_local][4]  level (0 = unrefined, 1 = child), x, y, z at the cell's own level
+ * and the hanging-node rows this rank needs (every hanging DoF of its cells, owned or ghost), CSR with
+ * partitioner-local indices, Dirichlet parents dropped:
+ *   h_hang_dof[n_hanging_rows], h_hang_row_ptr[n_hanging_rows+1], h_hang_col / h_hang_w[n_hanging_entries]:
+ *   u[hang_dof[r]] = sum_k hang_w[k] * u[hang_col[k]],  k in [row_ptr[r], row_ptr[r+1]) */
+int b200fe_hangmesh_fill(const b200fe_hangmesh *mesh, uint32_t *h_dof_indices, uint32_t *h_constrained,
+                         uint64_t *h_ghost_global, int32_t *h_ghost_owner, int32_t *h_cell_lxyz,
+                         uint64_t *h_rank_dof_begin, uint32_t *h_hang_dof, uint32_t *h_hang_row_ptr,
+                         uint32_t *h_hang_col, double *h_hang_w);
+/* As b200fe_boxmesh_nodes, for the cells of this mesh (children are half the size). */
+int b200fe_hangmesh_nodes(const b200fe_hangmesh *mesh, int p_geo, int deform_kind, double amplitude,
+                          double frequency, double *d_nodes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * 4. Geometry and the L-vector operator (drop-in for Portable::LaplaceOperator,
  *    CEED_bp/include/portable_laplace_operator.h:17-96, and for bp5_kokkos' HelmholtzOperator,
  *    bp5_kokkos/benchmark.cc:141-292).
@@ -210,6 +255,19 @@ int b200fe_op_create(const b200fe_op_desc *desc, b200fe_op **out);
 void b200fe_op_destroy(b200fe_op *op);
 /* Attach the ghost exchange (NULL detaches).  Borrowed. */
 int b200fe_op_set_halo(b200fe_op *op, b200fe_halo *halo);
+
+/* Hanging-node constraints (AffineConstraints with homogeneous, chain-free rows; b200fe_hangmesh_fill):
+ * the operator becomes C^T A C with identity on the constrained rows.  Inside every vmult-type call, after
+ * the ghost update, u[hang_dof[r]] = sum_k w[k] u[col[k]] is written into src (the hanging entries of src
+ * are scratch for the duration of the call and restored afterwards, like its ghost entries); after the cell
+ * kernel, dst[col[k]] += w[k] dst[hang_dof[r]] and dst[hang_dof[r]] = 0 before compress(add).  Hanging DoFs
+ * must also be listed in h_constrained of the descriptor.  The lists are copied.  n_rows = 0 detaches.
+ * The overlap split (n_phase0/n_phase1) is ignored while constraints are attached. */
+int b200fe_op_set_constraints(b200fe_op *op, uint32_t n_rows, const uint32_t *h_hang_dof,
+                              const uint32_t *h_hang_row_ptr, const uint32_t *h_hang_col, const double *h_hang_w);
+/* AffineConstraints::distribute on a local vector: fills the hanging entries of d_x from their parents
+ * (call after the solve; ghost entries of d_x must be up to date when parents are ghosts). */
+int b200fe_op_distribute(b200fe_op *op, double *d_x, void *stream);
 
 /* LaplaceOperator::vmult (portable_laplace_operator.h:124-172): dst = 0; update ghosts of src;
  * cell kernel (gather / sum factorisation / atomic scatter); compress(add); zero ghosts of src;

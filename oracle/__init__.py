@@ -7,6 +7,7 @@ import this package.  The product (benchmarks_b200/) never does.
   oracle.ref    ctypes view of oracle/_ref/*.so (the reference's own serial kernels compiled in
                 place from /root/reference by oracle/Makefile); None when not built
   oracle.fe     numpy restatement of bases / mesh / numbering / operator / CG (fe_oracle.py)
+  oracle.hanging  two-level mesh with hanging-node constraints (hanging_oracle.py)
 """
 from __future__ import annotations
 
@@ -17,6 +18,7 @@ import subprocess
 import numpy as np
 
 from . import fe_oracle as fe  # noqa: F401
+from . import hanging_oracle as hanging  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")

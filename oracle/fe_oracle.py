@@ -411,7 +411,8 @@ def geometric_factors(nodes, p_geo: int, bas):
     G = np.empty((nc, 6) + det.shape[1:])
     for ci, (a, b) in enumerate(comps):
         G[:, ci] = JxW * KKt[..., perm[a], perm[b]]
-    return G.reshape(nc, 6, -1), JxW.reshape(nc, -1)
+    nq3 = len(xq) ** 3
+    return G.reshape(nc, 6, nq3), JxW.reshape(nc, nq3)
 
 
 # --------------------------------------------------------------------------
