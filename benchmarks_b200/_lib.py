@@ -66,6 +66,7 @@ _SIGNATURES = {
     "b200fe_op_timing_read": (_i, [_vp, _pd, _pi]),
     "b200fe_launch_count": (C.c_ulonglong, []),
     "b200fe_cg_solve": (_i, [_vp, _vp, _vp, _vp, C.c_double, C.c_double, _i, _i, _vp, _vp]),
+    "b200fe_cg_solve_components": (_i, [_vp, _i, _vp, _vp, _vp, C.c_double, C.c_double, _i, _i, _vp, _vp]),
     "b200fe_cg_solve_host": (_i, [_vp, _vp, _vp, _vp, C.c_double, C.c_double, _i, _i, _vp, _vp]),
     "b200fe_comm_available": (_i, []),
     "b200fe_comm_unique_id": (_i, [_vp]),

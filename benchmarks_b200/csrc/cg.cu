@@ -35,9 +35,12 @@ struct CgScalars {      // device-resident
     int done, converged, its;
 };
 
-__global__ void cg_init_kernel(uint32_t n, const double *__restrict__ b, double *__restrict__ x, double *__restrict__ r,
+// Vector-valued problems (BP2/BP4/BP6): component-blocked vectors [component][stride]; blockIdx.y = component,
+// the (scalar-operator) inverse diagonal is shared by the components.
+__global__ void cg_init_kernel(uint32_t n, size_t stride, const double *__restrict__ b, double *__restrict__ x, double *__restrict__ r,
                                const double *__restrict__ inv_diag, CgScalars *sc)
 {
+    b += blockIdx.y * stride; x += blockIdx.y * stride; r += blockIdx.y * stride;
     double rr = 0.0, rz = 0.0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const double bi = b[i];
@@ -81,10 +84,11 @@ __global__ void cg_scalar_kernel(CgScalars *sc, int jacobi, int max_it, double a
     sc->it += 1;
 }
 
-__global__ void cg_update_p_kernel(uint32_t n, const double *__restrict__ r, const double *__restrict__ inv_diag,
+__global__ void cg_update_p_kernel(uint32_t n, size_t stride, const double *__restrict__ r, const double *__restrict__ inv_diag,
                                    double *__restrict__ p, const CgScalars *sc)
 {
     if (sc->done) return;
+    r += blockIdx.y * stride; p += blockIdx.y * stride;
     const bool first = sc->it == 1;
     const double beta = first ? 0.0 : sc->rho / sc->rho_old;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -93,11 +97,12 @@ __global__ void cg_update_p_kernel(uint32_t n, const double *__restrict__ r, con
     }
 }
 
-__global__ void cg_update_xr_kernel(uint32_t n, const double *__restrict__ p, const double *__restrict__ v,
+__global__ void cg_update_xr_kernel(uint32_t n, size_t stride, const double *__restrict__ p, const double *__restrict__ v,
                                     const double *__restrict__ inv_diag, double *__restrict__ x, double *__restrict__ r,
                                     CgScalars *sc)
 {
     if (sc->done) return;
+    p += blockIdx.y * stride; v += blockIdx.y * stride; x += blockIdx.y * stride; r += blockIdx.y * stride;
     const double alpha = sc->rho / sc->acc[0];
     double rr = 0.0, rz = 0.0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -132,7 +137,7 @@ __global__ void cg_update_xr_kernel(uint32_t n, const double *__restrict__ p, co
 }  // namespace
 
 struct CgWork {
-    uint32_t n_local = 0;
+    size_t n_local = 0;  // total length: components * (n_owned + n_ghost)
     double *r = nullptr, *p = nullptr, *v = nullptr, *xb = nullptr;  // xb: x and b for the host-buffer entry point
     CgScalars *sc = nullptr;
     CgScalars *h_sc = nullptr;  // pinned
@@ -143,19 +148,19 @@ struct CgWork {
     }
 };
 
-static int ensure_work(std::unique_ptr<CgWork> &w, uint32_t n_local, bool need_xb)
+static int ensure_work(std::unique_ptr<CgWork> &w, size_t n_local, bool need_xb)
 {
     if (!w || w->n_local != n_local) {
         w = std::make_unique<CgWork>();
         w->n_local = n_local;
-        const size_t bytes = sizeof(double) * std::max<uint32_t>(n_local, 1);
+        const size_t bytes = sizeof(double) * std::max<size_t>(n_local, 1);
         B200FE_CUDA_TRY(cudaMalloc(&w->r, bytes));
         B200FE_CUDA_TRY(cudaMalloc(&w->p, bytes));
         B200FE_CUDA_TRY(cudaMalloc(&w->v, bytes));
         B200FE_CUDA_TRY(cudaMalloc(&w->sc, sizeof(CgScalars)));
         B200FE_CUDA_TRY(cudaMallocHost(&w->h_sc, sizeof(CgScalars)));
     }
-    if (need_xb && !w->xb) B200FE_CUDA_TRY(cudaMalloc(&w->xb, 2 * sizeof(double) * std::max<uint32_t>(n_local, 1)));
+    if (need_xb && !w->xb) B200FE_CUDA_TRY(cudaMalloc(&w->xb, 2 * sizeof(double) * std::max<size_t>(n_local, 1)));
     return B200FE_OK;
 }
 
@@ -175,17 +180,19 @@ void cg_release_work(Operator *op)
     w.reset();
 }
 
-static int cg_run(Operator &op, CgWork &w, double *d_x, const double *d_b, const double *d_inv_diag, double abs_tol,
+static int cg_run(Operator &op, int ncomp, CgWork &w, double *d_x, const double *d_b, const double *d_inv_diag, double abs_tol,
                   double rel_tol, int max_it, int check_every, b200fe_cg_result *res, cudaStream_t s)
 {
     const uint32_t n = op.n_owned;
-    const unsigned blocks = n == 0 ? 1u : std::min<unsigned>((n + 1023) / 1024, 148u * 8u);
+    const size_t stride = op.n_local();
+    const unsigned bx = n == 0 ? 1u : std::min<unsigned>((n + 1023) / 1024, std::max(148u * 8u / (unsigned)ncomp, 148u));
+    const dim3 blocks(bx, (unsigned)ncomp);
     const int jacobi = d_inv_diag != nullptr;
     if (check_every < 1) check_every = 1;
     B200FE_CUDA_TRY(cudaMemsetAsync(w.sc, 0, sizeof(CgScalars), s));
     // p and v carry ghost entries: start from a clean ghost segment
-    B200FE_CUDA_TRY(cudaMemsetAsync(w.p, 0, sizeof(double) * op.n_local(), s));
-    cg_init_kernel<<<blocks, 256, 0, s>>>(n, d_b, d_x, w.r, d_inv_diag, w.sc);
+    B200FE_CUDA_TRY(cudaMemsetAsync(w.p, 0, sizeof(double) * stride * ncomp, s));
+    cg_init_kernel<<<blocks, 256, 0, s>>>(n, stride, d_b, d_x, w.r, d_inv_diag, w.sc);
     B200FE_CUDA_TRY(cudaGetLastError());
     ++g_launch_count;
     if (op.halo)
@@ -205,13 +212,14 @@ static int cg_run(Operator &op, CgWork &w, double *d_x, const double *d_b, const
         return B200FE_OK;
     };
     auto iteration = [&]() -> int {
-        cg_update_p_kernel<<<blocks, 256, 0, s>>>(n, w.r, d_inv_diag, w.p, w.sc);
+        cg_update_p_kernel<<<blocks, 256, 0, s>>>(n, stride, w.r, d_inv_diag, w.p, w.sc);
         B200FE_CUDA_TRY(cudaGetLastError());
         ++g_launch_count;
-        if (int rc = op_vmult(op, w.v, w.p, &w.sc->acc[0], true, true, s)) return rc;
+        for (int c = 0; c < ncomp; ++c)  // block-diagonal operator: the fused p.Ap of every component lands in acc[0]
+            if (int rc = op_vmult(op, w.v + c * stride, w.p + c * stride, &w.sc->acc[0], true, true, s)) return rc;
         if (op.halo)
             if (int rc = halo_allreduce_sum(*op.halo, w.sc->acc, 1, s)) return rc;
-        cg_update_xr_kernel<<<blocks, 256, 0, s>>>(n, w.p, w.v, d_inv_diag, d_x, w.r, w.sc);
+        cg_update_xr_kernel<<<blocks, 256, 0, s>>>(n, stride, w.p, w.v, d_inv_diag, d_x, w.r, w.sc);
         B200FE_CUDA_TRY(cudaGetLastError());
         ++g_launch_count;
         if (op.halo)
@@ -283,17 +291,24 @@ using namespace b200fe;
 
 extern "C" {
 
-int b200fe_cg_solve(b200fe_op *o, double *d_x, const double *d_b, const double *d_inv_diag, double abs_tol,
-                    double rel_tol, int max_it, int check_every, b200fe_cg_result *result, void *stream)
+int b200fe_cg_solve_components(b200fe_op *o, int n_components, double *d_x, const double *d_b, const double *d_inv_diag,
+                               double abs_tol, double rel_tol, int max_it, int check_every, b200fe_cg_result *result, void *stream)
 {
     B200FE_REQUIRE(o && d_x && d_b, "b200fe_cg_solve: null pointer");
     B200FE_REQUIRE(max_it >= 0, "b200fe_cg_solve: max_it < 0");
+    B200FE_REQUIRE(n_components >= 1 && n_components <= 16, "b200fe_cg_solve: n_components outside 1..16");
     Operator &op = *reinterpret_cast<Operator *>(o);
     auto &w = work_of(&op);
-    if (int rc = ensure_work(w, op.n_local(), false)) return rc;
-    int rc = cg_run(op, *w, d_x, d_b, d_inv_diag, abs_tol, rel_tol, max_it, check_every, result, (cudaStream_t)stream);
+    if (int rc = ensure_work(w, (size_t)op.n_local() * n_components, false)) return rc;
+    int rc = cg_run(op, n_components, *w, d_x, d_b, d_inv_diag, abs_tol, rel_tol, max_it, check_every, result, (cudaStream_t)stream);
     if (rc == B200FE_ERR_NO_CONVERGENCE) fail(rc, "CG did not converge in %d iterations", max_it);
     return rc;
+}
+
+int b200fe_cg_solve(b200fe_op *o, double *d_x, const double *d_b, const double *d_inv_diag, double abs_tol,
+                    double rel_tol, int max_it, int check_every, b200fe_cg_result *result, void *stream)
+{
+    return b200fe_cg_solve_components(o, 1, d_x, d_b, d_inv_diag, abs_tol, rel_tol, max_it, check_every, result, stream);
 }
 
 int b200fe_cg_solve_host(b200fe_op *o, double *h_x, const double *h_b, const double *d_inv_diag, double abs_tol,
@@ -305,8 +320,9 @@ int b200fe_cg_solve_host(b200fe_op *o, double *h_x, const double *h_b, const dou
     if (int rc = ensure_work(w, op.n_local(), true)) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     double *d_x = w->xb, *d_b = w->xb + std::max<uint32_t>(op.n_local(), 1);
+    // (the ghost entries of x and b are never read: CG works on the owned range, the operator on p and v)
     B200FE_CUDA_TRY(cudaMemcpyAsync(d_b, h_b, sizeof(double) * op.n_owned, cudaMemcpyHostToDevice, s));
-    int rc = cg_run(op, *w, d_x, d_b, d_inv_diag, abs_tol, rel_tol, max_it, check_every, result, s);
+    int rc = cg_run(op, 1, *w, d_x, d_b, d_inv_diag, abs_tol, rel_tol, max_it, check_every, result, s);
     if (rc != B200FE_OK && rc != B200FE_ERR_NO_CONVERGENCE) return rc;
     B200FE_CUDA_TRY(cudaMemcpyAsync(h_x, d_x, sizeof(double) * op.n_owned, cudaMemcpyDeviceToHost, s));
     B200FE_CUDA_TRY(cudaStreamSynchronize(s));

@@ -248,10 +248,14 @@ class SolverCG:
         self.control = control
         self.check_every = check_every
 
-    def solve(self, A: LaplaceOperator, x: torch.Tensor, b: torch.Tensor, preconditioner=None, stream=None):
+    def solve(self, A: LaplaceOperator, x: torch.Tensor, b: torch.Tensor, preconditioner=None, stream=None,
+              n_components: int = 1):
+        """n_components > 1: vector-valued problem (BP2/BP4/BP6), x and b component-blocked
+        [component][n_owned + n_ghost]."""
         res = _CgResult()
-        rc = lib.b200fe_cg_solve(A._h, _dp(x), _dp(b), _dp(preconditioner), self.control.tolerance, self.control.reduction,
-                                 self.control.max_steps, self.check_every, C.byref(res), _sp(stream))
+        rc = lib.b200fe_cg_solve_components(A._h, n_components, _dp(x), _dp(b), _dp(preconditioner), self.control.tolerance,
+                                            self.control.reduction, self.control.max_steps, self.check_every, C.byref(res),
+                                            _sp(stream))
         self.control._res = res
         if rc == 5:
             raise NoConvergence(f"CG: {res.iterations} iterations, residual {res.final_residual:g}")

@@ -316,6 +316,12 @@ typedef struct {
 
 int b200fe_cg_solve(b200fe_op *op, double *d_x, const double *d_b, const double *d_inv_diag, double abs_tol,
                     double rel_tol, int max_it, int check_every, b200fe_cg_result *result, void *stream);
+/* Vector-valued problems (CEED BP2/BP4/BP6): one CG on the block-diagonal system of n_components copies of the
+ * scalar operator; x and b are component-blocked, [component][n_owned + n_ghost] (b200fe_op_vmult_components);
+ * d_inv_diag (n_owned entries, or NULL) is shared by the components. */
+int b200fe_cg_solve_components(b200fe_op *op, int n_components, double *d_x, const double *d_b, const double *d_inv_diag,
+                               double abs_tol, double rel_tol, int max_it, int check_every, b200fe_cg_result *result,
+                               void *stream);
 /* Same with HOST x and b (n_owned doubles): H2D of b, solve, D2H of x, synchronises. */
 int b200fe_cg_solve_host(b200fe_op *op, double *h_x, const double *h_b, const double *d_inv_diag, double abs_tol,
                          double rel_tol, int max_it, int check_every, b200fe_cg_result *result, void *stream);

@@ -1,0 +1,144 @@
+"""GPU parity of the constrained operator C^T A C on two-level meshes with hanging nodes (BASELINE config C5,
+north-star subsystem 1) and of the vector-valued CG (BP2/BP4/BP6), through the C ABI, against the CPU oracle
+(oracle/hanging_oracle.py; "parity unpinned": the reference holds no hanging-node or vector-valued code).
+
+Tolerances: one FP64 application <= 1e-12 relative max-norm; CG iteration counts within +-1 of the oracle's loop.
+(The file sorts last on purpose: these paths are the newest.)
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+DEFORM = (0.04, 2.0)
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def _setup(oracle_mod, p, sub, nref, lo, hi, nq, quad, kind, p_geo=2, deform=DEFORM):
+    import benchmarks_b200 as b
+    fe, ho = oracle_mod.fe, oracle_mod.hanging
+    om = ho.TwoLevelMesh(sub, nref, (lo, hi))
+    sp = ho.build_space(om, p, 1)
+    rd = ho.rank_data(om, sp, 0)
+    bas = fe.basis_1d(p, nq, quad)
+    dfm = None if deform is None else (lambda P: P + deform[0] * np.sin(deform[1] * P[..., [1, 2, 0]]))
+    G, JxW = fe.geometric_factors(ho.cell_nodes(om, rd["cells"], p_geo, dfm), p_geo, bas)
+    mesh = b.HangingBoxMesh(sub, nref, p, lo, hi)
+    A = b.LaplaceOperator(mesh, nq=nq, quad=quad, kind=kind, p_geo=p_geo, deform=deform)
+    return fe, ho, rd, bas, G, JxW, mesh, A
+
+
+VARIANTS = [("bp3", 2, "gauss", "laplace"), ("bp5", 1, "gll", "laplace"), ("bp1", 2, "gauss", "mass"), ("helmholtz", 1, "gauss", "helmholtz")]
+
+
+@pytest.mark.parametrize("p", [1, 2, 3, 4, 6, 8])
+@pytest.mark.parametrize("name,dq,quad,kind", VARIANTS)
+def test_constrained_vmult_matches_oracle(oracle_mod, p, name, dq, quad, kind):
+    sub, nref, lo, hi = ((2, 2, 1), 0, (0, 0, 0), (1, 2, 1)) if p >= 6 else ((1, 1, 1), 1, (1, 0, 1), (2, 1, 2))
+    fe, ho, rd, bas, G, JxW, mesh, A = _setup(oracle_mod, p, sub, nref, lo, hi, p + dq, quad, kind)
+    assert len(mesh.hang_dof) > 0
+    assert rel(A.JxW.cpu().numpy().reshape(JxW.shape), JxW) <= TOL  # children are half-size cells of the same map
+    rng = np.random.default_rng(100 + p)
+    src = rng.standard_normal(mesh.n_owned)  # arbitrary values on the hanging entries too: rows act as identity
+    ref = ho.op_apply(rd, bas, G, src, JxW, laplace=kind != "mass", mass=kind != "laplace")
+    d_src = torch.from_numpy(src).cuda()
+    dst = torch.full((mesh.n_owned,), 7.0, dtype=torch.float64, device="cuda")
+    A.vmult(dst, d_src)
+    assert rel(dst.cpu().numpy(), ref) <= TOL, name
+    assert torch.equal(d_src.cpu(), torch.from_numpy(src))  # the hanging entries of src were restored
+    dst2 = A.initialize_dof_vector()
+    dot = A.vmult_dot(dst2, d_src)
+    assert abs(dot.item() - float(src @ ref)) <= 1e-11 * np.abs(src).dot(np.abs(ref))
+    # distribute (AffineConstraints::distribute) and the right-hand side b = C^T int phi
+    x = d_src.clone()
+    A.distribute(x)
+    assert rel(x.cpu().numpy(), ho.distribute(rd, src)) <= TOL
+    assert rel(A.compute_rhs().cpu().numpy(), ho.rhs_one(rd, bas, JxW)) <= TOL
+
+
+@pytest.mark.parametrize("p,dq,quad", [(2, 2, "gauss"), (4, 1, "gll"), (7, 1, "gll")])
+def test_cg_on_hanging_mesh_matches_oracle_loop(oracle_mod, p, dq, quad):
+    """bp3 protocol (rhs = int phi, x0 = 0, ReductionControl(., 1e-16, 1e-9)) on the constrained operator; the solution is
+    compared after distributing the constraints."""
+    import benchmarks_b200 as b
+    sub, nref, lo, hi = ((2, 2, 1), 0, (1, 0, 0), (2, 1, 1)) if p >= 6 else ((1, 1, 1), 1, (0, 0, 0), (1, 1, 2))
+    fe, ho, rd, bas, G, JxW, mesh, A = _setup(oracle_mod, p, sub, nref, lo, hi, p + dq, quad, "laplace")
+    rhs_o = ho.rhs_one(rd, bas, JxW)
+    xo, its_o, r0_o, rn_o, ok_o = fe.solver_cg(lambda u: ho.op_apply(rd, bas, G, u, JxW), rhs_o, 5000, 1e-16, 1e-9)
+    rhs = A.compute_rhs()
+    x = A.initialize_dof_vector()
+    ctl = b.ReductionControl(5000, 1e-16, 1e-9)
+    b.SolverCG(ctl).solve(A, x, rhs)
+    assert ok_o and abs(ctl.last_step() - its_o) <= 1
+    assert ctl.initial_value() == pytest.approx(r0_o, rel=1e-12)
+    A.distribute(x)
+    assert rel(x.cpu().numpy(), ho.distribute(rd, xo)) <= 1e-6
+    # explicit stream: CUDA-graph replay of iteration chunks with the constraint kernels inside
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    x1 = A.initialize_dof_vector()
+    c1 = b.ReductionControl(5000, 1e-16, 1e-9)
+    with torch.cuda.stream(side):
+        b.SolverCG(c1).solve(A, x1, rhs, stream=side)
+    torch.cuda.synchronize()
+    assert abs(c1.last_step() - ctl.last_step()) <= 1
+
+
+@pytest.mark.parametrize("hanging", [False, True])
+def test_vector_valued_cg_bp6_style(oracle_mod, hanging):
+    """One CG on the 3-component block system (shared alpha / beta), component-blocked vectors: iteration count and
+    solution against the oracle's CG loop run on the stacked operator."""
+    import benchmarks_b200 as b
+    fe, ho = oracle_mod.fe, oracle_mod.hanging
+    p, nc = 3, 3
+    if hanging:
+        _, _, rd, bas, G, JxW, mesh, A = _setup(oracle_mod, p, (1, 1, 1), 1, (0, 0, 0), (1, 1, 1), p + 1, "gll", "laplace")
+        apply1 = lambda u: ho.op_apply(rd, bas, G, u, JxW)
+    else:
+        om = fe.BoxMesh((2, 1, 1), 1)
+        od = fe.distribute_dofs(om, p, 1)
+        rd = fe.rank_data(om, od, 0)
+        bas = fe.basis_1d(p, p + 1, "gll")
+        G, JxW = fe.geometric_factors(fe.cell_nodes(om, rd["cells"], 1), 1, bas)
+        mesh = b.BoxMesh((2, 1, 1), 1, p)
+        A = b.LaplaceOperator(mesh, quad="gll")
+        apply1 = lambda u: fe.op_apply(u, rd, bas, G)
+    n = mesh.n_owned
+    rng = np.random.default_rng(5)
+    rhs = rng.standard_normal((nc, n))
+    rhs[:, mesh.constrained] = 0.0
+    stacked = lambda u: np.concatenate([apply1(u[c * n:(c + 1) * n]) for c in range(nc)])
+    xo, its_o, r0_o, _, ok_o = fe.solver_cg(stacked, rhs.ravel().copy(), 5000, 1e-16, 1e-9)
+    x = torch.zeros(nc * n, dtype=torch.float64, device="cuda")
+    ctl = b.ReductionControl(5000, 1e-16, 1e-9)
+    b.SolverCG(ctl).solve(A, x, torch.from_numpy(rhs.ravel()).cuda(), n_components=nc)
+    assert ok_o and abs(ctl.last_step() - its_o) <= 1
+    assert ctl.initial_value() == pytest.approx(r0_o, rel=1e-12)
+    assert rel(x.cpu().numpy(), xo) <= 1e-6
+    # the component-blocked apply agrees with the per-component oracle on the same operator
+    y = torch.empty_like(x)
+    A.vmult_components(y, x, nc)
+    assert rel(y.cpu().numpy(), stacked(x.cpu().numpy())) <= TOL
+
+
+def test_constraint_rows_are_validated():
+    import benchmarks_b200 as b
+    from benchmarks_b200._lib import lib
+    mesh = b.BoxMesh((1, 1, 1), 1, 2)
+    A = b.LaplaceOperator(mesh)
+    u32 = lambda *v: np.array(v, dtype=np.uint32)
+    ptr = lambda a: a.ctypes.data
+    w = np.array([0.5, 0.5])
+    # chain: row 0 constrains DoF 5 to (6, 7), row 1 constrains 6
+    hd, rp, col, w4 = u32(5, 6), u32(0, 2, 4), u32(6, 7, 8, 9), np.array([0.5, 0.5, 0.5, 0.5])
+    assert lib.b200fe_op_set_constraints(A._h, 2, ptr(hd), ptr(rp), ptr(col), ptr(w4)) == 1
+    hd, rp, col = u32(5), u32(0, 2), u32(6, mesh.n_owned + 3)  # parent outside the local vector
+    assert lib.b200fe_op_set_constraints(A._h, 1, ptr(hd), ptr(rp), ptr(col), ptr(w)) == 1
+    with pytest.raises(b.B200feError):  # no diagonal with constraints attached
+        hd, rp, col = u32(13), u32(0, 2), u32(6, 7)
+        assert lib.b200fe_op_set_constraints(A._h, 1, ptr(hd), ptr(rp), ptr(col), ptr(w)) == 0
+        A.compute_diagonal()
