@@ -10,6 +10,7 @@
 //   b200fe::SolverCG          <-> dealii::SolverCG                (bp3.cc:269-278)
 //   b200fe::BoxMesh           <-> Triangulation + DoFHandler + AffineConstraints of the drivers
 //        (GridGenerator::subdivided_hyper_rectangle + refine_global + distribute_dofs, bp3.cc:452-488)
+//   b200fe::HangingBoxMesh    <-> the same after one local refinement (hanging-node constraints; config C5)
 // Needs the CUDA runtime only for device allocations (cudaMalloc / cudaMemcpy).
 #pragma once
 #include <cuda_runtime.h>
@@ -80,17 +81,19 @@ class DeviceArray {
     size_t n_ = 0;
 };
 
-// owned DoFs followed by ghosts, like LinearAlgebra::distributed::Vector
+// owned DoFs followed by ghosts, like LinearAlgebra::distributed::Vector; vector-valued problems (BP2/BP4/BP6)
+// store n_components such blocks one after the other (component-blocked)
 class Vector {
   public:
     Vector() = default;
-    void reinit(size_t n_owned, size_t n_ghost)
+    void reinit(size_t n_owned, size_t n_ghost, int n_components = 1)
     {
-        n_owned_ = n_owned; n_ghost_ = n_ghost;
-        d_.resize(n_owned + n_ghost);
+        n_owned_ = n_owned; n_ghost_ = n_ghost; n_comp_ = n_components;
+        d_.resize((n_owned + n_ghost) * n_components);
         *this = 0.0;
     }
-    void reinit(const Vector &o) { reinit(o.n_owned_, o.n_ghost_); }
+    void reinit(const Vector &o) { reinit(o.n_owned_, o.n_ghost_, o.n_comp_); }
+    int n_components() const { return n_comp_; }
     Vector &operator=(double v)
     {
         if (v != 0.0) throw Error(B200FE_ERR_INVALID_ARG, "Vector = s only implemented for s = 0");
@@ -101,11 +104,12 @@ class Vector {
     const double *get_values() const { return d_.data(); }
     size_t locally_owned_size() const { return n_owned_; }
     size_t size_with_ghosts() const { return n_owned_ + n_ghost_; }
-    std::vector<double> to_host() const
+    std::vector<double> to_host() const  // owned entries (of every component)
     {
         std::vector<double> h(d_.size());
         d_.download(h.data());
-        h.resize(n_owned_);
+        for (int c = 1; c < n_comp_; ++c) std::memmove(h.data() + c * n_owned_, h.data() + c * (n_owned_ + n_ghost_), n_owned_ * sizeof(double));
+        h.resize(n_owned_ * n_comp_);
         return h;
     }
     void from_host(const std::vector<double> &h)
@@ -115,15 +119,20 @@ class Vector {
     double l2_norm() const
     {
         DeviceArray<double> s(1);
-        check(b200fe_sum_squares(n_owned_, d_.data(), s.data(), nullptr));
-        double h = 0;
-        s.download(&h);
-        return std::sqrt(h);
+        double sum = 0;
+        for (int c = 0; c < n_comp_; ++c) {
+            check(b200fe_sum_squares(n_owned_, d_.data() + c * (n_owned_ + n_ghost_), s.data(), nullptr));
+            double h = 0;
+            s.download(&h);
+            sum += h;
+        }
+        return std::sqrt(sum);
     }
 
   private:
     DeviceArray<double> d_;
     size_t n_owned_ = 0, n_ghost_ = 0;
+    int n_comp_ = 1;
 };
 
 class BoxMesh {
@@ -169,6 +178,42 @@ class BoxMesh {
     b200fe_boxmesh *h_ = nullptr;
 };
 
+// BoxMesh whose cells [refine_lo, refine_hi) are refined once more: Triangulation with hanging nodes + DoFHandler +
+// AffineConstraints (make_hanging_node_constraints + Dirichlet) of a deal.II driver (BASELINE config C5).
+class HangingBoxMesh {
+  public:
+    HangingBoxMesh(const int (&subdivisions)[3], int n_refine, int p, const int (&refine_lo)[3], const int (&refine_hi)[3],
+                   const double (&p1)[3], const double (&p2)[3], int n_ranks = 1, int rank = 0, bool dirichlet = true)
+    {
+        b200fe_hangmesh_desc d{};
+        for (int k = 0; k < 3; ++k) {
+            d.box.subdivisions[k] = subdivisions[k]; d.box.p1[k] = p1[k]; d.box.p2[k] = p2[k];
+            d.refine_lo[k] = refine_lo[k]; d.refine_hi[k] = refine_hi[k];
+        }
+        d.box.n_refine = n_refine; d.box.p = p; d.box.n_ranks = n_ranks; d.box.rank = rank;
+        d.box.partition = B200FE_PARTITION_P4EST; d.box.ghosts = B200FE_GHOSTS_MINIMAL; d.box.dirichlet = dirichlet ? 1 : 0;
+        check(b200fe_hangmesh_create(&d, &h_));
+        check(b200fe_hangmesh_info(h_, &info));
+        degree = p;
+    }
+    HangingBoxMesh(HangingBoxMesh &&o) noexcept : info(o.info), degree(o.degree), h_(o.h_) { o.h_ = nullptr; }
+    HangingBoxMesh(const HangingBoxMesh &) = delete;
+    ~HangingBoxMesh() { if (h_) b200fe_hangmesh_destroy(h_); }
+    const b200fe_hangmesh *handle() const { return h_; }
+    unsigned long long n_dofs() const { return info.n_dofs_global; }
+    unsigned long long n_global_active_cells() const { return info.n_cells_global; }
+    b200fe_hangmesh_info_t info{};
+    int degree = 0;
+
+  private:
+    b200fe_hangmesh *h_ = nullptr;
+};
+
+// smooth mesh deformation of b200fe_boxmesh_nodes (deform_kind 1); amplitude 0 = the box itself
+struct Deformation {
+    double amplitude = 0.0, frequency = 0.0;
+};
+
 enum class Quadrature { Gauss, GaussLobatto };
 
 template <int dim, int fe_degree, int nq, typename number = double>
@@ -178,46 +223,58 @@ class LaplaceOperator {
 
   public:
     // p_geo: degree of the mapping (MappingQ(p_geo)); op_kind: B200FE_OP_*
-    LaplaceOperator(const BoxMesh &mesh, Quadrature quad = Quadrature::Gauss, int op_kind = B200FE_OP_LAPLACE, int p_geo = 1)
+    LaplaceOperator(const BoxMesh &mesh, Quadrature quad = Quadrature::Gauss, int op_kind = B200FE_OP_LAPLACE, int p_geo = 1,
+                    Deformation deform = {})
         : n_dofs_global_(mesh.n_dofs()), n_owned_(mesh.info.n_owned), n_ghost_(mesh.info.n_ghost)
     {
         if (mesh.degree != fe_degree) throw Error(B200FE_ERR_INVALID_ARG, "mesh degree != fe_degree");
-        const int nm = fe_degree + 1, qk = quad == Quadrature::Gauss ? B200FE_QUAD_GAUSS : B200FE_QUAD_GLL;
-        const bool collocated = quad == Quadrature::GaussLobatto && nq == nm;
         const uint32_t nc = mesh.info.n_cells_local;
-        std::vector<double> sv(nm * nq), cg(nq * nq);
-        check(b200fe_basis_1d(fe_degree, nq, qk, sv.data(), cg.data(), nullptr, nullptr, nullptr));
-        std::vector<uint32_t> idx((size_t)nc * nm * nm * nm), con(mesh.info.n_constrained);
+        std::vector<uint32_t> idx((size_t)nc * nm3()), con(mesh.info.n_constrained);
         check(b200fe_boxmesh_fill(mesh.handle(), idx.data(), con.data(), nullptr, nullptr, nullptr, nullptr));
-        idx_.upload(idx.data(), idx.size());
-        const size_t ng3 = (size_t)(p_geo + 1) * (p_geo + 1) * (p_geo + 1), nq3 = (size_t)nq * nq * nq;
-        DeviceArray<double> nodes((size_t)nc * 3 * ng3);
-        check(b200fe_boxmesh_nodes(mesh.handle(), p_geo, 0, 0.0, 0.0, nodes.data(), nullptr));
-        if (op_kind & B200FE_OP_LAPLACE) G_.resize((size_t)nc * 6 * nq3);
-        JxW_.resize((size_t)nc * nq3);
-        check(b200fe_geometry_from_nodes(p_geo, nq, qk, nc, nodes.data(), G_.data(), JxW_.data(), nullptr));
-        check_cuda(cudaDeviceSynchronize(), "geometry");
-        b200fe_op_desc d{};
-        d.p = fe_degree; d.nq = nq; d.op_kind = op_kind; d.collocated = collocated;
-        d.n_cells = nc; d.n_owned = n_owned_; d.n_ghost = n_ghost_;
-        d.h_shape_values = sv.data(); d.h_co_shape_gradients = cg.data();
-        d.d_dof_indices = idx_.data(); d.d_G = G_.data(); d.d_JxW = JxW_.data();
-        d.h_constrained = con.data(); d.n_constrained = (uint32_t)con.size();
-        check(b200fe_op_create(&d, &op_));
+        DeviceArray<double> nodes((size_t)nc * 3 * ng3(p_geo));
+        check(b200fe_boxmesh_nodes(mesh.handle(), p_geo, deform.amplitude != 0.0, deform.amplitude, deform.frequency, nodes.data(), nullptr));
+        init(nc, idx, con, nodes, quad, op_kind, p_geo);
+    }
+    // two-level mesh with hanging nodes: the operator is C^T A C with identity on the constrained rows
+    LaplaceOperator(const HangingBoxMesh &mesh, Quadrature quad = Quadrature::Gauss, int op_kind = B200FE_OP_LAPLACE, int p_geo = 1,
+                    Deformation deform = {})
+        : n_dofs_global_(mesh.n_dofs()), n_owned_(mesh.info.n_owned), n_ghost_(mesh.info.n_ghost)
+    {
+        if (mesh.degree != fe_degree) throw Error(B200FE_ERR_INVALID_ARG, "mesh degree != fe_degree");
+        const uint32_t nc = mesh.info.n_cells_local, nr = mesh.info.n_hanging_rows;
+        std::vector<uint32_t> idx((size_t)nc * nm3()), con(mesh.info.n_constrained), hd(nr), hp(nr + 1), hc(mesh.info.n_hanging_entries);
+        std::vector<double> hw(mesh.info.n_hanging_entries);
+        check(b200fe_hangmesh_fill(mesh.handle(), idx.data(), con.data(), nullptr, nullptr, nullptr, nullptr, hd.data(), hp.data(), hc.data(), hw.data()));
+        DeviceArray<double> nodes((size_t)nc * 3 * ng3(p_geo));
+        check(b200fe_hangmesh_nodes(mesh.handle(), p_geo, deform.amplitude != 0.0, deform.amplitude, deform.frequency, nodes.data(), nullptr));
+        init(nc, idx, con, nodes, quad, op_kind, p_geo);
+        check(b200fe_op_set_constraints(op_, nr, hd.data(), hp.data(), hc.data(), hw.data()));
     }
     LaplaceOperator(const LaplaceOperator &) = delete;
     ~LaplaceOperator() { if (op_) b200fe_op_destroy(op_); }
 
-    void vmult(Vector &dst, const Vector &src) const { check(b200fe_op_vmult(op_, dst.get_values(), src.get_values(), nullptr)); }
+    void vmult(Vector &dst, const Vector &src) const  // vector-valued: the scalar operator on every component
+    {
+        if (src.n_components() == 1) check(b200fe_op_vmult(op_, dst.get_values(), src.get_values(), nullptr));
+        else check(b200fe_op_vmult_components(op_, src.n_components(), dst.get_values(), src.get_values(), nullptr));
+    }
     void Tvmult(Vector &dst, const Vector &src) const { vmult(dst, src); }
     void vmult_dummy(Vector &dst, const Vector &src, const bool ghost_exchange_on, const bool computation_on) const
     {
         check(b200fe_op_vmult_dummy(op_, dst.get_values(), src.get_values(), ghost_exchange_on, computation_on, nullptr));
     }
-    void initialize_dof_vector(Vector &vec) const { vec.reinit(n_owned_, n_ghost_); }
+    void initialize_dof_vector(Vector &vec, int n_components = 1) const { vec.reinit(n_owned_, n_ghost_, n_components); }
+    // AffineConstraints::distribute: hanging-node values of a solution from their parents
+    void distribute(Vector &x) const
+    {
+        for (int c = 0; c < x.n_components(); ++c) check(b200fe_op_distribute(op_, x.get_values() + c * x.size_with_ghosts(), nullptr));
+    }
     unsigned long long m() const { return n_dofs_global_; }
     unsigned long long n() const { return n_dofs_global_; }
-    void compute_rhs(Vector &b) const { check(b200fe_op_rhs_one(op_, b.get_values(), nullptr)); }  // bp3.cc:184-239
+    void compute_rhs(Vector &b) const  // bp3.cc:184-239 (f = 1 in every component)
+    {
+        for (int c = 0; c < b.n_components(); ++c) check(b200fe_op_rhs_one(op_, b.get_values() + c * b.size_with_ghosts(), nullptr));
+    }
     void compute_diagonal()                                                                      // benchmark.cc:218-251
     {
         Vector d;
@@ -235,6 +292,29 @@ class LaplaceOperator {
     b200fe_op *handle() const { return op_; }
 
   private:
+    static constexpr size_t nm3() { return (size_t)(fe_degree + 1) * (fe_degree + 1) * (fe_degree + 1); }
+    static size_t ng3(int p_geo) { return (size_t)(p_geo + 1) * (p_geo + 1) * (p_geo + 1); }
+    void init(uint32_t nc, const std::vector<uint32_t> &idx, const std::vector<uint32_t> &con, const DeviceArray<double> &nodes,
+              Quadrature quad, int op_kind, int p_geo)
+    {
+        const int nm = fe_degree + 1, qk = quad == Quadrature::Gauss ? B200FE_QUAD_GAUSS : B200FE_QUAD_GLL;
+        const bool collocated = quad == Quadrature::GaussLobatto && nq == nm;
+        std::vector<double> sv(nm * nq), cg(nq * nq);
+        check(b200fe_basis_1d(fe_degree, nq, qk, sv.data(), cg.data(), nullptr, nullptr, nullptr));
+        idx_.upload(idx.data(), idx.size());
+        const size_t nq3 = (size_t)nq * nq * nq;
+        if (op_kind & B200FE_OP_LAPLACE) G_.resize((size_t)nc * 6 * nq3);
+        JxW_.resize((size_t)nc * nq3);
+        check(b200fe_geometry_from_nodes(p_geo, nq, qk, nc, nodes.data(), G_.data(), JxW_.data(), nullptr));
+        check_cuda(cudaDeviceSynchronize(), "geometry");
+        b200fe_op_desc d{};
+        d.p = fe_degree; d.nq = nq; d.op_kind = op_kind; d.collocated = collocated;
+        d.n_cells = nc; d.n_owned = n_owned_; d.n_ghost = n_ghost_;
+        d.h_shape_values = sv.data(); d.h_co_shape_gradients = cg.data();
+        d.d_dof_indices = idx_.data(); d.d_G = G_.data(); d.d_JxW = JxW_.data();
+        d.h_constrained = con.data(); d.n_constrained = (uint32_t)con.size();
+        check(b200fe_op_create(&d, &op_));
+    }
     b200fe_op *op_ = nullptr;
     unsigned long long n_dofs_global_;
     uint32_t n_owned_, n_ghost_;
@@ -271,8 +351,9 @@ class SolverCG {
     void run(b200fe_op *op, Vector &x, const Vector &b, const double *inv_diag)
     {
         const int max_it = control_.max_steps_ > 2000000000u ? 2000000000 : (int)control_.max_steps_;
-        const int rc = b200fe_cg_solve(op, x.get_values(), b.get_values(), inv_diag, control_.tol_, control_.red_, max_it,
-                                       check_every_, &control_.res_, stream_);
+        if (x.n_components() != b.n_components()) throw Error(B200FE_ERR_INVALID_ARG, "SolverCG: x and b differ in components");
+        const int rc = b200fe_cg_solve_components(op, x.n_components(), x.get_values(), b.get_values(), inv_diag, control_.tol_,
+                                                  control_.red_, max_it, check_every_, &control_.res_, stream_);
         if (rc == B200FE_ERR_NO_CONVERGENCE) throw NoConvergence(rc, b200fe_last_error());
         check(rc);
     }

@@ -142,3 +142,32 @@ def test_constraint_rows_are_validated():
         hd, rp, col = u32(13), u32(0, 2), u32(6, 7)
         assert lib.b200fe_op_set_constraints(A._h, 1, ptr(hd), ptr(rp), ptr(col), ptr(w)) == 0
         A.compute_diagonal()
+
+
+def test_bp6_driver_matches_python_path():
+    """C++ host layer (include/b200fe/operator.hpp: HangingBoxMesh, component-blocked Vector, SolverCG) through the bp6
+    driver: mesh sizes and CG iteration counts equal the Python mirror's on the same meshes."""
+    import os
+    import subprocess
+    import benchmarks_b200 as b
+    drv = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "benchmarks_b200", "drivers")
+    exe = os.path.join(drv, "bp6")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", drv], check=True)
+    r = subprocess.run([exe, "2", "1", "12000"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    rows = [[x.strip() for x in l.split("|")] for l in r.stdout.splitlines() if l.count("|") == 8 and l.split("|")[0].strip().isdigit()]
+    assert len(rows) >= 2
+    for row, cycle in zip(rows, (3, 4)):
+        n_refine, rem = cycle // 3, cycle % 3
+        sub = [2 if d < rem else 1 for d in range(3)]
+        hi = [(s << n_refine) // 2 for s in sub]
+        mesh = b.HangingBoxMesh(sub, n_refine, 2, (0, 0, 0), hi)
+        assert (int(row[0]), int(row[1]), int(row[2])) == (mesh.n_cells_global, 3 * mesh.n_dofs_global, len(mesh.hang_dof))
+        A = b.LaplaceOperator(mesh, quad="gll", p_geo=2, deform=(0.05, 2.0))
+        rhs1 = A.compute_rhs()
+        rhs = torch.cat([rhs1, rhs1, rhs1])
+        x = torch.zeros_like(rhs)
+        ctl = b.ReductionControl(10 ** 9, 1e-16, 1e-9)
+        b.SolverCG(ctl).solve(A, x, rhs, n_components=3)
+        assert abs(int(row[6]) - ctl.last_step()) <= 1
