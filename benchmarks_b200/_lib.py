@@ -48,6 +48,7 @@ _SIGNATURES = {
     "b200fe_hangmesh_fill": (_i, [_vp] * 11),
     "b200fe_hangmesh_nodes": (_i, [_vp, _i, _i, C.c_double, C.c_double, _vp, _vp]),
     "b200fe_geometry_from_nodes": (_i, [_i, _i, _i, _u32, _vp, _vp, _vp, _vp]),
+    "b200fe_geometry_from_inv_jacobian": (_i, [_u32, _i, _vp, _vp, _vp, _vp]),
     "b200fe_geometry_affine_from_nodes": (_i, [_u32, _vp, _vp, _vp]),
     "b200fe_op_create": (_i, [_vp, C.POINTER(_vp)]),
     "b200fe_op_destroy": (None, [_vp]),

@@ -215,8 +215,8 @@ static int cg_run(Operator &op, int ncomp, CgWork &w, double *d_x, const double 
         cg_update_p_kernel<<<blocks, 256, 0, s>>>(n, stride, w.r, d_inv_diag, w.p, w.sc);
         B200FE_CUDA_TRY(cudaGetLastError());
         ++g_launch_count;
-        for (int c = 0; c < ncomp; ++c)  // block-diagonal operator: the fused p.Ap of every component lands in acc[0]
-            if (int rc = op_vmult(op, w.v + c * stride, w.p + c * stride, &w.sc->acc[0], true, true, s)) return rc;
+        // block-diagonal operator: the fused p.Ap of every component lands in acc[0]
+        if (int rc = op_vmult(op, w.v, w.p, &w.sc->acc[0], true, true, s, ncomp)) return rc;
         if (op.halo)
             if (int rc = halo_allreduce_sum(*op.halo, w.sc->acc, 1, s)) return rc;
         cg_update_xr_kernel<<<blocks, 256, 0, s>>>(n, stride, w.p, w.v, d_inv_diag, d_x, w.r, w.sc);

@@ -154,11 +154,38 @@ __global__ void affine_geometry_kernel(uint32_t n_cells, const double *__restric
     o[7] = 0.0;
 }
 
-__global__ void copy_constrained_kernel(uint32_t n, const uint32_t *__restrict__ list,
+// deal.II MatrixFree data -> G: inv_jacobian(q, cell, ref, real) and JxW(q, cell) as Kokkos LayoutLeft views (q fastest)
+__global__ void g_from_inv_jacobian_kernel(uint32_t n_cells, int nq3, const double *__restrict__ K, const double *__restrict__ JxW,
+                                           double *__restrict__ G)
+{
+    const size_t total = (size_t)n_cells * nq3, plane = total;  // plane: stride between (ref, real) entries
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        double k[3][3];  // k[ref][real]
+#pragma unroll
+        for (int real = 0; real < 3; ++real)
+#pragma unroll
+            for (int ref = 0; ref < 3; ++ref) k[ref][real] = K[i + plane * (ref + 3 * real)];
+        const double jxw = JxW[i];
+        const size_t cell = i / nq3, q = i - cell * nq3;
+        double *g = G + cell * 6 * (size_t)nq3 + q;
+        const int perm[3] = {2, 1, 0};  // kernel directions (r,s,t) = (z^, y^, x^), as in geometry_kernel
+        int ci = 0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = a; b < 3; ++b, ++ci) {
+                const double *ka = k[perm[a]], *kb = k[perm[b]];
+                g[(size_t)ci * nq3] = jxw * (ka[0] * kb[0] + ka[1] * kb[1] + ka[2] * kb[2]);
+            }
+    }
+}
+
+__global__ void copy_constrained_kernel(uint32_t n, const uint32_t *__restrict__ list, size_t stride,
                                         const double *__restrict__ src, double *__restrict__ dst,
                                         double *__restrict__ dot, const int *__restrict__ skip)
 {
     if (skip != nullptr && *skip != 0) return;
+    src += blockIdx.y * stride; dst += blockIdx.y * stride;  // blockIdx.y = component
     double s = 0.0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t c = list[i];
@@ -234,23 +261,43 @@ __global__ void set_constrained_kernel(uint32_t n, const uint32_t *__restrict__ 
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v[list[i]] = value;
 }
 
-// hanging-node rows, one warp per row (rows hold 2 ... (p+1)^2 parents): v[h] = sum_k w[k] v[col[k]]
+// hanging-node rows, one warp per row (rows hold 2 ... (p+1)^2 parents): v[h] = sum_k w[k] v[col[k]].
+// Vector-valued problems: the row is applied to all components (component-blocked vectors, `stride` apart) while its
+// weights / parent indices are read once (the CSR arrays are the only DRAM traffic of these kernels; r01h: 87 us per
+// component for 130 k rows at p = 8 when launched per component).
+constexpr int kCompChunk = 4;
+
 __global__ void distribute_kernel(uint32_t n_rows, const uint32_t *__restrict__ hdof, const uint32_t *__restrict__ ptr,
                                   const uint32_t *__restrict__ col, const double *__restrict__ w, double *__restrict__ v,
-                                  double *__restrict__ save, const int *__restrict__ skip)
+                                  int ncomp, size_t stride, double *__restrict__ save, const int *__restrict__ skip)
 {
     if (skip != nullptr && *skip != 0) return;
     const int lane = threadIdx.x & 31;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_rows; r += warps) {
-        const uint32_t b = ptr[r], e = ptr[r + 1];
-        double s = 0.0;
-        for (uint32_t k = b + lane; k < e; k += 32) s = fma(w[k], v[col[k]], s);
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) {
-            const uint32_t h = hdof[r];
-            if (save) save[r] = v[h];
-            v[h] = s;  // a hanging DoF is never a parent (chain-free rows): no other warp reads v[h]
+        const uint32_t b = ptr[r], e = ptr[r + 1], h = hdof[r];
+        for (int c0 = 0; c0 < ncomp; c0 += kCompChunk) {
+            const int nc = min(kCompChunk, ncomp - c0);
+            double s[kCompChunk] = {0.0, 0.0, 0.0, 0.0};
+            for (uint32_t k = b + lane; k < e; k += 32) {
+                const double wk = w[k];
+                const double *vk = v + (size_t)c0 * stride + col[k];
+#pragma unroll
+                for (int c = 0; c < kCompChunk; ++c)
+                    if (c < nc) s[c] = fma(wk, vk[c * stride], s[c]);
+            }
+#pragma unroll
+            for (int c = 0; c < kCompChunk; ++c)
+                for (int o = 16; o > 0; o >>= 1) s[c] += __shfl_xor_sync(0xffffffffu, s[c], o);
+            if (lane == 0) {
+#pragma unroll
+                for (int c = 0; c < kCompChunk; ++c)
+                    if (c < nc) {
+                        double *vh = v + (size_t)(c0 + c) * stride + h;
+                        if (save) save[(size_t)(c0 + c) * n_rows + r] = *vh;
+                        *vh = s[c];  // a hanging DoF is never a parent (chain-free rows): no other warp reads v[h]
+                    }
+            }
         }
     }
 }
@@ -258,19 +305,35 @@ __global__ void distribute_kernel(uint32_t n_rows, const uint32_t *__restrict__ 
 // transpose: dst[col[k]] += w[k] dst[h]; dst[h] = 0; optionally src[h] = save[r]
 __global__ void condense_kernel(uint32_t n_rows, const uint32_t *__restrict__ hdof, const uint32_t *__restrict__ ptr,
                                 const uint32_t *__restrict__ col, const double *__restrict__ w, double *__restrict__ dst,
-                                double *__restrict__ src, const double *__restrict__ save, const int *__restrict__ skip)
+                                int ncomp, size_t stride, double *__restrict__ src, const double *__restrict__ save,
+                                const int *__restrict__ skip)
 {
     if (skip != nullptr && *skip != 0) return;
     const int lane = threadIdx.x & 31;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_rows; r += warps) {
         const uint32_t h = hdof[r], b = ptr[r], e = ptr[r + 1];
-        const double t = dst[h];
-        for (uint32_t k = b + lane; k < e; k += 32) atomicAdd(dst + col[k], w[k] * t);
-        __syncwarp();
-        if (lane == 0) {
-            dst[h] = 0.0;
-            if (src) src[h] = save[r];
+        for (int c0 = 0; c0 < ncomp; c0 += kCompChunk) {
+            const int nc = min(kCompChunk, ncomp - c0);
+            double t[kCompChunk];
+#pragma unroll
+            for (int c = 0; c < kCompChunk; ++c) t[c] = c < nc ? dst[(size_t)(c0 + c) * stride + h] : 0.0;
+            for (uint32_t k = b + lane; k < e; k += 32) {
+                const double wk = w[k];
+                double *dk = dst + (size_t)c0 * stride + col[k];
+#pragma unroll
+                for (int c = 0; c < kCompChunk; ++c)
+                    if (c < nc) atomicAdd(dk + c * stride, wk * t[c]);
+            }
+            __syncwarp();
+            if (lane == 0) {
+#pragma unroll
+                for (int c = 0; c < kCompChunk; ++c)
+                    if (c < nc) {
+                        dst[(size_t)(c0 + c) * stride + h] = 0.0;
+                        if (src) src[(size_t)(c0 + c) * stride + h] = save[(size_t)(c0 + c) * n_rows + r];
+                    }
+            }
         }
     }
 }
@@ -301,46 +364,66 @@ int op_apply_cells(Operator &op, double *d_dst, const double *d_src, uint32_t cb
     return B200FE_OK;
 }
 
-int op_copy_constrained(Operator &op, double *d_dst, const double *d_src, double *d_dot, cudaStream_t s)
+int op_copy_constrained(Operator &op, double *d_dst, const double *d_src, double *d_dot, cudaStream_t s, int ncomp)
 {
     if (op.n_constrained == 0) return B200FE_OK;
-    const unsigned blocks = std::min<unsigned>((op.n_constrained + 255) / 256, 1184);
-    copy_constrained_kernel<<<blocks, 256, 0, s>>>(op.n_constrained, op.d_constrained, d_src, d_dst, d_dot, op.d_skip);
+    const dim3 blocks(std::min<unsigned>((op.n_constrained + 255) / 256, 1184), (unsigned)ncomp);
+    copy_constrained_kernel<<<blocks, 256, 0, s>>>(op.n_constrained, op.d_constrained, op.n_local(), d_src, d_dst, d_dot, op.d_skip);
     B200FE_CUDA_TRY(cudaGetLastError());
     ++g_launch_count;
     return B200FE_OK;
 }
 
-int op_distribute(Operator &op, double *d_v, bool save, cudaStream_t s)
+// the save buffer holds n_hang doubles per component; grown on first use with more components
+static int ensure_hang_save(Operator &op, int ncomp)
+{
+    if (ncomp <= op.hang_save_comps) return B200FE_OK;
+    cudaFree(op.d_hang_save);
+    op.d_hang_save = nullptr;
+    op.hang_save_comps = 0;
+    B200FE_CUDA_TRY(cudaMalloc(&op.d_hang_save, (size_t)op.n_hang * ncomp * sizeof(double)));
+    op.hang_save_comps = ncomp;
+    return B200FE_OK;
+}
+
+int op_distribute(Operator &op, double *d_v, bool save, cudaStream_t s, int ncomp)
 {
     if (op.n_hang == 0) return B200FE_OK;
+    if (save)
+        if (int rc = ensure_hang_save(op, ncomp)) return rc;
     const unsigned blocks = std::min<unsigned>((op.n_hang + 7) / 8, 148u * 8u);  // 8 warps (rows) per CTA
-    distribute_kernel<<<blocks, 256, 0, s>>>(op.n_hang, op.d_hang_dof, op.d_hang_ptr, op.d_hang_col, op.d_hang_w, d_v,
-                                             save ? op.d_hang_save : nullptr, op.d_skip);
+    distribute_kernel<<<blocks, 256, 0, s>>>(op.n_hang, op.d_hang_dof, op.d_hang_ptr, op.d_hang_col, op.d_hang_w, d_v, ncomp,
+                                             op.n_local(), save ? op.d_hang_save : nullptr, op.d_skip);
     B200FE_CUDA_TRY(cudaGetLastError());
     ++g_launch_count;
     return B200FE_OK;
 }
 
-int op_condense(Operator &op, double *d_dst, double *d_src_restore, cudaStream_t s)
+int op_condense(Operator &op, double *d_dst, double *d_src_restore, cudaStream_t s, int ncomp)
 {
     if (op.n_hang == 0) return B200FE_OK;
     const unsigned blocks = std::min<unsigned>((op.n_hang + 7) / 8, 148u * 8u);
-    condense_kernel<<<blocks, 256, 0, s>>>(op.n_hang, op.d_hang_dof, op.d_hang_ptr, op.d_hang_col, op.d_hang_w, d_dst,
-                                           d_src_restore, op.d_hang_save, op.d_skip);
+    condense_kernel<<<blocks, 256, 0, s>>>(op.n_hang, op.d_hang_dof, op.d_hang_ptr, op.d_hang_col, op.d_hang_w, d_dst, ncomp,
+                                           op.n_local(), d_src_restore, op.d_hang_save, op.d_skip);
     B200FE_CUDA_TRY(cudaGetLastError());
     ++g_launch_count;
     return B200FE_OK;
 }
 
 int op_vmult(Operator &op, double *d_dst, const double *d_src, double *d_dot, bool ghost_on, bool compute_on,
-             cudaStream_t s)
+             cudaStream_t s, int ncomp)
 {
     Halo *h = op.halo;
+    const size_t stride = op.n_local();
     double *src_mut = const_cast<double *>(d_src);  // ghost (and hanging) entries of src are scratch, as in deal.II
     // hanging-node rows need the parents' ghost values before the first cell runs: no overlap split with constraints
     const bool split = h && ghost_on && compute_on && (op.n_phase0 + op.n_phase1 > 0) && op.n_hang == 0;
-    if (compute_on) B200FE_CUDA_TRY(cudaMemsetAsync(d_dst, 0, sizeof(double) * op.n_local(), s));
+    if (split && ncomp > 1) {  // the overlap schedule is per vector: one component after the other
+        for (int c = 0; c < ncomp; ++c)
+            if (int rc = op_vmult(op, d_dst + c * stride, d_src + c * stride, d_dot, ghost_on, compute_on, s, 1)) return rc;
+        return B200FE_OK;
+    }
+    if (compute_on) B200FE_CUDA_TRY(cudaMemsetAsync(d_dst, 0, sizeof(double) * stride * ncomp, s));
     if (split) {
         // 3-phase overlap (bakeoff_problems_dealii/include/portable_laplace_operator.h:643-696)
         if (int rc = halo_update_ghosts_start(*h, src_mut, s)) return rc;
@@ -351,21 +434,26 @@ int op_vmult(Operator &op, double *d_dst, const double *d_src, double *d_dot, bo
         if (int rc = op_apply_cells(op, d_dst, d_src, op.n_phase0 + op.n_phase1, op.n_cells, d_dot, s)) return rc;
         if (int rc = halo_compress_finish(*h, d_dst, s)) return rc;
         if (int rc = halo_zero_ghosts(*h, src_mut, s)) return rc;
-        return op_copy_constrained(op, d_dst, d_src, d_dot, s);
+        return op_copy_constrained(op, d_dst, d_src, d_dot, s, 1);
+    }
+    // vector-valued: the scalar operator on every component; constraint rows and identity rows are applied to all
+    // components in one launch each (their index lists are read once)
+    if (h && ghost_on)
+        for (int c = 0; c < ncomp; ++c)
+            if (int rc = halo_update_ghosts(*h, src_mut + c * stride, s)) return rc;
+    if (compute_on) {
+        if (int rc = op_distribute(op, src_mut, true, s, ncomp)) return rc;
+        for (int c = 0; c < ncomp; ++c)
+            if (int rc = op_apply_cells(op, d_dst + c * stride, d_src + c * stride, 0, op.n_cells, d_dot, s)) return rc;
+        if (int rc = op_condense(op, d_dst, src_mut, s, ncomp)) return rc;
     }
     if (h && ghost_on)
-        if (int rc = halo_update_ghosts(*h, src_mut, s)) return rc;
-    if (compute_on) {
-        if (int rc = op_distribute(op, src_mut, true, s)) return rc;
-        if (int rc = op_apply_cells(op, d_dst, d_src, 0, op.n_cells, d_dot, s)) return rc;
-        if (int rc = op_condense(op, d_dst, src_mut, s)) return rc;
-    }
-    if (h && ghost_on) {
-        if (int rc = halo_compress_add(*h, d_dst, s)) return rc;
-        if (int rc = halo_zero_ghosts(*h, src_mut, s)) return rc;
-    }
+        for (int c = 0; c < ncomp; ++c) {
+            if (int rc = halo_compress_add(*h, d_dst + c * stride, s)) return rc;
+            if (int rc = halo_zero_ghosts(*h, src_mut + c * stride, s)) return rc;
+        }
     if (ghost_on)  // reference: copy_constrained_values sits inside the ghost_exchange_on branch (:229-234)
-        if (int rc = op_copy_constrained(op, d_dst, d_src, d_dot, s)) return rc;
+        if (int rc = op_copy_constrained(op, d_dst, d_src, d_dot, s, ncomp)) return rc;
     return B200FE_OK;
 }
 
@@ -467,6 +555,19 @@ int b200fe_geometry_from_nodes(int p_geo, int nq, int quad_kind, uint32_t n_cell
     const int threads = std::min(256, ((nq * nq * nq + 31) / 32) * 32);
     const unsigned blocks = std::min<uint32_t>(n_cells, 148u * 16u);
     geometry_kernel<<<blocks, threads, 3 * ng * ng * ng * sizeof(double), (cudaStream_t)stream>>>(gm, n_cells, ng, nq, d_nodes, d_G, d_JxW);
+    B200FE_CUDA_TRY(cudaGetLastError());
+    return B200FE_OK;
+}
+
+int b200fe_geometry_from_inv_jacobian(uint32_t n_cells, int nq, const double *d_inv_jacobian, const double *d_JxW, double *d_G,
+                                      void *stream)
+{
+    B200FE_REQUIRE(nq >= 2 && nq <= 10, "b200fe_geometry_from_inv_jacobian: nq outside 2..10");
+    B200FE_REQUIRE(n_cells == 0 || (d_inv_jacobian && d_JxW && d_G), "b200fe_geometry_from_inv_jacobian: null pointer");
+    if (n_cells == 0) return B200FE_OK;
+    const size_t total = (size_t)n_cells * nq * nq * nq;
+    const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 148u * 16u);
+    g_from_inv_jacobian_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(n_cells, nq * nq * nq, d_inv_jacobian, d_JxW, d_G);
     B200FE_CUDA_TRY(cudaGetLastError());
     return B200FE_OK;
 }
@@ -588,7 +689,6 @@ int b200fe_op_set_constraints(b200fe_op *o, uint32_t n_rows, const uint32_t *h_h
     if (e == cudaSuccess) e = upload(&op.d_hang_ptr, h_hang_row_ptr, (size_t)n_rows + 1);
     if (e == cudaSuccess) e = upload(&op.d_hang_col, h_hang_col, nnz);
     if (e == cudaSuccess) e = upload(&op.d_hang_w, h_hang_w, nnz);
-    if (e == cudaSuccess) e = cudaMalloc(&op.d_hang_save, n_rows * sizeof(double));
     if (e != cudaSuccess) {
         op.free_constraints();
         return fail_cuda(e, "b200fe_op_set_constraints");
@@ -600,7 +700,7 @@ int b200fe_op_set_constraints(b200fe_op *o, uint32_t n_rows, const uint32_t *h_h
 int b200fe_op_distribute(b200fe_op *o, double *d_x, void *stream)
 {
     B200FE_REQUIRE(o && d_x, "b200fe_op_distribute: null pointer");
-    return op_distribute(*reinterpret_cast<Operator *>(o), d_x, false, (cudaStream_t)stream);
+    return op_distribute(*reinterpret_cast<Operator *>(o), d_x, false, (cudaStream_t)stream, 1);
 }
 
 int b200fe_op_vmult(b200fe_op *o, double *d_dst, const double *d_src, void *stream)
@@ -614,11 +714,7 @@ int b200fe_op_vmult_components(b200fe_op *o, int n_components, double *d_dst, co
 {
     B200FE_REQUIRE(o && d_dst && d_src && n_components >= 1, "b200fe_op_vmult_components: bad arguments");
     B200FE_REQUIRE(d_dst != d_src, "b200fe_op_vmult_components: dst and src must not alias");
-    Operator &op = *reinterpret_cast<Operator *>(o);
-    const size_t n = op.n_local();
-    for (int c = 0; c < n_components; ++c)
-        if (int rc = op_vmult(op, d_dst + c * n, d_src + c * n, nullptr, true, true, (cudaStream_t)stream)) return rc;
-    return B200FE_OK;
+    return op_vmult(*reinterpret_cast<Operator *>(o), d_dst, d_src, nullptr, true, true, (cudaStream_t)stream, n_components);
 }
 
 int b200fe_op_vmult_dot(b200fe_op *o, double *d_dst, const double *d_src, double *d_dot, void *stream)
@@ -673,7 +769,7 @@ int b200fe_op_rhs_one(b200fe_op *o, double *d_b, void *stream)
         rhs_one_kernel<<<std::min<uint32_t>(op.n_cells, 148u * 8u), 128, 0, s>>>(op.n_cells, op.nm, op.nq, op.d_mats, op.d_JxW, op.d_idx, d_b);
         B200FE_CUDA_TRY(cudaGetLastError());
     }
-    if (int rc = op_condense(op, d_b, nullptr, s)) return rc;  // b = C^T b_hat, hanging rows 0
+    if (int rc = op_condense(op, d_b, nullptr, s, 1)) return rc;  // b = C^T b_hat, hanging rows 0
     if (op.halo)
         if (int rc = halo_compress_add(*op.halo, d_b, s)) return rc;
     return B200FE_OK;

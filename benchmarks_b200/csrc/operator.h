@@ -27,6 +27,7 @@ struct Operator {
     uint32_t n_hang = 0;
     uint32_t *d_hang_dof = nullptr, *d_hang_ptr = nullptr, *d_hang_col = nullptr;
     double *d_hang_w = nullptr, *d_hang_save = nullptr;  // save: src values of the hanging entries during a vmult
+    int hang_save_comps = 0;                              // components the save buffer has room for
     const int *d_skip = nullptr;        // set by the CG driver for the duration of a solve (see KArgs::skip)
     // overlap split: cells [0, n_phase0) and [n_phase0+n_phase1, n_cells) touch no ghost DoF
     uint32_t n_phase0 = 0, n_phase1 = 0;
@@ -53,6 +54,7 @@ struct Operator {
         d_hang_dof = d_hang_ptr = d_hang_col = nullptr;
         d_hang_w = d_hang_save = nullptr;
         n_hang = 0;
+        hang_save_comps = 0;
     }
 };
 
@@ -60,14 +62,16 @@ struct Operator {
 int op_apply_cells(Operator &op, double *d_dst, const double *d_src, uint32_t cell_begin, uint32_t cell_end,
                    double *d_dot, cudaStream_t s);
 // dst[c] = src[c] on owned constrained DoFs; optional dot += sum src[c]^2
-int op_copy_constrained(Operator &op, double *d_dst, const double *d_src, double *d_dot, cudaStream_t s);
+int op_copy_constrained(Operator &op, double *d_dst, const double *d_src, double *d_dot, cudaStream_t s, int ncomp = 1);
 // hanging-node rows: src[h] = sum w src[parents] (old values saved when `save`), and its transpose on dst
 // (dst[parents] += w dst[h]; dst[h] = 0; src[h] restored when `restore`)
-int op_distribute(Operator &op, double *d_v, bool save, cudaStream_t s);
-int op_condense(Operator &op, double *d_dst, double *d_src_restore, cudaStream_t s);
+// (all `ncomp` components of component-blocked vectors in one launch)
+int op_distribute(Operator &op, double *d_v, bool save, cudaStream_t s, int ncomp = 1);
+int op_condense(Operator &op, double *d_dst, double *d_src_restore, cudaStream_t s, int ncomp = 1);
 // full local vmult: zero, cells, constrained rows (+ halo exchange when attached)
+// ncomp > 1: component-blocked vectors [component][n_local], the scalar operator on each
 int op_vmult(Operator &op, double *d_dst, const double *d_src, double *d_dot, bool ghost_on, bool compute_on,
-             cudaStream_t s);
+             cudaStream_t s, int ncomp = 1);
 
 // number of kernels this library has launched so far (all kinds)
 extern unsigned long long g_launch_count;

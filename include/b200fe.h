@@ -213,6 +213,13 @@ int b200fe_hangmesh_nodes(const b200fe_hangmesh *mesh, int p_geo, int deform_kin
 int b200fe_geometry_from_nodes(int p_geo, int nq, int quad_kind, uint32_t n_cells, const double *d_nodes,
                                double *d_G, double *d_JxW, void *stream);
 
+/* The same factors from deal.II's own MatrixFree data (what the deal.II-kernel variant of the operator reads,
+ * bakeoff_problems_dealii/include/portable_laplace_operator.h:227-258): d_inv_jacobian(q, cell, ref, real) =
+ * d xi_ref / d x_real and d_JxW(q, cell) as Kokkos LayoutLeft views, i.e. element (q, cell, ref, real) at
+ * q + nq^3 * (cell + n_cells * (ref + 3 * real)), q = x + nq (y + nq z).  d_G[cell][6][nq^3] as above. */
+int b200fe_geometry_from_inv_jacobian(uint32_t n_cells, int nq, const double *d_inv_jacobian, const double *d_JxW,
+                                      double *d_G, void *stream);
+
 /* Per-cell constants for the on-the-fly geometry of affine (parallelepiped) cells from MappingQ1 support points
  * d_nodes[cell][3][2][2][2] (b200fe_boxmesh_nodes with p_geo = 1): d_cell_G[cell][8], see b200fe_op_desc. */
 int b200fe_geometry_affine_from_nodes(uint32_t n_cells, const double *d_nodes, double *d_cell_G, void *stream);

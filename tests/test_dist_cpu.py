@@ -125,3 +125,83 @@ def test_overlap_permutation_splits_cells():
     touches = ((idx >= mesh.n_owned) & (idx != 0xFFFFFFFF)).any(axis=1)
     assert not touches[:n0].any() and touches[n0:n0 + n1].all() and not touches[n0 + n1:].any()
     assert n1 > 0
+
+
+def _worker_hanging(rank, world, port, sub, nref, p, lo, hi, q):
+    """Same emulation on a two-level mesh with hanging nodes: the ghost set must also carry the parents of the
+    hanging DoFs, and distribute / condense run between the exchanges (the sequence of b200fe_op_vmult)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import benchmarks_b200 as b
+        from benchmarks_b200.dist import exchange_lists
+        import oracle
+        fe, ho = oracle.fe, oracle.hanging
+        mesh = b.HangingBoxMesh(sub, nref, p, lo, hi, n_ranks=world, rank=rank)
+        L = exchange_lists(mesh)
+        om = ho.TwoLevelMesh(sub, nref, (lo, hi))
+        spP, sp1 = ho.build_space(om, p, world), ho.build_space(om, p, 1)
+        ser_of = {k: d for d, k in enumerate(sp1["keys"])}
+        perm = np.array([ser_of[k] for k in spP["keys"]])
+        bas = fe.basis_1d(p, p + 2)
+        rd = dict(dof_indices=mesh.dof_indices, hang_dof=mesh.hang_dof, hang_row_ptr=mesh.hang_row_ptr, hang_col=mesh.hang_col,
+                  hang_w=mesh.hang_w)
+        cells = [tuple(int(v) for v in c) for c in mesh.cell_lxyz]
+        G, _ = fe.geometric_factors(ho.cell_nodes(om, cells, 1), 1, bas)
+        u1 = np.random.default_rng(3).standard_normal(sp1["n_dofs"])
+        u_global = u1[perm]
+        n_own = mesh.n_owned
+        v = np.zeros(n_own + mesh.n_ghost)
+        v[:n_own] = u_global[mesh.owned_begin:mesh.owned_begin + n_own]
+
+        def exchange(send_bufs, recv_sizes):
+            out, reqs = {}, []
+            for t, buf in send_bufs.items():
+                reqs.append(dist.isend(torch.from_numpy(buf.copy()), t))
+            for t, n in recv_sizes.items():
+                out[t] = torch.empty(n, dtype=torch.float64)
+                reqs.append(dist.irecv(out[t], t))
+            for r in reqs:
+                r.wait()
+            return {t: o.numpy() for t, o in out.items()}
+
+        peers = [int(t) for t in L["peers"]]
+        send_sl = {t: L["send_indices"][so:so + sc] for t, so, sc in zip(peers, L["send_offset"], L["send_count"]) if sc}
+        recv_sl = {t: (n_own + int(off), int(cnt)) for t, off, cnt in zip(peers, L["recv_offset"], L["recv_count"]) if cnt}
+        got = exchange({t: v[ix] for t, ix in send_sl.items()}, {t: c for t, (_, c) in recv_sl.items()})  # update_ghost_values
+        for t, (o, c) in recv_sl.items():
+            v[o:o + c] = got[t]
+        ok = bool(np.array_equal(v[n_own:], u_global[mesh.ghost_global.astype(np.int64)]))
+        uh = ho.distribute(rd, v)
+        y = ho.condense(rd, fe.op_apply(uh, mesh.dof_indices, bas, G, n_local=len(v), constrained=np.zeros(0, np.uint32)))
+        got = exchange({t: y[o:o + c] for t, (o, c) in recv_sl.items()}, {t: len(ix) for t, ix in send_sl.items()})  # compress(add)
+        for t, ix in send_sl.items():
+            np.add.at(y, ix, got[t])
+        y = y[:n_own]
+        y[mesh.constrained] = v[mesh.constrained]
+        rd1 = ho.rank_data(om, sp1, 0)
+        G1, _ = fe.geometric_factors(ho.cell_nodes(om, rd1["cells"], 1), 1, bas)
+        y1 = ho.op_apply(rd1, bas, G1, u1)
+        mine = np.arange(mesh.owned_begin, mesh.owned_begin + n_own)
+        err = np.abs(y - y1[perm[mine]]).max() / np.abs(y1).max()
+        q.put((rank, ok, float(err)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,sub,nref,p,lo,hi", [(2, (1, 1, 1), 1, 2, (0, 0, 0), (1, 1, 1)), (3, (2, 1, 1), 1, 3, (1, 0, 0), (3, 1, 2))])
+def test_hanging_mesh_exchange_and_distributed_apply_gloo(world, sub, nref, p, lo, hi):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_hanging, args=(r, world, port, sub, nref, p, lo, hi, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    results = [q.get(timeout=240) for _ in range(world)]
+    for pr in procs:
+        pr.join(timeout=60)
+    assert len(results) == world
+    for rank, ok, err in results:
+        assert ok, f"rank {rank}: ghost values differ after update_ghost_values"
+        assert err <= 1e-12, f"rank {rank}: distributed constrained apply differs ({err})"

@@ -171,3 +171,31 @@ def test_bp6_driver_matches_python_path():
         ctl = b.ReductionControl(10 ** 9, 1e-16, 1e-9)
         b.SolverCG(ctl).solve(A, x, rhs, n_components=3)
         assert abs(int(row[6]) - ctl.last_step()) <= 1
+
+
+def test_geometry_from_dealii_inv_jacobian_views(oracle_mod):
+    """G from MatrixFree's inv_jacobian(q, cell, ref, real) / JxW(q, cell) (Kokkos LayoutLeft), checked
+    against the oracle's G of the same deformed cells, with K = J^-1 produced independently by numpy."""
+    import ctypes as C
+    import benchmarks_b200 as b
+    from benchmarks_b200._lib import check, lib
+    fe = oracle_mod.fe
+    p, nq, p_geo = 3, 5, 2
+    om = fe.BoxMesh((2, 1, 1), 1)
+    cells = np.arange(om.n_cells)
+    bas = fe.basis_1d(p, nq)
+    nodes = fe.cell_nodes(om, cells, p_geo, lambda P: P + 0.05 * np.sin(2.0 * P[..., [1, 2, 0]]))
+    G, JxW = fe.geometric_factors(nodes, p_geo, bas)
+    # J at the points from the mapping nodes (same einsums as the oracle), K = J^-1 as deal.II stores it
+    tg, _ = fe.gll_01(p_geo + 1)
+    V, dV = fe.lagrange_values(tg, bas["xq"]), fe.lagrange_derivs(tg, bas["xq"])
+    J = np.stack([np.einsum("cdzyx,rz,qy,px->cdrqp", nodes, V, V, dV), np.einsum("cdzyx,rz,qy,px->cdrqp", nodes, V, dV, V),
+                  np.einsum("cdzyx,rz,qy,px->cdrqp", nodes, dV, V, V)], axis=2)          # [c, real, ref, z, y, x]
+    K = np.linalg.inv(np.moveaxis(J, (1, 2), (-2, -1)))                                   # [c, z, y, x, ref, real]
+    nc, nq3 = om.n_cells, nq ** 3
+    view = np.ascontiguousarray(np.transpose(K.reshape(nc, nq3, 3, 3), (3, 2, 0, 1)))      # (real, ref, cell, q): q fastest
+    d_K, d_J = torch.from_numpy(view.ravel()).cuda(), torch.from_numpy(JxW.ravel().copy()).cuda()
+    d_G = torch.empty(nc * 6 * nq3, dtype=torch.float64, device="cuda")
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    check(lib.b200fe_geometry_from_inv_jacobian(nc, nq, vp(d_K), vp(d_J), vp(d_G), None))
+    assert rel(d_G.cpu().numpy().reshape(G.shape), G) <= TOL

@@ -30,6 +30,81 @@ def lattice_of_local(mesh, A):
     return out, int(np.prod(n))
 
 
+def keys_of_local(mesh):
+    """Numbering-independent identity of every local DoF of a HangingBoxMesh that an owned cell touches (convention H1 of
+    csrc/hangmesh.cc): coarse-level DoFs by their point on the coarse lattice, fine-level DoFs (everything of a child cell
+    that is not a vertex of the coarse mesh) by their point on the fine lattice, offset by the coarse lattice size."""
+    p, nm = mesh.p, mesh.p + 1
+    n0 = [c * p + 1 for c in mesh.cells]
+    n1 = [2 * c * p + 1 for c in mesh.cells]
+    l = np.arange(nm ** 3)
+    a = np.stack([l % nm, (l // nm) % nm, l // (nm * nm)], axis=1)              # [nm^3, 3]
+    lvl = mesh.cell_lxyz[:, 0].astype(np.int64)
+    F = mesh.cell_lxyz[:, None, 1:].astype(np.int64) * p + a[None]                # lattice point at the cell's own level
+    coarse_vertex = (F % (2 * p) == 0).all(axis=2)
+    as_coarse = (lvl[:, None] == 0) | coarse_vertex
+    C = np.where((lvl == 0)[:, None, None], F, F // 2)                            # coarse lattice point where it applies
+    key0 = (C[..., 2] * n0[1] + C[..., 1]) * n0[0] + C[..., 0]
+    key1 = int(np.prod(n0)) + (F[..., 2] * n1[1] + F[..., 1]) * n1[0] + F[..., 0]
+    key = np.where(as_coarse, key0, key1)
+    out = np.full(mesh.n_owned + mesh.n_ghost, -1, dtype=np.int64)
+    idx = mesh.dof_indices.astype(np.int64)
+    valid = idx != 0xFFFFFFFF
+    out[idx[valid]] = key[valid]
+    return out, int(np.prod(n0)) + int(np.prod(n1))
+
+
+def check_hanging(rank, world, gloo):
+    """Distributed C^T A C (hanging-node rows whose parents are ghosts, condensation before compress) and the 3-component CG
+    against the same two-level mesh on one GPU."""
+    blocks = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[world]
+    ok = True
+    for p, quad, nref in ((2, "gauss", 2), (4, "gll", 2), (7, "gll", 1)):
+        cells = [s << nref for s in blocks]
+        lo, hi = (0, 0, 0), tuple(max(c // 2, 1) for c in cells)
+        mesh = b.HangingBoxMesh(blocks, nref, p, lo, hi, n_ranks=world, rank=rank)
+        halo = Halo(mesh, group=gloo)
+        kw = dict(quad=quad, deform=(0.03, 1.5), p_geo=2)
+        A = b.LaplaceOperator(mesh, halo=halo, **kw)
+        m1 = b.HangingBoxMesh(blocks, nref, p, lo, hi)
+        A1 = b.LaplaceOperator(m1, **kw)
+        key, n_key = keys_of_local(mesh)
+        key1, _ = keys_of_local(m1)
+        field = np.random.default_rng(9).standard_normal(n_key)
+        own = key[: mesh.n_owned]
+        sel = own >= 0
+        src = A.initialize_dof_vector()
+        src[: mesh.n_owned] = torch.from_numpy(np.where(sel, field[np.maximum(own, 0)], 0.0)).cuda()
+        dst = A.initialize_dof_vector()
+        A.vmult(dst, src)
+        s1 = A1.initialize_dof_vector()
+        s1[:] = torch.from_numpy(np.where(key1 >= 0, field[np.maximum(key1, 0)], 0.0)).cuda()
+        d1 = A1.initialize_dof_vector()
+        A1.vmult(d1, s1)
+        full = np.zeros(n_key)
+        full[key1[key1 >= 0]] = d1.cpu().numpy()[key1 >= 0]
+        err = np.abs(dst[: mesh.n_owned].cpu().numpy()[sel] - full[own[sel]]).max() / np.abs(full).max()
+        # BP6-style CG: three components, rhs = int phi in each
+        nloc, nloc1 = mesh.n_owned + mesh.n_ghost, m1.n_owned
+        rhs = A.compute_rhs().repeat(3)
+        x = torch.zeros(3 * nloc, dtype=torch.float64, device="cuda")
+        ctl = b.ReductionControl(20000, 1e-16, 1e-9)
+        b.SolverCG(ctl).solve(A, x, rhs, n_components=3)
+        rhs1 = A1.compute_rhs().repeat(3)
+        x1 = torch.zeros(3 * nloc1, dtype=torch.float64, device="cuda")
+        ctl1 = b.ReductionControl(20000, 1e-16, 1e-9)
+        b.SolverCG(ctl1).solve(A1, x1, rhs1, n_components=3)
+        xs = np.zeros(n_key)
+        xs[key1[key1 >= 0]] = x1[2 * nloc1:].cpu().numpy()[key1 >= 0]
+        xerr = np.abs(x[2 * nloc: 2 * nloc + mesh.n_owned].cpu().numpy()[sel] - xs[own[sel]]).max() / np.abs(xs).max()
+        good = err <= 1e-12 and abs(ctl.last_step() - ctl1.last_step()) <= 1 and xerr <= 1e-6
+        ok &= bool(good)
+        print(f"[rank {rank}/{world}] hanging p={p} {quad}: {len(mesh.hang_dof)} rows, vmult rel err {err:.2e}, BP6 CG its {ctl.last_step()} vs "
+              f"{ctl1.last_step()} (1 GPU), x rel err {xerr:.1e} -> {'OK' if good else 'FAIL'}", flush=True)
+        del A, A1, halo
+    return ok
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
@@ -82,6 +157,11 @@ def main():
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
         print("DIST_CHECK", "PASS" if t.item() == 1 else "FAIL", flush=True)
+    th = torch.tensor([int(check_hanging(rank, world, gloo))], device="cuda")
+    dist.all_reduce(th, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("DIST_CHECK_HANGING", "PASS" if th.item() == 1 else "FAIL", flush=True)
+    t = torch.minimum(t, th)
     dist.destroy_process_group()
     sys.exit(0 if t.item() == 1 else 1)
 
