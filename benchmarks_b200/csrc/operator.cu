@@ -261,96 +261,80 @@ __global__ void set_constrained_kernel(uint32_t n, const uint32_t *__restrict__ 
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v[list[i]] = value;
 }
 
-// Hanging-node rows  v[h] = sum_k w[k] v[col[k]]  and their transpose, ENTRY-parallel: one thread per CSR entry
-// (coalesced reads of w / col / row-of-entry), so the work is throughput-bound.  The first version ran one warp per
-// row and was bound by the dependent-load chain ptr -> col -> v of each row: 106 / 112 us for 130 k rows of <= 81
-// entries against a byte bound of ~20 us (profiles/r01i_bp6_launches.csv).
-// Vector-valued problems: a thread applies its entry to all components (component-blocked vectors, `stride` apart).
+// hanging-node rows, one warp per row (rows hold 2 ... (p+1)^2 parents): v[h] = sum_k w[k] v[col[k]].
+// Vector-valued problems: the row is applied to all components (component-blocked vectors, `stride` apart) while its
+// weights / parent indices are read once (the CSR arrays are the only DRAM traffic of these kernels; r01h: 87 us per
+// component for 130 k rows at p = 8 when launched per component).
 constexpr int kCompChunk = 4;
 
-// row-parallel prologue of distribute: save[r] = v[h]; v[h] = 0
-__global__ void hang_save_zero_kernel(uint32_t n_rows, const uint32_t *__restrict__ hdof, double *__restrict__ v, int ncomp,
-                                      size_t stride, double *__restrict__ save, const int *__restrict__ skip)
-{
-    if (skip != nullptr && *skip != 0) return;
-    const size_t total = (size_t)n_rows * ncomp;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const uint32_t r = (uint32_t)(i % n_rows);
-        const size_t c = i / n_rows;
-        double *vh = v + c * stride + hdof[r];
-        if (save) save[i] = *vh;
-        *vh = 0.0;
-    }
-}
-
-// v[h(row[k])] += w[k] v[col[k]]: consecutive lanes hold consecutive entries, rows are contiguous runs of entries, so a
-// segmented warp reduction leaves one atomic per (row, warp).  A hanging DoF is never a parent (chain-free rows), so
-// the gathers never see a partially summed value.
-__global__ void distribute_entries_kernel(uint32_t nnz, const uint32_t *__restrict__ hdof, const uint32_t *__restrict__ row,
-                                          const uint32_t *__restrict__ col, const double *__restrict__ w, double *__restrict__ v,
-                                          int ncomp, size_t stride, const int *__restrict__ skip)
+__global__ void distribute_kernel(uint32_t n_rows, const uint32_t *__restrict__ hdof, const uint32_t *__restrict__ ptr,
+                                  const uint32_t *__restrict__ col, const double *__restrict__ w, double *__restrict__ v,
+                                  int ncomp, size_t stride, double *__restrict__ save, const int *__restrict__ skip)
 {
     if (skip != nullptr && *skip != 0) return;
     const int lane = threadIdx.x & 31;
-    const uint32_t step = gridDim.x * blockDim.x;  // multiple of 32: whole warps stay together in the loop
-    const uint32_t rounds = (nnz + step - 1) / step;
-    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    for (uint32_t it = 0; it < rounds; ++it, k += step) {
-        const bool ok = k < nnz;
-        const uint32_t r = ok ? row[k] : 0xFFFFFFFFu;
-        const double wk = ok ? w[k] : 0.0;
-        const uint32_t ck = ok ? col[k] : 0u;
-        const uint32_t r_next = __shfl_down_sync(0xffffffffu, r, 1);
-        const bool tail = ok && (lane == 31 || r_next != r);
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_rows; r += warps) {
+        const uint32_t b = ptr[r], e = ptr[r + 1], h = hdof[r];
         for (int c0 = 0; c0 < ncomp; c0 += kCompChunk) {
             const int nc = min(kCompChunk, ncomp - c0);
-            double s[kCompChunk];
-#pragma unroll
-            for (int c = 0; c < kCompChunk; ++c) s[c] = (ok && c < nc) ? wk * v[(size_t)(c0 + c) * stride + ck] : 0.0;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {  // segmented inclusive scan over the lanes of equal row
-                const uint32_t ro = __shfl_up_sync(0xffffffffu, r, o);
-#pragma unroll
-                for (int c = 0; c < kCompChunk; ++c) {
-                    const double so = __shfl_up_sync(0xffffffffu, s[c], o);
-                    if (lane >= o && ro == r) s[c] += so;
-                }
-            }
-            if (tail) {
-                const uint32_t h = hdof[r];
+            double s[kCompChunk] = {0.0, 0.0, 0.0, 0.0};
+            for (uint32_t k = b + lane; k < e; k += 32) {
+                const double wk = w[k];
+                const double *vk = v + (size_t)c0 * stride + col[k];
 #pragma unroll
                 for (int c = 0; c < kCompChunk; ++c)
-                    if (c < nc) atomicAdd(v + (size_t)(c0 + c) * stride + h, s[c]);
+                    if (c < nc) s[c] = fma(wk, vk[c * stride], s[c]);
+            }
+#pragma unroll
+            for (int c = 0; c < kCompChunk; ++c)
+                for (int o = 16; o > 0; o >>= 1) s[c] += __shfl_xor_sync(0xffffffffu, s[c], o);
+            if (lane == 0) {
+#pragma unroll
+                for (int c = 0; c < kCompChunk; ++c)
+                    if (c < nc) {
+                        double *vh = v + (size_t)(c0 + c) * stride + h;
+                        if (save) save[(size_t)(c0 + c) * n_rows + r] = *vh;
+                        *vh = s[c];  // a hanging DoF is never a parent (chain-free rows): no other warp reads v[h]
+                    }
             }
         }
     }
 }
 
-// transpose: dst[col[k]] += w[k] dst[h(row[k])]
-__global__ void condense_entries_kernel(uint32_t nnz, const uint32_t *__restrict__ hdof, const uint32_t *__restrict__ row,
-                                        const uint32_t *__restrict__ col, const double *__restrict__ w, double *__restrict__ dst,
-                                        int ncomp, size_t stride, const int *__restrict__ skip)
+// transpose: dst[col[k]] += w[k] dst[h]; dst[h] = 0; optionally src[h] = save[r]
+__global__ void condense_kernel(uint32_t n_rows, const uint32_t *__restrict__ hdof, const uint32_t *__restrict__ ptr,
+                                const uint32_t *__restrict__ col, const double *__restrict__ w, double *__restrict__ dst,
+                                int ncomp, size_t stride, double *__restrict__ src, const double *__restrict__ save,
+                                const int *__restrict__ skip)
 {
     if (skip != nullptr && *skip != 0) return;
-    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += gridDim.x * blockDim.x) {
-        const uint32_t h = hdof[row[k]], ck = col[k];
-        const double wk = w[k];
-        for (int c = 0; c < ncomp; ++c) atomicAdd(dst + (size_t)c * stride + ck, wk * dst[(size_t)c * stride + h]);
-    }
-}
-
-// row-parallel epilogue of condense (after every entry has read dst[h]): dst[h] = 0; optionally src[h] = save[r]
-__global__ void hang_finish_kernel(uint32_t n_rows, const uint32_t *__restrict__ hdof, double *__restrict__ dst, int ncomp,
-                                   size_t stride, double *__restrict__ src, const double *__restrict__ save,
-                                   const int *__restrict__ skip)
-{
-    if (skip != nullptr && *skip != 0) return;
-    const size_t total = (size_t)n_rows * ncomp;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const uint32_t r = (uint32_t)(i % n_rows);
-        const size_t off = (i / n_rows) * stride + hdof[r];
-        dst[off] = 0.0;
-        if (src) src[off] = save[i];
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_rows; r += warps) {
+        const uint32_t h = hdof[r], b = ptr[r], e = ptr[r + 1];
+        for (int c0 = 0; c0 < ncomp; c0 += kCompChunk) {
+            const int nc = min(kCompChunk, ncomp - c0);
+            double t[kCompChunk];
+#pragma unroll
+            for (int c = 0; c < kCompChunk; ++c) t[c] = c < nc ? dst[(size_t)(c0 + c) * stride + h] : 0.0;
+            for (uint32_t k = b + lane; k < e; k += 32) {
+                const double wk = w[k];
+                double *dk = dst + (size_t)c0 * stride + col[k];
+#pragma unroll
+                for (int c = 0; c < kCompChunk; ++c)
+                    if (c < nc) atomicAdd(dk + c * stride, wk * t[c]);
+            }
+            __syncwarp();
+            if (lane == 0) {
+#pragma unroll
+                for (int c = 0; c < kCompChunk; ++c)
+                    if (c < nc) {
+                        dst[(size_t)(c0 + c) * stride + h] = 0.0;
+                        if (src) src[(size_t)(c0 + c) * stride + h] = save[(size_t)(c0 + c) * n_rows + r];
+                    }
+            }
+        }
     }
 }
 
@@ -407,34 +391,20 @@ int op_distribute(Operator &op, double *d_v, bool save, cudaStream_t s, int ncom
     if (op.n_hang == 0) return B200FE_OK;
     if (save)
         if (int rc = ensure_hang_save(op, ncomp)) return rc;
-    const unsigned row_blocks = std::min<unsigned>((unsigned)(((size_t)op.n_hang * ncomp + 255) / 256), 148u * 8u);
-    hang_save_zero_kernel<<<row_blocks, 256, 0, s>>>(op.n_hang, op.d_hang_dof, d_v, ncomp, op.n_local(), save ? op.d_hang_save : nullptr,
-                                                     op.d_skip);
+    const unsigned blocks = std::min<unsigned>((op.n_hang + 7) / 8, 148u * 8u);  // 8 warps (rows) per CTA
+    distribute_kernel<<<blocks, 256, 0, s>>>(op.n_hang, op.d_hang_dof, op.d_hang_ptr, op.d_hang_col, op.d_hang_w, d_v, ncomp,
+                                             op.n_local(), save ? op.d_hang_save : nullptr, op.d_skip);
     B200FE_CUDA_TRY(cudaGetLastError());
     ++g_launch_count;
-    if (op.n_hang_entries) {
-        const unsigned blocks = std::min<unsigned>((op.n_hang_entries + 255) / 256, 148u * 8u);
-        distribute_entries_kernel<<<blocks, 256, 0, s>>>(op.n_hang_entries, op.d_hang_dof, op.d_hang_row, op.d_hang_col, op.d_hang_w, d_v,
-                                                         ncomp, op.n_local(), op.d_skip);
-        B200FE_CUDA_TRY(cudaGetLastError());
-        ++g_launch_count;
-    }
     return B200FE_OK;
 }
 
 int op_condense(Operator &op, double *d_dst, double *d_src_restore, cudaStream_t s, int ncomp)
 {
     if (op.n_hang == 0) return B200FE_OK;
-    if (op.n_hang_entries) {
-        const unsigned blocks = std::min<unsigned>((op.n_hang_entries + 255) / 256, 148u * 8u);
-        condense_entries_kernel<<<blocks, 256, 0, s>>>(op.n_hang_entries, op.d_hang_dof, op.d_hang_row, op.d_hang_col, op.d_hang_w, d_dst,
-                                                       ncomp, op.n_local(), op.d_skip);
-        B200FE_CUDA_TRY(cudaGetLastError());
-        ++g_launch_count;
-    }
-    const unsigned row_blocks = std::min<unsigned>((unsigned)(((size_t)op.n_hang * ncomp + 255) / 256), 148u * 8u);
-    hang_finish_kernel<<<row_blocks, 256, 0, s>>>(op.n_hang, op.d_hang_dof, d_dst, ncomp, op.n_local(), d_src_restore, op.d_hang_save,
-                                                  op.d_skip);
+    const unsigned blocks = std::min<unsigned>((op.n_hang + 7) / 8, 148u * 8u);
+    condense_kernel<<<blocks, 256, 0, s>>>(op.n_hang, op.d_hang_dof, op.d_hang_ptr, op.d_hang_col, op.d_hang_w, d_dst, ncomp,
+                                           op.n_local(), d_src_restore, op.d_hang_save, op.d_skip);
     B200FE_CUDA_TRY(cudaGetLastError());
     ++g_launch_count;
     return B200FE_OK;
@@ -715,11 +685,8 @@ int b200fe_op_set_constraints(b200fe_op *o, uint32_t n_rows, const uint32_t *h_h
         if (e == cudaSuccess && n) e = cudaMemcpy(*dst, src, n * sizeof(**dst), cudaMemcpyHostToDevice);
         return e;
     };
-    std::vector<uint32_t> row_of(nnz);  // entry -> row (the kernels are entry-parallel)
-    for (uint32_t r = 0; r < n_rows; ++r)
-        for (uint32_t k = h_hang_row_ptr[r]; k < h_hang_row_ptr[r + 1]; ++k) row_of[k] = r;
     cudaError_t e = upload(&op.d_hang_dof, h_hang_dof, n_rows);
-    if (e == cudaSuccess) e = upload(&op.d_hang_row, row_of.data(), nnz);
+    if (e == cudaSuccess) e = upload(&op.d_hang_ptr, h_hang_row_ptr, (size_t)n_rows + 1);
     if (e == cudaSuccess) e = upload(&op.d_hang_col, h_hang_col, nnz);
     if (e == cudaSuccess) e = upload(&op.d_hang_w, h_hang_w, nnz);
     if (e != cudaSuccess) {
@@ -727,7 +694,6 @@ int b200fe_op_set_constraints(b200fe_op *o, uint32_t n_rows, const uint32_t *h_h
         return fail_cuda(e, "b200fe_op_set_constraints");
     }
     op.n_hang = n_rows;
-    op.n_hang_entries = nnz;
     return B200FE_OK;
 }
 

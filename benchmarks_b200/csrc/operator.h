@@ -24,8 +24,8 @@ struct Operator {
     double *d_mats = nullptr;           // owned: shape_values | co_shape_gradients | shape_gradients (setup kernels)
     Halo *halo = nullptr;               // borrowed, optional
     // hanging-node rows (b200fe_op_set_constraints), owned copies: u[hang_dof[r]] = sum_k w[k] u[col[k]]
-    uint32_t n_hang = 0, n_hang_entries = 0;
-    uint32_t *d_hang_dof = nullptr, *d_hang_row = nullptr, *d_hang_col = nullptr;  // row: entry -> row
+    uint32_t n_hang = 0;
+    uint32_t *d_hang_dof = nullptr, *d_hang_ptr = nullptr, *d_hang_col = nullptr;
     double *d_hang_w = nullptr, *d_hang_save = nullptr;  // save: src values of the hanging entries during a vmult
     int hang_save_comps = 0;                              // components the save buffer has room for
     const int *d_skip = nullptr;        // set by the CG driver for the duration of a solve (see KArgs::skip)
@@ -50,10 +50,10 @@ struct Operator {
     }
     void free_constraints()
     {
-        cudaFree(d_hang_dof); cudaFree(d_hang_row); cudaFree(d_hang_col); cudaFree(d_hang_w); cudaFree(d_hang_save);
-        d_hang_dof = d_hang_row = d_hang_col = nullptr;
+        cudaFree(d_hang_dof); cudaFree(d_hang_ptr); cudaFree(d_hang_col); cudaFree(d_hang_w); cudaFree(d_hang_save);
+        d_hang_dof = d_hang_ptr = d_hang_col = nullptr;
         d_hang_w = d_hang_save = nullptr;
-        n_hang = n_hang_entries = 0;
+        n_hang = 0;
         hang_save_comps = 0;
     }
 };
