@@ -46,6 +46,8 @@ _SIGNATURES = {
     "b200fe_hangmesh_destroy": (None, [_vp]),
     "b200fe_hangmesh_info": (_i, [_vp, _vp]),
     "b200fe_hangmesh_fill": (_i, [_vp] * 11),
+    "b200fe_hangmesh_fill_faces": (_i, [_vp, _vp, _vp]),
+    "b200fe_trace_weights": (_i, [_i, _vp]),
     "b200fe_hangmesh_nodes": (_i, [_vp, _i, _i, C.c_double, C.c_double, _vp, _vp]),
     "b200fe_geometry_from_nodes": (_i, [_i, _i, _i, _u32, _vp, _vp, _vp, _vp]),
     "b200fe_geometry_from_inv_jacobian": (_i, [_u32, _i, _vp, _vp, _vp, _vp]),
@@ -54,6 +56,7 @@ _SIGNATURES = {
     "b200fe_op_destroy": (None, [_vp]),
     "b200fe_op_set_halo": (_i, [_vp, _vp]),
     "b200fe_op_set_constraints": (_i, [_vp, _u32, _vp, _vp, _vp, _vp]),
+    "b200fe_op_set_face_constraints": (_i, [_vp, _i, _u32, _vp, _vp, _vp]),
     "b200fe_op_distribute": (_i, [_vp, _vp, _vp]),
     "b200fe_op_vmult": (_i, [_vp, _vp, _vp, _vp]),
     "b200fe_op_vmult_components": (_i, [_vp, _i, _vp, _vp, _vp]),

@@ -58,6 +58,9 @@ struct HangMesh {
     std::vector<uint32_t> constrained;   // owned local: Dirichlet + hanging
     std::vector<uint32_t> hang_dof, hang_row_ptr, hang_col;
     std::vector<double> hang_w;
+    // the same rows grouped by coarse face (tensor-product trace interpolation): [n_face_blocks][(p+1)^2], [..][(2p+1)^2]
+    std::vector<uint32_t> face_parents, face_children;
+    uint32_t n_face_blocks = 0;
     uint64_t first_cell = 0;  // position of the rank's first cell on the p4est curve
 
     bool refined(int64_t x, int64_t y, int64_t z) const
@@ -329,6 +332,71 @@ int HangMesh::build()
     hang_col.resize(col_g.size());
     for (size_t i = 0; i < col_g.size(); ++i) hang_col[i] = local_of(col_g[i]);
     hang_w.swap(wgt);
+
+    // ---- face-structured form of the same rows ------------------------------------------------------------------
+    // Every hanging DoF of a box-refined mesh lies on a face shared by an unrefined cell K and a refined cell; its
+    // (2p+1)^2 fine nodes are the tensor-product interpolation W (x) W of the (p+1)^2 coarse face nodes.  Blocks in
+    // (K position, axis, side) order; a DoF on several faces belongs to the first block that needs it.
+    {
+        const int nf = twop + 1;
+        std::vector<uint8_t> claimed(rows.size(), 0);
+        auto row_of_global = [&](uint32_t g) -> int64_t {
+            auto it = std::lower_bound(rows.begin(), rows.end(), g, [](const Row &r, uint32_t v) { return r.g < v; });
+            return (it != rows.end() && it->g == g) ? (int64_t)(it - rows.begin()) : -1;
+        };
+        auto local_or_invalid = [&](uint64_t g) -> uint32_t {
+            if (g >= owned_begin && g < owned_end) return (uint32_t)(g - owned_begin);
+            auto it = std::lower_bound(ghost_global.begin(), ghost_global.end(), g);
+            return (it != ghost_global.end() && *it == g) ? (uint32_t)(n_owned + (it - ghost_global.begin())) : B200FE_INVALID_INDEX;
+        };
+        std::vector<uint32_t> par((size_t)nm * nm), chi((size_t)nf * nf);
+        size_t n_claimed = 0;
+        for (int64_t ps = 0; ps < n_base && !rows.empty(); ++ps) {
+            int64_t K[3];
+            base_xyz((uint64_t)ps, K[0], K[1], K[2]);
+            if (refined(K[0], K[1], K[2])) continue;
+            for (int axis = 0; axis < 3; ++axis)
+                for (int side = 0; side < 2; ++side) {
+                    int64_t N[3] = {K[0], K[1], K[2]};
+                    N[axis] += side ? 1 : -1;
+                    if (N[axis] < 0 || N[axis] >= cells[axis] || !refined(N[0], N[1], N[2])) continue;
+                    const int u1 = axis == 0 ? 1 : 0, u2 = axis == 2 ? 1 : 2;  // in-face axes, u1 < u2
+                    bool any_child = false;
+                    for (int bb = 0; bb < nf; ++bb)
+                        for (int a = 0; a < nf; ++a) {
+                            chi[a + (size_t)nf * bb] = B200FE_INVALID_INDEX;
+                            int64_t F[3];
+                            F[axis] = (K[axis] + side) * twop; F[u1] = K[u1] * twop + a; F[u2] = K[u2] * twop + bb;
+                            if (F[0] % twop == 0 && F[1] % twop == 0 && F[2] % twop == 0) continue;  // coarse vertex
+                            const uint32_t g = L1[(uint64_t)(F[0] - (int64_t)lo[0] * twop) + d1[0] * ((uint64_t)(F[1] - (int64_t)lo[1] * twop) + d1[1] * (uint64_t)(F[2] - (int64_t)lo[2] * twop))];
+                            if (g == kNone) continue;
+                            const int64_t r = row_of_global(g);
+                            if (r < 0 || claimed[r]) continue;
+                            claimed[r] = 1;
+                            ++n_claimed;
+                            chi[a + (size_t)nf * bb] = hang_dof[r];
+                            any_child = true;
+                        }
+                    if (!any_child) continue;
+                    for (int bb = 0; bb < nm; ++bb)
+                        for (int a = 0; a < nm; ++a) {
+                            int64_t X[3];
+                            X[axis] = (K[axis] + side) * p; X[u1] = K[u1] * p + a; X[u2] = K[u2] * p + bb;
+                            uint32_t v = B200FE_INVALID_INDEX;
+                            const bool bnd = dirichlet && (X[0] == 0 || X[1] == 0 || X[2] == 0 || X[0] == d0[0] - 1 || X[1] == d0[1] - 1 || X[2] == d0[2] - 1);
+                            if (!bnd) {
+                                const uint32_t g = L0[(uint64_t)X[0] + d0[0] * ((uint64_t)X[1] + d0[1] * (uint64_t)X[2])];
+                                if (g != kNone) v = local_or_invalid(g);
+                            }
+                            par[a + (size_t)nm * bb] = v;
+                        }
+                    face_parents.insert(face_parents.end(), par.begin(), par.end());
+                    face_children.insert(face_children.end(), chi.begin(), chi.end());
+                    ++n_face_blocks;
+                }
+        }
+        if (n_claimed != rows.size()) return fail(B200FE_ERR_INVALID_ARG, "hanging mesh: internal error (%zu of %zu hanging DoFs lie on a hanging face)", n_claimed, rows.size());
+    }
     return B200FE_OK;
 }
 
@@ -379,6 +447,7 @@ int b200fe_hangmesh_info(const b200fe_hangmesh *mesh, b200fe_hangmesh_info_t *in
     info->n_constrained = (uint32_t)m->constrained.size();
     info->n_hanging_rows = (uint32_t)m->hang_dof.size();
     info->n_hanging_entries = (uint32_t)m->hang_col.size();
+    info->n_face_blocks = m->n_face_blocks;
     for (int d = 0; d < 3; ++d) { info->cells[d] = (uint32_t)m->cells[d]; info->h[d] = m->h[d]; info->origin[d] = m->p1[d]; }
     return B200FE_OK;
 }
@@ -402,6 +471,26 @@ int b200fe_hangmesh_fill(const b200fe_hangmesh *mesh, uint32_t *h_dof_indices, u
     put(h_hang_row_ptr, m->hang_row_ptr);
     put(h_hang_col, m->hang_col);
     put(h_hang_w, m->hang_w);
+    return B200FE_OK;
+}
+
+int b200fe_hangmesh_fill_faces(const b200fe_hangmesh *mesh, uint32_t *h_face_parents, uint32_t *h_face_children)
+{
+    B200FE_REQUIRE(mesh, "b200fe_hangmesh_fill_faces: null mesh");
+    const HangMesh *m = reinterpret_cast<const HangMesh *>(mesh);
+    if (h_face_parents && !m->face_parents.empty()) std::memcpy(h_face_parents, m->face_parents.data(), m->face_parents.size() * sizeof(uint32_t));
+    if (h_face_children && !m->face_children.empty()) std::memcpy(h_face_children, m->face_children.data(), m->face_children.size() * sizeof(uint32_t));
+    return B200FE_OK;
+}
+
+int b200fe_trace_weights(int p, double *h_W)
+{
+    B200FE_REQUIRE(h_W, "b200fe_trace_weights: null pointer");
+    if (p < 1 || p > 8) return fail(B200FE_ERR_UNSUPPORTED, "b200fe_trace_weights: degree p=%d outside 1..8", p);
+    std::vector<double> t(p + 1);
+    if (int rc = b200fe_basis_1d(p, p + 1, B200FE_QUAD_GLL, nullptr, nullptr, nullptr, t.data(), nullptr)) return rc;
+    const std::vector<double> W = trace_weights(p, t);
+    std::memcpy(h_W, W.data(), W.size() * sizeof(double));
     return B200FE_OK;
 }
 

@@ -338,6 +338,92 @@ __global__ void condense_kernel(uint32_t n_rows, const uint32_t *__restrict__ hd
     }
 }
 
+// ---- face-structured constraints (b200fe_op_set_face_constraints) ---------------------------------------------------
+// One CTA per coarse face: the (2p+1)^2 fine nodes of the face are W (x) W applied to its (p+1)^2 coarse nodes, so a face
+// costs (p+1)^2 + (2p+1)^2 scattered accesses and two small 1-D contractions in shared memory instead of the
+// (2p+1)^2 (p+1)^2 gathers of its CSR rows (the CSR kernels are L2-sector-bound).
+// W[rel*nm + j] row-major [nf][nm]; parents [blk][a + nm*b]; children [blk][a' + nf*b'].
+__global__ void distribute_faces_kernel(uint32_t n_blocks, int nm, int nf, const double *__restrict__ Wg, const uint32_t *__restrict__ parents,
+                                        const uint32_t *__restrict__ children, double *__restrict__ v, int ncomp, size_t stride,
+                                        double *__restrict__ save, const int *__restrict__ skip)
+{
+    if (skip != nullptr && *skip != 0) return;
+    extern __shared__ double fsm[];
+    double *W = fsm, *P = W + nf * nm, *T = P + nm * nm;  // T: [a' + nf*b]
+    for (int t = threadIdx.x; t < nf * nm; t += blockDim.x) W[t] = Wg[t];
+    for (uint32_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+        const uint32_t *par = parents + (size_t)blk * nm * nm, *chi = children + (size_t)blk * nf * nf;
+        for (int c = 0; c < ncomp; ++c) {
+            double *vc = v + (size_t)c * stride;
+            __syncthreads();  // W loaded / previous use of P and T finished
+            for (int t = threadIdx.x; t < nm * nm; t += blockDim.x) {
+                const uint32_t i = par[t];
+                P[t] = i == kInvalidIndex ? 0.0 : vc[i];
+            }
+            __syncthreads();
+            for (int t = threadIdx.x; t < nf * nm; t += blockDim.x) {
+                const int a1 = t % nf, b = t / nf;
+                double s = 0.0;
+                for (int a = 0; a < nm; ++a) s = fma(W[a1 * nm + a], P[a + nm * b], s);
+                T[t] = s;
+            }
+            __syncthreads();
+            for (int t = threadIdx.x; t < nf * nf; t += blockDim.x) {
+                const uint32_t i = chi[t];
+                if (i == kInvalidIndex) continue;
+                const int a1 = t % nf, b1 = t / nf;
+                double s = 0.0;
+                for (int b = 0; b < nm; ++b) s = fma(W[b1 * nm + b], T[a1 + nf * b], s);
+                if (save) save[((size_t)c * n_blocks + blk) * nf * nf + t] = vc[i];
+                vc[i] = s;  // every hanging DoF is the child of exactly one block and never a parent
+            }
+        }
+    }
+}
+
+__global__ void condense_faces_kernel(uint32_t n_blocks, int nm, int nf, const double *__restrict__ Wg, const uint32_t *__restrict__ parents,
+                                      const uint32_t *__restrict__ children, double *__restrict__ dst, int ncomp, size_t stride,
+                                      double *__restrict__ src, const double *__restrict__ save, const int *__restrict__ skip)
+{
+    if (skip != nullptr && *skip != 0) return;
+    extern __shared__ double fsm[];
+    double *W = fsm, *C = W + nf * nm, *T = C + nf * nf;  // T: [a' + nf*b]
+    for (int t = threadIdx.x; t < nf * nm; t += blockDim.x) W[t] = Wg[t];
+    for (uint32_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+        const uint32_t *par = parents + (size_t)blk * nm * nm, *chi = children + (size_t)blk * nf * nf;
+        for (int c = 0; c < ncomp; ++c) {
+            double *dc = dst + (size_t)c * stride;
+            __syncthreads();
+            for (int t = threadIdx.x; t < nf * nf; t += blockDim.x) {
+                const uint32_t i = chi[t];
+                double val = 0.0;
+                if (i != kInvalidIndex) {
+                    val = dc[i];
+                    dc[i] = 0.0;
+                    if (src) src[(size_t)c * stride + i] = save[((size_t)c * n_blocks + blk) * nf * nf + t];
+                }
+                C[t] = val;
+            }
+            __syncthreads();
+            for (int t = threadIdx.x; t < nf * nm; t += blockDim.x) {
+                const int a1 = t % nf, b = t / nf;
+                double s = 0.0;
+                for (int b1 = 0; b1 < nf; ++b1) s = fma(W[b1 * nm + b], C[a1 + nf * b1], s);
+                T[t] = s;
+            }
+            __syncthreads();
+            for (int t = threadIdx.x; t < nm * nm; t += blockDim.x) {
+                const uint32_t i = par[t];
+                if (i == kInvalidIndex) continue;
+                const int a = t % nm, b = t / nm;
+                double s = 0.0;
+                for (int a1 = 0; a1 < nf; ++a1) s = fma(W[a1 * nm + a], T[a1 + nf * b], s);
+                atomicAdd(dc + i, s);
+            }
+        }
+    }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -386,8 +472,34 @@ static int ensure_hang_save(Operator &op, int ncomp)
     return B200FE_OK;
 }
 
+static int ensure_face_save(Operator &op, int ncomp)
+{
+    if (ncomp <= op.face_save_comps) return B200FE_OK;
+    cudaFree(op.d_face_save);
+    op.d_face_save = nullptr;
+    op.face_save_comps = 0;
+    B200FE_CUDA_TRY(cudaMalloc(&op.d_face_save, (size_t)op.n_face_blocks * op.face_nf * op.face_nf * ncomp * sizeof(double)));
+    op.face_save_comps = ncomp;
+    return B200FE_OK;
+}
+
+static size_t face_smem(const Operator &op)
+{
+    return sizeof(double) * (size_t)(2 * op.face_nf * op.face_nm + op.face_nf * op.face_nf);  // W + max(P, C) + T
+}
+
 int op_distribute(Operator &op, double *d_v, bool save, cudaStream_t s, int ncomp)
 {
+    if (op.n_face_blocks) {  // face-structured form takes precedence over the CSR rows
+        if (save)
+            if (int rc = ensure_face_save(op, ncomp)) return rc;
+        distribute_faces_kernel<<<std::min<unsigned>(op.n_face_blocks, 148u * 8u), 128, face_smem(op), s>>>(
+            op.n_face_blocks, op.face_nm, op.face_nf, op.d_face_W, op.d_face_parents, op.d_face_children, d_v, ncomp, op.n_local(),
+            save ? op.d_face_save : nullptr, op.d_skip);
+        B200FE_CUDA_TRY(cudaGetLastError());
+        ++g_launch_count;
+        return B200FE_OK;
+    }
     if (op.n_hang == 0) return B200FE_OK;
     if (save)
         if (int rc = ensure_hang_save(op, ncomp)) return rc;
@@ -401,6 +513,14 @@ int op_distribute(Operator &op, double *d_v, bool save, cudaStream_t s, int ncom
 
 int op_condense(Operator &op, double *d_dst, double *d_src_restore, cudaStream_t s, int ncomp)
 {
+    if (op.n_face_blocks) {
+        condense_faces_kernel<<<std::min<unsigned>(op.n_face_blocks, 148u * 8u), 128, face_smem(op), s>>>(
+            op.n_face_blocks, op.face_nm, op.face_nf, op.d_face_W, op.d_face_parents, op.d_face_children, d_dst, ncomp, op.n_local(),
+            d_src_restore, op.d_face_save, op.d_skip);
+        B200FE_CUDA_TRY(cudaGetLastError());
+        ++g_launch_count;
+        return B200FE_OK;
+    }
     if (op.n_hang == 0) return B200FE_OK;
     const unsigned blocks = std::min<unsigned>((op.n_hang + 7) / 8, 148u * 8u);
     condense_kernel<<<blocks, 256, 0, s>>>(op.n_hang, op.d_hang_dof, op.d_hang_ptr, op.d_hang_col, op.d_hang_w, d_dst, ncomp,
@@ -417,7 +537,7 @@ int op_vmult(Operator &op, double *d_dst, const double *d_src, double *d_dot, bo
     const size_t stride = op.n_local();
     double *src_mut = const_cast<double *>(d_src);  // ghost (and hanging) entries of src are scratch, as in deal.II
     // hanging-node rows need the parents' ghost values before the first cell runs: no overlap split with constraints
-    const bool split = h && ghost_on && compute_on && (op.n_phase0 + op.n_phase1 > 0) && op.n_hang == 0;
+    const bool split = h && ghost_on && compute_on && (op.n_phase0 + op.n_phase1 > 0) && !op.has_constraints();
     if (split && ncomp > 1) {  // the overlap schedule is per vector: one component after the other
         for (int c = 0; c < ncomp; ++c)
             if (int rc = op_vmult(op, d_dst + c * stride, d_src + c * stride, d_dot, ghost_on, compute_on, s, 1)) return rc;
@@ -697,6 +817,47 @@ int b200fe_op_set_constraints(b200fe_op *o, uint32_t n_rows, const uint32_t *h_h
     return B200FE_OK;
 }
 
+int b200fe_op_set_face_constraints(b200fe_op *o, int p, uint32_t n_blocks, const uint32_t *h_face_parents,
+                                   const uint32_t *h_face_children, const double *h_W)
+{
+    B200FE_REQUIRE(o, "b200fe_op_set_face_constraints: null operator");
+    Operator &op = *reinterpret_cast<Operator *>(o);
+    op.free_face_constraints();
+    if (n_blocks == 0) return B200FE_OK;
+    B200FE_REQUIRE(p == op.p, "b200fe_op_set_face_constraints: degree %d differs from the operator's %d", p, op.p);
+    B200FE_REQUIRE(h_face_parents && h_face_children && h_W, "b200fe_op_set_face_constraints: null pointer");
+    const int nm = p + 1, nf = 2 * p + 1;
+    const size_t n_par = (size_t)n_blocks * nm * nm, n_chi = (size_t)n_blocks * nf * nf;
+    std::vector<uint8_t> is_child(op.n_local(), 0);
+    for (size_t i = 0; i < n_chi; ++i) {
+        const uint32_t c = h_face_children[i];
+        if (c == B200FE_INVALID_INDEX) continue;
+        B200FE_REQUIRE(c < op.n_local(), "b200fe_op_set_face_constraints: child index %u outside the local vector", c);
+        B200FE_REQUIRE(!is_child[c], "b200fe_op_set_face_constraints: index %u is the child of two blocks", c);
+        is_child[c] = 1;
+    }
+    for (size_t i = 0; i < n_par; ++i) {
+        const uint32_t q = h_face_parents[i];
+        if (q == B200FE_INVALID_INDEX) continue;
+        B200FE_REQUIRE(q < op.n_local(), "b200fe_op_set_face_constraints: parent index %u outside the local vector", q);
+        B200FE_REQUIRE(!is_child[q], "b200fe_op_set_face_constraints: constraint chain through index %u", q);
+    }
+    cudaError_t e = cudaMalloc(&op.d_face_parents, n_par * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemcpy(op.d_face_parents, h_face_parents, n_par * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&op.d_face_children, n_chi * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemcpy(op.d_face_children, h_face_children, n_chi * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&op.d_face_W, (size_t)nf * nm * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpy(op.d_face_W, h_W, (size_t)nf * nm * sizeof(double), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        op.free_face_constraints();
+        return fail_cuda(e, "b200fe_op_set_face_constraints");
+    }
+    op.n_face_blocks = n_blocks;
+    op.face_nm = nm;
+    op.face_nf = nf;
+    return B200FE_OK;
+}
+
 int b200fe_op_distribute(b200fe_op *o, double *d_x, void *stream)
 {
     B200FE_REQUIRE(o && d_x, "b200fe_op_distribute: null pointer");
@@ -742,7 +903,7 @@ int b200fe_op_diagonal(b200fe_op *o, double *d_diag, void *stream)
     B200FE_REQUIRE(o && d_diag, "b200fe_op_diagonal: null pointer");
     Operator &op = *reinterpret_cast<Operator *>(o);
     B200FE_REQUIRE(!(op.qop & QOP_LAPLACE) || op.d_G, "b200fe_op_diagonal: needs the stored geometric factors (d_G)");
-    if (op.n_hang) return fail(B200FE_ERR_UNSUPPORTED, "b200fe_op_diagonal: not built for operators with hanging-node constraints");
+    if (op.has_constraints()) return fail(B200FE_ERR_UNSUPPORTED, "b200fe_op_diagonal: not built for operators with hanging-node constraints");
     cudaStream_t s = (cudaStream_t)stream;
     B200FE_CUDA_TRY(cudaMemsetAsync(d_diag, 0, sizeof(double) * op.n_local(), s));
     if (op.n_cells) {

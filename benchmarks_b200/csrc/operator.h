@@ -22,6 +22,12 @@ struct Operator {
     std::vector<double> W;            // 1-D quadrature weights (affine geometry)
     uint32_t *d_constrained = nullptr;  // owned
     double *d_mats = nullptr;           // owned: shape_values | co_shape_gradients | shape_gradients (setup kernels)
+    // the same constraints grouped by coarse face (b200fe_op_set_face_constraints); takes precedence when set
+    uint32_t n_face_blocks = 0;
+    int face_nm = 0, face_nf = 0, face_save_comps = 0;
+    uint32_t *d_face_parents = nullptr, *d_face_children = nullptr;
+    double *d_face_W = nullptr, *d_face_save = nullptr;
+    bool has_constraints() const { return n_hang != 0 || n_face_blocks != 0; }
     Halo *halo = nullptr;               // borrowed, optional
     // hanging-node rows (b200fe_op_set_constraints), owned copies: u[hang_dof[r]] = sum_k w[k] u[col[k]]
     uint32_t n_hang = 0;
@@ -47,6 +53,15 @@ struct Operator {
         cudaFree(d_constrained);
         cudaFree(d_mats);
         free_constraints();
+        free_face_constraints();
+    }
+    void free_face_constraints()
+    {
+        cudaFree(d_face_parents); cudaFree(d_face_children); cudaFree(d_face_W); cudaFree(d_face_save);
+        d_face_parents = d_face_children = nullptr;
+        d_face_W = d_face_save = nullptr;
+        n_face_blocks = 0;
+        face_save_comps = 0;
     }
     void free_constraints()
     {

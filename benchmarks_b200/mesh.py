@@ -103,7 +103,8 @@ class _HangInfo(C.Structure):
     _fields_ = [("n_cells_global", C.c_uint64), ("n_dofs_global", C.c_uint64), ("first_cell", C.c_uint64),
                 ("owned_begin", C.c_uint64), ("n_cells_local", C.c_uint32), ("n_owned", C.c_uint32),
                 ("n_ghost", C.c_uint32), ("n_constrained", C.c_uint32), ("n_hanging_rows", C.c_uint32),
-                ("n_hanging_entries", C.c_uint32), ("cells", C.c_uint32 * 3), ("h", C.c_double * 3), ("origin", C.c_double * 3)]
+                ("n_hanging_entries", C.c_uint32), ("n_face_blocks", C.c_uint32), ("cells", C.c_uint32 * 3), ("h", C.c_double * 3),
+                ("origin", C.c_double * 3)]
 
 
 class HangingBoxMesh:
@@ -150,6 +151,12 @@ class HangingBoxMesh:
         check(lib.b200fe_hangmesh_fill(self._h, ptr(self.dof_indices), ptr(self.constrained), ptr(self.ghost_global),
                                        ptr(self.ghost_owner), ptr(self.cell_lxyz), ptr(self.rank_dof_begin), ptr(self.hang_dof),
                                        ptr(self.hang_row_ptr), ptr(self.hang_col), ptr(self.hang_w)))
+        # the same rows grouped by coarse face (tensor-product trace interpolation)
+        self.face_parents = np.empty((info.n_face_blocks, (p + 1) ** 2), dtype=np.uint32)
+        self.face_children = np.empty((info.n_face_blocks, (2 * p + 1) ** 2), dtype=np.uint32)
+        check(lib.b200fe_hangmesh_fill_faces(self._h, ptr(self.face_parents), ptr(self.face_children)))
+        self.trace_weights = np.empty((2 * p + 1, p + 1))
+        check(lib.b200fe_trace_weights(p, ptr(self.trace_weights)))
 
     @property
     def n_local(self):

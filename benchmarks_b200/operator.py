@@ -66,7 +66,7 @@ class LaplaceOperator:
 
     def __init__(self, mesh: BoxMesh, nq: int | None = None, quad: str = "gauss", kind: str = "laplace",
                  p_geo: int = 1, deform=None, overlap: bool = False, halo=None, with_jxw: bool = True,
-                 device=None, geometry: str = "stored"):
+                 device=None, geometry: str = "stored", constraints: str = "rows"):
         self.mesh = mesh
         p = mesh.p
         self.p, self.nm = p, p + 1
@@ -131,10 +131,16 @@ class LaplaceOperator:
         if halo is not None:
             check(lib.b200fe_op_set_halo(self._h, halo._h))
         n_rows = len(getattr(mesh, "hang_dof", ()))
+        if constraints not in ("rows", "faces"):
+            raise ValueError(constraints)
         if n_rows:  # hanging-node rows of a HangingBoxMesh: the operator becomes C^T A C
             ptr = lambda a: a.ctypes.data if a.size else None
-            check(lib.b200fe_op_set_constraints(self._h, n_rows, ptr(mesh.hang_dof), ptr(mesh.hang_row_ptr), ptr(mesh.hang_col),
-                                                ptr(mesh.hang_w)))
+            if constraints == "faces":  # experimental face-structured form (tensor-product trace interpolation per coarse face)
+                check(lib.b200fe_op_set_face_constraints(self._h, p, len(mesh.face_parents), ptr(mesh.face_parents),
+                                                         ptr(mesh.face_children), ptr(mesh.trace_weights)))
+            else:
+                check(lib.b200fe_op_set_constraints(self._h, n_rows, ptr(mesh.hang_dof), ptr(mesh.hang_row_ptr), ptr(mesh.hang_col),
+                                                    ptr(mesh.hang_w)))
         self._inv_diag = None
 
     # --- the reference operator's interface ------------------------------------------------

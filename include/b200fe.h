@@ -173,6 +173,7 @@ typedef struct {
     uint64_t owned_begin;
     uint32_t n_cells_local, n_owned, n_ghost, n_constrained;
     uint32_t n_hanging_rows, n_hanging_entries;
+    uint32_t n_face_blocks; /* the same rows grouped by coarse face, see b200fe_hangmesh_fill_faces */
     uint32_t cells[3]; /* of the unrefined box mesh */
     double h[3];       /* cell size of the unrefined box mesh */
     double origin[3];
@@ -195,6 +196,18 @@ int b200fe_hangmesh_fill(const b200fe_hangmesh *mesh, uint32_t *h_dof_indices, u
                          uint64_t *h_ghost_global, int32_t *h_ghost_owner, int32_t *h_cell_lxyz,
                          uint64_t *h_rank_dof_begin, uint32_t *h_hang_dof, uint32_t *h_hang_row_ptr,
                          uint32_t *h_hang_col, double *h_hang_w);
+/* Face-structured form of the same rows.  Every hanging DoF of such a mesh lies on a face shared by an unrefined
+ * cell K and a refined cell, and the (2p+1)^2 fine nodes of the face are the tensor-product interpolation
+ *   u_fine(a', b') = sum_{a,b} W[a'][a] W[b'][b] u_K(a, b),   W = b200fe_trace_weights (row-major [2p+1][p+1])
+ * of the (p+1)^2 face nodes of K (a, a' run along the lower in-face axis).  Per block, partitioner-local indices:
+ *   h_face_parents [n_face_blocks][(p+1)^2]   B200FE_INVALID_INDEX = Dirichlet / absent parent (value 0)
+ *   h_face_children[n_face_blocks][(2p+1)^2]  B200FE_INVALID_INDEX = not a child of this block (coarse vertex,
+ *        Dirichlet, not needed by this rank, or assigned to an earlier block: every hanging DoF appears once)
+ * 370 scattered accesses per face at p = 8 instead of the 23,400 of its CSR rows. */
+int b200fe_hangmesh_fill_faces(const b200fe_hangmesh *mesh, uint32_t *h_face_parents, uint32_t *h_face_children);
+/* 1-D trace matrix of FE_Q(p): W[rel][j] = l_j((half + t_a)/2) at the fine lattice positions rel = half*p + a of a
+ * coarse interval (t = Gauss-Lobatto nodes); exact unit rows where a fine node coincides with a coarse node. */
+int b200fe_trace_weights(int p, double *h_W);
 /* As b200fe_boxmesh_nodes, for the cells of this mesh (children are half the size). */
 int b200fe_hangmesh_nodes(const b200fe_hangmesh *mesh, int p_geo, int deform_kind, double amplitude,
                           double frequency, double *d_nodes, void *stream);
@@ -272,6 +285,12 @@ int b200fe_op_set_halo(b200fe_op *op, b200fe_halo *halo);
  * The overlap split (n_phase0/n_phase1) is ignored while constraints are attached. */
 int b200fe_op_set_constraints(b200fe_op *op, uint32_t n_rows, const uint32_t *h_hang_dof,
                               const uint32_t *h_hang_row_ptr, const uint32_t *h_hang_col, const double *h_hang_w);
+/* EXPERIMENTAL (round 1: parity-checked on CPU against the CSR rows, not yet validated or timed on a GPU; the
+ * Python mirror enables it only with constraints="faces").  The same constraints in the face-structured form of
+ * b200fe_hangmesh_fill_faces: one CTA per coarse face applies W (x) W (and its transpose) in shared memory.  When set
+ * (n_blocks > 0) it replaces the CSR rows inside vmult / distribute / rhs; h_W = b200fe_trace_weights(p).  Copied. */
+int b200fe_op_set_face_constraints(b200fe_op *op, int p, uint32_t n_blocks, const uint32_t *h_face_parents,
+                                   const uint32_t *h_face_children, const double *h_W);
 /* AffineConstraints::distribute on a local vector: fills the hanging entries of d_x from their parents
  * (call after the solve; ghost entries of d_x must be up to date when parents are ghosts). */
 int b200fe_op_distribute(b200fe_op *op, double *d_x, void *stream);

@@ -275,3 +275,116 @@ def distributed_apply(rds, bas, Gs, u_global, JxWs=None, laplace=True, mass=Fals
         c = rd["owned_begin"] + np.asarray(rd["constrained"], dtype=np.int64)
         dst[c] = u_global[c]
     return dst
+
+
+# --------------------------------------------------------------------------
+# Face-structured form of the same constraints (tensor-product trace interpolation)
+# --------------------------------------------------------------------------
+def trace_weights(p: int):
+    """W[rel, j] = l_j((half + t_a) / 2) for the fine lattice positions rel = half*p + a = 0..2p of a coarse interval:
+    1-D Lagrange values of the coarse GLL basis; exact unit rows where a fine node coincides with a coarse one."""
+    t, _ = fe.gll_01(p + 1)
+    W = np.zeros((2 * p + 1, p + 1))
+    for rel in range(2 * p + 1):
+        if rel == 0:
+            W[rel, 0] = 1.0
+        elif rel == 2 * p:
+            W[rel, p] = 1.0
+        elif rel == p and p % 2 == 0:
+            W[rel, p // 2] = 1.0
+        else:
+            half, a = divmod(rel, p)
+            W[rel] = fe.lagrange_values(t, np.array([0.5 * (half + t[a])]))[0]
+    return W
+
+
+def face_blocks(mesh: TwoLevelMesh, sp, rd):
+    """The hanging rows of rank data `rd` grouped by coarse face: every hanging DoF lies on a face shared by an
+    unrefined cell K and a refined cell; the (2p+1)^2 fine nodes of that face are the tensor-product interpolation
+    u_f(a', b') = sum_ab W[a', a] W[b', b] u_K(a, b) of the (p+1)^2 coarse face nodes.
+    Blocks are listed in (K position on the base mesh, axis, side) order; a hanging DoF shared by several faces is
+    assigned to the first block that needs it.  Returns parents [n, (p+1)^2] and children [n, (2p+1)^2] in local
+    indices (a / a' fastest along the lower in-face axis), INVALID = Dirichlet or absent parent (value 0) / not a child of this
+    block (coarse vertex, Dirichlet, not needed by this rank, or assigned to an earlier block)."""
+    p = sp["p"]
+    nm, nf = p + 1, 2 * p + 1
+    B = mesh.base
+    key_to_global = {k: d for d, k in enumerate(sp["keys"])}
+    begin, n_own = rd["owned_begin"], rd["n_owned"]
+    gl = {int(g): n_own + i for i, g in enumerate(rd["ghost_global"])}
+    loc = lambda g: g - begin if begin <= g < begin + n_own else gl.get(g)
+    needed = {}  # global hanging dof -> local index, for the rows this rank holds
+    inv = {v: k for k, v in gl.items()}
+    for h in rd["hang_dof"]:
+        h = int(h)
+        needed[h + begin if h < n_own else inv[h]] = h
+    claimed = set()
+    parents, children = [], []
+    for c in range(B.n_cells):
+        K = tuple(int(v) for v in B.cell_xyz[c])
+        if mesh.refined[K]:
+            continue
+        for axis in range(3):
+            for side in (0, 1):
+                N = list(K)
+                N[axis] += 1 if side else -1
+                if not (0 <= N[axis] < B.cells[axis]) or not mesh.refined[tuple(N)]:
+                    continue
+                d1, d2 = [d for d in range(3) if d != axis]
+                par = np.full(nm * nm, INVALID, dtype=np.uint32)
+                chi = np.full(nf * nf, INVALID, dtype=np.uint32)
+                for b in range(nm):
+                    for a in range(nm):
+                        X = [0, 0, 0]
+                        X[axis], X[d1], X[d2] = (K[axis] + side) * p, K[d1] * p + a, K[d2] * p + b
+                        g = key_to_global[(0, X[0], X[1], X[2])]
+                        if not sp["on_bnd"][g] and loc(g) is not None:
+                            par[a + nm * b] = loc(g)
+                any_child = False
+                for b in range(nf):
+                    for a in range(nf):
+                        F = [0, 0, 0]
+                        F[axis], F[d1], F[d2] = (K[axis] + side) * 2 * p, K[d1] * 2 * p + a, K[d2] * 2 * p + b
+                        if all(f % (2 * p) == 0 for f in F):
+                            continue
+                        g = key_to_global.get((1, F[0], F[1], F[2]))
+                        if g is None or g not in needed or g in claimed:
+                            continue
+                        claimed.add(g)
+                        chi[a + nf * b] = needed[g]
+                        any_child = True
+                if any_child:
+                    parents.append(par)
+                    children.append(chi)
+    assert claimed == set(needed), "every hanging DoF of a box-refined mesh lies on a hanging face"
+    n = len(parents)
+    return (np.array(parents, dtype=np.uint32).reshape(n, nm * nm), np.array(children, dtype=np.uint32).reshape(n, nf * nf))
+
+
+def distribute_faces(p, parents, children, u):
+    """u_hat = C u through the face blocks (what the face kernels do): two 1-D interpolations per face."""
+    W = trace_weights(p)
+    nm, nf = p + 1, 2 * p + 1
+    v = u.copy()
+    for par, chi in zip(parents, children):
+        P = np.where(par != INVALID, u[np.where(par != INVALID, par, 0)], 0.0).reshape(nm, nm)  # [b, a]
+        F = W @ P @ W.T                                                                        # [b', a']
+        ok = chi != INVALID
+        v[chi[ok]] = F.ravel()[ok]
+    return v
+
+
+def condense_faces(p, parents, children, v):
+    """C^T v through the face blocks: children gathered and zeroed, transposed interpolation added to the parents."""
+    W = trace_weights(p)
+    nm, nf = p + 1, 2 * p + 1
+    out = v.copy()
+    for par, chi in zip(parents, children):
+        ok = chi != INVALID
+        C = np.zeros(nf * nf)
+        C[ok] = v[chi[ok]]
+        out[chi[ok]] = 0.0
+        P = W.T @ C.reshape(nf, nf) @ W
+        okp = par != INVALID
+        np.add.at(out, par[okp], P.ravel()[okp])
+    return out

@@ -119,6 +119,28 @@ def test_multirank_lists_reproduce_single_rank_operator(oracle_mod, sub, nref, p
     assert np.abs(yP - y1[perm]).max() <= 1e-12 * np.abs(y1).max()
 
 
+@pytest.mark.parametrize("sub,nref,p,lo,hi,nranks", CASES)
+def test_face_blocks_bitexact_and_equivalent_to_rows(oracle_mod, sub, nref, p, lo, hi, nranks):
+    """The face-structured form of the constraints (one block per coarse face, tensor-product trace interpolation):
+    the product's blocks are bit-identical to the oracle's literal construction, every hanging row is the child of
+    exactly one block, and distribute / condense through the blocks equal the CSR rows to rounding."""
+    fe, ho = oracle_mod.fe, oracle_mod.hanging
+    om = ho.TwoLevelMesh(sub, nref, (lo, hi))
+    sp = ho.build_space(om, p, nranks)
+    for r in range(nranks):
+        rd = ho.rank_data(om, sp, r)
+        par, chi = ho.face_blocks(om, sp, rd)
+        m = b.HangingBoxMesh(sub, nref, p, lo, hi, n_ranks=nranks, rank=r)
+        assert np.array_equal(m.face_parents, par) and np.array_equal(m.face_children, chi)
+        assert np.abs(m.trace_weights - ho.trace_weights(p)).max() <= 1e-14
+        kids = m.face_children[m.face_children != 0xFFFFFFFF]
+        assert sorted(kids.tolist()) == sorted(m.hang_dof.tolist())
+        u = np.random.default_rng(r).standard_normal(m.n_owned + m.n_ghost)
+        md = _mesh_dict(m)
+        assert np.abs(ho.distribute_faces(p, m.face_parents, m.face_children, u) - ho.distribute(md, u)).max(initial=0.0) <= 1e-13
+        assert np.abs(ho.condense_faces(p, m.face_parents, m.face_children, u) - ho.condense(md, u)).max(initial=0.0) <= 1e-12
+
+
 def test_bad_descriptors_are_rejected():
     with pytest.raises(b.B200feError):
         b.HangingBoxMesh((1, 1, 1), 1, 2, (0, 0, 0), (3, 1, 1))  # box outside the mesh

@@ -5,6 +5,8 @@ north-star subsystem 1) and of the vector-valued CG (BP2/BP4/BP6), through the C
 Tolerances: one FP64 application <= 1e-12 relative max-norm; CG iteration counts within +-1 of the oracle's loop.
 (The file sorts last on purpose: these paths are the newest.)
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -199,3 +201,34 @@ def test_geometry_from_dealii_inv_jacobian_views(oracle_mod):
     vp = lambda t: C.c_void_p(t.data_ptr())
     check(lib.b200fe_geometry_from_inv_jacobian(nc, nq, vp(d_K), vp(d_J), vp(d_G), None))
     assert rel(d_G.cpu().numpy().reshape(G.shape), G) <= TOL
+
+
+@pytest.mark.skipif(os.environ.get("B200FE_TEST_FACE_CONSTRAINTS") != "1",
+                    reason="experimental face-structured constraint kernels: written after the round's GPU budget was spent; "
+                           "run with B200FE_TEST_FACE_CONSTRAINTS=1 to validate them")
+@pytest.mark.parametrize("p", [1, 2, 4, 7, 8])
+def test_face_structured_constraints_equal_rows(oracle_mod, p):
+    """constraints="faces" (one CTA per coarse face, W (x) W in shared memory) against the oracle and the CSR-row path."""
+    import benchmarks_b200 as b
+    sub, nref, lo, hi = ((2, 2, 1), 0, (0, 0, 0), (1, 2, 1)) if p >= 6 else ((1, 1, 1), 1, (1, 0, 1), (2, 1, 2))
+    fe, ho, rd, bas, G, JxW, mesh, A = _setup(oracle_mod, p, sub, nref, lo, hi, p + 1, "gll", "laplace")
+    Af = b.LaplaceOperator(mesh, nq=p + 1, quad="gll", p_geo=2, deform=DEFORM, constraints="faces")
+    src = np.random.default_rng(p).standard_normal(3 * mesh.n_owned)
+    ref = np.concatenate([ho.op_apply(rd, bas, G, src[c * mesh.n_owned:(c + 1) * mesh.n_owned], JxW) for c in range(3)])
+    d_src = torch.from_numpy(src).cuda()
+    y, yf = torch.empty_like(d_src), torch.empty_like(d_src)
+    A.vmult_components(y, d_src, 3)
+    Af.vmult_components(yf, d_src, 3)
+    assert rel(yf.cpu().numpy(), ref) <= TOL and rel(yf.cpu().numpy(), y.cpu().numpy()) <= TOL
+    assert torch.equal(d_src.cpu(), torch.from_numpy(src))
+    assert rel(Af.compute_rhs().cpu().numpy(), ho.rhs_one(rd, bas, JxW)) <= TOL
+    x = d_src[: mesh.n_owned].clone()
+    Af.distribute(x)
+    assert rel(x.cpu().numpy(), ho.distribute(rd, src[: mesh.n_owned])) <= TOL
+    rhs, xs = Af.compute_rhs(), [Af.initialize_dof_vector(), A.initialize_dof_vector()]
+    its = []
+    for op, xv in zip((Af, A), xs):
+        ctl = b.ReductionControl(5000, 1e-16, 1e-9)
+        b.SolverCG(ctl).solve(op, xv, rhs)
+        its.append(ctl.last_step())
+    assert abs(its[0] - its[1]) <= 1
