@@ -66,7 +66,7 @@ class LaplaceOperator:
 
     def __init__(self, mesh: BoxMesh, nq: int | None = None, quad: str = "gauss", kind: str = "laplace",
                  p_geo: int = 1, deform=None, overlap: bool = False, halo=None, with_jxw: bool = True,
-                 device=None, geometry: str = "stored", constraints: str = "rows"):
+                 device=None, geometry: str = "stored", constraints: str = "faces"):
         self.mesh = mesh
         p = mesh.p
         self.p, self.nm = p, p + 1
@@ -135,7 +135,7 @@ class LaplaceOperator:
             raise ValueError(constraints)
         if n_rows:  # hanging-node rows of a HangingBoxMesh: the operator becomes C^T A C
             ptr = lambda a: a.ctypes.data if a.size else None
-            if constraints == "faces":  # experimental face-structured form (tensor-product trace interpolation per coarse face)
+            if constraints == "faces" and len(mesh.face_parents):  # face-structured form: tensor-product trace interpolation, one CTA per coarse face
                 check(lib.b200fe_op_set_face_constraints(self._h, p, len(mesh.face_parents), ptr(mesh.face_parents),
                                                          ptr(mesh.face_children), ptr(mesh.trace_weights)))
             else:

@@ -237,7 +237,7 @@ class LaplaceOperator {
     }
     // two-level mesh with hanging nodes: the operator is C^T A C with identity on the constrained rows
     LaplaceOperator(const HangingBoxMesh &mesh, Quadrature quad = Quadrature::Gauss, int op_kind = B200FE_OP_LAPLACE, int p_geo = 1,
-                    Deformation deform = {})
+                    Deformation deform = {}, bool face_constraints = true)
         : n_dofs_global_(mesh.n_dofs()), n_owned_(mesh.info.n_owned), n_ghost_(mesh.info.n_ghost)
     {
         if (mesh.degree != fe_degree) throw Error(B200FE_ERR_INVALID_ARG, "mesh degree != fe_degree");
@@ -248,7 +248,16 @@ class LaplaceOperator {
         DeviceArray<double> nodes((size_t)nc * 3 * ng3(p_geo));
         check(b200fe_hangmesh_nodes(mesh.handle(), p_geo, deform.amplitude != 0.0, deform.amplitude, deform.frequency, nodes.data(), nullptr));
         init(nc, idx, con, nodes, quad, op_kind, p_geo);
-        check(b200fe_op_set_constraints(op_, nr, hd.data(), hp.data(), hc.data(), hw.data()));
+        if (face_constraints && mesh.info.n_face_blocks) {  // tensor-product trace interpolation per coarse face (the fast path)
+            const uint32_t nb = mesh.info.n_face_blocks;
+            const size_t nm = fe_degree + 1, nf = 2 * fe_degree + 1;
+            std::vector<uint32_t> fp((size_t)nb * nm * nm), fc((size_t)nb * nf * nf);
+            std::vector<double> W(nf * nm);
+            check(b200fe_hangmesh_fill_faces(mesh.handle(), fp.data(), fc.data()));
+            check(b200fe_trace_weights(fe_degree, W.data()));
+            check(b200fe_op_set_face_constraints(op_, fe_degree, nb, fp.data(), fc.data(), W.data()));
+        } else  // general AffineConstraints rows (CSR)
+            check(b200fe_op_set_constraints(op_, nr, hd.data(), hp.data(), hc.data(), hw.data()));
     }
     LaplaceOperator(const LaplaceOperator &) = delete;
     ~LaplaceOperator() { if (op_) b200fe_op_destroy(op_); }

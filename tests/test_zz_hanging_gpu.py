@@ -5,8 +5,6 @@ north-star subsystem 1) and of the vector-valued CG (BP2/BP4/BP6), through the C
 Tolerances: one FP64 application <= 1e-12 relative max-norm; CG iteration counts within +-1 of the oracle's loop.
 (The file sorts last on purpose: these paths are the newest.)
 """
-import os
-
 import numpy as np
 import pytest
 import torch
@@ -20,7 +18,7 @@ def rel(a, b):
     return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
 
 
-def _setup(oracle_mod, p, sub, nref, lo, hi, nq, quad, kind, p_geo=2, deform=DEFORM):
+def _setup(oracle_mod, p, sub, nref, lo, hi, nq, quad, kind, p_geo=2, deform=DEFORM, constraints="faces"):
     import benchmarks_b200 as b
     fe, ho = oracle_mod.fe, oracle_mod.hanging
     om = ho.TwoLevelMesh(sub, nref, (lo, hi))
@@ -30,7 +28,7 @@ def _setup(oracle_mod, p, sub, nref, lo, hi, nq, quad, kind, p_geo=2, deform=DEF
     dfm = None if deform is None else (lambda P: P + deform[0] * np.sin(deform[1] * P[..., [1, 2, 0]]))
     G, JxW = fe.geometric_factors(ho.cell_nodes(om, rd["cells"], p_geo, dfm), p_geo, bas)
     mesh = b.HangingBoxMesh(sub, nref, p, lo, hi)
-    A = b.LaplaceOperator(mesh, nq=nq, quad=quad, kind=kind, p_geo=p_geo, deform=deform)
+    A = b.LaplaceOperator(mesh, nq=nq, quad=quad, kind=kind, p_geo=p_geo, deform=deform, constraints=constraints)
     return fe, ho, rd, bas, G, JxW, mesh, A
 
 
@@ -39,9 +37,11 @@ VARIANTS = [("bp3", 2, "gauss", "laplace"), ("bp5", 1, "gll", "laplace"), ("bp1"
 
 @pytest.mark.parametrize("p", [1, 2, 3, 4, 6, 8])
 @pytest.mark.parametrize("name,dq,quad,kind", VARIANTS)
-def test_constrained_vmult_matches_oracle(oracle_mod, p, name, dq, quad, kind):
+@pytest.mark.parametrize("constraints", ["rows", "faces"])
+def test_constrained_vmult_matches_oracle(oracle_mod, p, name, dq, quad, kind, constraints):
+    """constraints = "rows": general CSR rows (AffineConstraints); "faces": tensor-product form per coarse face (default)."""
     sub, nref, lo, hi = ((2, 2, 1), 0, (0, 0, 0), (1, 2, 1)) if p >= 6 else ((1, 1, 1), 1, (1, 0, 1), (2, 1, 2))
-    fe, ho, rd, bas, G, JxW, mesh, A = _setup(oracle_mod, p, sub, nref, lo, hi, p + dq, quad, kind)
+    fe, ho, rd, bas, G, JxW, mesh, A = _setup(oracle_mod, p, sub, nref, lo, hi, p + dq, quad, kind, constraints=constraints)
     assert len(mesh.hang_dof) > 0
     assert rel(A.JxW.cpu().numpy().reshape(JxW.shape), JxW) <= TOL  # children are half-size cells of the same map
     rng = np.random.default_rng(100 + p)
@@ -62,13 +62,13 @@ def test_constrained_vmult_matches_oracle(oracle_mod, p, name, dq, quad, kind):
     assert rel(A.compute_rhs().cpu().numpy(), ho.rhs_one(rd, bas, JxW)) <= TOL
 
 
-@pytest.mark.parametrize("p,dq,quad", [(2, 2, "gauss"), (4, 1, "gll"), (7, 1, "gll")])
-def test_cg_on_hanging_mesh_matches_oracle_loop(oracle_mod, p, dq, quad):
+@pytest.mark.parametrize("p,dq,quad,constraints", [(2, 2, "gauss", "faces"), (4, 1, "gll", "rows"), (7, 1, "gll", "faces")])
+def test_cg_on_hanging_mesh_matches_oracle_loop(oracle_mod, p, dq, quad, constraints):
     """bp3 protocol (rhs = int phi, x0 = 0, ReductionControl(., 1e-16, 1e-9)) on the constrained operator; the solution is
     compared after distributing the constraints."""
     import benchmarks_b200 as b
     sub, nref, lo, hi = ((2, 2, 1), 0, (1, 0, 0), (2, 1, 1)) if p >= 6 else ((1, 1, 1), 1, (0, 0, 0), (1, 1, 2))
-    fe, ho, rd, bas, G, JxW, mesh, A = _setup(oracle_mod, p, sub, nref, lo, hi, p + dq, quad, "laplace")
+    fe, ho, rd, bas, G, JxW, mesh, A = _setup(oracle_mod, p, sub, nref, lo, hi, p + dq, quad, "laplace", constraints=constraints)
     rhs_o = ho.rhs_one(rd, bas, JxW)
     xo, its_o, r0_o, rn_o, ok_o = fe.solver_cg(lambda u: ho.op_apply(rd, bas, G, u, JxW), rhs_o, 5000, 1e-16, 1e-9)
     rhs = A.compute_rhs()
@@ -203,15 +203,12 @@ def test_geometry_from_dealii_inv_jacobian_views(oracle_mod):
     assert rel(d_G.cpu().numpy().reshape(G.shape), G) <= TOL
 
 
-@pytest.mark.skipif(os.environ.get("B200FE_TEST_FACE_CONSTRAINTS") != "1",
-                    reason="experimental face-structured constraint kernels: written after the round's GPU budget was spent; "
-                           "run with B200FE_TEST_FACE_CONSTRAINTS=1 to validate them")
 @pytest.mark.parametrize("p", [1, 2, 4, 7, 8])
 def test_face_structured_constraints_equal_rows(oracle_mod, p):
     """constraints="faces" (one CTA per coarse face, W (x) W in shared memory) against the oracle and the CSR-row path."""
     import benchmarks_b200 as b
     sub, nref, lo, hi = ((2, 2, 1), 0, (0, 0, 0), (1, 2, 1)) if p >= 6 else ((1, 1, 1), 1, (1, 0, 1), (2, 1, 2))
-    fe, ho, rd, bas, G, JxW, mesh, A = _setup(oracle_mod, p, sub, nref, lo, hi, p + 1, "gll", "laplace")
+    fe, ho, rd, bas, G, JxW, mesh, A = _setup(oracle_mod, p, sub, nref, lo, hi, p + 1, "gll", "laplace", constraints="rows")
     Af = b.LaplaceOperator(mesh, nq=p + 1, quad="gll", p_geo=2, deform=DEFORM, constraints="faces")
     src = np.random.default_rng(p).standard_normal(3 * mesh.n_owned)
     ref = np.concatenate([ho.op_apply(rd, bas, G, src[c * mesh.n_owned:(c + 1) * mesh.n_owned], JxW) for c in range(3)])

@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--its", type=int, default=50)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--constraints", default="faces", choices=["rows", "faces"])
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -65,7 +66,7 @@ def main():
     if world > 1:
         from benchmarks_b200.dist import Halo
         halo = Halo(mesh, group=gloo)
-    A = b.LaplaceOperator(mesh, quad="gll", p_geo=2, deform=(0.05, 2.0), halo=halo, with_jxw=True)
+    A = b.LaplaceOperator(mesh, quad="gll", p_geo=2, deform=(0.05, 2.0), halo=halo, with_jxw=True, constraints=args.constraints)
     rhs = A.compute_rhs().repeat(nc)
     nloc = mesh.n_owned + mesh.n_ghost
     x = torch.zeros(nc * nloc, dtype=torch.float64, device=dev)
@@ -110,7 +111,7 @@ def main():
             "higher_is_better": True, "scaling": "strong", "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"CEED BP6 vector Laplacian GLL, p={p}, {cells[0]}x{cells[1]}x{cells[2]} cells with the corner block "
                                    f"{hi[0]}x{hi[1]}x{hi[2]} refined once (hanging nodes), deformed MappingQ2 mesh, {args.its} CG iterations per step",
-                       "cells": int(mesh.n_cells_global), "n_dofs": n_dofs, "hanging_rows_rank0": int(len(mesh.hang_dof)), "setup_s": t_setup},
+                       "cells": int(mesh.n_cells_global), "n_dofs": n_dofs, "hanging_rows_rank0": int(len(mesh.hang_dof)), "constraints": args.constraints, "setup_s": t_setup},
             "apply_only": {"gdofs": 1e-9 * n_dofs / t_apply, "ms": 1e3 * t_apply}}))
     if world > 1:
         dist.destroy_process_group()
