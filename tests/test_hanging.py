@@ -148,3 +148,41 @@ def test_bad_descriptors_are_rejected():
         b.HangingBoxMesh((1, 1, 1), 1, 2, (1, 0, 0), (1, 1, 1))  # empty box
     with pytest.raises(b.B200feError):
         b.HangingBoxMesh((1, 1, 1), 1, 9, (0, 0, 0), (1, 1, 1))  # degree
+
+
+def test_random_two_level_meshes_bitexact_vs_oracle(oracle_mod):
+    """Property test over random small configurations (boxes, refinement regions, degrees, rank counts): every table of the
+    product's mesh builder equals the oracle's literal simulation; face blocks cover every hanging DoF exactly once."""
+    from hypothesis import given, settings, strategies as st
+    fe, ho = oracle_mod.fe, oracle_mod.hanging
+
+    @st.composite
+    def configs(draw):
+        sub = tuple(draw(st.integers(1, 2)) for _ in range(3))
+        nref = draw(st.integers(0, 1 if sub[0] * sub[1] * sub[2] <= 2 else 0))
+        cells = [s << nref for s in sub]
+        lo = [draw(st.integers(0, c - 1)) for c in cells]
+        hi = [draw(st.integers(l + 1, c)) for l, c in zip(lo, cells)]
+        p = draw(st.integers(1, 3))
+        n_cells = cells[0] * cells[1] * cells[2] + 7 * (hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2])
+        nranks = draw(st.integers(1, min(5, n_cells)))
+        return sub, nref, p, tuple(lo), tuple(hi), nranks
+
+    @settings(max_examples=20, deadline=None, derandomize=True)
+    @given(configs())
+    def check(cfg):
+        sub, nref, p, lo, hi, nranks = cfg
+        om = ho.TwoLevelMesh(sub, nref, (lo, hi))
+        sp = ho.build_space(om, p, nranks)
+        for r in range(nranks):
+            rd = ho.rank_data(om, sp, r)
+            m = b.HangingBoxMesh(sub, nref, p, lo, hi, n_ranks=nranks, rank=r)
+            assert (m.n_cells_global, m.n_dofs_global, m.owned_begin) == (om.n_cells, sp["n_dofs"], rd["owned_begin"])
+            for name in ("dof_indices", "ghost_owner", "constrained", "hang_dof", "hang_row_ptr", "hang_col"):
+                assert np.array_equal(getattr(m, name), rd[name]), (cfg, r, name)
+            assert np.array_equal(m.ghost_global.astype(np.int64), rd["ghost_global"])
+            assert np.abs(m.hang_w - rd["hang_w"]).max(initial=0.0) <= 1e-13
+            par, chi = ho.face_blocks(om, sp, rd)
+            assert np.array_equal(m.face_parents, par) and np.array_equal(m.face_children, chi), (cfg, r)
+
+    check()
