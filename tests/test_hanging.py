@@ -186,3 +186,28 @@ def test_random_two_level_meshes_bitexact_vs_oracle(oracle_mod):
             assert np.array_equal(m.face_parents, par) and np.array_equal(m.face_children, chi), (cfg, r)
 
     check()
+
+
+def test_golden_fixture_freezes_the_conventions(oracle_mod, golden_dir):
+    """tests/golden/hanging_meshes.json (written by make_hanging_golden.py from the oracle): the oracle still produces it,
+    and the product's builder matches the committed digests -- without importing the oracle for the product half."""
+    import hashlib
+    import json
+    import os
+    import sys
+    sys.path.insert(0, golden_dir)
+    import make_hanging_golden as mk
+    gold = json.load(open(os.path.join(golden_dir, "hanging_meshes.json")))["cases"]
+    dg = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    for want, case in zip(gold, mk.CASES):
+        assert json.loads(json.dumps(mk.tables(case))) == want      # oracle half
+        sub, nref, p, lo, hi, nranks = case
+        for r, wr in enumerate(want["ranks"]):                     # product half
+            m = b.HangingBoxMesh(sub, nref, p, lo, hi, n_ranks=nranks, rank=r)
+            assert (m.n_cells_global, m.n_dofs_global) == (want["n_cells"], want["n_dofs"])
+            assert (m.n_owned, m.n_ghost, int(m.owned_begin), m.n_cells) == (wr["n_owned"], wr["n_ghost"], wr["owned_begin"], wr["n_cells"])
+            got = dict(dof_indices=dg(m.dof_indices), ghost_global=dg(m.ghost_global), constrained=dg(m.constrained), hang_dof=dg(m.hang_dof),
+                       hang_row_ptr=dg(m.hang_row_ptr), hang_col=dg(m.hang_col), hang_w_rounded=dg(np.round(m.hang_w, 12) + 0.0),
+                       face_parents=dg(m.face_parents), face_children=dg(m.face_children))
+            for k, v in got.items():
+                assert v == wr[k], (case, r, k)

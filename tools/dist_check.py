@@ -59,12 +59,12 @@ def check_hanging(rank, world, gloo):
     against the same two-level mesh on one GPU."""
     blocks = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[world]
     ok = True
-    for p, quad, nref in ((2, "gauss", 2), (4, "gll", 2), (7, "gll", 1)):
+    for p, quad, nref, form in ((2, "gauss", 2, "faces"), (4, "gll", 2, "rows"), (7, "gll", 1, "faces")):
         cells = [s << nref for s in blocks]
         lo, hi = (0, 0, 0), tuple(max(c // 2, 1) for c in cells)
         mesh = b.HangingBoxMesh(blocks, nref, p, lo, hi, n_ranks=world, rank=rank)
         halo = Halo(mesh, group=gloo)
-        kw = dict(quad=quad, deform=(0.03, 1.5), p_geo=2)
+        kw = dict(quad=quad, deform=(0.03, 1.5), p_geo=2, constraints=form)
         A = b.LaplaceOperator(mesh, halo=halo, **kw)
         m1 = b.HangingBoxMesh(blocks, nref, p, lo, hi)
         A1 = b.LaplaceOperator(m1, **kw)
@@ -99,7 +99,7 @@ def check_hanging(rank, world, gloo):
         xerr = np.abs(x[2 * nloc: 2 * nloc + mesh.n_owned].cpu().numpy()[sel] - xs[own[sel]]).max() / np.abs(xs).max()
         good = err <= 1e-12 and abs(ctl.last_step() - ctl1.last_step()) <= 1 and xerr <= 1e-6
         ok &= bool(good)
-        print(f"[rank {rank}/{world}] hanging p={p} {quad}: {len(mesh.hang_dof)} rows, vmult rel err {err:.2e}, BP6 CG its {ctl.last_step()} vs "
+        print(f"[rank {rank}/{world}] hanging p={p} {quad} constraints={form}: {len(mesh.hang_dof)} rows, vmult rel err {err:.2e}, BP6 CG its {ctl.last_step()} vs "
               f"{ctl1.last_step()} (1 GPU), x rel err {xerr:.1e} -> {'OK' if good else 'FAIL'}", flush=True)
         del A, A1, halo
     return ok
