@@ -183,6 +183,7 @@ void cg_release_work(Operator *op)
 static int cg_run(Operator &op, int ncomp, CgWork &w, double *d_x, const double *d_b, const double *d_inv_diag, double abs_tol,
                   double rel_tol, int max_it, int check_every, b200fe_cg_result *res, cudaStream_t s)
 {
+    NvtxRange range("cg_solver");
     const uint32_t n = op.n_owned;
     const size_t stride = op.n_local();
     const unsigned bx = n == 0 ? 1u : std::min<unsigned>((n + 1023) / 1024, std::max(148u * 8u / (unsigned)ncomp, 148u));

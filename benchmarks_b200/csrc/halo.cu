@@ -143,6 +143,7 @@ int halo_zero_ghosts(Halo &h, double *v, cudaStream_t s)
 int halo_update_ghosts(Halo &h, double *v, cudaStream_t s)
 {
     if (h.n_ranks == 1) return B200FE_OK;
+    NvtxRange range("update_ghost_values");
     if (h.n_send && !h.d_send_idx) return fail(B200FE_ERR_INVALID_ARG, "halo was created in raw mode (no send indices)");
     return exchange_update(h, v, s);
 }
@@ -150,6 +151,7 @@ int halo_update_ghosts(Halo &h, double *v, cudaStream_t s)
 int halo_compress_add(Halo &h, double *v, cudaStream_t s)
 {
     if (h.n_ranks == 1) return B200FE_OK;
+    NvtxRange range("compress_add");
     if (h.n_send && !h.d_send_idx) return fail(B200FE_ERR_INVALID_ARG, "halo was created in raw mode (no send indices)");
     if (int rc = exchange_compress(h, v, s)) return rc;
     return unpack_and_zero(h, v, s);

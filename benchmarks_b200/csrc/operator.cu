@@ -533,6 +533,7 @@ int op_condense(Operator &op, double *d_dst, double *d_src_restore, cudaStream_t
 int op_vmult(Operator &op, double *d_dst, const double *d_src, double *d_dot, bool ghost_on, bool compute_on,
              cudaStream_t s, int ncomp)
 {
+    NvtxRange range("matvec");
     Halo *h = op.halo;
     const size_t stride = op.n_local();
     double *src_mut = const_cast<double *>(d_src);  // ghost (and hanging) entries of src are scratch, as in deal.II
