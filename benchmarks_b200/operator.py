@@ -15,7 +15,7 @@ import ctypes as C
 import numpy as np
 import torch
 
-from ._lib import B200feError, check, lib
+from ._lib import check, lib
 from .mesh import QUAD_GAUSS, QUAD_GLL, BoxMesh, basis_1d  # noqa: F401
 
 OP_LAPLACE, OP_MASS, OP_HELMHOLTZ = 1, 2, 3

@@ -10,7 +10,6 @@ ncu (l1tex__data_pipe_lsu_wavefronts_mem_shared) for BK3 p=4: measured 580 wavef
 """
 from __future__ import annotations
 
-import itertools
 import sys
 
 
