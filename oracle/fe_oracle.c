@@ -121,6 +121,148 @@ static void cell_apply(const cell_ctx *c, const double *G, const double *JxW, co
     }
 }
 
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Fast path of the same operator for the timed CPU baseline: LANES cells are processed side by side, the lane index
+ * being the fastest array dimension (the layout deal.II's CPU path uses: VectorizedArray over n_lanes cells,
+ * bk3_dealii/check_bk3.cc:86-113), and the 1-D sizes are compile-time constants (the reference dispatches fe_degree / nq
+ * at compile time as well, CEED_bp/src/bp3.cc:536-557).  Every lane performs exactly the arithmetic of cell_apply() in
+ * the same order (no FMA contraction, no reassociation), so the results are bitwise those of the generic path.
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define LANES 8
+#define AINLINE static inline __attribute__((always_inline))
+
+AINLINE void contract_k(const int na, const int nin, const int nout, const int nc, const double *M, const int rs, const int cs,
+                        const double *restrict in, double *restrict out)
+{
+    /* same sum order as contract() (n ascending from 0.0), accumulated in a register per output entry */
+    for (int a = 0; a < na; ++a)
+        for (int m = 0; m < nout; ++m) {
+            double *restrict o = out + ((size_t)a * nout + m) * nc;
+            const double *restrict x = in + (size_t)a * nin * nc;
+#pragma omp simd
+            for (int c = 0; c < nc; ++c) {
+                double sum = 0.0;
+                for (int n = 0; n < nin; ++n) sum += M[m * rs + n * cs] * x[(size_t)n * nc + c];
+                o[c] = sum;
+            }
+        }
+}
+
+/* u[nm^3][LANES] -> out[nm^3][LANES]; Gb[6][nq^3][LANES], Jb[nq^3][LANES] (lane-interleaved copies of the batch's
+ * geometric factors); ws: 7*nq^3*LANES doubles */
+AINLINE void cell_apply_lanes(const int nm, const int nq, const int collocated, const int flags, const double *S, const double *Dg,
+                              const double *restrict Gb, const double *restrict Jb, const double *restrict u, double *restrict out,
+                              double *restrict ws)
+{
+    const int L = LANES, n2 = nq * nq, n3 = n2 * nq, n3L = n3 * L;
+    double *t0 = ws, *t1 = ws + n3L, *v = ws + 2 * n3L, *gr = ws + 3 * n3L, *gs = ws + 4 * n3L, *gt = ws + 5 * n3L, *w = ws + 6 * n3L;
+    const double *vv = u;
+    if (!collocated) {
+        contract_k(1, nm, nq, nm * nm * L, S, 1, nq, u, t0);
+        contract_k(nq, nm, nq, nm * L, S, 1, nq, t0, t1);
+        contract_k(nq * nq, nm, nq, L, S, 1, nq, t1, v);
+        vv = v;
+    }
+    for (int i = 0; i < n3L; ++i) w[i] = 0.0;
+    if (flags & OP_LAPLACE) {
+        contract_k(1, nq, nq, n2 * L, Dg, 1, nq, vv, gr);
+        contract_k(nq, nq, nq, nq * L, Dg, 1, nq, vv, gs);
+        contract_k(n2, nq, nq, L, Dg, 1, nq, vv, gt);
+        const double *g0 = Gb, *g1 = Gb + n3L, *g2 = Gb + 2 * n3L, *g3 = Gb + 3 * n3L, *g4 = Gb + 4 * n3L, *g5 = Gb + 5 * n3L;
+#pragma omp simd
+        for (int i = 0; i < n3L; ++i) {
+            const double qr = gr[i], qs = gs[i], qt = gt[i];
+            gr[i] = g0[i] * qr + g1[i] * qs + g2[i] * qt;
+            gs[i] = g1[i] * qr + g3[i] * qs + g4[i] * qt;
+            gt[i] = g2[i] * qr + g4[i] * qs + g5[i] * qt;
+        }
+        contract_k(1, nq, nq, n2 * L, Dg, nq, 1, gr, t0);
+        for (int i = 0; i < n3L; ++i) w[i] += t0[i];
+        contract_k(nq, nq, nq, nq * L, Dg, nq, 1, gs, t0);
+        for (int i = 0; i < n3L; ++i) w[i] += t0[i];
+        contract_k(n2, nq, nq, L, Dg, nq, 1, gt, t0);
+        for (int i = 0; i < n3L; ++i) w[i] += t0[i];
+    }
+    if (flags & OP_MASS)
+        for (int i = 0; i < n3L; ++i) w[i] += Jb[i] * vv[i];
+    if (collocated)
+        memcpy(out, w, sizeof(double) * n3L);
+    else {
+        contract_k(nq * nq, nq, nm, L, S, nq, 1, w, t0);
+        contract_k(nq, nq, nm, nm * L, S, nq, 1, t0, t1);
+        contract_k(1, nq, nm, nm * nm * L, S, nq, 1, t1, out);
+    }
+}
+
+/* compile-time (nm, nq, collocated) instances of the batch kernel: nq = nm (collocated or not) and nq = nm + 1, degrees 1..8 */
+typedef void (*batch_fn)(int flags, const double *S, const double *Dg, const double *Gb, const double *Jb, const double *u, double *out,
+                         double *ws);
+#define LANES_DEF(NM, NQ, COLL)                                                                                                    \
+    static void batch_##NM##_##NQ##_##COLL(int flags, const double *S, const double *Dg, const double *Gb, const double *Jb,        \
+                                           const double *u, double *out, double *ws)                                               \
+    {                                                                                                                              \
+        cell_apply_lanes(NM, NQ, COLL, flags, S, Dg, Gb, Jb, u, out, ws);                                                           \
+    }
+#define LANES_DEGREE_DEF(NM, NP) LANES_DEF(NM, NM, 1) LANES_DEF(NM, NM, 0) LANES_DEF(NM, NP, 0)
+LANES_DEGREE_DEF(2, 3) LANES_DEGREE_DEF(3, 4) LANES_DEGREE_DEF(4, 5) LANES_DEGREE_DEF(5, 6)
+LANES_DEGREE_DEF(6, 7) LANES_DEGREE_DEF(7, 8) LANES_DEGREE_DEF(8, 9) LANES_DEGREE_DEF(9, 10)
+
+static batch_fn batch_kernel(int nm, int nq, int collocated)
+{
+#define LANES_CASE(NM, NQ, COLL) if (nm == NM && nq == NQ && (collocated != 0) == COLL) return batch_##NM##_##NQ##_##COLL;
+#define LANES_DEGREE(NM, NP) LANES_CASE(NM, NM, 1) LANES_CASE(NM, NM, 0) LANES_CASE(NM, NP, 0)
+    LANES_DEGREE(2, 3) LANES_DEGREE(3, 4) LANES_DEGREE(4, 5) LANES_DEGREE(5, 6)
+    LANES_DEGREE(6, 7) LANES_DEGREE(7, 8) LANES_DEGREE(8, 9) LANES_DEGREE(9, 10)
+    return NULL;
+}
+
+/* all cells [cb, ce) of one colour, LANES at a time (cells of a colour share no DoF, so the lanes' scatters are disjoint) */
+static void colour_loop_lanes(batch_fn kernel, int nm, int nq, int flags, const double *S, const double *Dg, const double *G,
+                              const double *JxW, const uint32_t *dof_indices, const uint32_t *color_cells, uint32_t cb, uint32_t ce,
+                              const double *src, double *dst)
+{
+    const int L = LANES;
+    const size_t nm3 = (size_t)nm * nm * nm, nq3 = (size_t)nq * nq * nq;
+    const uint32_t n_batches = (ce - cb + L - 1) / L;
+#pragma omp parallel
+    {
+        double *ws = (double *)aligned_alloc(64, sizeof(double) * L * (7 * nq3 + 2 * nm3 + 7 * nq3));
+        double *u = ws + 7 * nq3 * L, *o = u + nm3 * L, *Gb = o + nm3 * L, *Jb = Gb + 6 * nq3 * L;
+#pragma omp for schedule(static)
+        for (uint32_t bi = 0; bi < n_batches; ++bi) {
+            uint32_t cell[LANES];
+            int cnt = 0;
+            for (int l = 0; l < L; ++l) {
+                const uint32_t ci = cb + bi * L + l;
+                if (ci < ce) { cell[l] = color_cells ? color_cells[ci] : ci; cnt = l + 1; }
+                else cell[l] = cell[0];  /* padding lane: computed, never scattered */
+            }
+            const uint32_t *idx[LANES];
+            const double *Gc[LANES], *Jc[LANES];
+            for (int l = 0; l < L; ++l) {
+                idx[l] = dof_indices + (size_t)cell[l] * nm3;
+                Gc[l] = (flags & OP_LAPLACE) ? G + (size_t)cell[l] * 6 * nq3 : NULL;
+                Jc[l] = (flags & OP_MASS) ? JxW + (size_t)cell[l] * nq3 : NULL;
+            }
+            /* lane-interleave the batch's inputs: LANES sequential read streams, contiguous writes */
+            for (size_t k = 0; k < nm3; ++k)
+                for (int l = 0; l < L; ++l) u[k * L + l] = idx[l][k] == INVALID_INDEX ? 0.0 : src[idx[l][k]];
+            if (flags & OP_LAPLACE)
+                for (size_t k = 0; k < 6 * nq3; ++k)
+                    for (int l = 0; l < L; ++l) Gb[k * L + l] = Gc[l][k];
+            if (flags & OP_MASS)
+                for (size_t k = 0; k < nq3; ++k)
+                    for (int l = 0; l < L; ++l) Jb[k * L + l] = Jc[l][k];
+            kernel(flags, S, Dg, Gb, Jb, u, o, ws);
+            for (size_t k = 0; k < nm3; ++k)
+                for (int l = 0; l < cnt; ++l)
+                    if (idx[l][k] != INVALID_INDEX) dst[idx[l][k]] += o[k * L + l];
+        }
+        free(ws);
+    }
+}
+
 /*
  * dst = A src on one rank's local vector (no halo exchange).
  * color_offsets[n_colors+1] / color_cells[] : CSR list of cells per colour (NULL -> serial loop).
@@ -141,6 +283,12 @@ void oracle_op_apply(int nm, int nq, int collocated, int flags, uint32_t n_cells
     for (int col = 0; col < ncol; ++col) {
         const uint32_t cb = color_offsets ? color_offsets[col] : 0;
         const uint32_t ce = color_offsets ? color_offsets[col + 1] : n_cells;
+        /* coloured call (the timed baseline): lane-batched fast path with compile-time sizes; same arithmetic per cell */
+        batch_fn kernel = color_offsets != NULL ? batch_kernel(nm, nq, collocated) : NULL;
+        if (kernel) {
+            colour_loop_lanes(kernel, nm, nq, flags, shape_values, co_shape_gradients, G, JxW, dof_indices, color_cells, cb, ce, src, dst);
+            continue;
+        }
 #pragma omp parallel if (color_offsets != NULL)
         {
             double *ws = (double *)malloc(sizeof(double) * (7 * nq3 + 2 * nm3));
