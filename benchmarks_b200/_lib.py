@@ -72,6 +72,11 @@ _SIGNATURES = {
     "b200fe_cg_solve": (_i, [_vp, _vp, _vp, _vp, C.c_double, C.c_double, _i, _i, _vp, _vp]),
     "b200fe_cg_solve_components": (_i, [_vp, _i, _vp, _vp, _vp, C.c_double, C.c_double, _i, _i, _vp, _vp]),
     "b200fe_cg_solve_host": (_i, [_vp, _vp, _vp, _vp, C.c_double, C.c_double, _i, _i, _vp, _vp]),
+    "b200fe_exchange_create_box": (_i, [_vp, C.POINTER(_vp)]),
+    "b200fe_exchange_create_hang": (_i, [_vp, C.POINTER(_vp)]),
+    "b200fe_exchange_destroy": (None, [_vp]),
+    "b200fe_exchange_info": (_i, [_vp, _pi, C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32)]),
+    "b200fe_exchange_fill": (_i, [_vp] * 7),
     "b200fe_comm_available": (_i, []),
     "b200fe_comm_unique_id": (_i, [_vp]),
     "b200fe_halo_create": (_i, [_vp, C.POINTER(_vp)]),

@@ -58,6 +58,24 @@ def exchange_lists(mesh, group=None):
                 send_offset=send_offset, send_count=send_count, send_indices=send_indices)
 
 
+def exchange_lists_local(mesh):
+    """The same peer tables from the C ABI (b200fe_exchange_*): every rank replays the other ranks' mesh views, no
+    communication at all.  Same dict as exchange_lists()."""
+    h = C.c_void_p()
+    check(mesh._exchange_create(C.byref(mesh._desc), C.byref(h)))
+    try:
+        n_peers, n_send = C.c_int(), C.c_uint32()
+        check(lib.b200fe_exchange_info(h, C.byref(n_peers), C.byref(n_send), None, None))
+        peers = np.empty(n_peers.value, dtype=np.int32)
+        arrs = [np.empty(n_peers.value, dtype=np.uint32) for _ in range(4)]
+        send_indices = np.empty(n_send.value, dtype=np.uint32)
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+        check(lib.b200fe_exchange_fill(h, ptr(peers), *[ptr(a) for a in arrs], ptr(send_indices)))
+    finally:
+        lib.b200fe_exchange_destroy(h)
+    return dict(peers=peers, recv_offset=arrs[0], recv_count=arrs[1], send_offset=arrs[2], send_count=arrs[3], send_indices=send_indices)
+
+
 class Halo:
     """Ghost exchange object of one rank (NCCL communicator + pack lists on the device)."""
 

@@ -53,6 +53,7 @@ class BoxMesh:
         d.p1[:] = list(p1)
         d.p2[:] = list(p2)
         d.p, d.n_ranks, d.rank, d.partition, d.ghosts, d.dirichlet = p, n_ranks, rank, partition, ghosts, int(dirichlet)
+        self._desc, self._exchange_create = d, lib.b200fe_exchange_create_box
         self._h = C.c_void_p()
         check(lib.b200fe_boxmesh_create(C.byref(d), C.byref(self._h)))
         info = _Info()
@@ -126,6 +127,7 @@ class HangingBoxMesh:
         d.box.partition, d.box.ghosts, d.box.dirichlet = PARTITION_P4EST, GHOSTS_MINIMAL, int(dirichlet)
         d.refine_lo[:] = list(refine_lo)
         d.refine_hi[:] = list(refine_hi)
+        self._desc, self._exchange_create = d, lib.b200fe_exchange_create_hang
         self._h = C.c_void_p()
         check(lib.b200fe_hangmesh_create(C.byref(d), C.byref(self._h)))
         info = _HangInfo()

@@ -373,6 +373,18 @@ typedef struct {
     uint32_t n_send;
 } b200fe_halo_desc;
 
+/* The peer tables of b200fe_halo_desc for this rank, computed WITHOUT communication: the meshes above are replayable
+ * on every rank, so the rank builds every other rank's view and reads off who ghosts which of its DoFs (deal.II's
+ * Partitioner needs a message round for this).  desc->rank / desc->box.rank = this rank.
+ * Arrays: h_peers/recv_offset/recv_count/send_offset/send_count [n_peers], h_send_indices [n_send]. */
+typedef struct b200fe_exchange b200fe_exchange;
+int b200fe_exchange_create_box(const b200fe_boxmesh_desc *desc, b200fe_exchange **out);
+int b200fe_exchange_create_hang(const b200fe_hangmesh_desc *desc, b200fe_exchange **out);
+void b200fe_exchange_destroy(b200fe_exchange *ex);
+int b200fe_exchange_info(const b200fe_exchange *ex, int *n_peers, uint32_t *n_send, uint32_t *n_owned, uint32_t *n_ghost);
+int b200fe_exchange_fill(const b200fe_exchange *ex, int32_t *h_peers, uint32_t *h_recv_offset, uint32_t *h_recv_count,
+                         uint32_t *h_send_offset, uint32_t *h_send_count, uint32_t *h_send_indices);
+
 int b200fe_comm_available(void); /* 1 if libnccl.so.2 could be bound */
 int b200fe_comm_unique_id(char *id128);
 /* Collective over all ranks (ncclCommInitRank). */

@@ -94,3 +94,43 @@ def test_bench_partitions_are_consistent(n_ranks, sub):
             assert n1 < m.n_cells and n0 + n1 <= m.n_cells
             # lower ranks own the interfaces: rank 0 never ghosts anything
             assert (r > 0) or m.n_ghost == 0
+
+
+@pytest.mark.parametrize("sub,nref,p,nranks", [((1, 1, 1), 2, 2, 4), ((2, 2, 1), 1, 3, 3), ((2, 2, 2), 1, 2, 8), ((1, 1, 1), 1, 5, 2)])
+def test_exchange_lists_without_communication_match_oracle(oracle_mod, sub, nref, p, nranks):
+    """b200fe_exchange_* (every rank replays the other ranks' views; no message round) against the oracle's
+    Partitioner-style lists: recv slices of the ghost segment, send lists in the peer's ghost order."""
+    from benchmarks_b200.dist import exchange_lists_local
+    fe = oracle_mod.fe
+    om = fe.BoxMesh(sub, nref)
+    od = fe.distribute_dofs(om, p, nranks)
+    exs = fe.exchange_lists([fe.rank_data(om, od, r) for r in range(nranks)])
+    for r in range(nranks):
+        L = exchange_lists_local(b.BoxMesh(sub, nref, p, n_ranks=nranks, rank=r))
+        ex = exs[r]
+        assert sorted(ex["recv"]) == [int(t) for t, c in zip(L["peers"], L["recv_count"]) if c]
+        assert sorted(ex["send"]) == [int(t) for t, c in zip(L["peers"], L["send_count"]) if c]
+        for t, off, cnt, so, sc in zip(L["peers"], L["recv_offset"], L["recv_count"], L["send_offset"], L["send_count"]):
+            if cnt:
+                assert ex["recv"][int(t)] == (int(off), int(off + cnt))
+            if sc:
+                assert np.array_equal(ex["send"][int(t)], L["send_indices"][so:so + sc])
+
+
+@pytest.mark.parametrize("sub,nref,p,lo,hi,nranks", [((2, 1, 1), 1, 3, (1, 0, 0), (3, 1, 2), 3), ((1, 1, 1), 2, 2, (1, 1, 1), (3, 3, 3), 4),
+                                                     ((2, 1, 1), 1, 4, (0, 0, 0), (2, 2, 1), 8)])
+def test_exchange_lists_without_communication_hanging(sub, nref, p, lo, hi, nranks):
+    """Same for two-level meshes (the ghost sets carry the parents of hanging DoFs): against the lists derived from all
+    ranks' mesh objects."""
+    from benchmarks_b200.dist import exchange_lists_local
+    ms = [b.HangingBoxMesh(sub, nref, p, lo, hi, n_ranks=nranks, rank=r) for r in range(nranks)]
+    for r, m in enumerate(ms):
+        L = exchange_lists_local(m)
+        expect_peers = set(m.ghost_owner.tolist()) | {t for t in range(nranks) if t != r and (ms[t].ghost_owner == r).any()}
+        assert [int(t) for t in L["peers"]] == sorted(expect_peers)
+        for t, off, cnt, so, sc in zip(L["peers"], L["recv_offset"], L["recv_count"], L["send_offset"], L["send_count"]):
+            t = int(t)
+            sel = np.nonzero(m.ghost_owner == t)[0]
+            assert cnt == len(sel) and (cnt == 0 or (sel[0] == off and sel[-1] == off + cnt - 1))
+            want = (ms[t].ghost_global[ms[t].ghost_owner == r] - np.uint64(m.owned_begin)).astype(np.uint32)
+            assert np.array_equal(want, L["send_indices"][so:so + sc])
