@@ -8,13 +8,17 @@
 // ghost exchange / computation switched (:331-408).  Output: the reference's two tables
 // (cells, dofs, matvec, CG_tot_time, CG_time/iters, cg_its, cg_reduction) and
 // (cells, dofs, mv_ghost_and_compute, mv_compute_only, mv_ghost_only), plus GDoF/s.
-// Single process / single GPU (multi-GPU runs go through the Python launcher, bench.py).
+// One process per GPU: rank / size are taken from the launcher's environment (e.g. `torchrun --no-python --nproc-per-node N
+// ./bp3 4 ...`; b200fe::Communicator), the mesh is partitioned along the p4est curve like the reference's
+// parallel::distributed::Triangulation (bp3.cc:83), times are the maximum over ranks (:301-302).  The N > 1 path of this
+// driver has not been run yet (round 1 measured multi-GPU through the Python launcher); N = 1 is the tested path.
 #include <b200fe/operator.hpp>
 
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <iostream>
+#include <memory>
 
 using namespace b200fe;
 using clk = std::chrono::steady_clock;
@@ -27,16 +31,26 @@ struct LaplaceProblem {
 
     void run(std::size_t min_size, std::size_t max_size, Quadrature quad)
     {
-        std::printf("Testing FE_Q<3>(%d), n_q_points_1d = %d (%s)\nNo. of GPUs: 1\n", fe_degree, nq, quad == Quadrature::Gauss ? "QGauss" : "QGaussLobatto");
+        const Communicator comm = Communicator::from_environment();
+        check_cuda(cudaSetDevice(comm.local_rank), "cudaSetDevice");
+        const bool root = comm.rank == 0;
+        if (!root) std::fclose(stdout);  // the tables are printed by rank 0 only (pcout of bp3.cc:92)
+        std::printf("Testing FE_Q<3>(%d), n_q_points_1d = %d (%s)\nNo. of GPUs: %d\n", fe_degree, nq, quad == Quadrature::Gauss ? "QGauss" : "QGaussLobatto", comm.size);
         for (unsigned cycle = 0; cycle < 38; ++cycle) {
             const std::size_t projected = BoxMesh::bp3_projected_size(cycle, fe_degree);
             if (projected < min_size) continue;
             if (projected > max_size) { std::printf("Projected size %zu higher than max size, terminating.\n\n", projected); break; }
             std::printf("Cycle %u\n", cycle);
             auto t0 = clk::now();
-            BoxMesh mesh = BoxMesh::bp3_cycle(cycle, fe_degree);
+            BoxMesh mesh = BoxMesh::bp3_cycle(cycle, fe_degree, comm.size, comm.rank);
             std::printf("  Number of cells: %llu |   Number of DoFs: %llu\n", mesh.n_global_active_cells(), mesh.n_dofs());
             LaplaceOperator<3, fe_degree, nq, double> system_matrix(mesh, quad);
+            std::unique_ptr<Halo> halo;
+            if (comm.size > 1) {
+                halo = std::make_unique<Halo>(mesh, comm);
+                system_matrix.set_halo(*halo);
+            }
+            auto max_over_ranks = [&](double t) { return halo ? halo->max_over_ranks(t, comm.rank) : t; };
             Vector solution, rhs;
             system_matrix.initialize_dof_vector(solution);
             rhs.reinit(solution);
@@ -57,7 +71,7 @@ struct LaplaceProblem {
                 auto t = clk::now();
                 cg.solve(system_matrix, solution, rhs, PreconditionIdentity());
                 cudaDeviceSynchronize();
-                const double dt = since(t);
+                const double dt = max_over_ranks(since(t));
                 time_cg = std::min(time_cg, dt);
                 row.its = solver_control.last_step();
                 row.red = std::pow(solver_control.last_value() / solver_control.initial_value(), 1. / solver_control.last_step());
@@ -75,7 +89,7 @@ struct LaplaceProblem {
                         else system_matrix.vmult_dummy(solution, rhs, ghost_on, comp_on);
                     }
                     cudaDeviceSynchronize();
-                    best = std::min(best, since(t) / n_mv);
+                    best = std::min(best, max_over_ranks(since(t)) / n_mv);
                 }
                 return best;
             };

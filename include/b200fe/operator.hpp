@@ -15,8 +15,16 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <ctime>
+#include <initializer_list>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -148,6 +156,7 @@ class BoxMesh {
         check(b200fe_boxmesh_create(&d, &h_));
         check(b200fe_boxmesh_info(h_, &info));
         degree = p;
+        desc = d;
     }
     // mesh number `cycle` of the reference sweep (CEED_bp/src/bp3.cc:443-473)
     static BoxMesh bp3_cycle(unsigned cycle, int p, int n_ranks = 1, int rank = 0)
@@ -165,13 +174,20 @@ class BoxMesh {
         for (unsigned d = 0; d < 3; ++d) s *= (unsigned long long)((1u << n_refine) * (d < rem ? 2 : 1) * p + 1);
         return s;
     }
-    BoxMesh(BoxMesh &&o) noexcept : info(o.info), degree(o.degree), h_(o.h_) { o.h_ = nullptr; }
+    BoxMesh(BoxMesh &&o) noexcept : info(o.info), desc(o.desc), degree(o.degree), h_(o.h_) { o.h_ = nullptr; }
     BoxMesh(const BoxMesh &) = delete;
     ~BoxMesh() { if (h_) b200fe_boxmesh_destroy(h_); }
     const b200fe_boxmesh *handle() const { return h_; }
     unsigned long long n_dofs() const { return info.n_dofs_global; }
     unsigned long long n_global_active_cells() const { return info.n_cells_global; }
+    b200fe_exchange *make_exchange() const
+    {
+        b200fe_exchange *ex = nullptr;
+        check(b200fe_exchange_create_box(&desc, &ex));
+        return ex;
+    }
     b200fe_boxmesh_info_t info{};
+    b200fe_boxmesh_desc desc{};
     int degree = 0;
 
   private:
@@ -195,18 +211,131 @@ class HangingBoxMesh {
         check(b200fe_hangmesh_create(&d, &h_));
         check(b200fe_hangmesh_info(h_, &info));
         degree = p;
+        desc = d;
     }
-    HangingBoxMesh(HangingBoxMesh &&o) noexcept : info(o.info), degree(o.degree), h_(o.h_) { o.h_ = nullptr; }
+    HangingBoxMesh(HangingBoxMesh &&o) noexcept : info(o.info), desc(o.desc), degree(o.degree), h_(o.h_) { o.h_ = nullptr; }
     HangingBoxMesh(const HangingBoxMesh &) = delete;
     ~HangingBoxMesh() { if (h_) b200fe_hangmesh_destroy(h_); }
     const b200fe_hangmesh *handle() const { return h_; }
     unsigned long long n_dofs() const { return info.n_dofs_global; }
     unsigned long long n_global_active_cells() const { return info.n_cells_global; }
+    b200fe_exchange *make_exchange() const
+    {
+        b200fe_exchange *ex = nullptr;
+        check(b200fe_exchange_create_hang(&desc, &ex));
+        return ex;
+    }
     b200fe_hangmesh_info_t info{};
+    b200fe_hangmesh_desc desc{};
     int degree = 0;
 
   private:
     b200fe_hangmesh *h_ = nullptr;
+};
+
+// One process per GPU.  Rank / size come from the launcher's environment (RANK, WORLD_SIZE, LOCAL_RANK, MASTER_PORT as set
+// by `python -m torch.distributed.run --no-python`; a plain run has none of them = one rank); the only thing that has to
+// travel between the processes is the
+// 128-byte NCCL id, published by rank 0 through a file (the reference uses MPI for everything, bp3.cc:564; there is no MPI
+// in this image).  NOT YET RUN on more than one GPU: the multi-GPU evidence of round 1 went through the Python launcher.
+class Communicator {
+  public:
+    static Communicator from_environment()
+    {
+        Communicator c;
+        c.rank = env_int({"RANK"}, 0);
+        c.size = env_int({"WORLD_SIZE"}, 1);
+        c.local_rank = env_int({"LOCAL_RANK"}, c.rank);
+        if (c.size < 1 || c.rank < 0 || c.rank >= c.size) throw Error(B200FE_ERR_INVALID_ARG, "bad RANK / WORLD_SIZE in the environment");
+        const char *port = std::getenv("MASTER_PORT");
+        c.id_file = std::string("/tmp/b200fe_nccl_id_") + (port ? port : "default");
+        return c;
+    }
+    // collective: rank 0 creates the id and publishes it, the others wait for a file written during this launch
+    std::string unique_id() const
+    {
+        std::string id(128, '\0');
+        if (size == 1) return id;
+        if (rank == 0) {
+            std::remove(id_file.c_str());
+            check(b200fe_comm_unique_id(&id[0]));
+            const std::string tmp = id_file + ".tmp";
+            FILE *f = std::fopen(tmp.c_str(), "wb");
+            if (!f || std::fwrite(id.data(), 1, 128, f) != 128) throw Error(B200FE_ERR_COMM, "cannot write " + tmp);
+            std::fclose(f);
+            if (std::rename(tmp.c_str(), id_file.c_str()) != 0) throw Error(B200FE_ERR_COMM, "cannot publish " + id_file);
+            return id;
+        }
+        const std::time_t start = std::time(nullptr);
+        for (int tries = 0; tries < 6000; ++tries) {  // up to 10 minutes
+            struct stat st;
+            if (stat(id_file.c_str(), &st) == 0 && st.st_size == 128 && st.st_mtime + 120 >= start) {
+                FILE *f = std::fopen(id_file.c_str(), "rb");
+                if (f) {
+                    const size_t n = std::fread(&id[0], 1, 128, f);
+                    std::fclose(f);
+                    if (n == 128) return id;
+                }
+            }
+            usleep(100000);
+        }
+        throw Error(B200FE_ERR_COMM, "timed out waiting for the NCCL id in " + id_file);
+    }
+    void cleanup() const { if (rank == 0 && size > 1) std::remove(id_file.c_str()); }
+    int rank = 0, size = 1, local_rank = 0;
+    std::string id_file;
+
+  private:
+    static int env_int(std::initializer_list<const char *> names, int fallback)
+    {
+        for (const char *n : names)
+            if (const char *v = std::getenv(n)) return std::atoi(v);
+        return fallback;
+    }
+};
+
+// ghost exchange of one rank: peer tables from b200fe_exchange_* (no communication), NCCL communicator inside
+class Halo {
+  public:
+    template <class Mesh>
+    Halo(const Mesh &mesh, const Communicator &comm) : size_(comm.size)
+    {
+        b200fe_exchange *ex = mesh.make_exchange();
+        int n_peers = 0;
+        uint32_t n_send = 0, n_owned = 0, n_ghost = 0;
+        b200fe_exchange_info(ex, &n_peers, &n_send, &n_owned, &n_ghost);
+        std::vector<int32_t> peers(n_peers);
+        std::vector<uint32_t> ro(n_peers), rc(n_peers), so(n_peers), sc(n_peers), si(n_send);
+        b200fe_exchange_fill(ex, peers.data(), ro.data(), rc.data(), so.data(), sc.data(), si.data());
+        b200fe_exchange_destroy(ex);
+        const std::string id = comm.unique_id();
+        b200fe_halo_desc d{};
+        d.rank = comm.rank; d.n_ranks = comm.size; d.nccl_unique_id = id.data();
+        d.n_owned = n_owned; d.n_ghost = n_ghost; d.n_peers = n_peers; d.peers = peers.data();
+        d.recv_offset = ro.data(); d.recv_count = rc.data(); d.send_offset = so.data(); d.send_count = sc.data();
+        d.h_send_indices = si.data(); d.n_send = n_send;
+        check(b200fe_halo_create(&d, &h_));  // collective
+        comm.cleanup();
+    }
+    Halo(const Halo &) = delete;
+    ~Halo() { if (h_) b200fe_halo_destroy(h_); }
+    b200fe_halo *handle() const { return h_; }
+    // max over ranks of a host value (Utilities::MPI::min_max_avg(...).max of bp3.cc:301-302): every rank fills its slot
+    double max_over_ranks(double v, int rank) const
+    {
+        DeviceArray<double> d(size_);
+        std::vector<double> h(size_, 0.0);
+        h[rank] = v;
+        d.upload(h.data(), h.size());
+        check(b200fe_halo_allreduce_sum(h_, d.data(), size_, nullptr));
+        check_cuda(cudaDeviceSynchronize(), "allreduce");
+        d.download(h.data());
+        return *std::max_element(h.begin(), h.end());
+    }
+
+  private:
+    b200fe_halo *h_ = nullptr;
+    int size_ = 1;
 };
 
 // smooth mesh deformation of b200fe_boxmesh_nodes (deform_kind 1); amplitude 0 = the box itself
@@ -299,6 +428,8 @@ class LaplaceOperator {
         return inv_diag_.data();
     }
     b200fe_op *handle() const { return op_; }
+    // attach the ghost exchange (vmult then does update_ghost_values / compress(add) itself, and CG reduces its scalars)
+    void set_halo(const Halo &halo) { check(b200fe_op_set_halo(op_, halo.handle())); }
 
   private:
     static constexpr size_t nm3() { return (size_t)(fe_degree + 1) * (fe_degree + 1) * (fe_degree + 1); }
