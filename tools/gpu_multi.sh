@@ -4,6 +4,9 @@ N=${1:-2}; tag=${2:-r01}
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 $TR --master-port 29511 tools/dist_check.py > gpurun_out/${tag}_dist_check_${N}gpu.log 2>&1; tail -2 gpurun_out/${tag}_dist_check_${N}gpu.log
+# the C++ driver on N ranks (reference protocol: bp3 <degree> <minsize> <maxsize>)
+timeout 300 python -m torch.distributed.run --no-python --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29515 \
+    ./benchmarks_b200/drivers/bp3 4 1000000 40000000 > gpurun_out/${tag}_bp3_cxx_${N}gpu.log 2>&1; tail -4 gpurun_out/${tag}_bp3_cxx_${N}gpu.log
 # config C5, strong scaling
 $TR --master-port 29514 tools/bench_c5.py --cells-log2 6 --refine-frac 4 --its 50 --steps 3 > gpurun_out/${tag}_bench_c5_${N}gpu.json 2> gpurun_out/${tag}_bench_c5_${N}gpu.err; head -c 300 gpurun_out/${tag}_bench_c5_${N}gpu.json; echo
 $TR --master-port 29512 bench.py --gpus $N --steps 3 --warmup 3 > gpurun_out/${tag}_bench_${N}gpu.json 2> gpurun_out/${tag}_bench_${N}gpu.err
