@@ -205,3 +205,43 @@ def test_hanging_mesh_exchange_and_distributed_apply_gloo(world, sub, nref, p, l
     for rank, ok, err in results:
         assert ok, f"rank {rank}: ghost values differ after update_ghost_values"
         assert err <= 1e-12, f"rank {rank}: distributed constrained apply differs ({err})"
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_cxx_communicator_and_exchange_lists(world):
+    """C++ host layer (include/b200fe/operator.hpp) as `world` processes, no GPU: b200fe::Communicator hands every rank the
+    same NCCL id (rank 0 publishes it through a file), and the exchange lists the C++ Halo is built from equal the Python
+    mirror's."""
+    import re
+    import subprocess
+    import benchmarks_b200 as b
+    from benchmarks_b200.dist import exchange_lists_local
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    drv = os.path.join(root, "benchmarks_b200", "drivers")
+    exe = os.path.join(drv, "comm_check")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", drv, "comm_check"], check=True)
+    port = _free_port()
+    p = 3
+    procs = []
+    for r in reversed(range(world)):  # rank 0 last: the others must wait for its file
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_PORT=str(port))
+        procs.append((r, subprocess.Popen([exe, str(p)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    outs = {}
+    for r, pr in procs:
+        out, err = pr.communicate(timeout=120)
+        assert pr.returncode == 0, err
+        outs[r] = out
+    ids = {re.search(r"id=([0-9a-f]+)", outs[r]).group(1) for r in range(world)}
+    assert len(ids) == 1
+    sub, p1, p2 = (2, 1, 1), (-1.0, -1.0, -1.0), (2.8, 0.9, 0.9)
+    for r in range(world):
+        meshes = {"box": b.BoxMesh(sub, 1, p, p1=p1, p2=p2, n_ranks=world, rank=r),
+                  "hang": b.HangingBoxMesh(sub, 1, p, (1, 0, 0), (3, 1, 2), p1=p1, p2=p2, n_ranks=world, rank=r)}
+        for name, mesh in meshes.items():
+            line = next(l for l in outs[r].splitlines() if l.startswith(name + " "))
+            L = exchange_lists_local(mesh)
+            want = (f"{name} n_owned={mesh.n_owned} n_ghost={mesh.n_ghost} n_peers={len(L['peers'])} n_send={len(L['send_indices'])} "
+                    f"send_sum={int(L['send_indices'].astype(np.int64).sum())}"
+                    + "".join(f" peer{int(t)}:recv={int(c)},send={int(s)}" for t, c, s in zip(L["peers"], L["recv_count"], L["send_count"])))
+            assert line == want
