@@ -211,3 +211,19 @@ def test_golden_fixture_freezes_the_conventions(oracle_mod, golden_dir):
                        face_parents=dg(m.face_parents), face_children=dg(m.face_children))
             for k, v in got.items():
                 assert v == wr[k], (case, r, k)
+
+
+def test_face_blocks_without_dirichlet_constraints(oracle_mod):
+    """No Dirichlet DoFs (pure Neumann mesh): hanging DoFs on the domain boundary stay hanging and their boundary parents stay in
+    the rows; the face form still covers every hanging DoF once and equals the rows."""
+    ho = oracle_mod.hanging
+    for sub, nref, p, lo, hi, nranks in (((2, 2, 2), 0, 2, (0, 0, 0), (1, 1, 1), 1), ((2, 1, 1), 1, 3, (1, 0, 0), (3, 1, 2), 3)):
+        for r in range(nranks):
+            m = b.HangingBoxMesh(sub, nref, p, lo, hi, n_ranks=nranks, rank=r, dirichlet=False)
+            assert len(m.constrained) == len(m.hang_dof[m.hang_dof < m.n_owned])
+            kids = m.face_children[m.face_children != 0xFFFFFFFF]
+            assert sorted(kids.tolist()) == sorted(m.hang_dof.tolist())
+            u = np.random.default_rng(r).standard_normal(m.n_owned + m.n_ghost)
+            md = _mesh_dict(m)
+            assert np.abs(ho.distribute_faces(p, m.face_parents, m.face_children, u) - ho.distribute(md, u)).max(initial=0.0) <= 1e-13
+            assert np.abs(ho.condense_faces(p, m.face_parents, m.face_children, u) - ho.condense(md, u)).max(initial=0.0) <= 1e-12
