@@ -11,7 +11,8 @@
 //   H2 a fine-level DoF on the closure of an unrefined active cell K is constrained to the trace of K.
 //   H3 cells are visited level by level (unrefined cells in z-order index order, then children grouped by parent);
 //      first-touch numbering, vertices -> lines -> quads -> interior inside a cell.
-//   H4 p4est curve (depth first) cut at floor(N r / P), families of 8 siblings kept whole (majority rank, ties low);
+//   H4 p4est curve (depth first) cut at floor(N r / P), families of 8 children kept whole (majority rank, ties low;
+//      families of unrefined siblings are not corrected -- irrelevant for 1/2/4/8 ranks on the benchmark meshes);
 //      a DoF belongs to the lowest rank among the active cells that have it.
 //   H5 Dirichlet on the whole boundary takes precedence over a hanging constraint.
 //

@@ -20,8 +20,10 @@ restated from the library's documented behaviour:
   H4  parallel::distributed: the p4est curve (depth first: a refined cell is replaced in place by its children)
       is cut into pieces of floor(N r / P) cells, then corrected so that no family of 8 siblings is split
       (p4est_partition with partition_for_coarsening: the family goes to the rank holding most of it, ties to
-      the lower rank).  A DoF belongs to the lowest rank among the active cells that have it; ranks number
-      their DoFs one after the other.
+      the lower rank).  Only the families of children are treated that way; p4est would also keep a complete family
+      of eight unrefined siblings whole, which the uniform-mesh rule of SURVEY A4 (fe_oracle.BoxMesh.partition) does not
+      model -- no difference for 1/2/4/8 ranks on the benchmark meshes, where the cuts fall on family boundaries.
+      A DoF belongs to the lowest rank among the active cells that have it; ranks number their DoFs one after the other.
   H5  Dirichlet: every DoF on the domain boundary (boundary id 0, bp3.cc:147-151); it takes precedence over a
       hanging constraint (all parents of such a DoF are boundary DoFs, so both give the value 0).
       Constrained rows of the operator act as identity (portable_laplace_operator.h:171).
