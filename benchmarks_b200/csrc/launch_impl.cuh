@@ -141,6 +141,10 @@ cudaError_t launch_t(const double *hB, const double *hD, const double *hW, const
     if (hB) std::memcpy(m.B, hB, sizeof(m.B)); else std::memset(m.B, 0, sizeof(m.B));
     if (hD) std::memcpy(m.D, hD, sizeof(m.D)); else std::memset(m.D, 0, sizeof(m.D));
     if (hW) std::memcpy(m.W, hW, sizeof(m.W)); else std::memset(m.W, 0, sizeof(m.W));
+#ifdef B200FE_EVEN_ODD
+    // tuning variant: only the symmetric matrices of a real basis (not the reference's cos() test matrices)
+    if (eo::fill<NM, NQ>(m.B, m.D, m.E) > 1e-10) return cudaErrorNotSupported;
+#endif
     kern<<<grid, T, smem, s>>>(m, a);
     return cudaGetLastError();
 }

@@ -24,6 +24,10 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#ifdef B200FE_EVEN_ODD
+#include "eo_contract.h"
+#endif
+
 namespace b200fe {
 
 constexpr uint32_t kInvalidIndex = 0xFFFFFFFFu;  // numbers::invalid_unsigned_int
@@ -40,6 +44,9 @@ struct Mats {
     double B[NQ * NM];
     double D[NQ * NQ];
     double W[NQ];  // 1-D quadrature weights (affine on-the-fly geometry only)
+#ifdef B200FE_EVEN_ODD
+    eo::EoMats<NM, NQ> E;  // even / odd halves of B and D (tuning variant, eo_contract.h)
+#endif
 };
 
 struct KArgs {

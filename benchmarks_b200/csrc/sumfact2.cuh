@@ -162,6 +162,28 @@ __device__ __forceinline__ void col_mul(const MatT &mat, const double (&in)[NIN]
     }
 }
 
+// The four 1-D contractions of the kernel by name.  Default: plain register-column x constant-bank products.  With
+// -DB200FE_EVEN_ODD (tuning variant, see eo_contract.h) they use the even-odd split of the symmetric 1-D matrices.
+#ifdef B200FE_EVEN_ODD
+template <int NM, int NQ, typename MatsT>
+__device__ __forceinline__ void interp(const MatsT &m, const double (&in)[NM], double (&out)[NQ]) { eo::interp<NM, NQ>(m.E, in, out); }
+template <int NM, int NQ, typename MatsT>
+__device__ __forceinline__ void interp_t(const MatsT &m, const double (&in)[NQ], double (&out)[NM]) { eo::interp_t<NM, NQ>(m.E, in, out); }
+template <int NM, int NQ, typename MatsT>
+__device__ __forceinline__ void deriv(const MatsT &m, const double (&in)[NQ], double (&out)[NQ]) { eo::deriv<NM, NQ>(m.E, in, out); }
+template <int NM, int NQ, typename MatsT>
+__device__ __forceinline__ void deriv_t(const MatsT &m, const double (&in)[NQ], double (&out)[NQ]) { eo::deriv_t<NM, NQ>(m.E, in, out); }
+#else
+template <int NM, int NQ, typename MatsT>
+__device__ __forceinline__ void interp(const MatsT &m, const double (&in)[NM], double (&out)[NQ]) { col_mul<NQ, NM, NM, 1>(m.B, in, out); }
+template <int NM, int NQ, typename MatsT>
+__device__ __forceinline__ void interp_t(const MatsT &m, const double (&in)[NQ], double (&out)[NM]) { col_mul<NM, NQ, 1, NM>(m.B, in, out); }
+template <int NM, int NQ, typename MatsT>
+__device__ __forceinline__ void deriv(const MatsT &m, const double (&in)[NQ], double (&out)[NQ]) { col_mul<NQ, NQ, NQ, 1>(m.D, in, out); }
+template <int NM, int NQ, typename MatsT>
+__device__ __forceinline__ void deriv_t(const MatsT &m, const double (&in)[NQ], double (&out)[NQ]) { col_mul<NQ, NQ, 1, NQ>(m.D, in, out); }
+#endif
+
 }  // namespace v2
 
 // ---------------------------------------------------------------------------------------------
@@ -317,7 +339,7 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
                     double u[NM], o[NQ];
 #pragma unroll
                     for (int k = 0; k < NM; ++k) u[k] = cur_val[k];
-                    v2::col_mul<NQ, NM, NM, 1>(m.B, u, o);
+                    v2::interp<NM, NQ>(m, u, o);
 #pragma unroll
                     for (int r = 0; r < NQ; ++r) R1[(t2 / NM) * PA + (t2 % NM) * RA + r] = o[r];
                 }
@@ -332,7 +354,7 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
                     double u[NM], o[NQ];
 #pragma unroll
                     for (int k = 0; k < NM; ++k) u[k] = R0[t2 * RU + k];
-                    v2::col_mul<NQ, NM, NM, 1>(m.B, u, o);
+                    v2::interp<NM, NQ>(m, u, o);
 #pragma unroll
                     for (int r = 0; r < NQ; ++r) R1[(t2 / NM) * PA + (t2 % NM) * RA + r] = o[r];
                 }
@@ -343,7 +365,7 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
                 double u[NM], o[NQ];
 #pragma unroll
                 for (int j = 0; j < NM; ++j) u[j] = R1[i * PA + j * RA + r2];
-                v2::col_mul<NQ, NM, NM, 1>(m.B, u, o);
+                v2::interp<NM, NQ>(m, u, o);
 #pragma unroll
                 for (int q = 0; q < NQ; ++q) R2[i * PB + q * NQ + r2] = o[q];
             }
@@ -352,7 +374,7 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
                 double u[NM];
 #pragma unroll
                 for (int i = 0; i < NM; ++i) u[i] = R2[i * PB + t2];
-                v2::col_mul<NQ, NM, NM, 1>(m.B, u, v);
+                v2::interp<NM, NQ>(m, u, v);
             }
         }
 
@@ -360,7 +382,7 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
         double w[NQ];
         if constexpr (LAP) {
             double gr[NQ];  // d/dr (along p) from the register column; later the r-flux
-            v2::col_mul<NQ, NQ, NQ, 1>(m.D, v, gr);
+            v2::deriv<NM, NQ>(m, v, gr);
 #pragma unroll
             for (int p = 0; p < NQ; ++p) {
                 RQ[p * PSQ + t2] = v[p];
@@ -371,7 +393,7 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
                 double c[NQ], o[NQ];
 #pragma unroll
                 for (int q = 0; q < NQ; ++q) c[q] = RQ[ta * PSQ + q * NQ + tb];
-                v2::col_mul<NQ, NQ, NQ, 1>(m.D, c, o);
+                v2::deriv<NM, NQ>(m, c, o);
 #pragma unroll
                 for (int q = 0; q < NQ; ++q) RQ[ta * PSQ + q * NQ + tb] = o[q];
             }
@@ -379,7 +401,7 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
                 double c[NQ], o[NQ];
 #pragma unroll
                 for (int r = 0; r < NQ; ++r) c[r] = RR[ta * PSR + tb * RSR + r];
-                v2::col_mul<NQ, NQ, NQ, 1>(m.D, c, o);
+                v2::deriv<NM, NQ>(m, c, o);
 #pragma unroll
                 for (int r = 0; r < NQ; ++r) RR[ta * PSR + tb * RSR + r] = o[r];
             }
@@ -431,12 +453,12 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
                 }
             }
             if constexpr (LVEC && PREFETCH) load_val(nb, nxt_idx, nxt_val);  // next batch's gathers (indices arrived long ago)
-            v2::col_mul<NQ, NQ, 1, NQ>(m.D, gr, w);  // w[p'] = sum_p D[p][p'] f_r[p]
+            v2::deriv_t<NM, NQ>(m, gr, w);  // w[p'] = sum_p D[p][p'] f_r[p]
             {   // layout Q, transposed derivative along q, in place
                 double c[NQ], o[NQ];
 #pragma unroll
                 for (int q = 0; q < NQ; ++q) c[q] = RQ[ta * PSQ + q * NQ + tb];
-                v2::col_mul<NQ, NQ, 1, NQ>(m.D, c, o);
+                v2::deriv_t<NM, NQ>(m, c, o);
 #pragma unroll
                 for (int q = 0; q < NQ; ++q) RQ[ta * PSQ + q * NQ + tb] = o[q];
             }
@@ -444,7 +466,7 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
                 double c[NQ], o[NQ];
 #pragma unroll
                 for (int r = 0; r < NQ; ++r) c[r] = RR[ta * PSR + tb * RSR + r];
-                v2::col_mul<NQ, NQ, 1, NQ>(m.D, c, o);
+                v2::deriv_t<NM, NQ>(m, c, o);
 #pragma unroll
                 for (int r = 0; r < NQ; ++r) RR[ta * PSR + tb * RSR + r] = o[r];
             }
@@ -481,7 +503,7 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
         } else {
             {   // p -> i in registers; X[i][q][r] -> R2 (dense)
                 double x[NM];
-                v2::col_mul<NM, NQ, 1, NM>(m.B, w, x);
+                v2::interp_t<NM, NQ>(m, w, x);
 #pragma unroll
                 for (int i = 0; i < NM; ++i) R2[i * PB + t2] = x[i];
             }
@@ -491,7 +513,7 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
                 double x[NQ], o[NM];
 #pragma unroll
                 for (int q = 0; q < NQ; ++q) x[q] = R2[i * PB + q * NQ + r2];
-                v2::col_mul<NM, NQ, 1, NM>(m.B, x, o);
+                v2::interp_t<NM, NQ>(m, x, o);
 #pragma unroll
                 for (int j = 0; j < NM; ++j) R0[i * PA + j * RA + r2] = o[j];
             }
@@ -500,7 +522,7 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
                 double x[NQ], z[NM];
 #pragma unroll
                 for (int r = 0; r < NQ; ++r) x[r] = R0[(t2 / NM) * PA + (t2 % NM) * RA + r];
-                v2::col_mul<NM, NQ, 1, NM>(m.B, x, z);
+                v2::interp_t<NM, NQ>(m, x, z);
                 if constexpr (ROW_IO) {  // scatter the row straight from registers
 #pragma unroll
                     for (int k = 0; k < NM; ++k)
