@@ -34,6 +34,10 @@ namespace v2 {
 
 constexpr __host__ __device__ int pad_plane_q(int nq)
 {
+#ifdef B200FE_V2_NOPAD_MAXNQ
+    // tuning variant: tiny planes (p = 1, 2) trade the conflict-free padding (9 -> 19 doubles at nq = 3) for occupancy
+    if (nq <= B200FE_V2_NOPAD_MAXNQ) return nq * nq;
+#endif
     // smallest PS >= nq^2 with PS == nq (mod 16)
     int ps = nq * nq;
     while ((ps - nq) % 16 != 0) ++ps;
