@@ -1,7 +1,7 @@
 #!/bin/bash
 # A/B of the tuning variants (built beforehand on the CPU box with tools/build_variants.sh): parity tests of the operator
 # paths against the oracle with each variant library, then the operator-apply sweep.  usage: bash tools/gpu_variants.sh <tag> [variants]
-tag=${1:-v}; variants=${2:-"eo nopad3"}
+tag=${1:-v}; variants=${2:-"eo nopad3 eo_r112 eo_r136"}
 mkdir -p gpurun_out
 python tools/op_sweep.py --json gpurun_out/${tag}_sweep_default.json | tee gpurun_out/${tag}_sweep_default.txt
 for v in $variants; do
