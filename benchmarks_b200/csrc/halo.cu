@@ -9,6 +9,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 
@@ -83,6 +84,27 @@ __global__ void unpack_add_kernel(uint32_t n, const uint32_t *__restrict__ idx, 
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) atomicAdd(v + idx[i], buf[i]);
 }
 
+// component-blocked versions: buf[c][i], v + c*stride
+__global__ void pack_components_kernel(uint32_t n, int ncomp, size_t stride, const uint32_t *__restrict__ idx, const double *__restrict__ v,
+                                       double *__restrict__ buf)
+{
+    const size_t total = (size_t)n * ncomp;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t c = i / n;
+        buf[i] = v[c * stride + idx[i - c * n]];
+    }
+}
+
+__global__ void unpack_add_components_kernel(uint32_t n, int ncomp, size_t stride, const uint32_t *__restrict__ idx,
+                                             const double *__restrict__ buf, double *__restrict__ v)
+{
+    const size_t total = (size_t)n * ncomp;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t c = i / n;
+        atomicAdd(v + c * stride + idx[i - c * n], buf[i]);
+    }
+}
+
 inline unsigned blocks_for(uint32_t n) { return n == 0 ? 1u : std::min<unsigned>((n + 255) / 256, 148u * 8u); }
 
 int exchange_update(Halo &h, double *v, cudaStream_t s)
@@ -129,6 +151,7 @@ Halo::~Halo()
     if (comm && owns_comm) nccl().CommDestroy((ncclComm_t)comm);
     cudaFree(d_send_idx);
     cudaFree(d_pack);
+    cudaFree(d_pack_multi);
     if (comm_stream) cudaStreamDestroy(comm_stream);
     if (ev_ready) cudaEventDestroy(ev_ready);
     if (ev_done) cudaEventDestroy(ev_done);
@@ -155,6 +178,76 @@ int halo_compress_add(Halo &h, double *v, cudaStream_t s)
     if (h.n_send && !h.d_send_idx) return fail(B200FE_ERR_INVALID_ARG, "halo was created in raw mode (no send indices)");
     if (int rc = exchange_compress(h, v, s)) return rc;
     return unpack_and_zero(h, v, s);
+}
+
+namespace {
+bool halo_batching()
+{
+    static const bool on = [] { const char *e = std::getenv("B200FE_HALO_BATCH"); return !e || std::atoi(e) != 0; }();
+    return on;
+}
+int ensure_pack_multi(Halo &h, int ncomp)
+{
+    if (ncomp <= h.pack_multi_comps) return B200FE_OK;
+    cudaFree(h.d_pack_multi);
+    h.d_pack_multi = nullptr;
+    h.pack_multi_comps = 0;
+    B200FE_CUDA_TRY(cudaMalloc(&h.d_pack_multi, std::max<size_t>((size_t)h.n_send * ncomp, 1) * sizeof(double)));
+    h.pack_multi_comps = ncomp;
+    return B200FE_OK;
+}
+}  // namespace
+
+int halo_update_ghosts_components(Halo &h, double *v, int ncomp, size_t stride, cudaStream_t s)
+{
+    if (h.n_ranks == 1) return B200FE_OK;
+    if (ncomp == 1 || !halo_batching() || (h.n_send && !h.d_send_idx)) {
+        for (int c = 0; c < ncomp; ++c)
+            if (int rc = halo_update_ghosts(h, v + c * stride, s)) return rc;
+        return B200FE_OK;
+    }
+    NvtxRange range("update_ghost_values");
+    if (int rc = ensure_pack_multi(h, ncomp)) return rc;
+    Nccl &n = nccl();
+    if (h.n_send) {
+        pack_components_kernel<<<blocks_for(h.n_send * (uint32_t)ncomp), 256, 0, s>>>(h.n_send, ncomp, stride, h.d_send_idx, v, h.d_pack_multi);
+        B200FE_CUDA_TRY(cudaGetLastError());
+    }
+    B200FE_NCCL_TRY(n.GroupStart());
+    for (int c = 0; c < ncomp; ++c)
+        for (size_t k = 0; k < h.peers.size(); ++k) {
+            if (h.recv_cnt[k]) B200FE_NCCL_TRY(n.Recv(v + c * stride + h.n_owned + h.recv_off[k], h.recv_cnt[k], ncclDouble, h.peers[k], (ncclComm_t)h.comm, s));
+            if (h.send_cnt[k]) B200FE_NCCL_TRY(n.Send(h.d_pack_multi + (size_t)c * h.n_send + h.send_off[k], h.send_cnt[k], ncclDouble, h.peers[k], (ncclComm_t)h.comm, s));
+        }
+    B200FE_NCCL_TRY(n.GroupEnd());
+    return B200FE_OK;
+}
+
+int halo_compress_add_components(Halo &h, double *v, int ncomp, size_t stride, cudaStream_t s)
+{
+    if (h.n_ranks == 1) return B200FE_OK;
+    if (ncomp == 1 || !halo_batching() || (h.n_send && !h.d_send_idx)) {
+        for (int c = 0; c < ncomp; ++c)
+            if (int rc = halo_compress_add(h, v + c * stride, s)) return rc;
+        return B200FE_OK;
+    }
+    NvtxRange range("compress_add");
+    if (int rc = ensure_pack_multi(h, ncomp)) return rc;
+    Nccl &n = nccl();
+    B200FE_NCCL_TRY(n.GroupStart());
+    for (int c = 0; c < ncomp; ++c)
+        for (size_t k = 0; k < h.peers.size(); ++k) {
+            if (h.send_cnt[k]) B200FE_NCCL_TRY(n.Recv(h.d_pack_multi + (size_t)c * h.n_send + h.send_off[k], h.send_cnt[k], ncclDouble, h.peers[k], (ncclComm_t)h.comm, s));
+            if (h.recv_cnt[k]) B200FE_NCCL_TRY(n.Send(v + c * stride + h.n_owned + h.recv_off[k], h.recv_cnt[k], ncclDouble, h.peers[k], (ncclComm_t)h.comm, s));
+        }
+    B200FE_NCCL_TRY(n.GroupEnd());
+    if (h.n_send) {
+        unpack_add_components_kernel<<<blocks_for(h.n_send * (uint32_t)ncomp), 256, 0, s>>>(h.n_send, ncomp, stride, h.d_send_idx, h.d_pack_multi, v);
+        B200FE_CUDA_TRY(cudaGetLastError());
+    }
+    for (int c = 0; c < ncomp; ++c)
+        if (int rc = halo_zero_ghosts(h, v + c * stride, s)) return rc;
+    return B200FE_OK;
 }
 
 int halo_update_ghosts_start(Halo &h, double *v, cudaStream_t s)

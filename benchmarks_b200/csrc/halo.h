@@ -23,6 +23,8 @@ struct Halo {
     uint32_t n_send = 0;
     uint32_t *d_send_idx = nullptr;  // owned local indices to pack, grouped by peer
     double *d_pack = nullptr;        // [n_send] packed owner values (update) / incoming contributions (compress)
+    double *d_pack_multi = nullptr;  // [components][n_send], allocated on first use by the *_components calls
+    int pack_multi_comps = 0;
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
     Halo() = default;
@@ -35,6 +37,11 @@ struct Halo {
 int halo_update_ghosts(Halo &h, double *d_v, cudaStream_t s);
 // ghost -> owner additive reduction of v, ghosts zeroed afterwards
 int halo_compress_add(Halo &h, double *d_v, cudaStream_t s);
+// the same for `ncomp` component-blocked vectors (`stride` apart) in ONE pack kernel and ONE NCCL group per direction
+// (vector-valued problems: three exchanges per apply would triple the launch / group latency, which is what a
+// strong-scaled halo costs); B200FE_HALO_BATCH=0 falls back to one exchange per component
+int halo_update_ghosts_components(Halo &h, double *d_v, int ncomp, size_t stride, cudaStream_t s);
+int halo_compress_add_components(Halo &h, double *d_v, int ncomp, size_t stride, cudaStream_t s);
 // split-phase versions for the 3-phase overlap schedule: work is issued on h.comm_stream after
 // everything already queued on s; *_finish makes s wait for it.
 int halo_update_ghosts_start(Halo &h, double *d_v, cudaStream_t s);

@@ -560,19 +560,18 @@ int op_vmult(Operator &op, double *d_dst, const double *d_src, double *d_dot, bo
     // vector-valued: the scalar operator on every component; constraint rows and identity rows are applied to all
     // components in one launch each (their index lists are read once)
     if (h && ghost_on)
-        for (int c = 0; c < ncomp; ++c)
-            if (int rc = halo_update_ghosts(*h, src_mut + c * stride, s)) return rc;
+        if (int rc = halo_update_ghosts_components(*h, src_mut, ncomp, stride, s)) return rc;
     if (compute_on) {
         if (int rc = op_distribute(op, src_mut, true, s, ncomp)) return rc;
         for (int c = 0; c < ncomp; ++c)
             if (int rc = op_apply_cells(op, d_dst + c * stride, d_src + c * stride, 0, op.n_cells, d_dot, s)) return rc;
         if (int rc = op_condense(op, d_dst, src_mut, s, ncomp)) return rc;
     }
-    if (h && ghost_on)
-        for (int c = 0; c < ncomp; ++c) {
-            if (int rc = halo_compress_add(*h, d_dst + c * stride, s)) return rc;
+    if (h && ghost_on) {
+        if (int rc = halo_compress_add_components(*h, d_dst, ncomp, stride, s)) return rc;
+        for (int c = 0; c < ncomp; ++c)
             if (int rc = halo_zero_ghosts(*h, src_mut + c * stride, s)) return rc;
-        }
+    }
     if (ghost_on)  // reference: copy_constrained_values sits inside the ghost_exchange_on branch (:229-234)
         if (int rc = op_copy_constrained(op, d_dst, d_src, d_dot, s, ncomp)) return rc;
     return B200FE_OK;
