@@ -389,7 +389,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_cg_arm(p, CPU_SAMPLE_LOG2, args.cpu_its, repeats=1)
         cpu = {"value": 1e-9 * r["n_dofs"] * r["its"] / r["times"][0], "unit": "GDoF/s", "cores": r["cores"], "kind": "port",
-               "sample": f"BP5 p={p} CG, {2**CPU_SAMPLE_LOG2}^3 cells ({r['n_dofs']} DoFs), {r['its']} iterations, oracle/fe_oracle.c (C + OpenMP)"}
+               "sample": f"BP5 p={p} CG, {2**CPU_SAMPLE_LOG2}^3 cells ({r['n_dofs']} DoFs), {r['its']} iterations, oracle/fe_oracle.c (C + OpenMP, 8 cells side by side)"}
 
     if rank == 0:
         value = 1e-9 * n_dofs * its * args.steps / t_dev
