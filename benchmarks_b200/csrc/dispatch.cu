@@ -31,12 +31,10 @@ cudaError_t by_degree(int nq, bool coll, int qop, bool lvec, const double *hB, c
         if (coll && nq == NM && qop == QOP_LAPLACE) return launch_t<NM, NM, true, QOP_LAPLACE, true>(hB, hD, hW, a, s, info, dry);
         if (!coll && nq == NM + 1 && qop == QOP_MASS) return launch_t<NM, NM + 1, false, QOP_MASS, true>(hB, hD, hW, a, s, info, dry);
         if (!coll && nq == NM && qop == QOP_HELMHOLTZ) return launch_t<NM, NM, false, QOP_HELMHOLTZ, true>(hB, hD, hW, a, s, info, dry);
-#ifndef B200FE_KERNEL_V1
         constexpr int LA = QOP_LAPLACE | QOP_AFFINE;
         if (!coll && nq == NM + 1 && qop == LA) return launch_t<NM, NM + 1, false, LA, true>(hB, hD, hW, a, s, info, dry);
         if (!coll && nq == NM && qop == LA) return launch_t<NM, NM, false, LA, true>(hB, hD, hW, a, s, info, dry);
         if (coll && nq == NM && qop == LA) return launch_t<NM, NM, true, LA, true>(hB, hD, hW, a, s, info, dry);
-#endif
     }
     return cudaErrorInvalidValue;
 }

@@ -22,10 +22,8 @@ INST(NM, NM, false, QOP_LAPLACE, true)       // "bp35" (QGauss(p+1))
 INST(NM, NM, true, QOP_LAPLACE, true)        // BP5  (GLL collocated)
 INST(NM, NM + 1, false, QOP_MASS, true)      // BP1  (QGauss(p+2))
 INST(NM, NM, false, QOP_HELMHOLTZ, true)     // bp5_kokkos Helmholtz (QGauss(p+1))
-#ifndef B200FE_KERNEL_V1
 // L-vector Laplace operators with geometry evaluated on the fly (affine cells)
 INST(NM, NM + 1, false, QOP_LAPLACE | QOP_AFFINE, true)
 INST(NM, NM, false, QOP_LAPLACE | QOP_AFFINE, true)
 INST(NM, NM, true, QOP_LAPLACE | QOP_AFFINE, true)
-#endif
 }  // namespace b200fe

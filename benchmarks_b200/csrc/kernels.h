@@ -9,6 +9,7 @@ namespace b200fe {
 
 struct LaunchInfo {
     int elems_per_block, num_blocks, threads_per_block, smem_bytes, blocks_per_sm, regs_per_thread;
+    int even_odd;  // 1: the even-odd kernel ran (symmetric 1-D matrices), 0: plain contractions
 };
 
 // Defined (explicitly instantiated) in inst.cu, one translation unit per degree.

@@ -8,34 +8,6 @@
 
 namespace b200fe {
 
-// Launch-shape heuristics (round-1 ncu sweep, profiles/r01_bk_variants.md): small planes want
-// ~128-thread CTAs, large planes want two CTAs per SM (register cap 128).  -D overrides are
-// tuning knobs for tools/gpu_run*.sh only.
-constexpr int tpb_for(int nq)
-{
-#ifdef B200FE_TPB
-    return B200FE_TPB;
-#else
-    return nq <= 6 ? 128 : 256;
-#endif
-}
-constexpr int minb_for(int nq)
-{
-#ifdef B200FE_MINB
-    return B200FE_MINB;
-#else
-    return nq >= 6 ? 2 : 1;
-#endif
-}
-
-// elements per CTA: fill ~tpb_for(nq) threads with whole quadrature planes
-constexpr int epb_for(int nq)
-{
-    const int n2 = nq * nq;
-    int e = tpb_for(nq) / n2;
-    return e < 1 ? 1 : e;
-}
-
 // v2 kernel: target threads per CTA.  r01 sweeps (profiles/r01_v2_variants.txt): small planes want
 // several elements per CTA (~160 threads), nq >= 7 wants one element per CTA.
 #ifdef B200FE_V2_TPB
@@ -86,25 +58,27 @@ struct V2Cfg {
 #endif
 };
 
-template <int NM, int NQ, bool COLL, int QOP, bool LVEC>
-cudaError_t launch_t(const double *hB, const double *hD, const double *hW, const KArgs &a, cudaStream_t s,
-                     LaunchInfo *info, bool dry_run)
+// Even-odd kernels: built where the B200 sweeps show a gain (profiles/r02a_sweep_{default,eo}.txt): every interpolated
+// operator, and the collocated ones from nq = 9 on (below that the collocated kernels are at 0.87-0.93 of the HBM roofline
+// either way and the plain contraction is as fast or faster: BP5 p = 7 0.92 vs 0.87).
+constexpr bool eo_built(int nq, bool coll) { return coll ? nq >= 9 : true; }
+
+inline bool eo_enabled()
 {
-#ifdef B200FE_KERNEL_V1
-    constexpr int EPB = epb_for(NQ);
-    constexpr int T = EPB * NQ * NQ;
-    using L = Layout<NM, NQ, COLL>;
-    auto kern = sumfact_kernel<NM, NQ, COLL, QOP, LVEC, EPB, minb_for(NQ)>;
-    const size_t smem = L::smem_bytes(EPB);
-#else
+    static const bool on = [] { const char *e = std::getenv("B200FE_EVEN_ODD"); return !e || std::atoi(e) != 0; }();
+    return on;
+}
+
+template <int NM, int NQ, bool COLL, int QOP, bool LVEC, bool EO>
+cudaError_t launch_variant(const Mats<NM, NQ, EO> &m, const KArgs &a, cudaStream_t s, LaunchInfo *info, bool dry_run)
+{
     using C = V2Cfg<NM, NQ, COLL, QOP>;
     constexpr int EPB = C::EPB;
     constexpr int T = C::T;
-    auto kern = sumfact2_kernel<NM, NQ, COLL, QOP, LVEC, EPB, C::MINB>;
+    auto kern = sumfact2_kernel<NM, NQ, COLL, QOP, LVEC, EPB, C::MINB, EO>;
     const size_t smem = C::SMEM;
     // TMA bulk copies need a 16-byte aligned source (the batch block offset is a multiple of 48 nq^3 bytes)
     if ((QOP & QOP_LAPLACE) && !(QOP & QOP_AFFINE) && !dry_run && (reinterpret_cast<uintptr_t>(a.G) & 15u) != 0) return cudaErrorMisalignedAddress;
-#endif
 
     struct Cfg {
         bool ready = false;
@@ -134,19 +108,35 @@ cudaError_t launch_t(const double *hB, const double *hD, const double *hW, const
     const uint32_t n_batches = (a.n_elems + EPB - 1) / EPB;
     long long resident = (long long)c.sms * c.blocks_per_sm * grid_multiplier();
     const int grid = (int)(n_batches < (uint32_t)resident ? n_batches : resident);
-    if (info) *info = LaunchInfo{EPB, grid, T, (int)smem, c.blocks_per_sm, c.regs};
+    if (info) *info = LaunchInfo{EPB, grid, T, (int)smem, c.blocks_per_sm, c.regs, EO ? 1 : 0};
     if (dry_run || a.n_elems == 0) return cudaSuccess;
+    kern<<<grid, T, smem, s>>>(m, a);
+    return cudaGetLastError();
+}
 
-    Mats<NM, NQ> m;
+template <int NM, int NQ, bool COLL, int QOP, bool LVEC>
+cudaError_t launch_t(const double *hB, const double *hD, const double *hW, const KArgs &a, cudaStream_t s,
+                     LaunchInfo *info, bool dry_run)
+{
+    if constexpr (eo_built(NQ, COLL)) {
+        if (eo_enabled()) {
+            // the symmetric 1-D matrices of a real basis (not the reference drivers' cos() test matrices): even-odd kernel
+            double Bsym[NQ * NM], Dsym[NQ * NQ];
+            if (hB) std::memcpy(Bsym, hB, sizeof(Bsym));
+            else for (int q = 0; q < NQ; ++q) for (int i = 0; i < NM; ++i) Bsym[q * NM + i] = (COLL && q == i) ? 1.0 : 0.0;
+            if (hD) std::memcpy(Dsym, hD, sizeof(Dsym)); else std::memset(Dsym, 0, sizeof(Dsym));
+            Mats<NM, NQ, true> me;
+            if (eo::fill<NM, NQ>(Bsym, Dsym, me.E) <= 1e-10) {
+                if (hW) std::memcpy(me.W, hW, sizeof(me.W)); else std::memset(me.W, 0, sizeof(me.W));
+                return launch_variant<NM, NQ, COLL, QOP, LVEC, true>(me, a, s, info, dry_run);
+            }
+        }
+    }
+    Mats<NM, NQ, false> m;
     if (hB) std::memcpy(m.B, hB, sizeof(m.B)); else std::memset(m.B, 0, sizeof(m.B));
     if (hD) std::memcpy(m.D, hD, sizeof(m.D)); else std::memset(m.D, 0, sizeof(m.D));
     if (hW) std::memcpy(m.W, hW, sizeof(m.W)); else std::memset(m.W, 0, sizeof(m.W));
-#ifdef B200FE_EVEN_ODD
-    // tuning variant: only the symmetric matrices of a real basis (not the reference's cos() test matrices)
-    if (eo::fill<NM, NQ>(m.B, m.D, m.E) > 1e-10) return cudaErrorNotSupported;
-#endif
-    kern<<<grid, T, smem, s>>>(m, a);
-    return cudaGetLastError();
+    return launch_variant<NM, NQ, COLL, QOP, LVEC, false>(m, a, s, info, dry_run);
 }
 
 }  // namespace b200fe

@@ -978,13 +978,24 @@ int b200fe_op_launch_info(b200fe_op *o, int *elems_per_block, int *num_blocks, i
     Operator &op = *reinterpret_cast<Operator *>(o);
     KArgs a{op.n_cells, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     LaunchInfo li{};
-    B200FE_CUDA_TRY(launch_sumfact(op.nm, op.nq, op.collocated, op.qop | (op.d_cellG ? QOP_AFFINE : 0), true, nullptr, nullptr, a, nullptr, &li, true));
+    B200FE_CUDA_TRY(launch_sumfact(op.nm, op.nq, op.collocated, op.qop | (op.d_cellG ? QOP_AFFINE : 0), true, op.B.data(), op.D.data(), a, nullptr, &li, true));
     if (elems_per_block) *elems_per_block = li.elems_per_block;
     if (num_blocks) *num_blocks = li.num_blocks;
     if (threads_per_block) *threads_per_block = li.threads_per_block;
     if (smem_bytes) *smem_bytes = li.smem_bytes;
     if (blocks_per_sm) *blocks_per_sm = li.blocks_per_sm;
     if (regs_per_thread) *regs_per_thread = li.regs_per_thread;
+    return B200FE_OK;
+}
+
+int b200fe_op_kernel_variant(b200fe_op *o, int *even_odd)
+{
+    B200FE_REQUIRE(o && even_odd, "b200fe_op_kernel_variant: null pointer");
+    Operator &op = *reinterpret_cast<Operator *>(o);
+    KArgs a{op.n_cells, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    LaunchInfo li{};
+    B200FE_CUDA_TRY(launch_sumfact(op.nm, op.nq, op.collocated, op.qop | (op.d_cellG ? QOP_AFFINE : 0), true, op.B.data(), op.D.data(), a, nullptr, &li, true));
+    *even_odd = li.even_odd;
     return B200FE_OK;
 }
 

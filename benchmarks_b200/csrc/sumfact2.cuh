@@ -1,7 +1,7 @@
-// sumfact2.cuh -- second-generation cell kernel for sm_100a (FP64): TMA-staged geometric factors +
-// register-column contractions in all three directions.
+// sumfact2.cuh -- the cell kernel for sm_100a (FP64): TMA-staged geometric factors + register-column contractions in
+// all three directions.
 //
-// Why (ncu, profiles/r01a_bp5_p6_kernel_summary.txt): the first kernel (sumfact.cuh) was bound by
+// Why (ncu, profiles/r01a_bp5_p6_kernel_summary.txt): the first-generation kernel (removed in round 2) was bound by
 // exposed HBM latency (stall long_scoreboard 10.6 per issue at 25 % occupancy) and by shared-memory
 // wavefronts (881 per element at nq = 7, equal to the whole HBM-roofline cycle budget).  Changes:
 //
@@ -21,7 +21,7 @@
 //  * results (flux, transposed derivative) are written back in place, so two arrays per element
 //    suffice (three with interpolation).
 //
-// Same template signature, arguments and numerics contract as sumfact.cuh (<= 1e-12 vs the oracle).
+// Numerics contract: <= 1e-12 relative max-norm against the oracle (tests/test_bk_gpu.py, tests/test_operator_gpu.py).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -166,34 +166,40 @@ __device__ __forceinline__ void col_mul(const MatT &mat, const double (&in)[NIN]
     }
 }
 
-// The four 1-D contractions of the kernel by name.  Default: plain register-column x constant-bank products.  With
-// -DB200FE_EVEN_ODD (tuning variant, see eo_contract.h) they use the even-odd split of the symmetric 1-D matrices.
-#ifdef B200FE_EVEN_ODD
+// The four 1-D contractions of the kernel by name: plain register-column x constant-bank products, or (MatsT::kEvenOdd)
+// the even-odd split of the symmetric 1-D matrices of a real basis (eo_contract.h: 41-46 % fewer DFMAs; measured on B200,
+// profiles/r02a_*: BP3 p = 7 / 8 from 0.41 / 0.34 to 0.73 / 0.61 of the HBM roofline, spills gone).
 template <int NM, int NQ, typename MatsT>
-__device__ __forceinline__ void interp(const MatsT &m, const double (&in)[NM], double (&out)[NQ]) { eo::interp<NM, NQ>(m.E, in, out); }
+__device__ __forceinline__ void interp(const MatsT &m, const double (&in)[NM], double (&out)[NQ])
+{
+    if constexpr (MatsT::kEvenOdd) eo::interp<NM, NQ>(m.E, in, out);
+    else col_mul<NQ, NM, NM, 1>(m.B, in, out);
+}
 template <int NM, int NQ, typename MatsT>
-__device__ __forceinline__ void interp_t(const MatsT &m, const double (&in)[NQ], double (&out)[NM]) { eo::interp_t<NM, NQ>(m.E, in, out); }
+__device__ __forceinline__ void interp_t(const MatsT &m, const double (&in)[NQ], double (&out)[NM])
+{
+    if constexpr (MatsT::kEvenOdd) eo::interp_t<NM, NQ>(m.E, in, out);
+    else col_mul<NM, NQ, 1, NM>(m.B, in, out);
+}
 template <int NM, int NQ, typename MatsT>
-__device__ __forceinline__ void deriv(const MatsT &m, const double (&in)[NQ], double (&out)[NQ]) { eo::deriv<NM, NQ>(m.E, in, out); }
+__device__ __forceinline__ void deriv(const MatsT &m, const double (&in)[NQ], double (&out)[NQ])
+{
+    if constexpr (MatsT::kEvenOdd) eo::deriv<NM, NQ>(m.E, in, out);
+    else col_mul<NQ, NQ, NQ, 1>(m.D, in, out);
+}
 template <int NM, int NQ, typename MatsT>
-__device__ __forceinline__ void deriv_t(const MatsT &m, const double (&in)[NQ], double (&out)[NQ]) { eo::deriv_t<NM, NQ>(m.E, in, out); }
-#else
-template <int NM, int NQ, typename MatsT>
-__device__ __forceinline__ void interp(const MatsT &m, const double (&in)[NM], double (&out)[NQ]) { col_mul<NQ, NM, NM, 1>(m.B, in, out); }
-template <int NM, int NQ, typename MatsT>
-__device__ __forceinline__ void interp_t(const MatsT &m, const double (&in)[NQ], double (&out)[NM]) { col_mul<NM, NQ, 1, NM>(m.B, in, out); }
-template <int NM, int NQ, typename MatsT>
-__device__ __forceinline__ void deriv(const MatsT &m, const double (&in)[NQ], double (&out)[NQ]) { col_mul<NQ, NQ, NQ, 1>(m.D, in, out); }
-template <int NM, int NQ, typename MatsT>
-__device__ __forceinline__ void deriv_t(const MatsT &m, const double (&in)[NQ], double (&out)[NQ]) { col_mul<NQ, NQ, 1, NQ>(m.D, in, out); }
-#endif
+__device__ __forceinline__ void deriv_t(const MatsT &m, const double (&in)[NQ], double (&out)[NQ])
+{
+    if constexpr (MatsT::kEvenOdd) eo::deriv_t<NM, NQ>(m.E, in, out);
+    else col_mul<NQ, NQ, 1, NQ>(m.D, in, out);
+}
 
 }  // namespace v2
 
 // ---------------------------------------------------------------------------------------------
-template <int NM, int NQ, bool COLL, int QOP, bool LVEC, int EPB, int MINB>
+template <int NM, int NQ, bool COLL, int QOP, bool LVEC, int EPB, int MINB, bool EO>
 __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB)), MINB)
-    sumfact2_kernel(const __grid_constant__ Mats<NM, NQ> m, const KArgs a)
+    sumfact2_kernel(const __grid_constant__ Mats<NM, NQ, EO> m, const KArgs a)
 {
     using L = v2::Layout2<NM, NQ, COLL, QOP>;
     constexpr int N2 = L::N2, N3 = L::N3, M3 = L::M3, RA = L::RA, PA = L::PA, PB = L::PB;

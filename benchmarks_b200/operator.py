@@ -209,7 +209,9 @@ class LaplaceOperator:
         v = [C.c_int() for _ in range(6)]
         check(lib.b200fe_op_launch_info(self._h, *[C.byref(x) for x in v]))
         keys = ("elems_per_block", "num_blocks", "threads_per_block", "smem_bytes", "blocks_per_sm", "regs_per_thread")
-        return dict(zip(keys, [x.value for x in v]))
+        eo = C.c_int()
+        check(lib.b200fe_op_kernel_variant(self._h, C.byref(eo)))
+        return dict(zip(keys, [x.value for x in v]), even_odd=eo.value)
 
     # algorithmic bytes of one apply: G + indices per cell, 32 B per local DoF
     def algorithmic_bytes(self) -> int:

@@ -327,6 +327,12 @@ int b200fe_op_timing_read(b200fe_op *op, double *total_ms, int *launches);
 unsigned long long b200fe_launch_count(void);
 int b200fe_op_launch_info(b200fe_op *op, int *elems_per_block, int *num_blocks, int *threads_per_block,
                           int *smem_bytes, int *blocks_per_sm, int *regs_per_thread);
+/* Which contraction form the cell kernel of this operator runs: *even_odd = 1 when the operator's 1-D matrices have the
+ * point symmetry of a real basis and the even-odd kernel is built for its (degree, quadrature) -- deal.II's
+ * evaluate_evenodd, halving the multiply-adds of every 1-D sweep -- else 0 (plain contractions; always the case for the
+ * reference drivers' cos() test matrices, CEED_BK/src/BK3/templated_cuda_benchmark.cc:50-66).  B200FE_EVEN_ODD=0 in the
+ * environment forces 0. */
+int b200fe_op_kernel_variant(b200fe_op *op, int *even_odd);
 
 /* ------------------------------------------------------------------------------------------
  * 5. Conjugate gradients (dealii::SolverCG + ReductionControl as called at CEED_bp/src/bp3.cc:266-285

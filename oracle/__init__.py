@@ -46,6 +46,8 @@ class _Port:
         L.oracle_bk5.restype = C.c_double
         L.oracle_bk5.argtypes = [C.c_int, C.c_uint, _dp, _dp, C.c_int, _dp, _dp]
         L.oracle_num_threads.restype = C.c_int
+        L.oracle_set_num_threads.restype = None
+        L.oracle_set_num_threads.argtypes = [C.c_int]
         vp = C.c_void_p
         L.oracle_op_apply.restype = None
         L.oracle_op_apply.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32,
@@ -131,6 +133,10 @@ class _Port:
 
     def num_threads(self):
         return self.lib.oracle_num_threads()
+
+    def set_num_threads(self, n: int):
+        """OpenMP team size of the timed CPU arm (torchrun exports OMP_NUM_THREADS=1 to its ranks)."""
+        self.lib.oracle_set_num_threads(int(n))
 
 
 class _Ref:

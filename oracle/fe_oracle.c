@@ -52,6 +52,16 @@ int oracle_num_threads(void)
 #endif
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to every rank: the timed CPU arm sets its team size explicitly (bench.py) */
+void oracle_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n >= 1) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* out[a][m][c] = sum_n M(m,n) in[a][n][c]; M(m,n) = M[m*rs + n*cs] */
 static void contract(int na, int nin, int nout, int nc, const double *M, int rs, int cs,
                      const double *in, double *out)

@@ -279,6 +279,38 @@ def distribute_dofs(mesh: BoxMesh, p: int, nranks: int = 1, scheme: str = "p4est
                 owned_range=owned_range, subdomain=subdomain, dims=dims)
 
 
+def rank_data_single_fast(mesh: BoxMesh, p: int, dirichlet: bool = True):
+    """Vectorised equivalent of rank_data(mesh, distribute_dofs(mesh, p, 1), 0) for ONE rank (no Python loop over
+    DoFs): the first-touch number of a lattice point is the rank of its smallest key (active cell index, hierarchical
+    local index) among all lattice points.  Checked against the literal simulation in tests/test_mesh.py; used by
+    bench.py's CPU arm so that the reference arm stands on oracle/ alone."""
+    n = p + 1
+    n3 = n ** 3
+    h2l = hierarchic_to_lexicographic(p)
+    h_of_l = np.empty(n3, dtype=np.int64)
+    h_of_l[h2l] = np.arange(n3)
+    dims = tuple(c * p + 1 for c in mesh.cells)
+    l = np.arange(n3)
+    lx, ly, lz = l % n, (l // n) % n, l // (n * n)
+    cx, cy, cz = mesh.cell_xyz[:, 0], mesh.cell_xyz[:, 1], mesh.cell_xyz[:, 2]  # active order
+    X = cx[:, None] * p + lx[None, :]
+    Y = cy[:, None] * p + ly[None, :]
+    Z = cz[:, None] * p + lz[None, :]
+    lat = (X * dims[1] + Y) * dims[2] + Z                       # lattice id, [cell][lexicographic local]
+    key = np.arange(mesh.n_cells, dtype=np.int64)[:, None] * n3 + h_of_l[None, :]
+    n_lat = int(np.prod(dims))
+    first = np.full(n_lat, np.iinfo(np.int64).max, dtype=np.int64)
+    np.minimum.at(first, lat.ravel(), key.ravel())
+    glob = np.empty(n_lat, dtype=np.int64)
+    glob[np.argsort(first, kind="stable")] = np.arange(n_lat)
+    G = glob[lat]
+    on_bdry = ((X == 0) | (Y == 0) | (Z == 0) | (X == dims[0] - 1) | (Y == dims[1] - 1) | (Z == dims[2] - 1)) & dirichlet
+    idx = np.where(on_bdry, INVALID, G.astype(np.uint32)).astype(np.uint32)
+    constrained = np.unique(G[on_bdry]).astype(np.uint32)
+    return dict(rank=0, cells=np.arange(mesh.n_cells), n_owned=n_lat, n_ghost=0, owned_begin=0, ghost_global=np.zeros(0, np.int64),
+                ghost_owner=np.zeros(0, np.int64), dof_indices=idx, cell_global=G, constrained=constrained)
+
+
 def cell_dofs_global(mesh: BoxMesh, dofs, c: int):
     """Global DoF indices of active cell c in lexicographic local order (k = x fastest)."""
     p = dofs["p"]
