@@ -208,6 +208,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--overlap", type=int, default=1)
+    ap.add_argument("--transport", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="ghost exchange / reductions at N > 1: peer stores over CUDA-IPC windows, or NCCL; auto = p2p when every peer could be mapped")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -257,6 +259,8 @@ def main():
     if world > 1:
         from benchmarks_b200.dist import Halo
         halo = Halo(mesh, group=setup_group)
+        if args.transport != "auto":
+            halo.set_transport(args.transport)
     A = b.LaplaceOperator(mesh, quad="gll", halo=halo, overlap=bool(args.overlap))
     rhs = A.compute_rhs()
     x = A.initialize_dof_vector()
@@ -312,6 +316,37 @@ def main():
         solve_host()
     barrier()
     t_e2e = max_over_ranks(time.perf_counter() - t0)
+
+    # ---- N > 1: transport (P2P peer stores vs NCCL) x overlap (split cell launch vs one launch), one step each ------
+    comm_ab = None
+    if world > 1 and not args.no_sweep:
+        comm_ab = {}
+        def timed_step(op):
+            xx, rr = op.initialize_dof_vector(), op.compute_rhs()
+            sv = b.SolverCG(b.ReductionControl(its, 0.0, 0.0), check_every=1 << 30)
+            def run():
+                try:
+                    sv.solve(op, xx, rr)
+                except b.NoConvergence:
+                    pass
+            run()
+            barrier()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            run()
+            c1.record()
+            barrier()
+            return max_over_ranks(c0.elapsed_time(c1)) / its   # ms per CG iteration
+        start = halo.transport()
+        A_flat = b.LaplaceOperator(mesh, quad="gll", halo=halo, overlap=False)
+        for tr in (["p2p"] if halo.p2p_available() else []) + ["nccl"]:
+            halo.set_transport(tr)
+            comm_ab[f"{tr}_overlap_ms_per_it"] = timed_step(A)
+            comm_ab[f"{tr}_no_overlap_ms_per_it"] = timed_step(A_flat)
+        halo.set_transport(start)
+        halo.status()
+        del A_flat
+        torch.cuda.empty_cache()
 
     # ---- roofline of the dominant kernel ------------------------------------------------------
     peaks, peak_kind = measured_peaks()
@@ -509,6 +544,8 @@ def main():
             if world > 1 and p != 4:
                 from benchmarks_b200.dist import Halo
                 h4 = Halo(m4, group=setup_group)
+                if args.transport != "auto":
+                    h4.set_transport(args.transport)
             A4 = b.LaplaceOperator(m4, nq=6, quad="gauss", halo=h4, overlap=bool(args.overlap), with_jxw=True)
             rhs4 = A4.compute_rhs()
             x4 = A4.initialize_dof_vector()
@@ -564,6 +601,7 @@ def main():
                        "mesh_blocks": list(BLOCKS[world]), "n_dofs": n_dofs, "cg_iterations_per_step": its,
                        "l2_policy": "working set (G 4.3 GB + vectors) >> 126 MB L2; no flush needed",
                        "overlap_halo_with_interior_cells": bool(args.overlap) and world > 1,
+                       "transport": (halo.transport() if halo is not None else None),
                        "relative_residual_after_step": res_final, "setup_s": t_setup},
             "e2e": {"value": 1e-9 * n_dofs * its * args.steps / t_e2e, "unit": "GDoF/s",
                     "h2d_bytes_per_step": int(mesh.n_owned) * 8 * world, "d2h_bytes_per_step": int(mesh.n_owned) * 8 * world,
@@ -585,6 +623,8 @@ def main():
         if bk_sweeps:
             for k_, v_ in bk_sweeps.items():
                 out[f"degree_sweep_{k_}_evector" if not k_.endswith("_real_basis") else f"degree_sweep_{k_[:3]}_evector_real_basis"] = v_
+        if comm_ab:
+            out["comm_ab"] = comm_ab
         if ktb:
             out["kernel_to_beat"] = ktb
         if parity:

@@ -86,6 +86,9 @@ _SIGNATURES = {
     "b200fe_halo_compress_add": (_i, [_vp, _vp, _vp]),
     "b200fe_halo_zero_ghosts": (_i, [_vp, _vp, _vp]),
     "b200fe_halo_allreduce_sum": (_i, [_vp, _vp, _i, _vp]),
+    "b200fe_halo_transport": (_i, [_vp, _pi, _pi]),
+    "b200fe_halo_set_transport": (_i, [_vp, _i]),
+    "b200fe_halo_status": (_i, [_vp]),
     "b200fe_halo_exchange_raw": (_i, [_vp, _vp, _vp, _vp]),
 }
 for _name, (_res, _args) in _SIGNATURES.items():

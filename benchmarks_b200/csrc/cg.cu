@@ -18,7 +18,9 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <list>
 #include <memory>
+#include <mutex>
 
 #include "halo.h"
 #include "operator.h"
@@ -151,23 +153,31 @@ struct CgWork {
 static int ensure_work(std::unique_ptr<CgWork> &w, size_t n_local, bool need_xb)
 {
     if (!w || w->n_local != n_local) {
-        w = std::make_unique<CgWork>();
-        w->n_local = n_local;
+        w.reset();  // free the old workspace first (large problems: old + new may not fit together)
+        // built locally and cached only when complete: a failed allocation (OOM) must not leave a workspace with null
+        // vectors behind for the next call of the same size
+        auto fresh = std::make_unique<CgWork>();
+        fresh->n_local = n_local;
         const size_t bytes = sizeof(double) * std::max<size_t>(n_local, 1);
-        B200FE_CUDA_TRY(cudaMalloc(&w->r, bytes));
-        B200FE_CUDA_TRY(cudaMalloc(&w->p, bytes));
-        B200FE_CUDA_TRY(cudaMalloc(&w->v, bytes));
-        B200FE_CUDA_TRY(cudaMalloc(&w->sc, sizeof(CgScalars)));
-        B200FE_CUDA_TRY(cudaMallocHost(&w->h_sc, sizeof(CgScalars)));
+        B200FE_CUDA_TRY(cudaMalloc(&fresh->r, bytes));
+        B200FE_CUDA_TRY(cudaMalloc(&fresh->p, bytes));
+        B200FE_CUDA_TRY(cudaMalloc(&fresh->v, bytes));
+        B200FE_CUDA_TRY(cudaMalloc(&fresh->sc, sizeof(CgScalars)));
+        B200FE_CUDA_TRY(cudaMallocHost(&fresh->h_sc, sizeof(CgScalars)));
+        w = std::move(fresh);
     }
     if (need_xb && !w->xb) B200FE_CUDA_TRY(cudaMalloc(&w->xb, 2 * sizeof(double) * std::max<size_t>(n_local, 1)));
     return B200FE_OK;
 }
 
-// one workspace per operator, keyed by the operator pointer (small map; operators are few)
+// one workspace per operator, keyed by the operator pointer (small table; operators are few).  The table itself is
+// guarded; a solve on one operator from two host threads at once is not supported (the reference's operator is not
+// re-entrant either).
 static std::unique_ptr<CgWork> &work_of(Operator *op)
 {
-    static std::vector<std::pair<Operator *, std::unique_ptr<CgWork>>> table;
+    static std::mutex mu;
+    static std::list<std::pair<Operator *, std::unique_ptr<CgWork>>> table;  // list: references stay valid on growth
+    std::lock_guard<std::mutex> lock(mu);
     for (auto &e : table)
         if (e.first == op) return e.second;
     table.emplace_back(op, nullptr);
@@ -204,6 +214,8 @@ static int cg_run(Operator &op, int ncomp, CgWork &w, double *d_x, const double 
     auto poll = [&]() -> int {
         B200FE_CUDA_TRY(cudaMemcpyAsync(w.h_sc, w.sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, s));
         B200FE_CUDA_TRY(cudaStreamSynchronize(s));
+        if (op.halo && op.halo->p2p)  // a peer that never answered (bounded waits of the one-sided transport): fail, do not spin
+            if (int rc = p2p_status(*op.halo)) return rc;
         return B200FE_OK;
     };
     auto scalar_step = [&]() -> int {

@@ -28,6 +28,7 @@ struct Nccl {
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -49,11 +50,12 @@ Nccl &nccl()
         x.Send = (decltype(x.Send))sym("ncclSend");
         x.Recv = (decltype(x.Recv))sym("ncclRecv");
         x.AllReduce = (decltype(x.AllReduce))sym("ncclAllReduce");
+        x.AllGather = (decltype(x.AllGather))sym("ncclAllGather");
         x.GroupStart = (decltype(x.GroupStart))sym("ncclGroupStart");
         x.GroupEnd = (decltype(x.GroupEnd))sym("ncclGroupEnd");
         x.GetErrorString = (decltype(x.GetErrorString))sym("ncclGetErrorString");
         x.GetVersion = (decltype(x.GetVersion))sym("ncclGetVersion");
-        x.ok = x.GetUniqueId && x.CommInitRank && x.CommDestroy && x.Send && x.Recv && x.AllReduce && x.GroupStart &&
+        x.ok = x.GetUniqueId && x.CommInitRank && x.CommDestroy && x.Send && x.Recv && x.AllReduce && x.AllGather && x.GroupStart &&
                x.GroupEnd && x.GetErrorString;
         return x;
     }();
@@ -109,6 +111,10 @@ inline unsigned blocks_for(uint32_t n) { return n == 0 ? 1u : std::min<unsigned>
 
 int exchange_update(Halo &h, double *v, cudaStream_t s)
 {
+    if (h.use_p2p) {
+        if (int rc = p2p_update_send(h, v, 1, 0, nullptr, s)) return rc;
+        return p2p_update_wait(h, v, 1, 0, nullptr, s);
+    }
     Nccl &n = nccl();
     if (h.n_send) {
         pack_kernel<<<blocks_for(h.n_send), 256, 0, s>>>(h.n_send, h.d_send_idx, v, h.d_pack);
@@ -144,10 +150,31 @@ int unpack_and_zero(Halo &h, double *v, cudaStream_t s)
     return halo_zero_ghosts(h, v, s);
 }
 
+// setup-time collectives handed to p2p_setup (halo_p2p.cu does not bind NCCL itself)
+int setup_all_gather(Halo &h, const void *d_send, void *d_recv, size_t bytes)
+{
+    B200FE_NCCL_TRY(nccl().AllGather(d_send, d_recv, bytes, ncclChar, (ncclComm_t)h.comm, nullptr));
+    B200FE_CUDA_TRY(cudaStreamSynchronize(nullptr));
+    return B200FE_OK;
+}
+int setup_all_reduce_min(Halo &h, int *value)
+{
+    int *d = nullptr;
+    B200FE_CUDA_TRY(cudaMalloc(&d, sizeof(int)));
+    cudaError_t e = cudaMemcpy(d, value, sizeof(int), cudaMemcpyHostToDevice);
+    ncclResult_t r = e == cudaSuccess ? nccl().AllReduce(d, d, 1, ncclInt, ncclMin, (ncclComm_t)h.comm, nullptr) : ncclSuccess;
+    if (e == cudaSuccess && r == ncclSuccess) e = cudaMemcpy(value, d, sizeof(int), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (r != ncclSuccess) return fail_nccl(r, "ncclAllReduce(min)");
+    if (e != cudaSuccess) return fail_cuda(e, "setup_all_reduce_min");
+    return B200FE_OK;
+}
+
 }  // namespace
 
 Halo::~Halo()
 {
+    p2p_destroy(*this);
     if (comm && owns_comm) nccl().CommDestroy((ncclComm_t)comm);
     cudaFree(d_send_idx);
     cudaFree(d_pack);
@@ -176,6 +203,10 @@ int halo_compress_add(Halo &h, double *v, cudaStream_t s)
     if (h.n_ranks == 1) return B200FE_OK;
     NvtxRange range("compress_add");
     if (h.n_send && !h.d_send_idx) return fail(B200FE_ERR_INVALID_ARG, "halo was created in raw mode (no send indices)");
+    if (h.use_p2p) {
+        if (int rc = p2p_compress_send(h, v, 1, 0, s)) return rc;
+        return p2p_compress_wait(h, v, 1, 0, s);
+    }
     if (int rc = exchange_compress(h, v, s)) return rc;
     return unpack_and_zero(h, v, s);
 }
@@ -183,8 +214,11 @@ int halo_compress_add(Halo &h, double *v, cudaStream_t s)
 namespace {
 bool halo_batching()
 {
-    static const bool on = [] { const char *e = std::getenv("B200FE_HALO_BATCH"); return !e || std::atoi(e) != 0; }();
-    return on;
+    // NCCL transport only (the P2P transport always moves all components in one kernel).  On by default since the
+    // 2-GPU check of round 2 (profiles/r02b_dist_check_2gpu.log: batched == per-component, bitwise); B200FE_HALO_BATCH=0
+    // restores one exchange per component.
+    const char *e = std::getenv("B200FE_HALO_BATCH");  // read per call: tools/dist_check.py flips it to compare the two forms
+    return !e || std::atoi(e) != 0;
 }
 int ensure_pack_multi(Halo &h, int ncomp)
 {
@@ -201,6 +235,11 @@ int ensure_pack_multi(Halo &h, int ncomp)
 int halo_update_ghosts_components(Halo &h, double *v, int ncomp, size_t stride, cudaStream_t s)
 {
     if (h.n_ranks == 1) return B200FE_OK;
+    if (h.use_p2p && h.d_send_idx_ok() && ncomp <= p2p_max_components()) {
+        NvtxRange range("update_ghost_values");
+        if (int rc = p2p_update_send(h, v, ncomp, stride, nullptr, s)) return rc;
+        return p2p_update_wait(h, v, ncomp, stride, nullptr, s);
+    }
     if (ncomp == 1 || !halo_batching() || (h.n_send && !h.d_send_idx)) {
         for (int c = 0; c < ncomp; ++c)
             if (int rc = halo_update_ghosts(h, v + c * stride, s)) return rc;
@@ -226,6 +265,11 @@ int halo_update_ghosts_components(Halo &h, double *v, int ncomp, size_t stride, 
 int halo_compress_add_components(Halo &h, double *v, int ncomp, size_t stride, cudaStream_t s)
 {
     if (h.n_ranks == 1) return B200FE_OK;
+    if (h.use_p2p && h.d_send_idx_ok() && ncomp <= p2p_max_components()) {
+        NvtxRange range("compress_add");
+        if (int rc = p2p_compress_send(h, v, ncomp, stride, s)) return rc;
+        return p2p_compress_wait(h, v, ncomp, stride, s);
+    }
     if (ncomp == 1 || !halo_batching() || (h.n_send && !h.d_send_idx)) {
         for (int c = 0; c < ncomp; ++c)
             if (int rc = halo_compress_add(h, v + c * stride, s)) return rc;
@@ -253,6 +297,10 @@ int halo_compress_add_components(Halo &h, double *v, int ncomp, size_t stride, c
 int halo_update_ghosts_start(Halo &h, double *v, cudaStream_t s)
 {
     if (h.n_ranks == 1) return B200FE_OK;
+    if (h.use_p2p) {  // one-sided: post now on s, complete in *_finish on s (v is kept for the wait)
+        h.pending_v = v;
+        return p2p_update_send(h, v, 1, 0, nullptr, s);
+    }
     B200FE_CUDA_TRY(cudaEventRecord(h.ev_ready, s));
     B200FE_CUDA_TRY(cudaStreamWaitEvent(h.comm_stream, h.ev_ready, 0));
     if (int rc = exchange_update(h, v, h.comm_stream)) return rc;
@@ -263,6 +311,7 @@ int halo_update_ghosts_start(Halo &h, double *v, cudaStream_t s)
 int halo_update_ghosts_finish(Halo &h, cudaStream_t s)
 {
     if (h.n_ranks == 1) return B200FE_OK;
+    if (h.use_p2p) return p2p_update_wait(h, h.pending_v, 1, 0, nullptr, s);
     B200FE_CUDA_TRY(cudaStreamWaitEvent(s, h.ev_done, 0));
     return B200FE_OK;
 }
@@ -270,6 +319,7 @@ int halo_update_ghosts_finish(Halo &h, cudaStream_t s)
 int halo_compress_start(Halo &h, double *v, cudaStream_t s)
 {
     if (h.n_ranks == 1) return B200FE_OK;
+    if (h.use_p2p) return p2p_compress_send(h, v, 1, 0, s);
     B200FE_CUDA_TRY(cudaEventRecord(h.ev_ready, s));
     B200FE_CUDA_TRY(cudaStreamWaitEvent(h.comm_stream, h.ev_ready, 0));
     if (int rc = exchange_compress(h, v, h.comm_stream)) return rc;
@@ -280,6 +330,7 @@ int halo_compress_start(Halo &h, double *v, cudaStream_t s)
 int halo_compress_finish(Halo &h, double *v, cudaStream_t s)
 {
     if (h.n_ranks == 1) return B200FE_OK;
+    if (h.use_p2p) return p2p_compress_wait(h, v, 1, 0, s);
     B200FE_CUDA_TRY(cudaStreamWaitEvent(s, h.ev_done, 0));
     return unpack_and_zero(h, v, s);
 }
@@ -287,6 +338,7 @@ int halo_compress_finish(Halo &h, double *v, cudaStream_t s)
 int halo_allreduce_sum(Halo &h, double *d_vals, int count, cudaStream_t s)
 {
     if (h.n_ranks == 1) return B200FE_OK;
+    if (h.use_p2p && count <= 4) return p2p_allreduce(h, d_vals, count, s);
     B200FE_NCCL_TRY(nccl().AllReduce(d_vals, d_vals, count, ncclDouble, ncclSum, (ncclComm_t)h.comm, s));
     return B200FE_OK;
 }
@@ -346,6 +398,9 @@ int b200fe_halo_create(const b200fe_halo_desc *d, b200fe_halo **out)
         B200FE_CUDA_TRY(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
         B200FE_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
         B200FE_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
+        // one-sided transport over CUDA-IPC windows where every rank can map every peer (one NVSwitch domain); collective
+        const bool raw_mode = d->n_send > 0 && d->h_send_indices == nullptr;
+        if (int rc = p2p_setup(*h, raw_mode, setup_all_gather, setup_all_reduce_min)) return rc;
     }
     *out = reinterpret_cast<b200fe_halo *>(h.release());
     return B200FE_OK;
@@ -377,6 +432,10 @@ int b200fe_halo_exchange_raw(b200fe_halo *halo, const double *d_send, double *d_
     Halo &h = *reinterpret_cast<Halo *>(halo);
     if (h.n_ranks == 1) return B200FE_OK;
     cudaStream_t s = (cudaStream_t)stream;
+    if (h.use_p2p) {  // peer stores into the receivers' windows + flags, then wait + copy out (halo_p2p.cu)
+        if (int rc = p2p_update_send(h, nullptr, 1, 0, d_send, s)) return rc;
+        return p2p_update_wait(h, nullptr, 1, 0, d_recv, s);
+    }
     Nccl &n = nccl();
     // one round of p-halox: post all receives, all sends, complete together (phalox.cc:111-125)
     B200FE_NCCL_TRY(n.GroupStart());
@@ -386,6 +445,30 @@ int b200fe_halo_exchange_raw(b200fe_halo *halo, const double *d_send, double *d_
         if (h.send_cnt[k]) B200FE_NCCL_TRY(n.Send(d_send + h.send_off[k], h.send_cnt[k], ncclDouble, h.peers[k], (ncclComm_t)h.comm, s));
     B200FE_NCCL_TRY(n.GroupEnd());
     return B200FE_OK;
+}
+
+int b200fe_halo_transport(b200fe_halo *halo, int *p2p_available, int *p2p_in_use)
+{
+    B200FE_REQUIRE(halo, "b200fe_halo_transport: null pointer");
+    Halo &h = *reinterpret_cast<Halo *>(halo);
+    if (p2p_available) *p2p_available = h.p2p != nullptr;
+    if (p2p_in_use) *p2p_in_use = h.use_p2p;
+    return B200FE_OK;
+}
+
+int b200fe_halo_set_transport(b200fe_halo *halo, int use_p2p)
+{
+    B200FE_REQUIRE(halo, "b200fe_halo_set_transport: null pointer");
+    Halo &h = *reinterpret_cast<Halo *>(halo);
+    if (use_p2p && !h.p2p) return fail(B200FE_ERR_UNSUPPORTED, "b200fe_halo_set_transport: no peer windows on this halo (B200FE_HALO_P2P=0, or a peer could not be mapped)");
+    h.use_p2p = use_p2p != 0;
+    return B200FE_OK;
+}
+
+int b200fe_halo_status(b200fe_halo *halo)
+{
+    B200FE_REQUIRE(halo, "b200fe_halo_status: null pointer");
+    return p2p_status(*reinterpret_cast<Halo *>(halo));
 }
 
 int b200fe_halo_allreduce_sum(b200fe_halo *halo, double *d_vals, int count, void *stream)

@@ -12,7 +12,11 @@
 
 namespace b200fe {
 
+struct P2P;  // halo.cu: CUDA-IPC windows of the NVSwitch domain (direct peer stores + flags), optional
+
 struct Halo {
+    P2P *p2p = nullptr;    // owned; non-null once every rank has mapped every peer's window (b200fe_halo_create)
+    bool use_p2p = false;  // transport of the exchanges and of the scalar all-reduce: peer stores (true) or NCCL (false)
     void *comm = nullptr;  // ncclComm_t (owned when created from a unique id)
     bool owns_comm = false;
     int rank = 0, n_ranks = 1;
@@ -27,11 +31,29 @@ struct Halo {
     int pack_multi_comps = 0;
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
+    double *pending_v = nullptr;  // P2P split-phase update: the vector whose ghost segment *_finish fills
+    bool d_send_idx_ok() const { return n_send == 0 || d_send_idx != nullptr; }
     Halo() = default;
     Halo(const Halo &) = delete;
     Halo &operator=(const Halo &) = delete;
     ~Halo();  // halo.cu: frees the communicator (if owned), pack lists, stream and events
 };
+
+// ---- halo_p2p.cu: one-sided transport over CUDA-IPC peer memory (see the file header) --------------------------------
+using NcclAllGatherFn = int (*)(Halo &h, const void *d_send, void *d_recv, size_t bytes_per_rank);
+using NcclAllReduceMinFn = int (*)(Halo &h, int *host_value);
+// collective; on success on EVERY rank h.p2p is set and h.use_p2p = true, otherwise the halo keeps the NCCL transport
+int p2p_setup(Halo &h, bool raw_mode, NcclAllGatherFn all_gather, NcclAllReduceMinFn all_reduce_min);
+void p2p_destroy(Halo &h);
+// post (stores into the peers' windows + flags) and complete (wait for the peers' flags, move into place, acknowledge);
+// both on stream s, nothing else needed in between: "post early, wait late" is the overlap schedule
+int p2p_update_send(Halo &h, double *d_v, int ncomp, size_t stride, const double *d_raw_send, cudaStream_t s);
+int p2p_update_wait(Halo &h, double *d_v, int ncomp, size_t stride, double *d_raw_recv, cudaStream_t s);
+int p2p_compress_send(Halo &h, double *d_v, int ncomp, size_t stride, cudaStream_t s);  // also zeroes the ghost entries of v
+int p2p_compress_wait(Halo &h, double *d_v, int ncomp, size_t stride, cudaStream_t s);
+int p2p_allreduce(Halo &h, double *d_vals, int count, cudaStream_t s);
+int p2p_status(Halo &h);
+int p2p_max_components();  // synchronising health check: B200FE_ERR_COMM after a bounded wait has expired
 
 // owner -> ghost copy of v (all on stream s)
 int halo_update_ghosts(Halo &h, double *d_v, cudaStream_t s);

@@ -1,0 +1,439 @@
+// halo_p2p.cu -- one-sided ghost exchange and scalar all-reduce over CUDA-IPC peer memory (NVLink 5 / NVSwitch).
+//
+// Why: on one 8xB200 box a ghost exchange moves a few hundred KB per neighbour -- its cost is latency, not bandwidth
+// (profiles/r01b_phalox_8gpu.txt: 10-14 us per NCCL send/recv round; SCALE_r01: +0.16 ms per CG iteration at 8 GPUs from
+// 2 ncclAllReduce + 2 grouped send/recv rounds).  NVSwitch gives every GPU load/store access to every peer, so the pack
+// kernel can write straight into the receiver and raise a flag -- no proxy thread, no rendezvous, no second stream:
+//
+//   update_ghost_values  : owner's SEND kernel gathers v[import_indices] and stores them into each ghosting peer's receive
+//                          window, then (last block) releases one flag per peer; the receiver's WAIT kernel acquires the
+//                          flags, moves the window into the ghost segment of v and acknowledges.
+//   compress(add)        : the same in the other direction (ghost segments -> owner's window -> atomic add), ghosts zeroed
+//                          by the SEND kernel.
+//   CG inner products    : every rank stores its partial sums into its slot of every peer's window (all-gather), then each
+//                          rank adds the slots in rank order -- bitwise identical on all ranks, one 32-thread kernel.
+//
+// One-sided means "post early, wait late" on ONE stream: the 3-phase overlap schedule of
+// bakeoff_problems_dealii/include/portable_laplace_operator.h:669-696 becomes  send | interior cells | wait | boundary cells.
+// Replaces MPI_Isend/Irecv/Waitall of p-halox/phalox.cc:104-126 and deal.II's Partitioner exchange.
+//
+// Protocol: every (sender entry, receiver entry) pair owns one flag and one acknowledgement word, both monotonically
+// increasing epochs kept on the device (robust under replay).  A sender waits for the acknowledgement of its previous
+// message before overwriting the window; a SEND kernel therefore never depends on anything in flight, so the two-kernel
+// form cannot deadlock whatever the residency of its blocks.  All waits are bounded (kTimeoutNs): on expiry a sticky error
+// flag is raised, later waits return at once, and the host reports B200FE_ERR_COMM at its next check instead of hanging.
+#include <nccl.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "common.h"
+#include "halo.h"
+
+namespace b200fe {
+
+namespace {
+
+constexpr int kMaxEntries = 32;   // peer-table entries per rank (26 neighbours of a block + duplicates of periodic rings)
+constexpr int kMaxRanks = 32;
+constexpr int kMaxComps = 4;      // components per exchange (BP6: 3)
+constexpr unsigned long long kTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
+
+struct RedSlot {
+    double val[4];
+    unsigned long long epoch;
+    unsigned long long pad[3];
+};
+
+// head of every window; written by peers only (and zeroed once at creation)
+struct Ctrl {
+    unsigned long long upd_flag[kMaxEntries];  // [my entry k]  update data of epoch e from peers[k] has landed
+    unsigned long long upd_ack[kMaxEntries];   // [my entry j]  peers[j] has consumed my update data of epoch e
+    unsigned long long cmp_flag[kMaxEntries];  // [my entry j]  compress data of epoch e from peers[j] has landed
+    unsigned long long cmp_ack[kMaxEntries];   // [my entry k]  peers[k] has consumed my compress data of epoch e
+    RedSlot red[2][kMaxRanks];                 // [epoch parity][source rank]
+};
+
+struct EntryDev {
+    // this entry as a sender of update data / receiver of compress data (send_cnt > 0)
+    double *peer_recv;                  // peer's receive window at the matching entry's offset
+    unsigned long long *peer_upd_flag;  // peer's upd_flag[k_peer]
+    unsigned long long *peer_cmp_ack;   // peer's cmp_ack[k_peer]
+    uint32_t peer_n_ghost;              // component stride of the peer's receive window
+    // this entry as a receiver of update data / sender of compress data (recv_cnt > 0)
+    double *peer_back;                  // peer's compress window at the matching entry's offset
+    unsigned long long *peer_cmp_flag;  // peer's cmp_flag[j_peer]
+    unsigned long long *peer_upd_ack;   // peer's upd_ack[j_peer]
+    uint32_t peer_n_send;
+    uint32_t send_off, send_cnt, recv_off, recv_cnt;
+};
+
+struct DevState {  // local device memory, never touched by peers
+    EntryDev e[kMaxEntries];
+    RedSlot *peer_red[kMaxRanks];  // &window(r).ctrl.red[0][my_rank]; parity 1 is kMaxRanks slots further
+    int n_entries, n_ranks, rank;
+    unsigned long long upd_send_epoch, upd_wait_epoch, cmp_send_epoch, cmp_wait_epoch, red_epoch;
+    unsigned int ctr_send, ctr_wait;
+    int error;
+};
+
+struct Meta {  // exchanged once at creation
+    cudaIpcMemHandle_t handle;
+    uint32_t n_ghost, n_send, n_entries, ok, comps, pad[3];
+    uint32_t entry[kMaxEntries][5];  // peer, recv_off, recv_cnt, send_off, send_cnt
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// bounded wait for *flag >= target; false after a timeout or when another wait has already failed
+__device__ bool spin_until(const unsigned long long *flag, unsigned long long target, int *error)
+{
+    if (ld_acquire_sys(flag) >= target) return true;
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(flag) < target) {
+        if (*(volatile int *)error != 0) return false;
+        if (global_ns() - t0 > kTimeoutNs) {
+            atomicExch(error, 1);
+            return false;
+        }
+        __nanosleep(40);
+    }
+    return true;
+}
+
+enum : int { MODE_UPDATE = 0, MODE_COMPRESS = 1 };
+
+// entry that holds position j of the packed send list (update) or of the ghost segment (compress)
+__device__ __forceinline__ int find_entry(const uint32_t *off, const uint32_t *cnt, int n, uint32_t j)
+{
+    for (int k = 0; k < n; ++k)
+        if (j - off[k] < cnt[k]) return k;  // unsigned: j >= off && j < off + cnt
+    return -1;
+}
+
+// SEND: store this rank's data into the peers' windows, then release one flag per peer (last block).
+//   update   : src = v[c*stride + send_idx[j]] (or raw_send[j]),        j < n_send,  -> peer_recv[c*peer_n_ghost + j - send_off]
+//   compress : src = v[c*stride + n_owned + j], then zeroed,            j < n_ghost, -> peer_back[c*peer_n_send + j - recv_off]
+__global__ void p2p_send_kernel(DevState *st, Ctrl *my, int mode, double *v, uint32_t n_owned, uint32_t n_items,
+                                const uint32_t *__restrict__ send_idx, int ncomp, size_t stride, const double *__restrict__ raw_send)
+{
+    __shared__ uint32_t s_off[kMaxEntries], s_cnt[kMaxEntries];
+    __shared__ bool s_last;
+    const int n = st->n_entries;
+    const unsigned long long epoch = (mode == MODE_UPDATE ? st->upd_send_epoch : st->cmp_send_epoch) + 1;
+    if ((int)threadIdx.x < n) {
+        const EntryDev &e = st->e[threadIdx.x];
+        s_off[threadIdx.x] = mode == MODE_UPDATE ? e.send_off : e.recv_off;
+        s_cnt[threadIdx.x] = mode == MODE_UPDATE ? e.send_cnt : e.recv_cnt;
+        // the peer must have consumed my previous message before its window is overwritten
+        if (s_cnt[threadIdx.x] && epoch > 1)
+            spin_until(mode == MODE_UPDATE ? &my->upd_ack[threadIdx.x] : &my->cmp_ack[threadIdx.x], epoch - 1, &st->error);
+    }
+    __syncthreads();
+    const size_t total = (size_t)n_items * ncomp;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t c = (uint32_t)(i / n_items), j = (uint32_t)(i - (size_t)c * n_items);
+        const int k = find_entry(s_off, s_cnt, n, j);
+        if (k < 0) continue;
+        const EntryDev &e = st->e[k];
+        if (mode == MODE_UPDATE) {
+            const double x = raw_send ? raw_send[j] : v[c * stride + send_idx[j]];
+            e.peer_recv[(size_t)c * e.peer_n_ghost + (j - s_off[k])] = x;
+        } else {
+            double *g = v + c * stride + n_owned + j;
+            e.peer_back[(size_t)c * e.peer_n_send + (j - s_off[k])] = *g;
+            *g = 0.0;  // compress(add) leaves zeroed ghosts
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&st->ctr_send, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence_system();
+    if ((int)threadIdx.x < n && s_cnt[threadIdx.x]) {
+        const EntryDev &e = st->e[threadIdx.x];
+        st_release_sys(mode == MODE_UPDATE ? e.peer_upd_flag : e.peer_cmp_flag, epoch);
+    }
+    if (threadIdx.x == 0) {
+        st->ctr_send = 0;
+        if (mode == MODE_UPDATE) st->upd_send_epoch = epoch;
+        else st->cmp_send_epoch = epoch;
+    }
+}
+
+// WAIT: acquire the peers' flags, move the window into place, acknowledge (last block).
+//   update   : v[c*stride + n_owned + j] = recv[c*n_ghost + j]  (or raw_recv[j]),   j < n_ghost
+//   compress : v[c*stride + send_idx[j]] += back[c*n_send + j],                      j < n_send
+__global__ void p2p_wait_kernel(DevState *st, Ctrl *my, int mode, double *v, uint32_t n_owned, uint32_t n_items,
+                                const uint32_t *__restrict__ send_idx, int ncomp, size_t stride, const double *win, double *raw_recv)
+{
+    __shared__ bool s_last;
+    const int n = st->n_entries;
+    const unsigned long long epoch = (mode == MODE_UPDATE ? st->upd_wait_epoch : st->cmp_wait_epoch) + 1;
+    if ((int)threadIdx.x < n) {
+        const EntryDev &e = st->e[threadIdx.x];
+        if (mode == MODE_UPDATE ? e.recv_cnt : e.send_cnt)
+            spin_until(mode == MODE_UPDATE ? &my->upd_flag[threadIdx.x] : &my->cmp_flag[threadIdx.x], epoch, &st->error);
+    }
+    __syncthreads();
+    const size_t total = (size_t)n_items * ncomp;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t c = (uint32_t)(i / n_items), j = (uint32_t)(i - (size_t)c * n_items);
+        const double x = __ldcg(win + i);  // written by a peer: never through L1
+        if (mode == MODE_UPDATE) {
+            if (raw_recv) raw_recv[j] = x;
+            else v[c * stride + n_owned + j] = x;
+        } else {
+            atomicAdd(v + c * stride + send_idx[j], x);  // the same owned DoF may be ghosted by several peers
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&st->ctr_wait, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence_system();
+    if ((int)threadIdx.x < n) {
+        const EntryDev &e = st->e[threadIdx.x];
+        if (mode == MODE_UPDATE ? e.recv_cnt : e.send_cnt) st_release_sys(mode == MODE_UPDATE ? e.peer_upd_ack : e.peer_cmp_ack, epoch);
+    }
+    if (threadIdx.x == 0) {
+        st->ctr_wait = 0;
+        if (mode == MODE_UPDATE) st->upd_wait_epoch = epoch;
+        else st->cmp_wait_epoch = epoch;
+    }
+}
+
+// all-gather of the partial sums into every rank's window, then the sum in rank order (identical bits on every rank)
+__global__ void p2p_allreduce_kernel(DevState *st, Ctrl *my, double *vals, int count)
+{
+    const int lane = threadIdx.x, R = st->n_ranks;
+    const unsigned long long epoch = st->red_epoch + 1;
+    const int par = (int)(epoch & 1ull);
+    if (lane < R) {
+        RedSlot *dst = st->peer_red[lane] + par * kMaxRanks;
+        for (int i = 0; i < count; ++i) dst->val[i] = vals[i];
+        st_release_sys(&dst->epoch, epoch);  // release: the payload stores above are visible before the epoch
+        spin_until(&my->red[par][lane].epoch, epoch, &st->error);
+    }
+    __syncwarp();
+    if (lane < count) {
+        double s = 0.0;
+        for (int r = 0; r < R; ++r) s += __ldcg(&my->red[par][r].val[lane]);
+        vals[lane] = s;
+    }
+    if (lane == 0) st->red_epoch = epoch;
+}
+
+inline unsigned blocks_for(size_t n) { return n == 0 ? 1u : (unsigned)std::min<size_t>((n + 255) / 256, 148u * 4u); }
+
+}  // namespace
+
+struct P2P {
+    void *window = nullptr;               // my window (cudaMalloc, exported through CUDA IPC)
+    std::vector<void *> peer_base;        // mapped windows of the other ranks (null for my own rank)
+    DevState *d_state = nullptr;
+    double *recv = nullptr, *back = nullptr;  // regions of my window
+    int comps = 1;
+    ~P2P()
+    {
+        for (void *p : peer_base)
+            if (p) cudaIpcCloseMemHandle(p);
+        cudaFree(d_state);
+        cudaFree(window);
+    }
+};
+
+static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+static size_t recv_offset_bytes() { return align256(sizeof(Ctrl)); }
+static size_t back_offset_bytes(uint32_t n_ghost, int comps) { return recv_offset_bytes() + align256(sizeof(double) * (size_t)n_ghost * comps); }
+static size_t window_bytes(uint32_t n_ghost, uint32_t n_send, int comps)
+{
+    return back_offset_bytes(n_ghost, comps) + align256(sizeof(double) * (size_t)n_send * comps);
+}
+
+int p2p_max_components() { return kMaxComps; }
+
+void p2p_destroy(Halo &h)
+{
+    delete h.p2p;
+    h.p2p = nullptr;
+    h.use_p2p = false;
+}
+
+// Collective over the communicator of h.  On any failure on any rank every rank ends with h.p2p == nullptr (NCCL transport).
+int p2p_setup(Halo &h, bool raw_mode, NcclAllGatherFn all_gather, NcclAllReduceMinFn all_reduce_min)
+{
+    const char *env = std::getenv("B200FE_HALO_P2P");
+    const bool wanted = !env || std::atoi(env) != 0;
+    const int R = h.n_ranks, me = h.rank;
+    auto p = std::make_unique<P2P>();
+    p->comps = raw_mode ? 1 : kMaxComps;
+    Meta mine;
+    std::memset(&mine, 0, sizeof(mine));
+    mine.n_ghost = h.n_ghost; mine.n_send = raw_mode ? 0u : h.n_send; mine.n_entries = (uint32_t)h.peers.size(); mine.comps = (uint32_t)p->comps;
+    bool ok = wanted && R <= kMaxRanks && (int)h.peers.size() <= kMaxEntries;
+    if (ok) {
+        for (size_t k = 0; k < h.peers.size(); ++k) {
+            mine.entry[k][0] = (uint32_t)h.peers[k];
+            mine.entry[k][1] = h.recv_off[k]; mine.entry[k][2] = h.recv_cnt[k];
+            mine.entry[k][3] = h.send_off[k]; mine.entry[k][4] = h.send_cnt[k];
+        }
+        const size_t bytes = window_bytes(mine.n_ghost, mine.n_send, p->comps);
+        ok = cudaMalloc(&p->window, bytes) == cudaSuccess && cudaMemset(p->window, 0, bytes) == cudaSuccess &&
+             cudaIpcGetMemHandle(&mine.handle, p->window) == cudaSuccess;
+        if (!ok) cudaGetLastError();
+    }
+    mine.ok = ok ? 1u : 0u;
+    // all-gather of the descriptors through NCCL (device staging buffer)
+    std::vector<Meta> all(R);
+    {
+        Meta *d_all = nullptr;
+        B200FE_CUDA_TRY(cudaMalloc(&d_all, sizeof(Meta) * R));
+        B200FE_CUDA_TRY(cudaMemcpy(d_all + me, &mine, sizeof(Meta), cudaMemcpyHostToDevice));
+        int rc = all_gather(h, d_all + me, d_all, sizeof(Meta));
+        if (rc == B200FE_OK && cudaMemcpy(all.data(), d_all, sizeof(Meta) * R, cudaMemcpyDeviceToHost) != cudaSuccess) rc = B200FE_ERR_CUDA;
+        cudaFree(d_all);
+        if (rc != B200FE_OK) return rc;
+    }
+    for (int r = 0; r < R; ++r) ok = ok && all[r].ok;
+    p->peer_base.assign(R, nullptr);
+    if (ok) {
+        for (int r = 0; r < R && ok; ++r) {
+            if (r == me) continue;
+            ok = cudaIpcOpenMemHandle(&p->peer_base[r], all[r].handle, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+            if (!ok) { p->peer_base[r] = nullptr; cudaGetLastError(); }
+        }
+    }
+    DevState hs;
+    std::memset(&hs, 0, sizeof(hs));
+    if (ok) {
+        auto base_of = [&](int r) { return r == me ? (char *)p->window : (char *)p->peer_base[r]; };
+        hs.n_entries = (int)h.peers.size(); hs.n_ranks = R; hs.rank = me;
+        for (int r = 0; r < R; ++r) hs.peer_red[r] = &reinterpret_cast<Ctrl *>(base_of(r))->red[0][me];
+        // k-th message from me to B pairs with B's k-th receive from me, in table order (MPI / NCCL matching order)
+        for (int k = 0; k < hs.n_entries && ok; ++k) {
+            EntryDev &e = hs.e[k];
+            const int B = h.peers[k];
+            const Meta &mb = all[B];
+            e.send_off = h.send_off[k]; e.send_cnt = h.send_cnt[k]; e.recv_off = h.recv_off[k]; e.recv_cnt = h.recv_cnt[k];
+            Ctrl *cb = reinterpret_cast<Ctrl *>(base_of(B));
+            if (e.send_cnt) {
+                int occ = 0;
+                for (int q = 0; q < k; ++q) occ += (h.peers[q] == B && h.send_cnt[q]) ? 1 : 0;
+                int kb = -1;
+                for (uint32_t q = 0; q < mb.n_entries; ++q)
+                    if ((int)mb.entry[q][0] == me && mb.entry[q][2] && occ-- == 0) { kb = (int)q; break; }
+                if (kb < 0 || mb.entry[kb][2] != e.send_cnt) { ok = false; break; }
+                e.peer_recv = reinterpret_cast<double *>(base_of(B) + recv_offset_bytes()) + mb.entry[kb][1];
+                e.peer_upd_flag = &cb->upd_flag[kb];
+                e.peer_cmp_ack = &cb->cmp_ack[kb];
+                e.peer_n_ghost = mb.n_ghost;
+            }
+            if (e.recv_cnt) {
+                int occ = 0;
+                for (int q = 0; q < k; ++q) occ += (h.peers[q] == B && h.recv_cnt[q]) ? 1 : 0;
+                int jb = -1;
+                for (uint32_t q = 0; q < mb.n_entries; ++q)
+                    if ((int)mb.entry[q][0] == me && mb.entry[q][4] && occ-- == 0) { jb = (int)q; break; }
+                if (jb < 0 || mb.entry[jb][4] != e.recv_cnt) { ok = false; break; }
+                e.peer_back = reinterpret_cast<double *>(base_of(B) + back_offset_bytes(mb.n_ghost, (int)mb.comps)) + mb.entry[jb][3];
+                e.peer_cmp_flag = &cb->cmp_flag[jb];
+                e.peer_upd_ack = &cb->upd_ack[jb];
+                e.peer_n_send = mb.n_send;
+            }
+        }
+    }
+    if (ok) {
+        ok = cudaMalloc(&p->d_state, sizeof(DevState)) == cudaSuccess &&
+             cudaMemcpy(p->d_state, &hs, sizeof(DevState), cudaMemcpyHostToDevice) == cudaSuccess;
+        if (!ok) cudaGetLastError();
+        p->recv = reinterpret_cast<double *>((char *)p->window + recv_offset_bytes());
+        p->back = reinterpret_cast<double *>((char *)p->window + back_offset_bytes(mine.n_ghost, p->comps));
+    }
+    // agreement: P2P only if every rank got every mapping
+    int agreed = ok ? 1 : 0;
+    if (int rc = all_reduce_min(h, &agreed)) return rc;
+    if (agreed) {
+        h.p2p = p.release();
+        h.use_p2p = true;
+    }
+    return B200FE_OK;
+}
+
+int p2p_update_send(Halo &h, double *v, int ncomp, size_t stride, const double *raw_send, cudaStream_t s)
+{
+    P2P &p = *h.p2p;
+    if (ncomp > p.comps) return fail(B200FE_ERR_UNSUPPORTED, "P2P halo: %d components exceed the window (%d)", ncomp, p.comps);
+    p2p_send_kernel<<<blocks_for((size_t)h.n_send * ncomp), 256, 0, s>>>(p.d_state, (Ctrl *)p.window, MODE_UPDATE, v, h.n_owned, h.n_send, h.d_send_idx,
+                                                                         ncomp, stride, raw_send);
+    B200FE_CUDA_TRY(cudaGetLastError());
+    return B200FE_OK;
+}
+
+int p2p_update_wait(Halo &h, double *v, int ncomp, size_t stride, double *raw_recv, cudaStream_t s)
+{
+    P2P &p = *h.p2p;
+    p2p_wait_kernel<<<blocks_for((size_t)h.n_ghost * ncomp), 256, 0, s>>>(p.d_state, (Ctrl *)p.window, MODE_UPDATE, v, h.n_owned, h.n_ghost, h.d_send_idx,
+                                                                          ncomp, stride, p.recv, raw_recv);
+    B200FE_CUDA_TRY(cudaGetLastError());
+    return B200FE_OK;
+}
+
+int p2p_compress_send(Halo &h, double *v, int ncomp, size_t stride, cudaStream_t s)
+{
+    P2P &p = *h.p2p;
+    if (ncomp > p.comps) return fail(B200FE_ERR_UNSUPPORTED, "P2P halo: %d components exceed the window (%d)", ncomp, p.comps);
+    p2p_send_kernel<<<blocks_for((size_t)h.n_ghost * ncomp), 256, 0, s>>>(p.d_state, (Ctrl *)p.window, MODE_COMPRESS, v, h.n_owned, h.n_ghost, h.d_send_idx,
+                                                                          ncomp, stride, nullptr);
+    B200FE_CUDA_TRY(cudaGetLastError());
+    return B200FE_OK;
+}
+
+int p2p_compress_wait(Halo &h, double *v, int ncomp, size_t stride, cudaStream_t s)
+{
+    P2P &p = *h.p2p;
+    p2p_wait_kernel<<<blocks_for((size_t)h.n_send * ncomp), 256, 0, s>>>(p.d_state, (Ctrl *)p.window, MODE_COMPRESS, v, h.n_owned, h.n_send, h.d_send_idx,
+                                                                         ncomp, stride, p.back, nullptr);
+    B200FE_CUDA_TRY(cudaGetLastError());
+    return B200FE_OK;
+}
+
+int p2p_allreduce(Halo &h, double *d_vals, int count, cudaStream_t s)
+{
+    if (count > 4) return fail(B200FE_ERR_UNSUPPORTED, "P2P all-reduce: at most 4 values per call");
+    P2P &p = *h.p2p;
+    p2p_allreduce_kernel<<<1, 32, 0, s>>>(p.d_state, (Ctrl *)p.window, d_vals, count);
+    B200FE_CUDA_TRY(cudaGetLastError());
+    return B200FE_OK;
+}
+
+// Synchronises the device: 0 = healthy, B200FE_ERR_COMM after a wait has timed out.
+int p2p_status(Halo &h)
+{
+    if (!h.p2p) return B200FE_OK;
+    int err = 0;
+    B200FE_CUDA_TRY(cudaMemcpy(&err, &h.p2p->d_state->error, sizeof(int), cudaMemcpyDeviceToHost));
+    if (err) return fail(B200FE_ERR_COMM, "P2P halo: a peer did not answer within %llu s (rank %d of %d)", kTimeoutNs / 1000000000ull, h.rank, h.n_ranks);
+    return B200FE_OK;
+}
+
+}  // namespace b200fe

@@ -116,6 +116,25 @@ class Halo:
     def zero_out_ghost_values(self, v: torch.Tensor, stream=None):
         check(lib.b200fe_halo_zero_ghosts(self._h, C.c_void_p(v.data_ptr()), self._sp(stream)))
 
+    def transport(self) -> str:
+        """'p2p' (peer stores over CUDA-IPC windows) or 'nccl' (grouped send/recv)."""
+        avail, used = C.c_int(), C.c_int()
+        check(lib.b200fe_halo_transport(self._h, C.byref(avail), C.byref(used)))
+        return "p2p" if used.value else "nccl"
+
+    def p2p_available(self) -> bool:
+        avail, used = C.c_int(), C.c_int()
+        check(lib.b200fe_halo_transport(self._h, C.byref(avail), C.byref(used)))
+        return bool(avail.value)
+
+    def set_transport(self, name: str):
+        """Collective: every rank must switch before the next exchange."""
+        check(lib.b200fe_halo_set_transport(self._h, int(name == "p2p")))
+
+    def status(self):
+        """Synchronises; raises if a bounded wait of the P2P transport expired."""
+        check(lib.b200fe_halo_status(self._h))
+
     def allreduce_sum(self, vals: torch.Tensor, stream=None):
         check(lib.b200fe_halo_allreduce_sum(self._h, C.c_void_p(vals.data_ptr()), vals.numel(), self._sp(stream)))
 

@@ -34,7 +34,8 @@ struct LaplaceProblem {
         const Communicator comm = Communicator::from_environment();
         check_cuda(cudaSetDevice(comm.local_rank), "cudaSetDevice");
         const bool root = comm.rank == 0;
-        if (!root) std::fclose(stdout);  // the tables are printed by rank 0 only (pcout of bp3.cc:92)
+        // the tables are printed by rank 0 only (pcout of bp3.cc:92); the other ranks keep a valid stdout on /dev/null
+        if (!root && !std::freopen("/dev/null", "w", stdout)) throw Error(B200FE_ERR_INVALID_ARG, "cannot redirect stdout");
         std::printf("Testing FE_Q<3>(%d), n_q_points_1d = %d (%s)\nNo. of GPUs: %d\n", fe_degree, nq, quad == Quadrature::Gauss ? "QGauss" : "QGaussLobatto", comm.size);
         for (unsigned cycle = 0; cycle < 38; ++cycle) {
             const std::size_t projected = BoxMesh::bp3_projected_size(cycle, fe_degree);

@@ -1,8 +1,12 @@
 #!/usr/bin/env python
-"""phalox.py -- the reference's halo-exchange microbenchmark (p-halox/phalox.cc) over NCCL / NVLink.
+"""phalox.py -- the reference's halo-exchange microbenchmark (p-halox/phalox.cc) over NVLink: NCCL send/recv and
+CUDA P2P (peer stores into CUDA-IPC windows + flags, csrc/halo_p2p.cu), side by side.
 
   torchrun --nproc-per-node N --master-addr 127.0.0.1 --master-port P benchmarks_b200/drivers/phalox.py \
            [dim=2] [KB=64] [nMsg=2] [is_periodic=1] [warmup=30] [print_topo=0]
+  PHALOX_TRANSPORT=nccl|p2p|both (default both) selects the transports; every line ends with `transport= ... payload= ok`.
+  Every message carries a recognisable payload (sender rank, sender's message slot, position) that the receiver checks
+  after the timed rounds -- the reference only moves zeros.
 
 Same Cartesian decomposition (MPI_Dims_create / MPI_Cart_shift semantics, phalox.cc:49-88: self and
 non-periodic boundaries dropped, duplicates kept), same message schedule ((warmup + nMsg) rounds of
@@ -48,6 +52,16 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     gloo = dist.new_group(backend="gloo")
+    # PHALOX_SWEEP_DIMS / PHALOX_SWEEP_KB (comma lists): the README's sweep (p-halox/README.md:62-68) inside one launch
+    dims_list = [int(x) for x in os.environ.get("PHALOX_SWEEP_DIMS", str(dim)).split(",")]
+    kb_list = [int(x) for x in os.environ.get("PHALOX_SWEEP_KB", str(KB)).split(",")]
+    for dd in dims_list:
+        for kb in kb_list:
+            run_config(dd, kb, nMsg, periodic, warmup, print_topo, rank, world, gloo)
+    dist.destroy_process_group()
+
+
+def run_config(dim, KB, nMsg, periodic, warmup, print_topo, rank, world, gloo):
     dims = dims_create(world, dim)
     coords = list(np.unravel_index(rank, dims))  # row-major like MPI_Cart
     neighbors = []
@@ -66,6 +80,25 @@ def main():
     n_doubles = KB * 1024 // 8
     send = torch.zeros(max(nneigh * n_doubles, 1), dtype=torch.float64, device="cuda")
     recv = torch.zeros_like(send)
+    pos = (torch.arange(n_doubles, device="cuda") % 7).to(torch.float64) * 0.125
+    for j in range(nneigh):   # payload of my j-th message
+        send[j * n_doubles:(j + 1) * n_doubles] = rank * 1000.0 + j + pos
+    all_neighbors = [None] * world
+    dist.all_gather_object(all_neighbors, neighbors, group=gloo)
+
+    def expected_sender_slot(k):
+        """My k-th receive pairs with the sender's messages to me in posting order (MPI / NCCL matching rule)."""
+        B = neighbors[k]
+        occ = sum(1 for q in range(k) if neighbors[q] == B)
+        slots = [q for q, t in enumerate(all_neighbors[B]) if t == rank]
+        return slots[occ]
+
+    def payload_ok():
+        ok = True
+        for k in range(nneigh):
+            want = neighbors[k] * 1000.0 + expected_sender_slot(k) + pos
+            ok &= bool(torch.equal(recv[k * n_doubles:(k + 1) * n_doubles], want))
+        return ok
     uid = [None]
     if rank == 0:
         buf = C.create_string_buffer(128)
@@ -92,38 +125,50 @@ def main():
     def one_round():
         check(lib.b200fe_halo_exchange_raw(h, C.c_void_p(send.data_ptr()), C.c_void_p(recv.data_ptr()), sp))
 
-    results = {}
-    for mode in ("sync", "stream"):
-        torch.cuda.synchronize()
-        dist.barrier()
-        for msg in range(nMsg + warmup):
-            if msg == warmup:
-                torch.cuda.synchronize()
-                dist.barrier()
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                e0 = torch.cuda.Event(enable_timing=True)
-                e0.record()
-            one_round()
-            if mode == "sync":
-                stream.synchronize()
-        e1 = torch.cuda.Event(enable_timing=True)
-        e1.record()
-        torch.cuda.synchronize()
-        results[mode] = (time.perf_counter() - t0) if mode == "sync" else e0.elapsed_time(e1) * 1e-3
-    for mode, t in results.items():
-        times = [None] * world
-        dist.all_gather_object(times, (t, nneigh * nMsg * KB), group=gloo)
-        if rank == 0:
-            ts = np.array([x[0] for x in times])
-            kb = sum(x[1] for x in times)
-            print(f"P= {world} dim= {dim} KB= {KB} nMsg= {nMsg} is_periodic= {periodic} warmup= {warmup} print_topo= {print_topo}"
-                  f" min_time_s= {ts.min():.6g} min_Rank= {int(ts.argmin())} max_time_s= {ts.max():.6g} max_Rank= {int(ts.argmax())}"
-                  f" avg_time_s= {ts.mean():.6g} agg_BW_GBps= {kb / ts.max() / (1024.0 * 1024.0):.6g} mode= {mode}", flush=True)
+    def run_transport(transport):
+        results = {}
+        for mode in ("sync", "stream"):
+            recv.zero_()
+            torch.cuda.synchronize()
+            dist.barrier()
+            for msg in range(nMsg + warmup):
+                if msg == warmup:
+                    torch.cuda.synchronize()
+                    dist.barrier()
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    e0 = torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                one_round()
+                if mode == "sync":
+                    stream.synchronize()
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            torch.cuda.synchronize()
+            results[mode] = ((time.perf_counter() - t0) if mode == "sync" else e0.elapsed_time(e1) * 1e-3, payload_ok() and lib.b200fe_halo_status(h) == 0)
+        for mode, (t, ok) in results.items():
+            times = [None] * world
+            dist.all_gather_object(times, (t, nneigh * nMsg * KB, ok), group=gloo)
+            if rank == 0:
+                ts = np.array([x[0] for x in times])
+                kb = sum(x[1] for x in times)
+                print(f"P= {world} dim= {dim} KB= {KB} nMsg= {nMsg} is_periodic= {periodic} warmup= {warmup} print_topo= {print_topo}"
+                      f" min_time_s= {ts.min():.6g} min_Rank= {int(ts.argmin())} max_time_s= {ts.max():.6g} max_Rank= {int(ts.argmax())}"
+                      f" avg_time_s= {ts.mean():.6g} agg_BW_GBps= {kb / ts.max() / (1024.0 * 1024.0):.6g} mode= {mode}"
+                      f" transport= {transport} payload= {'ok' if all(x[2] for x in times) else 'WRONG'}", flush=True)
+
+    avail, used = C.c_int(), C.c_int()
+    check(lib.b200fe_halo_transport(h, C.byref(avail), C.byref(used)))
+    want = os.environ.get("PHALOX_TRANSPORT", "both")
+    transports = [t for t in ("nccl", "p2p") if want in (t, "both") and (t == "nccl" or avail.value)]
+    for transport in transports:
+        check(lib.b200fe_halo_set_transport(h, int(transport == "p2p")))
+        run_transport(transport)
     if print_topo and rank == 0:
         print("dims =", dims)
     lib.b200fe_halo_destroy(h)
-    dist.destroy_process_group()
+    del send, recv
+    torch.cuda.empty_cache()
 
 
 if __name__ == "__main__":

@@ -46,13 +46,15 @@ def _dp(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
-def overlap_permutation(dof_indices: np.ndarray, n_owned: int):
+def overlap_permutation(dof_indices: np.ndarray, n_owned: int, one_sided: bool = False):
     """Cell order [interior half | cells touching a ghost DoF | interior half] and the two sizes
-    (deal.II's three colours with overlap_communication_computation)."""
+    (deal.II's three colours with overlap_communication_computation).
+    one_sided (P2P transport): [all interior cells | cells touching a ghost DoF] -- the ghost values are posted before the
+    interior launch and only awaited before the boundary launch, so two launches instead of three hide the exchange."""
     touches = ((dof_indices >= n_owned) & (dof_indices != INVALID)).any(axis=1)
     interior = np.nonzero(~touches)[0]
     boundary = np.nonzero(touches)[0]
-    half = len(interior) // 2
+    half = len(interior) if one_sided else len(interior) // 2
     perm = np.concatenate([interior[:half], boundary, interior[half:]])
     return perm, half, len(boundary)
 
@@ -80,7 +82,7 @@ class LaplaceOperator:
         self.perm = None
         n_phase0 = n_phase1 = 0
         if overlap and mesh.n_ranks > 1 and not len(getattr(mesh, "hang_dof", ())):  # no split with hanging rows
-            self.perm, n_phase0, n_phase1 = overlap_permutation(idx, mesh.n_owned)
+            self.perm, n_phase0, n_phase1 = overlap_permutation(idx, mesh.n_owned, one_sided=halo is not None and halo.transport() == "p2p")
             idx = idx[self.perm]
         self.dof_indices = torch.from_numpy(np.ascontiguousarray(idx)).to(self.device)
         # geometry: mapping support points -> G, JxW on the device

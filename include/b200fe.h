@@ -400,6 +400,16 @@ int b200fe_halo_update_ghosts(b200fe_halo *halo, double *d_v, void *stream);
 int b200fe_halo_compress_add(b200fe_halo *halo, double *d_v, void *stream);
 int b200fe_halo_zero_ghosts(b200fe_halo *halo, double *d_v, void *stream);
 int b200fe_halo_allreduce_sum(b200fe_halo *halo, double *d_vals, int count, void *stream);
+/* Transport of the calls above.  b200fe_halo_create maps one CUDA-IPC window per peer when every rank can reach every
+ * other one by load/store (one NVLink/NVSwitch domain; B200FE_HALO_P2P=0 disables): exchanges are then peer stores + flags
+ * issued by the pack kernel itself and the all-reduce is an all-gather of partial sums added in rank order (identical bits
+ * on every rank) -- the "CUDA P2P over NVLink" transport next to "NCCL send/recv" (p-halox/README.md:62-68 compares MPI
+ * transports the same way).  *p2p_available: windows exist; *p2p_in_use: current choice.  set_transport switches between
+ * the two (collective: every rank must make the same choice before the next exchange).  b200fe_halo_status synchronises
+ * the device and returns B200FE_ERR_COMM if a bounded wait of the P2P transport has expired (a peer never answered). */
+int b200fe_halo_transport(b200fe_halo *halo, int *p2p_available, int *p2p_in_use);
+int b200fe_halo_set_transport(b200fe_halo *halo, int use_p2p);
+int b200fe_halo_status(b200fe_halo *halo);
 /* One exchange round of p-halox (p-halox/phalox.cc:111-125: Irecv all, Isend all, Waitall) without
  * pack lists: per peer k, d_send[send_offset[k] .. +send_count[k]) goes to peers[k] and
  * d_recv[recv_offset[k] .. +recv_count[k]) is filled from it.  A halo created with

@@ -15,6 +15,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <fcntl.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -237,18 +238,28 @@ class HangingBoxMesh {
 // by `python -m torch.distributed.run --no-python`; a plain run has none of them = one rank); the only thing that has to
 // travel between the processes is the
 // 128-byte NCCL id, published by rank 0 through a file (the reference uses MPI for everything, bp3.cc:564; there is no MPI
-// in this image).  NOT YET RUN on more than one GPU: the multi-GPU evidence of round 1 went through the Python launcher.
+// in this image).
 class Communicator {
   public:
     static Communicator from_environment()
     {
         Communicator c;
+        process_start();
         c.rank = env_int({"RANK"}, 0);
         c.size = env_int({"WORLD_SIZE"}, 1);
         c.local_rank = env_int({"LOCAL_RANK"}, c.rank);
         if (c.size < 1 || c.rank < 0 || c.rank >= c.size) throw Error(B200FE_ERR_INVALID_ARG, "bad RANK / WORLD_SIZE in the environment");
+        // per-launch name: the launcher's run id (torchrun exports TORCHELASTIC_RUN_ID to every rank) or, for other
+        // launchers, B200FE_RUN_ID; plus the port and the user id.  A file left by an earlier or crashed launch then has a
+        // different name or is replaced before use (rank 0 creates it with O_EXCL | O_NOFOLLOW after unlinking).
         const char *port = std::getenv("MASTER_PORT");
-        c.id_file = std::string("/tmp/b200fe_nccl_id_") + (port ? port : "default");
+        const char *run = std::getenv("B200FE_RUN_ID");
+        if (!run) run = std::getenv("TORCHELASTIC_RUN_ID");
+        const char *dir = std::getenv("XDG_RUNTIME_DIR");
+        c.id_file = std::string(dir && *dir ? dir : "/tmp") + "/b200fe_nccl_id_" + std::to_string((unsigned long)getuid()) + "_" +
+                    (port ? port : "default") + "_" + (run ? run : "norun");
+        for (char &ch : c.id_file)
+            if (ch == ' ' || ch == ':') ch = '_';
         return c;
     }
     // collective: rank 0 creates the id and publishes it, the others wait for a file written during this launch
@@ -260,20 +271,27 @@ class Communicator {
             std::remove(id_file.c_str());
             check(b200fe_comm_unique_id(&id[0]));
             const std::string tmp = id_file + ".tmp";
-            FILE *f = std::fopen(tmp.c_str(), "wb");
-            if (!f || std::fwrite(id.data(), 1, 128, f) != 128) throw Error(B200FE_ERR_COMM, "cannot write " + tmp);
-            std::fclose(f);
+            std::remove(tmp.c_str());
+            // never follow a planted symlink, never reuse an existing file
+            const int fd = ::open(tmp.c_str(), O_WRONLY | O_CREAT | O_EXCL | O_NOFOLLOW, 0600);
+            if (fd < 0 || ::write(fd, id.data(), 128) != 128) {
+                if (fd >= 0) ::close(fd);
+                throw Error(B200FE_ERR_COMM, "cannot write " + tmp);
+            }
+            ::close(fd);
             if (std::rename(tmp.c_str(), id_file.c_str()) != 0) throw Error(B200FE_ERR_COMM, "cannot publish " + id_file);
             return id;
         }
-        const std::time_t start = std::time(nullptr);
+        const std::time_t start = process_start();
         for (int tries = 0; tries < 6000; ++tries) {  // up to 10 minutes
             struct stat st;
-            if (stat(id_file.c_str(), &st) == 0 && st.st_size == 128 && st.st_mtime + 120 >= start) {
-                FILE *f = std::fopen(id_file.c_str(), "rb");
-                if (f) {
-                    const size_t n = std::fread(&id[0], 1, 128, f);
-                    std::fclose(f);
+            // a regular file of ours, complete, and not older than this process (1 s of clock granularity)
+            if (lstat(id_file.c_str(), &st) == 0 && S_ISREG(st.st_mode) && st.st_uid == getuid() && st.st_size == 128 &&
+                st.st_mtime + 30 >= start) {  // written during this launch (ranks of one launch start within seconds)
+                const int fd = ::open(id_file.c_str(), O_RDONLY | O_NOFOLLOW);
+                if (fd >= 0) {
+                    const ssize_t n = ::read(fd, &id[0], 128);
+                    ::close(fd);
                     if (n == 128) return id;
                 }
             }
@@ -286,6 +304,11 @@ class Communicator {
     std::string id_file;
 
   private:
+    static std::time_t process_start()
+    {
+        static const std::time_t t = std::time(nullptr);  // first call = from_environment() at program start
+        return t;
+    }
     static int env_int(std::initializer_list<const char *> names, int fallback)
     {
         for (const char *n : names)

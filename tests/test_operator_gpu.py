@@ -97,12 +97,16 @@ def cg_golden(golden_dir):
         return json.load(f)["rows"]
 
 
-@pytest.mark.parametrize("row", range(0, 7))
+@pytest.mark.parametrize("row", range(0, 13))
 @pytest.mark.parametrize("nq", [6, 5])
 def test_cg_reference_goldens_p4(cg_golden, row, nq):
-    """bp3 protocol: rhs = int phi, x0 = 0, ReductionControl(1e9, 1e-16, 1e-9) (bp3.cc:266-285)."""
+    """bp3 protocol: rhs = int phi, x0 = 0, ReductionControl(1e9, 1e-16, 1e-9) (bp3.cc:266-285).  Rows 0-12 are every
+    single-GPU row of CEED_bp/results/1xGH200_P4.txt:636-648 (18,513 ... 67,634,433 DoFs, 92 ... 1389 iterations); rows
+    13-14 (135 M / 270 M DoFs, 4_GPU.out:779-780) are checked by bench.py's `parity` block on 8 GPUs."""
     import benchmarks_b200 as b
     cycle, cells, ndofs, its_g, red_g = cg_golden[row]
+    if nq == 5 and row > 10:
+        pytest.skip("the nq = 5 goldens are the same numbers; the two largest meshes run once (nq = 6)")
     mesh = b.BoxMesh.bp3_cycle(cycle, 4)
     assert (mesh.n_cells_global, mesh.n_dofs_global) == (cells, ndofs)
     A = b.LaplaceOperator(mesh, nq=nq)
@@ -112,7 +116,7 @@ def test_cg_reference_goldens_p4(cg_golden, row, nq):
     b.SolverCG(ctl).solve(A, x, rhs)
     assert abs(ctl.last_step() - its_g) <= 1
     red = (ctl.last_value() / ctl.initial_value()) ** (1.0 / ctl.last_step())
-    assert red == pytest.approx(red_g, abs=2e-3)
+    assert red == pytest.approx(red_g, abs=2e-3 if row < 7 else 5e-4)
     # the solve really solved: ||b - A x|| <= 1e-9 ||b|| (recomputed residual)
     r = A.initialize_dof_vector()
     A.vmult(r, x)

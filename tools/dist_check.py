@@ -15,6 +15,17 @@ import benchmarks_b200 as b  # noqa: E402
 from benchmarks_b200.dist import Halo  # noqa: E402
 
 
+TRANSPORT = "p2p"   # set by main(): every halo of a pass uses this transport
+
+
+def make_halo(mesh, gloo):
+    halo = Halo(mesh, group=gloo)
+    if TRANSPORT == "p2p" and not halo.p2p_available():
+        raise RuntimeError("P2P windows not available on this box")
+    halo.set_transport(TRANSPORT)
+    return halo
+
+
 def lattice_of_local(mesh, A):
     """Global lattice index (Z*ny + Y)*nx + X of every local DoF that an owned cell touches."""
     p, nm = mesh.p, mesh.p + 1
@@ -63,7 +74,7 @@ def check_hanging(rank, world, gloo):
         cells = [s << nref for s in blocks]
         lo, hi = (0, 0, 0), tuple(max(c // 2, 1) for c in cells)
         mesh = b.HangingBoxMesh(blocks, nref, p, lo, hi, n_ranks=world, rank=rank)
-        halo = Halo(mesh, group=gloo)
+        halo = make_halo(mesh, gloo)
         kw = dict(quad=quad, deform=(0.03, 1.5), p_geo=2, constraints=form)
         A = b.LaplaceOperator(mesh, halo=halo, **kw)
         m1 = b.HangingBoxMesh(blocks, nref, p, lo, hi)
@@ -86,6 +97,20 @@ def check_hanging(rank, world, gloo):
         err = np.abs(dst[: mesh.n_owned].cpu().numpy()[sel] - full[own[sel]]).max() / np.abs(full).max()
         # BP6-style CG: three components, rhs = int phi in each
         nloc, nloc1 = mesh.n_owned + mesh.n_ghost, m1.n_owned
+        batch_same = True
+        if TRANSPORT == "nccl":  # component-batched ghost update / compress against one exchange per component
+            s3 = torch.from_numpy(np.random.default_rng(11 + rank).standard_normal(3 * nloc)).cuda()
+            outs = []
+            for flag in ("1", "0"):
+                os.environ["B200FE_HALO_BATCH"] = flag
+                for c in range(3):
+                    s3[c * nloc + mesh.n_owned:(c + 1) * nloc] = 0.0
+                d3 = torch.zeros_like(s3)
+                A.vmult_components(d3, s3.clone(), 3)
+                outs.append(d3.clone())
+            os.environ["B200FE_HALO_BATCH"] = "1"
+            # (atomics reorder the sums inside the cell kernel, so the applies agree to rounding, not bitwise)
+            batch_same = bool(((outs[0] - outs[1]).abs().max() <= 1e-12 * outs[1].abs().max()).item())
         rhs = A.compute_rhs().repeat(3)
         x = torch.zeros(3 * nloc, dtype=torch.float64, device="cuda")
         ctl = b.ReductionControl(20000, 1e-16, 1e-9)
@@ -97,9 +122,10 @@ def check_hanging(rank, world, gloo):
         xs = np.zeros(n_key)
         xs[key1[key1 >= 0]] = x1[2 * nloc1:].cpu().numpy()[key1 >= 0]
         xerr = np.abs(x[2 * nloc: 2 * nloc + mesh.n_owned].cpu().numpy()[sel] - xs[own[sel]]).max() / np.abs(xs).max()
-        good = err <= 1e-12 and abs(ctl.last_step() - ctl1.last_step()) <= 1 and xerr <= 1e-6
+        halo.status()
+        good = err <= 1e-12 and abs(ctl.last_step() - ctl1.last_step()) <= 1 and xerr <= 1e-6 and batch_same
         ok &= bool(good)
-        print(f"[rank {rank}/{world}] hanging p={p} {quad} constraints={form}: {len(mesh.hang_dof)} rows, vmult rel err {err:.2e}, BP6 CG its {ctl.last_step()} vs "
+        print(f"[rank {rank}/{world}] [{TRANSPORT}] batched==per-component {batch_same}; hanging p={p} {quad} constraints={form}: {len(mesh.hang_dof)} rows, vmult rel err {err:.2e}, BP6 CG its {ctl.last_step()} vs "
               f"{ctl1.last_step()} (1 GPU), x rel err {xerr:.1e} -> {'OK' if good else 'FAIL'}", flush=True)
         del A, A1, halo
     return ok
@@ -110,11 +136,25 @@ def main():
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
     gloo = dist.new_group(backend="gloo")
+    global TRANSPORT
+    probe = Halo(b.BoxMesh({1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[world], 1, 1, n_ranks=world, rank=rank), group=gloo)
+    transports = (["p2p"] if probe.p2p_available() else []) + ["nccl"]
+    del probe
+    if rank == 0:
+        print("transports:", transports, flush=True)
+    total = 1
+    for TRANSPORT in transports:
+        total = min(total, one_pass(rank, world, gloo))
+    dist.destroy_process_group()
+    sys.exit(0 if total == 1 else 1)
+
+
+def one_pass(rank, world, gloo):
     blocks = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[world]
     ok = True
     for p, quad, nq, nref, overlap in ((2, "gauss", 4, 3, False), (4, "gauss", 6, 3, True), (6, "gll", 7, 2, True), (3, "gauss", 4, 2, True)):
         mesh = b.BoxMesh(blocks, nref, p, n_ranks=world, rank=rank)
-        halo = Halo(mesh, group=gloo)
+        halo = make_halo(mesh, gloo)
         A = b.LaplaceOperator(mesh, nq=nq, quad=quad, halo=halo, overlap=overlap, deform=(0.03, 1.5), p_geo=2)
         lat, n_lat = lattice_of_local(mesh, A)
         # a global field defined on the lattice so every rank can evaluate its part
@@ -149,21 +189,20 @@ def main():
         xs = np.zeros(n_lat)
         xs[lat1[lat1 >= 0]] = x1.cpu().numpy()[lat1 >= 0]
         xerr = np.abs(x[: mesh.n_owned].cpu().numpy()[sel] - xs[own[sel]]).max() / np.abs(xs).max()
+        halo.status()
         good = err <= 1e-12 and abs(ctl.last_step() - ctl1.last_step()) <= 1 and xerr <= 1e-6
         ok &= bool(good)
-        print(f"[rank {rank}/{world}] p={p} {quad} nq={nq} overlap={overlap}: vmult rel err {err:.2e}, CG its {ctl.last_step()} vs {ctl1.last_step()} (1 GPU), x rel err {xerr:.1e} -> {'OK' if good else 'FAIL'}", flush=True)
+        print(f"[rank {rank}/{world}] [{TRANSPORT}] p={p} {quad} nq={nq} overlap={overlap}: vmult rel err {err:.2e}, CG its {ctl.last_step()} vs {ctl1.last_step()} (1 GPU), x rel err {xerr:.1e} -> {'OK' if good else 'FAIL'}", flush=True)
         del A, A1, halo
     t = torch.tensor([int(ok)], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print("DIST_CHECK", "PASS" if t.item() == 1 else "FAIL", flush=True)
+        print(f"DIST_CHECK [{TRANSPORT}]", "PASS" if t.item() == 1 else "FAIL", flush=True)
     th = torch.tensor([int(check_hanging(rank, world, gloo))], device="cuda")
     dist.all_reduce(th, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print("DIST_CHECK_HANGING", "PASS" if th.item() == 1 else "FAIL", flush=True)
-    t = torch.minimum(t, th)
-    dist.destroy_process_group()
-    sys.exit(0 if t.item() == 1 else 1)
+        print(f"DIST_CHECK_HANGING [{TRANSPORT}]", "PASS" if th.item() == 1 else "FAIL", flush=True)
+    return int(torch.minimum(t, th).item())
 
 
 if __name__ == "__main__":
