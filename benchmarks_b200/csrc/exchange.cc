@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "common.h"
+#include "mesh_common.h"
 
 namespace b200fe {
 
@@ -81,6 +82,40 @@ int b200fe_exchange_create_box(const b200fe_boxmesh_desc *desc, b200fe_exchange 
 {
     B200FE_REQUIRE(desc && out, "b200fe_exchange_create_box: null pointer");
     auto ex = std::make_unique<Exchange>();
+    if (desc->ghosts == B200FE_GHOSTS_MINIMAL) {
+        // from this rank's own view only (mesh.cc: boxmesh_send_lists) -- no replay of the other ranks' meshes
+        b200fe_boxmesh *m = nullptr;
+        if (int rc = b200fe_boxmesh_create(desc, &m)) return rc;
+        struct Guard { b200fe_boxmesh *m; ~Guard() { b200fe_boxmesh_destroy(m); } } guard{m};
+        b200fe_boxmesh_info_t info;
+        if (int rc = b200fe_boxmesh_info(m, &info)) return rc;
+        std::vector<uint64_t> gg(info.n_ghost);
+        std::vector<int32_t> go(info.n_ghost);
+        if (int rc = b200fe_boxmesh_fill(m, nullptr, nullptr, gg.data(), go.data(), nullptr, nullptr)) return rc;
+        std::vector<std::vector<uint32_t>> send;
+        if (int rc = boxmesh_send_lists(m, send)) return rc;
+        const int R = desc->n_ranks, me = desc->rank;
+        ex->n_owned = info.n_owned; ex->n_ghost = info.n_ghost;
+        std::vector<uint32_t> r_off(R, 0), r_cnt(R, 0);
+        for (size_t k = 0; k < go.size(); ++k) {
+            const int t = go[k];
+            if (t < 0 || t >= R || t == me) return fail(B200FE_ERR_INVALID_ARG, "exchange lists: ghost %zu has owner %d", k, t);
+            if (r_cnt[t] == 0) r_off[t] = (uint32_t)k;
+            else if (r_off[t] + r_cnt[t] != k) return fail(B200FE_ERR_INVALID_ARG, "exchange lists: ghosts of rank %d are not contiguous", t);
+            ++r_cnt[t];
+        }
+        for (int t = 0; t < R; ++t) {
+            if (r_cnt[t] == 0 && send[t].empty()) continue;
+            ex->peers.push_back(t);
+            ex->recv_off.push_back(r_off[t]);
+            ex->recv_cnt.push_back(r_cnt[t]);
+            ex->send_off.push_back((uint32_t)ex->send_idx.size());
+            ex->send_cnt.push_back((uint32_t)send[t].size());
+            ex->send_idx.insert(ex->send_idx.end(), send[t].begin(), send[t].end());
+        }
+        *out = reinterpret_cast<b200fe_exchange *>(ex.release());
+        return B200FE_OK;
+    }
     auto view = [&](int t, RankView &v) -> int {
         b200fe_boxmesh_desc d = *desc;
         d.rank = t;

@@ -112,8 +112,7 @@ inline unsigned blocks_for(uint32_t n) { return n == 0 ? 1u : std::min<unsigned>
 int exchange_update(Halo &h, double *v, cudaStream_t s)
 {
     if (h.use_p2p) {
-        if (int rc = p2p_update_send(h, v, 1, 0, nullptr, s)) return rc;
-        return p2p_update_wait(h, v, 1, 0, nullptr, s);
+        return p2p_update(h, v, 1, 0, nullptr, nullptr, s);
     }
     Nccl &n = nccl();
     if (h.n_send) {
@@ -204,8 +203,7 @@ int halo_compress_add(Halo &h, double *v, cudaStream_t s)
     NvtxRange range("compress_add");
     if (h.n_send && !h.d_send_idx) return fail(B200FE_ERR_INVALID_ARG, "halo was created in raw mode (no send indices)");
     if (h.use_p2p) {
-        if (int rc = p2p_compress_send(h, v, 1, 0, s)) return rc;
-        return p2p_compress_wait(h, v, 1, 0, s);
+        return p2p_compress(h, v, 1, 0, s);
     }
     if (int rc = exchange_compress(h, v, s)) return rc;
     return unpack_and_zero(h, v, s);
@@ -237,8 +235,7 @@ int halo_update_ghosts_components(Halo &h, double *v, int ncomp, size_t stride, 
     if (h.n_ranks == 1) return B200FE_OK;
     if (h.use_p2p && h.d_send_idx_ok() && ncomp <= p2p_max_components()) {
         NvtxRange range("update_ghost_values");
-        if (int rc = p2p_update_send(h, v, ncomp, stride, nullptr, s)) return rc;
-        return p2p_update_wait(h, v, ncomp, stride, nullptr, s);
+        return p2p_update(h, v, ncomp, stride, nullptr, nullptr, s);
     }
     if (ncomp == 1 || !halo_batching() || (h.n_send && !h.d_send_idx)) {
         for (int c = 0; c < ncomp; ++c)
@@ -267,8 +264,7 @@ int halo_compress_add_components(Halo &h, double *v, int ncomp, size_t stride, c
     if (h.n_ranks == 1) return B200FE_OK;
     if (h.use_p2p && h.d_send_idx_ok() && ncomp <= p2p_max_components()) {
         NvtxRange range("compress_add");
-        if (int rc = p2p_compress_send(h, v, ncomp, stride, s)) return rc;
-        return p2p_compress_wait(h, v, ncomp, stride, s);
+        return p2p_compress(h, v, ncomp, stride, s);
     }
     if (ncomp == 1 || !halo_batching() || (h.n_send && !h.d_send_idx)) {
         for (int c = 0; c < ncomp; ++c)
@@ -433,8 +429,7 @@ int b200fe_halo_exchange_raw(b200fe_halo *halo, const double *d_send, double *d_
     if (h.n_ranks == 1) return B200FE_OK;
     cudaStream_t s = (cudaStream_t)stream;
     if (h.use_p2p) {  // peer stores into the receivers' windows + flags, then wait + copy out (halo_p2p.cu)
-        if (int rc = p2p_update_send(h, nullptr, 1, 0, d_send, s)) return rc;
-        return p2p_update_wait(h, nullptr, 1, 0, d_recv, s);
+        return p2p_update(h, nullptr, 1, 0, d_send, d_recv, s);
     }
     Nccl &n = nccl();
     // one round of p-halox: post all receives, all sends, complete together (phalox.cc:111-125)

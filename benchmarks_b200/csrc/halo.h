@@ -51,6 +51,9 @@ int p2p_update_send(Halo &h, double *d_v, int ncomp, size_t stride, const double
 int p2p_update_wait(Halo &h, double *d_v, int ncomp, size_t stride, double *d_raw_recv, cudaStream_t s);
 int p2p_compress_send(Halo &h, double *d_v, int ncomp, size_t stride, cudaStream_t s);  // also zeroes the ghost entries of v
 int p2p_compress_wait(Halo &h, double *d_v, int ncomp, size_t stride, cudaStream_t s);
+// whole rounds (post + complete back to back; one single-block kernel for small messages)
+int p2p_update(Halo &h, double *d_v, int ncomp, size_t stride, const double *d_raw_send, double *d_raw_recv, cudaStream_t s);
+int p2p_compress(Halo &h, double *d_v, int ncomp, size_t stride, cudaStream_t s);
 int p2p_allreduce(Halo &h, double *d_vals, int count, cudaStream_t s);
 int p2p_status(Halo &h);
 int p2p_max_components();  // synchronising health check: B200FE_ERR_COMM after a bounded wait has expired

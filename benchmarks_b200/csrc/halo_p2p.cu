@@ -18,10 +18,14 @@
 // Replaces MPI_Isend/Irecv/Waitall of p-halox/phalox.cc:104-126 and deal.II's Partitioner exchange.
 //
 // Protocol: every (sender entry, receiver entry) pair owns one flag and one acknowledgement word, both monotonically
-// increasing epochs kept on the device (robust under replay).  A sender waits for the acknowledgement of its previous
-// message before overwriting the window; a SEND kernel therefore never depends on anything in flight, so the two-kernel
-// form cannot deadlock whatever the residency of its blocks.  All waits are bounded (kTimeoutNs): on expiry a sticky error
-// flag is raised, later waits return at once, and the host reports B200FE_ERR_COMM at its next check instead of hanging.
+// increasing epochs kept on the device (robust under replay).  Windows are double-buffered by epoch parity: a sender only
+// needs the acknowledgement of the message before the previous one, so consecutive rounds pipeline and no round trip sits on
+// the critical path.  A SEND kernel never depends on anything in flight, so the two-kernel form cannot deadlock whatever
+// the residency of its blocks; small messages use ONE single-block kernel per round (send, flag, wait, copy out, ack: a
+// block that has sent everything before it waits cannot deadlock either) -- r02b: the two-kernel round cost 20 us against
+// NCCL's 12 us at 1 KiB.  Ordering: the data stores of a block are ordered before its flag by bar.sync + ONE system-scope
+// release (cumulativity), not by a fence in every thread.  All waits are bounded (kTimeoutNs): on expiry a sticky error flag
+// is raised, later waits return at once, and the host reports B200FE_ERR_COMM at its next check instead of hanging.
 #include <nccl.h>
 
 #include <cstdlib>
@@ -62,11 +66,13 @@ struct EntryDev {
     unsigned long long *peer_upd_flag;  // peer's upd_flag[k_peer]
     unsigned long long *peer_cmp_ack;   // peer's cmp_ack[k_peer]
     uint32_t peer_n_ghost;              // component stride of the peer's receive window
+    unsigned long long peer_recv_half;  // doubles per half of the peer's receive window (double buffering by epoch parity)
     // this entry as a receiver of update data / sender of compress data (recv_cnt > 0)
     double *peer_back;                  // peer's compress window at the matching entry's offset
     unsigned long long *peer_cmp_flag;  // peer's cmp_flag[j_peer]
     unsigned long long *peer_upd_ack;   // peer's upd_ack[j_peer]
     uint32_t peer_n_send;
+    unsigned long long peer_back_half;
     uint32_t send_off, send_cnt, recv_off, recv_cnt;
 };
 
@@ -74,6 +80,7 @@ struct DevState {  // local device memory, never touched by peers
     EntryDev e[kMaxEntries];
     RedSlot *peer_red[kMaxRanks];  // &window(r).ctrl.red[0][my_rank]; parity 1 is kMaxRanks slots further
     int n_entries, n_ranks, rank;
+    unsigned long long recv_half, back_half;  // doubles per window half of THIS rank (receive / compress regions)
     unsigned long long upd_send_epoch, upd_wait_epoch, cmp_send_epoch, cmp_wait_epoch, red_epoch;
     unsigned int ctr_send, ctr_wait;
     int error;
@@ -106,6 +113,8 @@ __device__ __forceinline__ unsigned long long global_ns()
 __device__ bool spin_until(const unsigned long long *flag, unsigned long long target, int *error)
 {
     if (ld_acquire_sys(flag) >= target) return true;
+    for (int i = 0; i < 2000; ++i)  // tight polling first: the common wait is a few hundred ns of NVLink latency
+        if (ld_acquire_sys(flag) >= target) return true;
     const unsigned long long t0 = global_ns();
     while (ld_acquire_sys(flag) < target) {
         if (*(volatile int *)error != 0) return false;
@@ -113,7 +122,7 @@ __device__ bool spin_until(const unsigned long long *flag, unsigned long long ta
             atomicExch(error, 1);
             return false;
         }
-        __nanosleep(40);
+        __nanosleep(100);
     }
     return true;
 }
@@ -142,9 +151,9 @@ __global__ void p2p_send_kernel(DevState *st, Ctrl *my, int mode, double *v, uin
         const EntryDev &e = st->e[threadIdx.x];
         s_off[threadIdx.x] = mode == MODE_UPDATE ? e.send_off : e.recv_off;
         s_cnt[threadIdx.x] = mode == MODE_UPDATE ? e.send_cnt : e.recv_cnt;
-        // the peer must have consumed my previous message before its window is overwritten
-        if (s_cnt[threadIdx.x] && epoch > 1)
-            spin_until(mode == MODE_UPDATE ? &my->upd_ack[threadIdx.x] : &my->cmp_ack[threadIdx.x], epoch - 1, &st->error);
+        // the peer must have consumed the message that used this half of its window (two epochs ago)
+        if (s_cnt[threadIdx.x] && epoch > 2)
+            spin_until(mode == MODE_UPDATE ? &my->upd_ack[threadIdx.x] : &my->cmp_ack[threadIdx.x], epoch - 2, &st->error);
     }
     __syncthreads();
     const size_t total = (size_t)n_items * ncomp;
@@ -155,19 +164,20 @@ __global__ void p2p_send_kernel(DevState *st, Ctrl *my, int mode, double *v, uin
         const EntryDev &e = st->e[k];
         if (mode == MODE_UPDATE) {
             const double x = raw_send ? raw_send[j] : v[c * stride + send_idx[j]];
-            e.peer_recv[(size_t)c * e.peer_n_ghost + (j - s_off[k])] = x;
+            e.peer_recv[(epoch & 1ull) * e.peer_recv_half + (size_t)c * e.peer_n_ghost + (j - s_off[k])] = x;
         } else {
             double *g = v + c * stride + n_owned + j;
-            e.peer_back[(size_t)c * e.peer_n_send + (j - s_off[k])] = *g;
+            e.peer_back[(epoch & 1ull) * e.peer_back_half + (size_t)c * e.peer_n_send + (j - s_off[k])] = *g;
             *g = 0.0;  // compress(add) leaves zeroed ghosts
         }
     }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(&st->ctr_send, 1u) == gridDim.x - 1;
+    __syncthreads();  // the block's stores happen-before thread 0's fence (bar.sync), which is cumulative
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        s_last = atomicAdd(&st->ctr_send, 1u) == gridDim.x - 1;
+    }
     __syncthreads();
     if (!s_last) return;
-    __threadfence_system();
     if ((int)threadIdx.x < n && s_cnt[threadIdx.x]) {
         const EntryDev &e = st->e[threadIdx.x];
         st_release_sys(mode == MODE_UPDATE ? e.peer_upd_flag : e.peer_cmp_flag, epoch);
@@ -186,6 +196,7 @@ __global__ void p2p_wait_kernel(DevState *st, Ctrl *my, int mode, double *v, uin
                                 const uint32_t *__restrict__ send_idx, int ncomp, size_t stride, const double *win, double *raw_recv)
 {
     __shared__ bool s_last;
+    const unsigned long long half = mode == MODE_UPDATE ? st->recv_half : st->back_half;
     const int n = st->n_entries;
     const unsigned long long epoch = (mode == MODE_UPDATE ? st->upd_wait_epoch : st->cmp_wait_epoch) + 1;
     if ((int)threadIdx.x < n) {
@@ -197,7 +208,7 @@ __global__ void p2p_wait_kernel(DevState *st, Ctrl *my, int mode, double *v, uin
     const size_t total = (size_t)n_items * ncomp;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const uint32_t c = (uint32_t)(i / n_items), j = (uint32_t)(i - (size_t)c * n_items);
-        const double x = __ldcg(win + i);  // written by a peer: never through L1
+        const double x = __ldcg(win + (epoch & 1ull) * half + i);  // written by a peer: never through L1
         if (mode == MODE_UPDATE) {
             if (raw_recv) raw_recv[j] = x;
             else v[c * stride + n_owned + j] = x;
@@ -205,12 +216,13 @@ __global__ void p2p_wait_kernel(DevState *st, Ctrl *my, int mode, double *v, uin
             atomicAdd(v + c * stride + send_idx[j], x);  // the same owned DoF may be ghosted by several peers
         }
     }
-    __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(&st->ctr_wait, 1u) == gridDim.x - 1;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(&st->ctr_wait, 1u) == gridDim.x - 1;
+    }
     __syncthreads();
     if (!s_last) return;
-    __threadfence_system();
     if ((int)threadIdx.x < n) {
         const EntryDev &e = st->e[threadIdx.x];
         if (mode == MODE_UPDATE ? e.recv_cnt : e.send_cnt) st_release_sys(mode == MODE_UPDATE ? e.peer_upd_ack : e.peer_cmp_ack, epoch);
@@ -219,6 +231,71 @@ __global__ void p2p_wait_kernel(DevState *st, Ctrl *my, int mode, double *v, uin
         st->ctr_wait = 0;
         if (mode == MODE_UPDATE) st->upd_wait_epoch = epoch;
         else st->cmp_wait_epoch = epoch;
+    }
+}
+
+// One round in ONE single-block kernel (small messages): send, flag, wait, copy out, acknowledge.  The block has sent
+// everything before it waits, and waits only for peers' sends, so it cannot deadlock; no second launch, no grid-wide counter.
+__global__ void __launch_bounds__(1024) p2p_round_kernel(DevState *st, Ctrl *my, int mode, double *v, uint32_t n_owned, uint32_t n_out, uint32_t n_in,
+                                                          const uint32_t *__restrict__ send_idx, int ncomp, size_t stride,
+                                                          const double *__restrict__ raw_send, const double *win, double *raw_recv)
+{
+    __shared__ uint32_t s_off[kMaxEntries], s_cnt[kMaxEntries];
+    const int n = st->n_entries, tid = threadIdx.x;
+    const unsigned long long epoch = (mode == MODE_UPDATE ? st->upd_send_epoch : st->cmp_send_epoch) + 1;
+    const unsigned long long par = epoch & 1ull;
+    bool out_k = false, in_k = false;
+    if (tid < n) {
+        const EntryDev &e = st->e[tid];
+        s_off[tid] = mode == MODE_UPDATE ? e.send_off : e.recv_off;
+        s_cnt[tid] = mode == MODE_UPDATE ? e.send_cnt : e.recv_cnt;
+        out_k = s_cnt[tid] != 0;
+        in_k = (mode == MODE_UPDATE ? e.recv_cnt : e.send_cnt) != 0;
+        if (out_k && epoch > 2) spin_until(mode == MODE_UPDATE ? &my->upd_ack[tid] : &my->cmp_ack[tid], epoch - 2, &st->error);
+    }
+    __syncthreads();
+    const uint32_t total_out = n_out * (uint32_t)ncomp;
+    for (uint32_t i = tid; i < total_out; i += blockDim.x) {
+        const uint32_t c = i / n_out, j = i - c * n_out;
+        const int k = find_entry(s_off, s_cnt, n, j);
+        if (k < 0) continue;
+        const EntryDev &e = st->e[k];
+        if (mode == MODE_UPDATE) {
+            const double x = raw_send ? raw_send[j] : v[c * stride + send_idx[j]];
+            e.peer_recv[par * e.peer_recv_half + (size_t)c * e.peer_n_ghost + (j - s_off[k])] = x;
+        } else {
+            double *g = v + c * stride + n_owned + j;
+            e.peer_back[par * e.peer_back_half + (size_t)c * e.peer_n_send + (j - s_off[k])] = *g;
+            *g = 0.0;
+        }
+    }
+    __syncthreads();
+    if (tid < n) {
+        const EntryDev &e = st->e[tid];
+        if (out_k) st_release_sys(mode == MODE_UPDATE ? e.peer_upd_flag : e.peer_cmp_flag, epoch);  // release: cumulative over the block's stores
+        if (in_k) spin_until(mode == MODE_UPDATE ? &my->upd_flag[tid] : &my->cmp_flag[tid], epoch, &st->error);
+    }
+    __syncthreads();
+    const unsigned long long half = mode == MODE_UPDATE ? st->recv_half : st->back_half;
+    const uint32_t total_in = n_in * (uint32_t)ncomp;
+    for (uint32_t i = tid; i < total_in; i += blockDim.x) {
+        const uint32_t c = i / n_in, j = i - c * n_in;
+        const double x = __ldcg(win + par * half + i);
+        if (mode == MODE_UPDATE) {
+            if (raw_recv) raw_recv[j] = x;
+            else v[c * stride + n_owned + j] = x;
+        } else {
+            atomicAdd(v + c * stride + send_idx[j], x);
+        }
+    }
+    __syncthreads();
+    if (tid < n && in_k) {
+        const EntryDev &e = st->e[tid];
+        st_release_sys(mode == MODE_UPDATE ? e.peer_upd_ack : e.peer_cmp_ack, epoch);
+    }
+    if (tid == 0) {  // both halves of the split protocol advance together
+        if (mode == MODE_UPDATE) { st->upd_send_epoch = epoch; st->upd_wait_epoch = epoch; }
+        else { st->cmp_send_epoch = epoch; st->cmp_wait_epoch = epoch; }
     }
 }
 
@@ -264,10 +341,12 @@ struct P2P {
 
 static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 static size_t recv_offset_bytes() { return align256(sizeof(Ctrl)); }
-static size_t back_offset_bytes(uint32_t n_ghost, int comps) { return recv_offset_bytes() + align256(sizeof(double) * (size_t)n_ghost * comps); }
+// every region holds two halves (epoch parity); a half is a multiple of 32 doubles
+static size_t half_doubles(uint32_t n, int comps) { return ((size_t)n * comps + 31) & ~size_t(31); }
+static size_t back_offset_bytes(uint32_t n_ghost, int comps) { return recv_offset_bytes() + 2 * sizeof(double) * half_doubles(n_ghost, comps); }
 static size_t window_bytes(uint32_t n_ghost, uint32_t n_send, int comps)
 {
-    return back_offset_bytes(n_ghost, comps) + align256(sizeof(double) * (size_t)n_send * comps);
+    return back_offset_bytes(n_ghost, comps) + 2 * sizeof(double) * half_doubles(n_send, comps);
 }
 
 int p2p_max_components() { return kMaxComps; }
@@ -328,6 +407,7 @@ int p2p_setup(Halo &h, bool raw_mode, NcclAllGatherFn all_gather, NcclAllReduceM
     if (ok) {
         auto base_of = [&](int r) { return r == me ? (char *)p->window : (char *)p->peer_base[r]; };
         hs.n_entries = (int)h.peers.size(); hs.n_ranks = R; hs.rank = me;
+        hs.recv_half = half_doubles(mine.n_ghost, p->comps); hs.back_half = half_doubles(mine.n_send, p->comps);
         for (int r = 0; r < R; ++r) hs.peer_red[r] = &reinterpret_cast<Ctrl *>(base_of(r))->red[0][me];
         // k-th message from me to B pairs with B's k-th receive from me, in table order (MPI / NCCL matching order)
         for (int k = 0; k < hs.n_entries && ok; ++k) {
@@ -347,6 +427,7 @@ int p2p_setup(Halo &h, bool raw_mode, NcclAllGatherFn all_gather, NcclAllReduceM
                 e.peer_upd_flag = &cb->upd_flag[kb];
                 e.peer_cmp_ack = &cb->cmp_ack[kb];
                 e.peer_n_ghost = mb.n_ghost;
+                e.peer_recv_half = half_doubles(mb.n_ghost, (int)mb.comps);
             }
             if (e.recv_cnt) {
                 int occ = 0;
@@ -359,6 +440,7 @@ int p2p_setup(Halo &h, bool raw_mode, NcclAllGatherFn all_gather, NcclAllReduceM
                 e.peer_cmp_flag = &cb->cmp_flag[jb];
                 e.peer_upd_ack = &cb->upd_ack[jb];
                 e.peer_n_send = mb.n_send;
+                e.peer_back_half = half_doubles(mb.n_send, (int)mb.comps);
             }
         }
     }
@@ -415,6 +497,41 @@ int p2p_compress_wait(Halo &h, double *v, int ncomp, size_t stride, cudaStream_t
                                                                          ncomp, stride, p.back, nullptr);
     B200FE_CUDA_TRY(cudaGetLastError());
     return B200FE_OK;
+}
+
+// whole rounds (post + complete back to back): one single-block kernel when the messages are small, else SEND + WAIT
+static size_t fused_max()
+{
+    static const size_t n = [] { const char *e = std::getenv("B200FE_P2P_FUSED_MAX"); return e ? (size_t)std::atoll(e) : (size_t)32768; }();
+    return n;
+}
+
+int p2p_update(Halo &h, double *v, int ncomp, size_t stride, const double *raw_send, double *raw_recv, cudaStream_t s)
+{
+    P2P &p = *h.p2p;
+    if (ncomp > p.comps) return fail(B200FE_ERR_UNSUPPORTED, "P2P halo: %d components exceed the window (%d)", ncomp, p.comps);
+    if ((size_t)h.n_send * ncomp <= fused_max() && (size_t)h.n_ghost * ncomp <= fused_max()) {
+        p2p_round_kernel<<<1, 1024, 0, s>>>(p.d_state, (Ctrl *)p.window, MODE_UPDATE, v, h.n_owned, h.n_send, h.n_ghost, h.d_send_idx, ncomp, stride,
+                                            raw_send, p.recv, raw_recv);
+        B200FE_CUDA_TRY(cudaGetLastError());
+        return B200FE_OK;
+    }
+    if (int rc = p2p_update_send(h, v, ncomp, stride, raw_send, s)) return rc;
+    return p2p_update_wait(h, v, ncomp, stride, raw_recv, s);
+}
+
+int p2p_compress(Halo &h, double *v, int ncomp, size_t stride, cudaStream_t s)
+{
+    P2P &p = *h.p2p;
+    if (ncomp > p.comps) return fail(B200FE_ERR_UNSUPPORTED, "P2P halo: %d components exceed the window (%d)", ncomp, p.comps);
+    if ((size_t)h.n_send * ncomp <= fused_max() && (size_t)h.n_ghost * ncomp <= fused_max()) {
+        p2p_round_kernel<<<1, 1024, 0, s>>>(p.d_state, (Ctrl *)p.window, MODE_COMPRESS, v, h.n_owned, h.n_ghost, h.n_send, h.d_send_idx, ncomp, stride,
+                                            nullptr, p.back, nullptr);
+        B200FE_CUDA_TRY(cudaGetLastError());
+        return B200FE_OK;
+    }
+    if (int rc = p2p_compress_send(h, v, ncomp, stride, s)) return rc;
+    return p2p_compress_wait(h, v, ncomp, stride, s);
 }
 
 int p2p_allreduce(Halo &h, double *d_vals, int count, cudaStream_t s)

@@ -114,6 +114,7 @@ std::vector<double> trace_weights(int p, const std::vector<double> &t)
 
 int HangMesh::build()
 {
+    meshdetail::use_setup_threads();
     const int nm = p + 1, nm3 = nm * nm * nm;
     for (int d = 0; d < 3; ++d) {
         cells[d] = (int64_t)sub[d] << nref;

@@ -3,8 +3,19 @@
 #include <cstdint>
 #include <vector>
 
+struct b200fe_boxmesh;
+
 namespace b200fe {
+
+// mesh.cc: owned local indices every other rank ghosts (ascending), from this rank's own view (minimal ghost sets)
+int boxmesh_send_lists(const b200fe_boxmesh *mesh, std::vector<std::vector<uint32_t>> &send);
+
 namespace meshdetail {
+
+// OpenMP team of the host-side mesh builders.  Launchers export OMP_NUM_THREADS=1 to every rank (torchrun does), which
+// would serialise a setup that is embarrassingly parallel: take cores_available / ranks_on_this_node instead
+// (B200FE_SETUP_THREADS overrides).  mesh.cc.
+void use_setup_threads();
 
 // hierarchical entity order of a hex: 8 vertices, 12 lines, 6 quads, 1 interior.
 // code per axis: 0 = low plane, 1 = interior, 2 = high plane  (x, y, z)
