@@ -18,8 +18,19 @@ namespace b200fe {
 // v2 kernel: registers per thread that the occupancy target (MINB) must leave.  Data-driven
 // (profiles/r01_v2_variants.txt): with the software-pipelined inputs the large planes need 160-240
 // registers to stay spill-free; below nq = 7 a 96-register floor (more CTAs per SM) wins.
-constexpr int v2_rmin(int nq, bool coll, int qop)
+constexpr int v2_rmin(int nq, bool coll, int qop, bool eo = false)
 {
+    // even-odd kernels of the interpolated operators at nq = 9, 10: their own floors (tuning knobs; r02c ncu: the nq = 10
+    // kernel still spills 104 B/thread at the 168-register cap of three resident CTAs)
+#ifdef B200FE_V2_RMIN_EO9
+    if (eo && !coll && nq == 9 && (qop & QOP_LAPLACE)) return B200FE_V2_RMIN_EO9;
+#endif
+#ifdef B200FE_V2_RMIN_EO10
+    if (eo && !coll && nq == 10 && (qop & QOP_LAPLACE)) return B200FE_V2_RMIN_EO10;
+#endif
+#ifdef B200FE_V2_RMIN_MASS9
+    if (!(qop & QOP_LAPLACE) && nq == 9) return B200FE_V2_RMIN_MASS9;
+#endif
 #ifdef B200FE_V2_RMIN_FIXED
     return B200FE_V2_RMIN_FIXED;
 #else
@@ -35,7 +46,7 @@ constexpr int v2_rmin(int nq, bool coll, int qop)
 #endif
 }
 
-template <int NM, int NQ, bool COLL, int QOP>
+template <int NM, int NQ, bool COLL, int QOP, bool EO = false>
 struct V2Cfg {
     using L = v2::Layout2<NM, NQ, COLL, QOP>;
 #ifndef B200FE_V2_WL_WARPS
@@ -47,7 +58,7 @@ struct V2Cfg {
     static constexpr int T32 = (T + 31) / 32 * 32;
     static constexpr size_t SMEM = L::smem_bytes(EPB);
     static constexpr int BY_SMEM = (int)((227 * 1024) / (SMEM + 1024));
-    static constexpr int BY_REGS = 65536 / (v2_rmin(NQ, COLL, QOP) * T32);
+    static constexpr int BY_REGS = 65536 / (v2_rmin(NQ, COLL, QOP, EO) * T32);
     static constexpr int BY_THREADS = 2048 / T32;
     static constexpr int M0 = BY_SMEM < BY_REGS ? BY_SMEM : BY_REGS;
     static constexpr int M1 = M0 < BY_THREADS ? M0 : BY_THREADS;
@@ -72,7 +83,7 @@ inline bool eo_enabled()
 template <int NM, int NQ, bool COLL, int QOP, bool LVEC, bool EO>
 cudaError_t launch_variant(const Mats<NM, NQ, EO> &m, const KArgs &a, cudaStream_t s, LaunchInfo *info, bool dry_run)
 {
-    using C = V2Cfg<NM, NQ, COLL, QOP>;
+    using C = V2Cfg<NM, NQ, COLL, QOP, EO>;
     constexpr int EPB = C::EPB;
     constexpr int T = C::T;
     auto kern = sumfact2_kernel<NM, NQ, COLL, QOP, LVEC, EPB, C::MINB, EO>;
