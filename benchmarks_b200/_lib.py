@@ -73,6 +73,8 @@ _SIGNATURES = {
     "b200fe_cg_solve": (_i, [_vp, _vp, _vp, _vp, C.c_double, C.c_double, _i, _i, _vp, _vp]),
     "b200fe_cg_solve_components": (_i, [_vp, _i, _vp, _vp, _vp, C.c_double, C.c_double, _i, _i, _vp, _vp]),
     "b200fe_cg_solve_host": (_i, [_vp, _vp, _vp, _vp, C.c_double, C.c_double, _i, _i, _vp, _vp]),
+    "b200fe_cg_solve_chebyshev": (_i, [_vp, _vp, _vp, _vp, _i, C.c_double, C.c_double, C.c_double, C.c_double, _i, _i, _vp, _vp]),
+    "b200fe_op_estimate_max_eigenvalue": (_i, [_vp, _vp, _i, _pd, _vp]),
     "b200fe_exchange_create_box": (_i, [_vp, C.POINTER(_vp)]),
     "b200fe_exchange_create_hang": (_i, [_vp, C.POINTER(_vp)]),
     "b200fe_exchange_destroy": (None, [_vp]),

@@ -136,16 +136,63 @@ __global__ void cg_update_xr_kernel(uint32_t n, size_t stride, const double *__r
     }
 }
 
+// ---- Chebyshev polynomial preconditioner on the Jacobi-scaled operator (deal.II PreconditionChebyshev) -------------------
+// first term: d = c0 D^-1 r, z = d
+__global__ void cheb_first_kernel(uint32_t n, double c0, const double *__restrict__ r, const double *__restrict__ inv_diag, double *__restrict__ d,
+                                  double *__restrict__ z, const CgScalars *sc)
+{
+    if (sc != nullptr && sc->done) return;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double di = c0 * inv_diag[i] * r[i];
+        d[i] = di;
+        z[i] = di;
+    }
+}
+// next term, t = A z given: d = a d + b D^-1 (r - t), z += d
+__global__ void cheb_step_kernel(uint32_t n, double a, double b, const double *__restrict__ r, const double *__restrict__ t,
+                                 const double *__restrict__ inv_diag, double *__restrict__ d, double *__restrict__ z, const CgScalars *sc)
+{
+    if (sc != nullptr && sc->done) return;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double di = fma(a, d[i], b * inv_diag[i] * (r[i] - t[i]));
+        d[i] = di;
+        z[i] += di;
+    }
+}
+// *out += x . y over the owned range
+__global__ void dot_kernel(uint32_t n, const double *__restrict__ x, const double *__restrict__ y, double *out, const CgScalars *sc)
+{
+    if (sc != nullptr && sc->done) return;
+    double s = 0.0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s = fma(x[i], y[i], s);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __shared__ double sh[32];
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) atomicAdd(out, s);
+    }
+}
+// y = D^-1 x / scale  (power iteration), norms through dot_kernel
+__global__ void scale_diag_kernel(uint32_t n, const double *__restrict__ x, const double *__restrict__ inv_diag, const double *norm2, double *__restrict__ y)
+{
+    const double f = 1.0 / sqrt(*norm2);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) y[i] = f * (inv_diag ? inv_diag[i] * x[i] : x[i]);
+}
+
 }  // namespace
 
 struct CgWork {
     size_t n_local = 0;  // total length: components * (n_owned + n_ghost)
     double *r = nullptr, *p = nullptr, *v = nullptr, *xb = nullptr;  // xb: x and b for the host-buffer entry point
+    double *cheb = nullptr;  // z | d | t of the Chebyshev preconditioner (3 vectors, allocated on first use)
     CgScalars *sc = nullptr;
     CgScalars *h_sc = nullptr;  // pinned
     ~CgWork()
     {
-        cudaFree(r); cudaFree(p); cudaFree(v); cudaFree(xb); cudaFree(sc);
+        cudaFree(r); cudaFree(p); cudaFree(v); cudaFree(xb); cudaFree(sc); cudaFree(cheb);
         if (h_sc) cudaFreeHost(h_sc);
     }
 };
@@ -190,22 +237,61 @@ void cg_release_work(Operator *op)
     w.reset();
 }
 
+struct ChebSpec {  // degree >= 1 terms of the polynomial in D^-1 A on [lambda_max / smoothing_range, lambda_max]
+    int degree = 0;
+    double lambda_max = 0.0, smoothing_range = 0.0;
+};
+
+// z = p_k(D^-1 A) D^-1 r  (three-term recurrence, Saad Alg. 12.1; k - 1 operator applications)
+static int cheb_apply(Operator &op, CgWork &w, const ChebSpec &c, const double *d_inv_diag, const double *d_r, dim3 blocks, cudaStream_t s)
+{
+    const uint32_t n = op.n_owned;
+    const size_t nl = op.n_local();
+    double *z = w.cheb, *d = w.cheb + nl, *t = w.cheb + 2 * nl;
+    const double lmax = c.lambda_max, lmin = c.lambda_max / c.smoothing_range;
+    const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma1 = theta / delta;
+    double rho = 1.0 / sigma1;
+    cheb_first_kernel<<<blocks, 256, 0, s>>>(n, 1.0 / theta, d_r, d_inv_diag, d, z, w.sc);
+    B200FE_CUDA_TRY(cudaGetLastError());
+    ++g_launch_count;
+    for (int k = 1; k < c.degree; ++k) {
+        if (int rc = op_vmult(op, t, z, nullptr, true, true, s, 1)) return rc;
+        const double rho_new = 1.0 / (2.0 * sigma1 - rho);
+        cheb_step_kernel<<<blocks, 256, 0, s>>>(n, rho_new * rho, 2.0 * rho_new / delta, d_r, t, d_inv_diag, d, z, w.sc);
+        B200FE_CUDA_TRY(cudaGetLastError());
+        ++g_launch_count;
+        rho = rho_new;
+    }
+    return B200FE_OK;
+}
+
 static int cg_run(Operator &op, int ncomp, CgWork &w, double *d_x, const double *d_b, const double *d_inv_diag, double abs_tol,
-                  double rel_tol, int max_it, int check_every, b200fe_cg_result *res, cudaStream_t s)
+                  double rel_tol, int max_it, int check_every, b200fe_cg_result *res, cudaStream_t s, const ChebSpec *cheb = nullptr)
 {
     NvtxRange range("cg_solver");
     const uint32_t n = op.n_owned;
     const size_t stride = op.n_local();
     const unsigned bx = n == 0 ? 1u : std::min<unsigned>((n + 1023) / 1024, std::max(148u * 8u / (unsigned)ncomp, 148u));
     const dim3 blocks(bx, (unsigned)ncomp);
-    const int jacobi = d_inv_diag != nullptr;
+    const int jacobi = d_inv_diag != nullptr;  // (Chebyshev: rho = r.z as well, z = w.cheb)
+    // the vector kernels fuse z = D^-1 r for Jacobi; with the polynomial preconditioner z is a vector of its own
+    const double *fused_diag = cheb ? nullptr : d_inv_diag;
     if (check_every < 1) check_every = 1;
     B200FE_CUDA_TRY(cudaMemsetAsync(w.sc, 0, sizeof(CgScalars), s));
     // p and v carry ghost entries: start from a clean ghost segment
     B200FE_CUDA_TRY(cudaMemsetAsync(w.p, 0, sizeof(double) * stride * ncomp, s));
-    cg_init_kernel<<<blocks, 256, 0, s>>>(n, stride, d_b, d_x, w.r, d_inv_diag, w.sc);
+    cg_init_kernel<<<blocks, 256, 0, s>>>(n, stride, d_b, d_x, w.r, fused_diag, w.sc);
     B200FE_CUDA_TRY(cudaGetLastError());
     ++g_launch_count;
+    auto precondition = [&]() -> int {  // Chebyshev only: z = M^-1 r, acc[2] = r.z
+        if (int rc = cheb_apply(op, w, *cheb, d_inv_diag, w.r, blocks, s)) return rc;
+        dot_kernel<<<blocks, 256, 0, s>>>(n, w.r, w.cheb, &w.sc->acc[2], w.sc);
+        B200FE_CUDA_TRY(cudaGetLastError());
+        ++g_launch_count;
+        return B200FE_OK;
+    };
+    if (cheb)
+        if (int rc = precondition()) return rc;
     if (op.halo)
         if (int rc = halo_allreduce_sum(*op.halo, w.sc->acc + 1, 2, s)) return rc;
     // Sequence: S [U V X S] [U V X S] ...  (S = ReductionControl check + rho bookkeeping, U = p update,
@@ -225,16 +311,18 @@ static int cg_run(Operator &op, int ncomp, CgWork &w, double *d_x, const double 
         return B200FE_OK;
     };
     auto iteration = [&]() -> int {
-        cg_update_p_kernel<<<blocks, 256, 0, s>>>(n, stride, w.r, d_inv_diag, w.p, w.sc);
+        cg_update_p_kernel<<<blocks, 256, 0, s>>>(n, stride, cheb ? w.cheb : w.r, fused_diag, w.p, w.sc);
         B200FE_CUDA_TRY(cudaGetLastError());
         ++g_launch_count;
         // block-diagonal operator: the fused p.Ap of every component lands in acc[0]
         if (int rc = op_vmult(op, w.v, w.p, &w.sc->acc[0], true, true, s, ncomp)) return rc;
         if (op.halo)
             if (int rc = halo_allreduce_sum(*op.halo, w.sc->acc, 1, s)) return rc;
-        cg_update_xr_kernel<<<blocks, 256, 0, s>>>(n, stride, w.p, w.v, d_inv_diag, d_x, w.r, w.sc);
+        cg_update_xr_kernel<<<blocks, 256, 0, s>>>(n, stride, w.p, w.v, fused_diag, d_x, w.r, w.sc);
         B200FE_CUDA_TRY(cudaGetLastError());
         ++g_launch_count;
+        if (cheb)
+            if (int rc = precondition()) return rc;
         if (op.halo)
             if (int rc = halo_allreduce_sum(*op.halo, w.sc->acc + 1, 2, s)) return rc;
         return scalar_step();
@@ -316,6 +404,80 @@ int b200fe_cg_solve_components(b200fe_op *o, int n_components, double *d_x, cons
     int rc = cg_run(op, n_components, *w, d_x, d_b, d_inv_diag, abs_tol, rel_tol, max_it, check_every, result, (cudaStream_t)stream);
     if (rc == B200FE_ERR_NO_CONVERGENCE) fail(rc, "CG did not converge in %d iterations", max_it);
     return rc;
+}
+
+static int ensure_cheb(CgWork &w, size_t n_local, cudaStream_t s)
+{
+    if (!w.cheb) B200FE_CUDA_TRY(cudaMalloc(&w.cheb, 3 * sizeof(double) * std::max<size_t>(n_local, 1)));
+    B200FE_CUDA_TRY(cudaMemsetAsync(w.cheb, 0, 3 * sizeof(double) * std::max<size_t>(n_local, 1), s));  // clean ghost segments
+    return B200FE_OK;
+}
+
+int b200fe_cg_solve_chebyshev(b200fe_op *o, double *d_x, const double *d_b, const double *d_inv_diag, int degree, double lambda_max,
+                              double smoothing_range, double abs_tol, double rel_tol, int max_it, int check_every,
+                              b200fe_cg_result *result, void *stream)
+{
+    B200FE_REQUIRE(o && d_x && d_b && d_inv_diag, "b200fe_cg_solve_chebyshev: null pointer (the inverse diagonal is required)");
+    B200FE_REQUIRE(degree >= 1 && degree <= 64, "b200fe_cg_solve_chebyshev: degree outside 1..64");
+    B200FE_REQUIRE(lambda_max > 0.0 && smoothing_range > 1.0, "b200fe_cg_solve_chebyshev: need lambda_max > 0 and smoothing_range > 1");
+    B200FE_REQUIRE(max_it >= 0, "b200fe_cg_solve_chebyshev: max_it < 0");
+    Operator &op = *reinterpret_cast<Operator *>(o);
+    auto &w = work_of(&op);
+    if (int rc = ensure_work(w, op.n_local(), false)) return rc;
+    if (int rc = ensure_cheb(*w, op.n_local(), (cudaStream_t)stream)) return rc;
+    const ChebSpec spec{degree, lambda_max, smoothing_range};
+    int rc = cg_run(op, 1, *w, d_x, d_b, d_inv_diag, abs_tol, rel_tol, max_it, check_every, result, (cudaStream_t)stream, &spec);
+    if (rc == B200FE_ERR_NO_CONVERGENCE) fail(rc, "CG did not converge in %d iterations", max_it);
+    return rc;
+}
+
+int b200fe_op_estimate_max_eigenvalue(b200fe_op *o, const double *d_inv_diag, int n_iterations, double *lambda_max, void *stream)
+{
+    B200FE_REQUIRE(o && lambda_max, "b200fe_op_estimate_max_eigenvalue: null pointer");
+    B200FE_REQUIRE(n_iterations >= 1 && n_iterations <= 1000, "b200fe_op_estimate_max_eigenvalue: n_iterations outside 1..1000");
+    Operator &op = *reinterpret_cast<Operator *>(o);
+    cudaStream_t s = (cudaStream_t)stream;
+    auto &w = work_of(&op);
+    if (int rc = ensure_work(w, op.n_local(), false)) return rc;
+    if (int rc = ensure_cheb(*w, op.n_local(), s)) return rc;
+    const uint32_t n = op.n_owned;
+    const size_t nl = op.n_local();
+    double *y = w->cheb, *t = w->cheb + nl, *u = w->cheb + 2 * nl;  // iterate (unit norm), A y, D^-1 A y
+    const unsigned bx = n == 0 ? 1u : std::min<unsigned>((n + 1023) / 1024, 148u * 8u);
+    double *acc = &w->sc->acc[0];
+    // start vector: deterministic, all frequencies (deal.II starts its eigenvalue CG from a non-constant vector as well)
+    std::vector<double> h(n);
+    uint64_t g = op.halo ? 1 + (uint64_t)op.halo->rank * 0x9E3779B97F4A7C15ull : 1;
+    for (uint32_t i = 0; i < n; ++i) {
+        g = g * 6364136223846793005ull + 1442695040888963407ull;
+        h[i] = (double)(g >> 11) * (1.0 / 9007199254740992.0) - 0.5;
+    }
+    B200FE_CUDA_TRY(cudaMemcpyAsync(u, h.data(), sizeof(double) * n, cudaMemcpyHostToDevice, s));
+    double lam = 0.0;
+    for (int it = 0; it <= n_iterations; ++it) {
+        // y = u / |u| ; t = A y ; u = D^-1 t ; lambda = y . u  (Rayleigh quotient of D^-1 A in the D-inner product up to scaling)
+        B200FE_CUDA_TRY(cudaMemsetAsync(acc, 0, 3 * sizeof(double), s));
+        dot_kernel<<<bx, 256, 0, s>>>(n, u, u, acc, nullptr);
+        if (op.halo)
+            if (int rc = halo_allreduce_sum(*op.halo, acc, 1, s)) return rc;
+        scale_diag_kernel<<<bx, 256, 0, s>>>(n, u, nullptr, acc, y);
+        B200FE_CUDA_TRY(cudaGetLastError());
+        if (it == n_iterations) break;
+        if (int rc = op_vmult(op, t, y, nullptr, true, true, s, 1)) return rc;
+        B200FE_CUDA_TRY(cudaMemsetAsync(acc + 1, 0, sizeof(double), s));
+        // u = D^-1 t (norm factor 1: acc[2] holds 1.0)
+        const double one = 1.0;
+        B200FE_CUDA_TRY(cudaMemcpyAsync(acc + 2, &one, sizeof(double), cudaMemcpyHostToDevice, s));
+        scale_diag_kernel<<<bx, 256, 0, s>>>(n, t, d_inv_diag, acc + 2, u);
+        dot_kernel<<<bx, 256, 0, s>>>(n, y, u, acc + 1, nullptr);
+        B200FE_CUDA_TRY(cudaGetLastError());
+        if (op.halo)
+            if (int rc = halo_allreduce_sum(*op.halo, acc + 1, 1, s)) return rc;
+        B200FE_CUDA_TRY(cudaMemcpyAsync(&lam, acc + 1, sizeof(double), cudaMemcpyDeviceToHost, s));
+        B200FE_CUDA_TRY(cudaStreamSynchronize(s));
+    }
+    *lambda_max = 1.2 * lam;  // deal.II's safety factor on the estimate (PreconditionChebyshev::estimate_eigenvalues)
+    return B200FE_OK;
 }
 
 int b200fe_cg_solve(b200fe_op *o, double *d_x, const double *d_b, const double *d_inv_diag, double abs_tol,

@@ -102,6 +102,12 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ unsigned long long global_ns()
 {
     unsigned long long t;
@@ -112,11 +118,11 @@ __device__ __forceinline__ unsigned long long global_ns()
 // bounded wait for *flag >= target; false after a timeout or when another wait has already failed
 __device__ bool spin_until(const unsigned long long *flag, unsigned long long target, int *error)
 {
-    if (ld_acquire_sys(flag) >= target) return true;
-    for (int i = 0; i < 2000; ++i)  // tight polling first: the common wait is a few hundred ns of NVLink latency
-        if (ld_acquire_sys(flag) >= target) return true;
+    // poll with relaxed loads (no fence per poll), acquire once the flag is there
+    for (int i = 0; i < 4000; ++i)  // tight polling first: the common wait is NVLink latency
+        if (ld_relaxed_sys(flag) >= target) return ld_acquire_sys(flag) >= target;
     const unsigned long long t0 = global_ns();
-    while (ld_acquire_sys(flag) < target) {
+    while (ld_relaxed_sys(flag) < target) {
         if (*(volatile int *)error != 0) return false;
         if (global_ns() - t0 > kTimeoutNs) {
             atomicExch(error, 1);
@@ -124,7 +130,7 @@ __device__ bool spin_until(const unsigned long long *flag, unsigned long long ta
         }
         __nanosleep(100);
     }
-    return true;
+    return ld_acquire_sys(flag) >= target;
 }
 
 enum : int { MODE_UPDATE = 0, MODE_COMPRESS = 1 };
@@ -502,7 +508,7 @@ int p2p_compress_wait(Halo &h, double *v, int ncomp, size_t stride, cudaStream_t
 // whole rounds (post + complete back to back): one single-block kernel when the messages are small, else SEND + WAIT
 static size_t fused_max()
 {
-    static const size_t n = [] { const char *e = std::getenv("B200FE_P2P_FUSED_MAX"); return e ? (size_t)std::atoll(e) : (size_t)32768; }();
+    static const size_t n = [] { const char *e = std::getenv("B200FE_P2P_FUSED_MAX"); return e ? (size_t)std::atoll(e) : (size_t)4096; }();  // r02d: one block moves 32 KB in ~13 us, 256 KB in 35 us
     return n;
 }
 

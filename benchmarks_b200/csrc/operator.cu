@@ -203,11 +203,12 @@ __global__ void copy_constrained_kernel(uint32_t n, const uint32_t *__restrict__
 // diag_local[l] = sum_q sum_ab G_ab d_a phi_l d_b phi_l (+ JxW phi_l^2), scattered with atomics
 __global__ void diagonal_kernel(uint32_t n_cells, int nm, int nq, int qop, const double *__restrict__ mats,
                                 const double *__restrict__ G, const double *__restrict__ JxW,
-                                const uint32_t *__restrict__ idx, double *__restrict__ diag)
+                                const uint32_t *__restrict__ idx, double *__restrict__ diag, const uint8_t *__restrict__ skip_cell)
 {
     const int nm3 = nm * nm * nm, nq3 = nq * nq * nq;
     const double *S = mats, *Sg = mats + nm * nq + nq * nq;
-    for (uint32_t cell = blockIdx.x; cell < n_cells; cell += gridDim.x)
+    for (uint32_t cell = blockIdx.x; cell < n_cells; cell += gridDim.x) {
+        if (skip_cell != nullptr && skip_cell[cell]) continue;  // interface cells of a constrained operator: handled as C^T A_c C
         for (int l = threadIdx.x; l < nm3; l += blockDim.x) {
             const uint32_t id = idx[(size_t)cell * nm3 + l];
             if (id == kInvalidIndex) continue;
@@ -231,6 +232,55 @@ __global__ void diagonal_kernel(uint32_t n_cells, int nm, int nq, int qop, const
                     }
             atomicAdd(diag + id, s);
         }
+    }
+}
+
+// ---- diagonal of C^T A C on the cells that hold hanging DoFs (b200fe_op_diagonal with constraints) -------------------
+// MatrixFreeTools::compute_diagonal semantics (bp5_kokkos/benchmark.cc:231): column b of the cell matrix from the cell
+// kernel applied to the local unit vector e_b, the local constraint matrix C_c applied on both sides, diagonal kept.
+// gather the geometric factors of the listed cells into a contiguous block: dst[i][n] = src[cells[i]][n]
+__global__ void gather_cells_kernel(uint32_t n_list, const uint32_t *__restrict__ cells, size_t per_cell, const double *__restrict__ src,
+                                    double *__restrict__ dst)
+{
+    const size_t total = (size_t)n_list * per_cell;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t c = i / per_cell;
+        dst[i] = src[(size_t)cells[c] * per_cell + (i - c * per_cell)];
+    }
+}
+
+// src = e_b in every listed cell (element-vector layout [cell][nm^3]; masked local DoFs stay 0), dst = 0
+__global__ void unit_vectors_kernel(uint32_t n_list, int nm3, int b, const uint32_t *__restrict__ idx_if, double *__restrict__ src,
+                                    double *__restrict__ dst)
+{
+    const size_t total = (size_t)n_list * nm3;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int l = (int)(i % nm3);
+        src[i] = (l == b && idx_if[i] != kInvalidIndex) ? 1.0 : 0.0;
+        dst[i] = 0.0;
+    }
+}
+
+// one CTA per listed cell: t = C_c^T (A_c e_b) into shared memory (compact target ids), then diag[target] += C_c(b, target) t[target]
+__global__ void diag_constrained_reduce_kernel(uint32_t n_list, int nm3, int b, const double *__restrict__ col, const uint32_t *__restrict__ ent_ptr,
+                                               const uint16_t *__restrict__ ent_cid, const double *__restrict__ ent_w,
+                                               const uint32_t *__restrict__ tgt_ptr, const uint32_t *__restrict__ tgt, double *__restrict__ diag)
+{
+    extern __shared__ double t_sh[];
+    for (uint32_t c = blockIdx.x; c < n_list; c += gridDim.x) {
+        const uint32_t rb = ent_ptr[(size_t)c * nm3 + b], re = ent_ptr[(size_t)c * nm3 + b + 1];
+        if (rb == re) continue;  // masked local DoF: no column (uniform across the CTA)
+        const uint32_t t0 = tgt_ptr[c], nt = tgt_ptr[c + 1] - t0;
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < nt; i += blockDim.x) t_sh[i] = 0.0;
+        __syncthreads();
+        for (int a = threadIdx.x; a < nm3; a += blockDim.x) {
+            const double v = col[(size_t)c * nm3 + a];
+            for (uint32_t e = ent_ptr[(size_t)c * nm3 + a]; e < ent_ptr[(size_t)c * nm3 + a + 1]; ++e) atomicAdd(&t_sh[ent_cid[e]], ent_w[e] * v);
+        }
+        __syncthreads();
+        for (uint32_t e = rb + threadIdx.x; e < re; e += blockDim.x) atomicAdd(diag + tgt[t0 + ent_cid[e]], ent_w[e] * t_sh[ent_cid[e]]);
+    }
 }
 
 // b[l] += sum_q JxW(q) phi_l(q)    (bp3.cc:208-224: f = 1, constrained rows dropped)
@@ -577,6 +627,137 @@ int op_vmult(Operator &op, double *d_dst, const double *d_src, double *d_dot, bo
     return B200FE_OK;
 }
 
+namespace {
+struct SetupScratch {  // setup-time device scratch, freed on every exit path
+    std::vector<void *> p;
+    ~SetupScratch() { for (void *q : p) cudaFree(q); }
+    template <class T> cudaError_t put(T **d, const std::vector<T> &h)
+    {
+        cudaError_t e = cudaMalloc(d, std::max<size_t>(h.size(), 1) * sizeof(T));
+        if (e != cudaSuccess) return e;
+        p.push_back(*d);
+        return h.empty() ? cudaSuccess : cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+    }
+    template <class T> cudaError_t make(T **d, size_t n)
+    {
+        cudaError_t e = cudaMalloc(d, std::max<size_t>(n, 1) * sizeof(T));
+        if (e == cudaSuccess) p.push_back(*d);
+        return e;
+    }
+};
+}  // namespace
+
+// diag(C^T A C): plain cell diagonals on the cells without hanging DoFs, local C_c^T A_c C_c on the others (setup path).
+int op_diagonal_constrained(Operator &op, double *d_diag, cudaStream_t s)
+{
+    const int nm3 = op.nm * op.nm * op.nm, nq3 = op.nq * op.nq * op.nq;
+    const uint32_t n_local = op.n_local();
+    // host view of the index table and of the rows
+    std::vector<uint32_t> idx((size_t)op.n_cells * nm3);
+    B200FE_CUDA_TRY(cudaMemcpyAsync(idx.data(), op.d_idx, idx.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    B200FE_CUDA_TRY(cudaStreamSynchronize(s));
+    std::vector<int32_t> row_of(n_local, -1);
+    for (uint32_t r = 0; r < op.n_hang; ++r) row_of[op.h_hang_dof[r]] = (int32_t)r;
+    std::vector<uint8_t> is_if(op.n_cells, 0);
+    std::vector<uint32_t> cells_if;
+    for (uint32_t c = 0; c < op.n_cells; ++c) {
+        bool any = false;
+        for (int a = 0; a < nm3 && !any; ++a) {
+            const uint32_t id = idx[(size_t)c * nm3 + a];
+            any = id != kInvalidIndex && row_of[id] >= 0;
+        }
+        if (any) { is_if[c] = 1; cells_if.push_back(c); }
+    }
+    const uint32_t n_if = (uint32_t)cells_if.size();
+    // local constraint matrices C_c: per (cell, local a) a run of (compact target id, weight); targets per cell deduplicated
+    std::vector<uint32_t> ent_ptr((size_t)n_if * nm3 + 1, 0), tgt_ptr(n_if + 1, 0), tgt, idx_if((size_t)n_if * nm3);
+    std::vector<uint16_t> ent_cid;
+    std::vector<double> ent_w;
+    std::vector<int32_t> cid_of(n_local, -1);
+    uint32_t max_targets = 1;
+    for (uint32_t i = 0; i < n_if; ++i) {
+        const uint32_t c = cells_if[i];
+        const uint32_t t0 = (uint32_t)tgt.size();
+        auto cid = [&](uint32_t j) -> uint16_t {
+            if (cid_of[j] < 0) { cid_of[j] = (int32_t)(tgt.size() - t0); tgt.push_back(j); }
+            return (uint16_t)cid_of[j];
+        };
+        for (int a = 0; a < nm3; ++a) {
+            const uint32_t id = idx[(size_t)c * nm3 + a];
+            idx_if[(size_t)i * nm3 + a] = id == kInvalidIndex ? kInvalidIndex : (uint32_t)((size_t)i * nm3 + a);
+            if (id != kInvalidIndex) {
+                if (row_of[id] < 0) { ent_cid.push_back(cid(id)); ent_w.push_back(1.0); }
+                else
+                    for (uint32_t k = op.h_hang_ptr[row_of[id]]; k < op.h_hang_ptr[row_of[id] + 1]; ++k) {
+                        ent_cid.push_back(cid(op.h_hang_col[k])); ent_w.push_back(op.h_hang_w[k]);
+                    }
+            }
+            ent_ptr[(size_t)i * nm3 + a + 1] = (uint32_t)ent_cid.size();
+        }
+        for (uint32_t k = t0; k < tgt.size(); ++k) cid_of[tgt[k]] = -1;
+        tgt_ptr[i + 1] = (uint32_t)tgt.size();
+        max_targets = std::max<uint32_t>(max_targets, (uint32_t)tgt.size() - t0);
+        if (tgt.size() - t0 > 0xFFFFu) return fail(B200FE_ERR_UNSUPPORTED, "b200fe_op_diagonal: more than 65535 constraint targets in one cell");
+    }
+    if ((size_t)n_if * nm3 >= 0xFFFFFFFFull) return fail(B200FE_ERR_UNSUPPORTED, "b200fe_op_diagonal: too many interface cells");
+    if (max_targets * sizeof(double) > 200 * 1024) return fail(B200FE_ERR_UNSUPPORTED, "b200fe_op_diagonal: constraint targets of one cell exceed shared memory");
+
+    SetupScratch dev;
+    uint8_t *d_is_if = nullptr;
+    B200FE_CUDA_TRY(dev.put(&d_is_if, is_if));
+    B200FE_CUDA_TRY(cudaMemsetAsync(d_diag, 0, sizeof(double) * n_local, s));
+    if (op.n_cells) {
+        diagonal_kernel<<<std::min<uint32_t>(op.n_cells, 148u * 8u), 128, 0, s>>>(op.n_cells, op.nm, op.nq, op.qop, op.d_mats, op.d_G, op.d_JxW, op.d_idx, d_diag, d_is_if);
+        B200FE_CUDA_TRY(cudaGetLastError());
+    }
+    if (n_if) {
+        uint32_t *d_cells = nullptr, *d_ent_ptr = nullptr, *d_tgt_ptr = nullptr, *d_tgt = nullptr, *d_idx_if = nullptr;
+        uint16_t *d_ent_cid = nullptr;
+        double *d_ent_w = nullptr, *d_G = nullptr, *d_J = nullptr, *d_src = nullptr, *d_dst = nullptr;
+        B200FE_CUDA_TRY(dev.put(&d_cells, cells_if));
+        B200FE_CUDA_TRY(dev.put(&d_ent_ptr, ent_ptr));
+        B200FE_CUDA_TRY(dev.put(&d_ent_cid, ent_cid));
+        B200FE_CUDA_TRY(dev.put(&d_ent_w, ent_w));
+        B200FE_CUDA_TRY(dev.put(&d_tgt_ptr, tgt_ptr));
+        B200FE_CUDA_TRY(dev.put(&d_tgt, tgt));
+        B200FE_CUDA_TRY(dev.put(&d_idx_if, idx_if));
+        B200FE_CUDA_TRY(dev.make(&d_src, (size_t)n_if * nm3));
+        B200FE_CUDA_TRY(dev.make(&d_dst, (size_t)n_if * nm3));
+        const unsigned gb = 148u * 8u;
+        if (op.qop & QOP_LAPLACE) {
+            B200FE_CUDA_TRY(dev.make(&d_G, (size_t)n_if * 6 * nq3));
+            gather_cells_kernel<<<gb, 256, 0, s>>>(n_if, d_cells, (size_t)6 * nq3, op.d_G, d_G);
+        }
+        if (op.qop & QOP_MASS) {
+            B200FE_CUDA_TRY(dev.make(&d_J, (size_t)n_if * nq3));
+            gather_cells_kernel<<<gb, 256, 0, s>>>(n_if, d_cells, (size_t)nq3, op.d_JxW, d_J);
+        }
+        B200FE_CUDA_TRY(cudaGetLastError());
+        const size_t red_smem = max_targets * sizeof(double);
+        if (red_smem > 48 * 1024)
+            B200FE_CUDA_TRY(cudaFuncSetAttribute(diag_constrained_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)red_smem));
+        KArgs a{n_if, d_G, d_J, d_src, d_dst, d_idx_if, nullptr, nullptr, nullptr};
+        for (int b = 0; b < nm3; ++b) {
+            unit_vectors_kernel<<<std::min<unsigned>((unsigned)(((size_t)n_if * nm3 + 255) / 256), gb), 256, 0, s>>>(n_if, nm3, b, d_idx_if, d_src, d_dst);
+            B200FE_CUDA_TRY(launch_sumfact(op.nm, op.nq, op.collocated, op.qop, true, op.B.data(), op.D.data(), a, s, nullptr, false));
+            diag_constrained_reduce_kernel<<<std::min<unsigned>(n_if, gb), 128, red_smem, s>>>(n_if, nm3, b, d_dst, d_ent_ptr, d_ent_cid, d_ent_w, d_tgt_ptr,
+                                                                                              d_tgt, d_diag);
+            B200FE_CUDA_TRY(cudaGetLastError());
+        }
+    }
+    if (op.halo)
+        if (int rc = halo_compress_add(*op.halo, d_diag, s)) return rc;
+    // constrained rows (Dirichlet and hanging) act as identity in the preconditioner: 1 on the diagonal
+    if (op.n_constrained) {
+        set_constrained_kernel<<<std::min<unsigned>((op.n_constrained + 255) / 256, 1184), 256, 0, s>>>(op.n_constrained, op.d_constrained, 1.0, d_diag);
+        B200FE_CUDA_TRY(cudaGetLastError());
+    }
+    set_constrained_kernel<<<std::min<unsigned>((op.n_hang + 255) / 256, 1184), 256, 0, s>>>(op.n_hang, op.d_hang_dof, 1.0, d_diag);
+    B200FE_CUDA_TRY(cudaGetLastError());
+    B200FE_CUDA_TRY(cudaStreamSynchronize(s));  // the scratch arrays are freed on return
+    return B200FE_OK;
+}
+
 }  // namespace b200fe
 
 using namespace b200fe;
@@ -814,6 +995,10 @@ int b200fe_op_set_constraints(b200fe_op *o, uint32_t n_rows, const uint32_t *h_h
         return fail_cuda(e, "b200fe_op_set_constraints");
     }
     op.n_hang = n_rows;
+    op.h_hang_dof.assign(h_hang_dof, h_hang_dof + n_rows);
+    op.h_hang_ptr.assign(h_hang_row_ptr, h_hang_row_ptr + n_rows + 1);
+    op.h_hang_col.assign(h_hang_col, h_hang_col + nnz);
+    op.h_hang_w.assign(h_hang_w, h_hang_w + nnz);
     return B200FE_OK;
 }
 
@@ -903,11 +1088,16 @@ int b200fe_op_diagonal(b200fe_op *o, double *d_diag, void *stream)
     B200FE_REQUIRE(o && d_diag, "b200fe_op_diagonal: null pointer");
     Operator &op = *reinterpret_cast<Operator *>(o);
     B200FE_REQUIRE(!(op.qop & QOP_LAPLACE) || op.d_G, "b200fe_op_diagonal: needs the stored geometric factors (d_G)");
-    if (op.has_constraints()) return fail(B200FE_ERR_UNSUPPORTED, "b200fe_op_diagonal: not built for operators with hanging-node constraints");
     cudaStream_t s = (cudaStream_t)stream;
+    if (op.has_constraints()) {
+        if (op.n_hang == 0)
+            return fail(B200FE_ERR_UNSUPPORTED, "b200fe_op_diagonal: an operator with face-structured constraints also needs the constraint rows "
+                                                "(b200fe_op_set_constraints) for its diagonal");
+        return op_diagonal_constrained(op, d_diag, s);
+    }
     B200FE_CUDA_TRY(cudaMemsetAsync(d_diag, 0, sizeof(double) * op.n_local(), s));
     if (op.n_cells) {
-        diagonal_kernel<<<std::min<uint32_t>(op.n_cells, 148u * 8u), 128, 0, s>>>(op.n_cells, op.nm, op.nq, op.qop, op.d_mats, op.d_G, op.d_JxW, op.d_idx, d_diag);
+        diagonal_kernel<<<std::min<uint32_t>(op.n_cells, 148u * 8u), 128, 0, s>>>(op.n_cells, op.nm, op.nq, op.qop, op.d_mats, op.d_G, op.d_JxW, op.d_idx, d_diag, nullptr);
         B200FE_CUDA_TRY(cudaGetLastError());
     }
     if (op.halo)

@@ -34,6 +34,8 @@ struct Operator {
     uint32_t *d_hang_dof = nullptr, *d_hang_ptr = nullptr, *d_hang_col = nullptr;
     double *d_hang_w = nullptr, *d_hang_save = nullptr;  // save: src values of the hanging entries during a vmult
     int hang_save_comps = 0;                              // components the save buffer has room for
+    std::vector<uint32_t> h_hang_dof, h_hang_ptr, h_hang_col;  // host copies of the rows (compute_diagonal with constraints)
+    std::vector<double> h_hang_w;
     const int *d_skip = nullptr;        // set by the CG driver for the duration of a solve (see KArgs::skip)
     // overlap split: cells [0, n_phase0) and [n_phase0+n_phase1, n_cells) touch no ghost DoF
     uint32_t n_phase0 = 0, n_phase1 = 0;
@@ -70,6 +72,7 @@ struct Operator {
         d_hang_w = d_hang_save = nullptr;
         n_hang = 0;
         hang_save_comps = 0;
+        h_hang_dof.clear(); h_hang_ptr.clear(); h_hang_col.clear(); h_hang_w.clear();
     }
 };
 
@@ -87,6 +90,9 @@ int op_condense(Operator &op, double *d_dst, double *d_src_restore, cudaStream_t
 // ncomp > 1: component-blocked vectors [component][n_local], the scalar operator on each
 int op_vmult(Operator &op, double *d_dst, const double *d_src, double *d_dot, bool ghost_on, bool compute_on,
              cudaStream_t s, int ncomp = 1);
+
+// compute_diagonal of C^T A C (needs the constraint rows on the operator)
+int op_diagonal_constrained(Operator &op, double *d_diag, cudaStream_t s);
 
 // number of kernels this library has launched so far (all kinds)
 extern unsigned long long g_launch_count;

@@ -137,12 +137,13 @@ class LaplaceOperator:
             raise ValueError(constraints)
         if n_rows:  # hanging-node rows of a HangingBoxMesh: the operator becomes C^T A C
             ptr = lambda a: a.ctypes.data if a.size else None
-            if constraints == "faces" and len(mesh.face_parents):  # face-structured form: tensor-product trace interpolation, one CTA per coarse face
+            # the CSR rows are always handed over (compute_diagonal of C^T A C reads them); the face-structured form, when
+            # chosen, takes precedence in the apply: tensor-product trace interpolation, one CTA per coarse face
+            check(lib.b200fe_op_set_constraints(self._h, n_rows, ptr(mesh.hang_dof), ptr(mesh.hang_row_ptr), ptr(mesh.hang_col),
+                                                ptr(mesh.hang_w)))
+            if constraints == "faces" and len(mesh.face_parents):
                 check(lib.b200fe_op_set_face_constraints(self._h, p, len(mesh.face_parents), ptr(mesh.face_parents),
                                                          ptr(mesh.face_children), ptr(mesh.trace_weights)))
-            else:
-                check(lib.b200fe_op_set_constraints(self._h, n_rows, ptr(mesh.hang_dof), ptr(mesh.hang_row_ptr), ptr(mesh.hang_col),
-                                                    ptr(mesh.hang_w)))
         self._inv_diag = None
 
     # --- the reference operator's interface ------------------------------------------------
@@ -250,9 +251,25 @@ class NoConvergence(RuntimeError):
     """dealii::SolverControl::NoConvergence."""
 
 
+class PreconditionChebyshev:
+    """dealii::PreconditionChebyshev<Operator, Vector, DiagonalMatrix> as a CG preconditioner: a polynomial of `degree` terms in
+    D^-1 A, optimal on [lambda_max / smoothing_range, lambda_max]; lambda_max from `eig_iterations` power iterations times 1.2
+    (estimate_eigenvalues) unless given (AdditionalData::max_eigenvalue)."""
+
+    def __init__(self, A: "LaplaceOperator", degree: int = 5, smoothing_range: float = 20.0, eig_iterations: int = 10,
+                 max_eigenvalue: float | None = None):
+        self.A, self.degree, self.smoothing_range = A, int(degree), float(smoothing_range)
+        self.inv_diag = A.get_matrix_diagonal_inverse()
+        if max_eigenvalue is None:
+            lam = C.c_double()
+            check(lib.b200fe_op_estimate_max_eigenvalue(A._h, _dp(self.inv_diag), int(eig_iterations), C.byref(lam), _sp()))
+            max_eigenvalue = lam.value
+        self.max_eigenvalue = float(max_eigenvalue)
+
+
 class SolverCG:
     """dealii::SolverCG: solve(A, x, b, preconditioner); preconditioner None = PreconditionIdentity,
-    or a tensor holding the inverse diagonal (DiagonalMatrix)."""
+    a tensor holding the inverse diagonal (DiagonalMatrix / Jacobi), or a PreconditionChebyshev."""
 
     def __init__(self, control: ReductionControl, check_every: int = 8):
         self.control = control
@@ -263,9 +280,17 @@ class SolverCG:
         """n_components > 1: vector-valued problem (BP2/BP4/BP6), x and b component-blocked
         [component][n_owned + n_ghost]."""
         res = _CgResult()
-        rc = lib.b200fe_cg_solve_components(A._h, n_components, _dp(x), _dp(b), _dp(preconditioner), self.control.tolerance,
-                                            self.control.reduction, self.control.max_steps, self.check_every, C.byref(res),
-                                            _sp(stream))
+        if isinstance(preconditioner, PreconditionChebyshev):
+            if n_components != 1:
+                raise ValueError("PreconditionChebyshev: scalar problems only")
+            c = preconditioner
+            rc = lib.b200fe_cg_solve_chebyshev(A._h, _dp(x), _dp(b), _dp(c.inv_diag), c.degree, c.max_eigenvalue, c.smoothing_range,
+                                               self.control.tolerance, self.control.reduction, self.control.max_steps, self.check_every,
+                                               C.byref(res), _sp(stream))
+        else:
+            rc = lib.b200fe_cg_solve_components(A._h, n_components, _dp(x), _dp(b), _dp(preconditioner), self.control.tolerance,
+                                                self.control.reduction, self.control.max_steps, self.check_every, C.byref(res),
+                                                _sp(stream))
         self.control._res = res
         if rc == 5:
             raise NoConvergence(f"CG: {res.iterations} iterations, residual {res.final_residual:g}")

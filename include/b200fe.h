@@ -314,7 +314,11 @@ int b200fe_op_vmult_dummy(b200fe_op *op, double *d_dst, const double *d_src, int
 /* vmult with HOST vectors of n_owned doubles (H2D, apply, D2H; synchronises the stream). */
 int b200fe_op_vmult_host(b200fe_op *op, double *h_dst, const double *h_src, void *stream);
 /* HelmholtzOperator::compute_diagonal (bp5_kokkos/benchmark.cc:218-251): matrix diagonal, 1 on
- * constrained rows.  (The reciprocal of :240-250 is one elementwise op on the caller's side.) */
+ * constrained rows.  (The reciprocal of :240-250 is one elementwise op on the caller's side.)
+ * With hanging-node constraints attached the result is diag(C^T A C) (MatrixFreeTools::compute_diagonal semantics): plain
+ * cell diagonals on the cells without hanging DoFs; on the others the columns of the cell matrix (cell kernel on unit
+ * vectors) with the local constraint matrix applied on both sides.  Needs the CSR rows (b200fe_op_set_constraints) on the
+ * operator, also when the face-structured form is the one used by the apply; setup path, synchronises. */
 int b200fe_op_diagonal(b200fe_op *op, double *d_diag, void *stream);
 /* compute_rhs of the BP drivers (CEED_bp/src/bp3.cc:184-239): b_i = int phi_i * 1, constrained rows 0. */
 int b200fe_op_rhs_one(b200fe_op *op, double *d_b, void *stream);
@@ -356,6 +360,17 @@ int b200fe_cg_solve(b200fe_op *op, double *d_x, const double *d_b, const double 
 int b200fe_cg_solve_components(b200fe_op *op, int n_components, double *d_x, const double *d_b, const double *d_inv_diag,
                                double abs_tol, double rel_tol, int max_it, int check_every, b200fe_cg_result *result,
                                void *stream);
+/* CG preconditioned by a Chebyshev polynomial of the Jacobi-scaled operator -- dealii::PreconditionChebyshev<Operator, Vector,
+ * DiagonalMatrix> as a SolverCG preconditioner (the step after Jacobi; the reference includes the multigrid transfer header for
+ * it, CEED_bp/src/bp3.cc:27, without using it yet).  z = p_k(D^-1 A) D^-1 r with the polynomial of `degree` terms that is
+ * optimal on [lambda_max / smoothing_range, lambda_max] (three-term recurrence, degree - 1 operator applications per CG
+ * iteration).  lambda_max: b200fe_op_estimate_max_eigenvalue.  Scalar problems (one component). */
+int b200fe_cg_solve_chebyshev(b200fe_op *op, double *d_x, const double *d_b, const double *d_inv_diag, int degree, double lambda_max,
+                              double smoothing_range, double abs_tol, double rel_tol, int max_it, int check_every,
+                              b200fe_cg_result *result, void *stream);
+/* Largest eigenvalue of D^-1 A by n_iterations power iterations from a fixed pseudo-random start vector, times deal.II's
+ * safety factor 1.2 (PreconditionChebyshev::estimate_eigenvalues).  d_inv_diag = NULL: of A itself.  Synchronises. */
+int b200fe_op_estimate_max_eigenvalue(b200fe_op *op, const double *d_inv_diag, int n_iterations, double *lambda_max, void *stream);
 /* Same with HOST x and b (n_owned doubles): H2D of b, solve, D2H of x, synchronises. */
 int b200fe_cg_solve_host(b200fe_op *op, double *h_x, const double *h_b, const double *d_inv_diag, double abs_tol,
                          double rel_tol, int max_it, int check_every, b200fe_cg_result *result, void *stream);

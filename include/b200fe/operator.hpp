@@ -407,6 +407,7 @@ class LaplaceOperator {
             std::vector<double> W(nf * nm);
             check(b200fe_hangmesh_fill_faces(mesh.handle(), fp.data(), fc.data()));
             check(b200fe_trace_weights(fe_degree, W.data()));
+            check(b200fe_op_set_constraints(op_, nr, hd.data(), hp.data(), hc.data(), hw.data()));  // compute_diagonal reads the rows
             check(b200fe_op_set_face_constraints(op_, fe_degree, nb, fp.data(), fc.data(), W.data()));
         } else  // general AffineConstraints rows (CSR)
             check(b200fe_op_set_constraints(op_, nr, hd.data(), hp.data(), hc.data(), hw.data()));

@@ -550,8 +550,44 @@ def kron_apply(mesh, bas, u):
 # --------------------------------------------------------------------------
 # deal.II SolverCG + ReductionControl (bp3.cc:268-285)
 # --------------------------------------------------------------------------
-def solver_cg(apply, b, max_it, abs_tol, rel_tol, precond_inv_diag=None, dot=np.dot):
-    """Returns (x, its, res0, resn, converged).  x0 = 0."""
+def estimate_max_eigenvalue(apply, inv_diag, n_owned, n_iterations, rank=0):
+    """Power iteration on D^-1 A from the product's fixed pseudo-random start vector (64-bit LCG), times deal.II's safety
+    factor 1.2 (PreconditionChebyshev::estimate_eigenvalues uses a CG/Lanczos estimate with the same factor)."""
+    g = (1 + rank * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    u = np.empty(n_owned)
+    for i in range(n_owned):
+        g = (g * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
+        u[i] = (g >> 11) * (1.0 / 9007199254740992.0) - 0.5
+    lam = 0.0
+    for _ in range(n_iterations):
+        y = u / np.sqrt(u @ u)
+        u = inv_diag * apply(y)
+        lam = y @ u
+    return 1.2 * lam
+
+
+def chebyshev_preconditioner(apply, inv_diag, degree, lambda_max, smoothing_range):
+    """z = p_k(D^-1 A) D^-1 r: `degree` terms of the Chebyshev polynomial that is optimal on
+    [lambda_max / smoothing_range, lambda_max] (three-term recurrence; dealii::PreconditionChebyshev)."""
+    lmin = lambda_max / smoothing_range
+    theta, delta = 0.5 * (lambda_max + lmin), 0.5 * (lambda_max - lmin)
+    sigma1 = theta / delta
+
+    def M(r):
+        rho = 1.0 / sigma1
+        d = inv_diag * r / theta
+        z = d.copy()
+        for _ in range(1, degree):
+            rho_new = 1.0 / (2.0 * sigma1 - rho)
+            d = rho_new * rho * d + (2.0 * rho_new / delta) * inv_diag * (r - apply(z))
+            z = z + d
+            rho = rho_new
+        return z
+    return M
+
+
+def solver_cg(apply, b, max_it, abs_tol, rel_tol, precond_inv_diag=None, dot=np.dot, precond=None):
+    """Returns (x, its, res0, resn, converged).  x0 = 0.  precond: callable z = M(r) (overrides precond_inv_diag)."""
     x = np.zeros_like(b)
     r = b.copy()
     res0 = res = np.sqrt(dot(r, r))
@@ -562,7 +598,10 @@ def solver_cg(apply, b, max_it, abs_tol, rel_tol, precond_inv_diag=None, dot=np.
     it = 0
     while True:
         it += 1
-        if precond_inv_diag is None:
+        if precond is not None:
+            z = precond(r)
+            rho_old, rho = rho, dot(r, z)
+        elif precond_inv_diag is None:
             z = r
             rho_old, rho = rho, res * res
         else:

@@ -91,6 +91,37 @@ def test_diagonal_rhs_and_dummy(oracle_mod, p):
     assert torch.equal(ghost_only[con], src[con]) and (ghost_only[free] == 3.0).all()  # no dst = 0 without computation
 
 
+@pytest.mark.parametrize("p,name,dq,quad,kind", [(2, "bp3", 2, "gauss", "laplace"), (4, "bp5", 1, "gll", "laplace"), (3, "helmholtz", 1, "gauss", "helmholtz")])
+def test_chebyshev_preconditioned_cg_matches_oracle(oracle_mod, p, name, dq, quad, kind):
+    """PreconditionChebyshev (degree 4 polynomial in D^-1 A) inside SolverCG: eigenvalue estimate and iteration count
+    against the numpy restatement of the same algorithm; fewer iterations than Jacobi."""
+    import benchmarks_b200 as b
+    fe = oracle_mod.fe
+    sub, nref, nq = (2, 1, 1), 1, p + dq
+    om, od, rd, bas, G, JxW = _oracle_setup(fe, sub, nref, p, nq, quad, 2, DEFORM)
+    mesh = b.BoxMesh(sub, nref, p)
+    A = b.LaplaceOperator(mesh, nq=nq, quad=quad, kind=kind, p_geo=2, deform=DEFORM)
+    kw = dict(laplace=kind != "mass", mass=kind != "laplace")
+    apply = lambda v: fe.op_apply(v, rd, bas, G, JxW, **kw)
+    inv_diag = 1.0 / fe.op_diagonal(rd, bas, G, JxW, **kw)
+    lam_ref = fe.estimate_max_eigenvalue(apply, inv_diag, mesh.n_owned, 12)
+    P = b.PreconditionChebyshev(A, degree=4, smoothing_range=15.0, eig_iterations=12)
+    assert P.max_eigenvalue == pytest.approx(lam_ref, rel=1e-9)
+    rhs_ref = fe.rhs_one(rd, bas, JxW)
+    M = fe.chebyshev_preconditioner(apply, inv_diag, 4, lam_ref, 15.0)
+    _, its_ref, _, _, ok = fe.solver_cg(apply, rhs_ref, 500, 1e-16, 1e-9, precond=M)
+    rhs, x = A.compute_rhs(), A.initialize_dof_vector()
+    ctl = b.ReductionControl(500, 1e-16, 1e-9)
+    b.SolverCG(ctl).solve(A, x, rhs, P)
+    assert ok and abs(ctl.last_step() - its_ref) <= 1
+    r = A.initialize_dof_vector()
+    A.vmult(r, x)
+    assert (rhs - r).norm().item() <= 5e-9 * rhs.norm().item()
+    ctl_j = b.ReductionControl(2000, 1e-16, 1e-9)
+    b.SolverCG(ctl_j).solve(A, A.initialize_dof_vector(), rhs, A.get_matrix_diagonal_inverse())
+    assert ctl.last_step() < ctl_j.last_step()
+
+
 @pytest.fixture(scope="module")
 def cg_golden(golden_dir):
     with open(os.path.join(golden_dir, "bp3_cg_p4.json")) as f:

@@ -212,3 +212,24 @@ def test_operator_matches_kronecker_and_c_oracle(oracle_mod, nq, quad):
                                       G=G, JxW=JxW, dof_indices=rd["dof_indices"],
                                       colors=_colors(mesh, rd["cells"]), constrained=rd["constrained"])
         assert np.abs(y0 - y1).max() <= 1e-13 * np.abs(y0).max()
+
+
+def test_chebyshev_preconditioner_algebra():
+    """oracle.fe.chebyshev_preconditioner: the recurrence reproduces the Chebyshev polynomial exactly -- on a diagonal
+    operator the residual polynomial 1 - lambda p_k(lambda) equals T_k((theta - lambda) / delta) / T_k(theta / delta) -- and
+    the power iteration finds the largest eigenvalue of D^-1 A (times the safety factor 1.2)."""
+    import numpy as np
+    from numpy.polynomial import chebyshev as T
+    import oracle
+    fe = oracle.fe
+    lam = np.linspace(0.05, 2.0, 64)
+    apply = lambda v: lam * v
+    inv_diag = np.ones_like(lam)
+    degree, lmax, rng = 5, 2.0, 20.0
+    M = fe.chebyshev_preconditioner(apply, inv_diag, degree, lmax, rng)
+    z = M(np.ones_like(lam))                       # p_k(lambda) on every eigenvalue at once
+    theta, delta = 0.5 * (lmax + lmax / rng), 0.5 * (lmax - lmax / rng)
+    Tk = lambda x: T.chebval(x, [0] * degree + [1])
+    assert np.allclose(1.0 - lam * z, Tk((theta - lam) / delta) / Tk(theta / delta), rtol=1e-10, atol=1e-12)
+    est = fe.estimate_max_eigenvalue(apply, inv_diag, len(lam), 200)
+    assert est == pytest.approx(1.2 * 2.0, rel=1e-3)

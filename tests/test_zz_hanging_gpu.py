@@ -62,6 +62,31 @@ def test_constrained_vmult_matches_oracle(oracle_mod, p, name, dq, quad, kind, c
     assert rel(A.compute_rhs().cpu().numpy(), ho.rhs_one(rd, bas, JxW)) <= TOL
 
 
+@pytest.mark.parametrize("p,name,dq,quad,kind,constraints", [(1, "bp3", 2, "gauss", "laplace", "faces"), (2, "bp5", 1, "gll", "laplace", "rows"),
+                                                             (3, "helmholtz", 1, "gauss", "helmholtz", "faces"), (2, "bp1", 2, "gauss", "mass", "faces"),
+                                                             (4, "bp5", 1, "gll", "laplace", "faces")])
+def test_diagonal_with_constraints_matches_oracle(oracle_mod, p, name, dq, quad, kind, constraints):
+    """compute_diagonal of C^T A C (bp5_kokkos/benchmark.cc:218-251 semantics on a mesh with hanging nodes): every entry
+    against the oracle's constrained operator applied to unit vectors; 1 on Dirichlet and hanging rows."""
+    fe, ho, rd, bas, G, JxW, mesh, A = _setup(oracle_mod, p, (1, 1, 1), 1, (1, 0, 1), (2, 1, 2), p + dq, quad, kind, constraints=constraints)
+    n = mesh.n_owned
+    ref = np.empty(n)
+    for j in range(n):
+        e = np.zeros(n)
+        e[j] = 1.0
+        ref[j] = ho.op_apply(rd, bas, G, e, JxW, laplace=kind != "mass", mass=kind != "laplace")[j]
+    diag = A.compute_diagonal().cpu().numpy()[:n]
+    assert rel(diag, ref) <= TOL, name
+    con = np.concatenate([mesh.constrained, mesh.hang_dof]).astype(np.int64)
+    assert (diag[con] == 1.0).all()
+    # and the Jacobi-preconditioned CG on the constrained operator runs with it
+    import benchmarks_b200 as b
+    rhs, x = A.compute_rhs(), A.initialize_dof_vector()
+    ctl = b.ReductionControl(2000, 1e-16, 1e-9)
+    b.SolverCG(ctl).solve(A, x, rhs, A.get_matrix_diagonal_inverse())
+    assert ctl.last_step() > 0
+
+
 @pytest.mark.parametrize("p,dq,quad,constraints", [(2, 2, "gauss", "faces"), (4, 1, "gll", "rows"), (7, 1, "gll", "faces")])
 def test_cg_on_hanging_mesh_matches_oracle_loop(oracle_mod, p, dq, quad, constraints):
     """bp3 protocol (rhs = int phi, x0 = 0, ReductionControl(., 1e-16, 1e-9)) on the constrained operator; the solution is
