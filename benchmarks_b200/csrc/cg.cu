@@ -33,6 +33,8 @@ struct CgScalars {      // device-resident
     double rho, rho_old;
     double acc[3];      // [0] p.Ap  [1] r.r  [2] r.z   (summed over ranks in place)
     double res0, res;
+    double alpha_pending;  // x += alpha p of the iteration just finished is applied by the NEXT p-update pass (or the flush)
+    int has_pending;
     int it;             // iterations started
     int done, converged, its;
 };
@@ -86,29 +88,52 @@ __global__ void cg_scalar_kernel(CgScalars *sc, int jacobi, int max_it, double a
     sc->it += 1;
 }
 
-__global__ void cg_update_p_kernel(uint32_t n, size_t stride, const double *__restrict__ r, const double *__restrict__ inv_diag,
-                                   double *__restrict__ p, const CgScalars *sc)
+// One pass over the vectors between two operator applications: p = z + beta p; the pending x += alpha p_old of the
+// previous iteration (p_old is read here anyway: 8 B/DoF less than updating x together with r); v = 0 for the scatter of
+// the coming apply (owned and ghost entries; replaces a separate memset launch).
+__global__ void cg_update_p_kernel(uint32_t n, uint32_t n_local, size_t stride, const double *__restrict__ r, const double *__restrict__ inv_diag,
+                                   double *__restrict__ p, double *__restrict__ x, double *__restrict__ v, const CgScalars *sc)
 {
     if (sc->done) return;
-    r += blockIdx.y * stride; p += blockIdx.y * stride;
+    r += blockIdx.y * stride; p += blockIdx.y * stride; x += blockIdx.y * stride; v += blockIdx.y * stride;
     const bool first = sc->it == 1;
     const double beta = first ? 0.0 : sc->rho / sc->rho_old;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const double z = inv_diag ? inv_diag[i] * r[i] : r[i];
-        p[i] = first ? z : fma(beta, p[i], z);
+    const bool pending = sc->has_pending != 0;
+    const double alpha = sc->alpha_pending;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += gridDim.x * blockDim.x) {
+        v[i] = 0.0;
+        if (i < n) {
+            const double z = inv_diag ? inv_diag[i] * r[i] : r[i];
+            const double pi = first ? 0.0 : p[i];
+            if (pending) x[i] = fma(alpha, pi, x[i]);
+            p[i] = first ? z : fma(beta, pi, z);
+        }
     }
 }
 
-__global__ void cg_update_xr_kernel(uint32_t n, size_t stride, const double *__restrict__ p, const double *__restrict__ v,
-                                    const double *__restrict__ inv_diag, double *__restrict__ x, double *__restrict__ r,
-                                    CgScalars *sc)
+// after the loop: the x update of the last iteration (p still holds its search direction: the p pass is a no-op once done)
+__global__ void cg_flush_x_kernel(uint32_t n, size_t stride, const double *__restrict__ p, double *__restrict__ x, CgScalars *sc)
+{
+    if (!sc->has_pending) return;
+    p += blockIdx.y * stride; x += blockIdx.y * stride;
+    const double alpha = sc->alpha_pending;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) x[i] = fma(alpha, p[i], x[i]);
+}
+__global__ void cg_clear_pending_kernel(CgScalars *sc) { sc->has_pending = 0; }
+
+// r -= alpha v with r.r (and r.z) fused; x += alpha p is left pending for the next p pass (cg_update_p_kernel)
+__global__ void cg_update_xr_kernel(uint32_t n, size_t stride, const double *__restrict__ v,
+                                    const double *__restrict__ inv_diag, double *__restrict__ r, CgScalars *sc)
 {
     if (sc->done) return;
-    p += blockIdx.y * stride; v += blockIdx.y * stride; x += blockIdx.y * stride; r += blockIdx.y * stride;
+    v += blockIdx.y * stride; r += blockIdx.y * stride;
     const double alpha = sc->rho / sc->acc[0];
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {  // (every block reads rho and acc[0] only; separate fields)
+        sc->alpha_pending = alpha;
+        sc->has_pending = 1;
+    }
     double rr = 0.0, rz = 0.0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        x[i] = fma(alpha, p[i], x[i]);
         const double ri = fma(-alpha, v[i], r[i]);
         r[i] = ri;
         rr = fma(ri, ri, rr);
@@ -273,6 +298,7 @@ static int cg_run(Operator &op, int ncomp, CgWork &w, double *d_x, const double 
     const size_t stride = op.n_local();
     const unsigned bx = n == 0 ? 1u : std::min<unsigned>((n + 1023) / 1024, std::max(148u * 8u / (unsigned)ncomp, 148u));
     const dim3 blocks(bx, (unsigned)ncomp);
+    const dim3 blocks_local(stride == 0 ? 1u : std::min<unsigned>((unsigned)((stride + 1023) / 1024), std::max(148u * 8u / (unsigned)ncomp, 148u)), (unsigned)ncomp);
     const int jacobi = d_inv_diag != nullptr;  // (Chebyshev: rho = r.z as well, z = w.cheb)
     // the vector kernels fuse z = D^-1 r for Jacobi; with the polynomial preconditioner z is a vector of its own
     const double *fused_diag = cheb ? nullptr : d_inv_diag;
@@ -311,14 +337,14 @@ static int cg_run(Operator &op, int ncomp, CgWork &w, double *d_x, const double 
         return B200FE_OK;
     };
     auto iteration = [&]() -> int {
-        cg_update_p_kernel<<<blocks, 256, 0, s>>>(n, stride, cheb ? w.cheb : w.r, fused_diag, w.p, w.sc);
+        cg_update_p_kernel<<<blocks_local, 256, 0, s>>>(n, (uint32_t)stride, stride, cheb ? w.cheb : w.r, fused_diag, w.p, d_x, w.v, w.sc);
         B200FE_CUDA_TRY(cudaGetLastError());
         ++g_launch_count;
-        // block-diagonal operator: the fused p.Ap of every component lands in acc[0]
-        if (int rc = op_vmult(op, w.v, w.p, &w.sc->acc[0], true, true, s, ncomp)) return rc;
+        // block-diagonal operator: the fused p.Ap of every component lands in acc[0]; v was cleared by the p pass
+        if (int rc = op_vmult(op, w.v, w.p, &w.sc->acc[0], true, true, s, ncomp, true)) return rc;
         if (op.halo)
             if (int rc = halo_allreduce_sum(*op.halo, w.sc->acc, 1, s)) return rc;
-        cg_update_xr_kernel<<<blocks, 256, 0, s>>>(n, stride, w.p, w.v, fused_diag, d_x, w.r, w.sc);
+        cg_update_xr_kernel<<<blocks, 256, 0, s>>>(n, stride, w.v, fused_diag, w.r, w.sc);
         B200FE_CUDA_TRY(cudaGetLastError());
         ++g_launch_count;
         if (cheb)
@@ -377,6 +403,10 @@ static int cg_run(Operator &op, int ncomp, CgWork &w, double *d_x, const double 
     }
     if (exec) cudaGraphExecDestroy(exec);
     if (rc_loop != B200FE_OK) return rc_loop;
+    cg_flush_x_kernel<<<blocks, 256, 0, s>>>(n, stride, w.p, d_x, w.sc);
+    cg_clear_pending_kernel<<<1, 1, 0, s>>>(w.sc);
+    B200FE_CUDA_TRY(cudaGetLastError());
+    g_launch_count += 2;
     if (res) {
         res->iterations = w.h_sc->its;
         res->converged = w.h_sc->converged;

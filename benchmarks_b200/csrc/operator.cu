@@ -581,7 +581,7 @@ int op_condense(Operator &op, double *d_dst, double *d_src_restore, cudaStream_t
 }
 
 int op_vmult(Operator &op, double *d_dst, const double *d_src, double *d_dot, bool ghost_on, bool compute_on,
-             cudaStream_t s, int ncomp)
+             cudaStream_t s, int ncomp, bool dst_is_zero)
 {
     NvtxRange range("matvec");
     Halo *h = op.halo;
@@ -591,10 +591,10 @@ int op_vmult(Operator &op, double *d_dst, const double *d_src, double *d_dot, bo
     const bool split = h && ghost_on && compute_on && (op.n_phase0 + op.n_phase1 > 0) && !op.has_constraints();
     if (split && ncomp > 1) {  // the overlap schedule is per vector: one component after the other
         for (int c = 0; c < ncomp; ++c)
-            if (int rc = op_vmult(op, d_dst + c * stride, d_src + c * stride, d_dot, ghost_on, compute_on, s, 1)) return rc;
+            if (int rc = op_vmult(op, d_dst + c * stride, d_src + c * stride, d_dot, ghost_on, compute_on, s, 1, dst_is_zero)) return rc;
         return B200FE_OK;
     }
-    if (compute_on) B200FE_CUDA_TRY(cudaMemsetAsync(d_dst, 0, sizeof(double) * stride * ncomp, s));
+    if (compute_on && !dst_is_zero) B200FE_CUDA_TRY(cudaMemsetAsync(d_dst, 0, sizeof(double) * stride * ncomp, s));
     if (split) {
         // 3-phase overlap (bakeoff_problems_dealii/include/portable_laplace_operator.h:643-696)
         if (int rc = halo_update_ghosts_start(*h, src_mut, s)) return rc;

@@ -88,8 +88,9 @@ int op_distribute(Operator &op, double *d_v, bool save, cudaStream_t s, int ncom
 int op_condense(Operator &op, double *d_dst, double *d_src_restore, cudaStream_t s, int ncomp = 1);
 // full local vmult: zero, cells, constrained rows (+ halo exchange when attached)
 // ncomp > 1: component-blocked vectors [component][n_local], the scalar operator on each
+// dst_is_zero: the caller has already cleared dst (owned + ghost entries of every component), e.g. inside its own vector pass
 int op_vmult(Operator &op, double *d_dst, const double *d_src, double *d_dot, bool ghost_on, bool compute_on,
-             cudaStream_t s, int ncomp = 1);
+             cudaStream_t s, int ncomp = 1, bool dst_is_zero = false);
 
 // compute_diagonal of C^T A C (needs the constraint rows on the operator)
 int op_diagonal_constrained(Operator &op, double *d_diag, cudaStream_t s);

@@ -9,3 +9,8 @@ for v in default t1; do
   B200FE_LIB=$lib python tools/op_sweep.py --degrees 8 --json gpurun_out/${tag}_sweep_$v.json | tee gpurun_out/${tag}_sweep_$v.txt
   B200FE_LIB=$lib python tools/bk_bench.py --kinds bk1 --degrees 6,7,8 --reps 10 --json gpurun_out/${tag}_bk_$v.json | tail -n +2 | tee -a gpurun_out/${tag}_sweep_$v.txt
 done
+python bench.py --steps 5 --warmup 3 --no-sweep --no-cpu-baseline | python -c "
+import sys, json
+d = json.loads(sys.stdin.read().strip().splitlines()[-1])
+print('headline', d['value'], 'ms/step', d['ms_per_step'], 'kernel share', d['roofline']['kernel_share_of_step'], 'frac', d['roofline']['frac'], 'launches', d['gpu_launches'], 'e2e', d['e2e']['value'])
+" | tee gpurun_out/${tag}_headline.txt
