@@ -20,17 +20,22 @@ namespace b200fe {
 // registers to stay spill-free; below nq = 7 a 96-register floor (more CTAs per SM) wins.
 constexpr int v2_rmin(int nq, bool coll, int qop, bool eo = false)
 {
-    // even-odd kernels of the interpolated operators at nq = 9, 10: their own floors (tuning knobs; r02c ncu: the nq = 10
-    // kernel still spills 104 B/thread at the 168-register cap of three resident CTAs)
+    // Register caps come in steps: the register file is split over 4 SM sub-partitions, so a CTA of 3 warps is capped at
+    // 168 registers with 3 or 4 resident CTAs and at 255 with 2 (ptxas honours exactly that).  Measured A/B (profiles/r02f_*):
+    //  * even-odd interpolated Laplace at nq = 10: 2 CTAs x 255 registers, no spill (was 3 x 168 with 104 B/thread of local
+    //    memory): BP3 p = 8 0.611 -> 0.649 of the HBM roofline;
+    //  * mass at nq = 9 (plain contractions): 2 x 255 instead of 3 x 168 + 208 B spill: BK1 p = 7 55.9 -> 61.9 GDoF/s.
+#ifndef B200FE_V2_RMIN_EO10
+#define B200FE_V2_RMIN_EO10 255
+#endif
+#ifndef B200FE_V2_RMIN_MASS9
+#define B200FE_V2_RMIN_MASS9 255
+#endif
 #ifdef B200FE_V2_RMIN_EO9
     if (eo && !coll && nq == 9 && (qop & QOP_LAPLACE)) return B200FE_V2_RMIN_EO9;
 #endif
-#ifdef B200FE_V2_RMIN_EO10
     if (eo && !coll && nq == 10 && (qop & QOP_LAPLACE)) return B200FE_V2_RMIN_EO10;
-#endif
-#ifdef B200FE_V2_RMIN_MASS9
     if (!(qop & QOP_LAPLACE) && nq == 9) return B200FE_V2_RMIN_MASS9;
-#endif
 #ifdef B200FE_V2_RMIN_FIXED
     return B200FE_V2_RMIN_FIXED;
 #else
@@ -80,13 +85,16 @@ inline bool eo_enabled()
     return on;
 }
 
-template <int NM, int NQ, bool COLL, int QOP, bool LVEC, bool EO>
+// multi-component kernels (G streamed once for all components of a vector-valued operator): collocated Laplace L-vector
+constexpr bool mc_built(bool coll, int qop, bool lvec) { return coll && lvec && qop == QOP_LAPLACE; }
+
+template <int NM, int NQ, bool COLL, int QOP, bool LVEC, bool EO, bool MC = false>
 cudaError_t launch_variant(const Mats<NM, NQ, EO> &m, const KArgs &a, cudaStream_t s, LaunchInfo *info, bool dry_run)
 {
     using C = V2Cfg<NM, NQ, COLL, QOP, EO>;
     constexpr int EPB = C::EPB;
     constexpr int T = C::T;
-    auto kern = sumfact2_kernel<NM, NQ, COLL, QOP, LVEC, EPB, C::MINB, EO>;
+    auto kern = sumfact2_kernel<NM, NQ, COLL, QOP, LVEC, EPB, C::MINB, EO, MC>;
     const size_t smem = C::SMEM;
     // TMA bulk copies need a 16-byte aligned source (the batch block offset is a multiple of 48 nq^3 bytes)
     if ((QOP & QOP_LAPLACE) && !(QOP & QOP_AFFINE) && !dry_run && (reinterpret_cast<uintptr_t>(a.G) & 15u) != 0) return cudaErrorMisalignedAddress;
@@ -139,6 +147,10 @@ cudaError_t launch_t(const double *hB, const double *hD, const double *hW, const
             Mats<NM, NQ, true> me;
             if (eo::fill<NM, NQ>(Bsym, Dsym, me.E) <= 1e-10) {
                 if (hW) std::memcpy(me.W, hW, sizeof(me.W)); else std::memset(me.W, 0, sizeof(me.W));
+                if (a.ncomp > 1) {
+                    if constexpr (mc_built(COLL, QOP, LVEC)) return launch_variant<NM, NQ, COLL, QOP, LVEC, true, true>(me, a, s, info, dry_run);
+                    else return cudaErrorNotSupported;
+                }
                 return launch_variant<NM, NQ, COLL, QOP, LVEC, true>(me, a, s, info, dry_run);
             }
         }
@@ -147,6 +159,10 @@ cudaError_t launch_t(const double *hB, const double *hD, const double *hW, const
     if (hB) std::memcpy(m.B, hB, sizeof(m.B)); else std::memset(m.B, 0, sizeof(m.B));
     if (hD) std::memcpy(m.D, hD, sizeof(m.D)); else std::memset(m.D, 0, sizeof(m.D));
     if (hW) std::memcpy(m.W, hW, sizeof(m.W)); else std::memset(m.W, 0, sizeof(m.W));
+    if (a.ncomp > 1) {
+        if constexpr (mc_built(COLL, QOP, LVEC)) return launch_variant<NM, NQ, COLL, QOP, LVEC, false, true>(m, a, s, info, dry_run);
+        else return cudaErrorNotSupported;
+    }
     return launch_variant<NM, NQ, COLL, QOP, LVEC, false>(m, a, s, info, dry_run);
 }
 

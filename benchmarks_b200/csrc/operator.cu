@@ -479,14 +479,22 @@ __global__ void condense_faces_kernel(uint32_t n_blocks, int nm, int nf, const d
 // ---------------------------------------------------------------------------------------------
 // operator pieces
 // ---------------------------------------------------------------------------------------------
+bool op_has_mc_kernel(const Operator &op)
+{
+    static const bool on = [] { const char *e = std::getenv("B200FE_MULTI_COMPONENT"); return !e || std::atoi(e) != 0; }();
+    return on && op.collocated && op.qop == QOP_LAPLACE && op.d_cellG == nullptr;
+}
+
 int op_apply_cells(Operator &op, double *d_dst, const double *d_src, uint32_t cb, uint32_t ce,
-                   double *d_dot, cudaStream_t s)
+                   double *d_dot, cudaStream_t s, int ncomp)
 {
     if (ce <= cb) return B200FE_OK;
     const size_t nm3 = (size_t)op.nm * op.nm * op.nm, nq3 = (size_t)op.nq * op.nq * op.nq;
     const bool affine = op.d_cellG != nullptr;
     KArgs a{ce - cb, (op.d_G && !affine) ? op.d_G + cb * 6 * nq3 : nullptr, op.d_JxW ? op.d_JxW + cb * nq3 : nullptr,
             d_src, d_dst, op.d_idx + cb * nm3, d_dot, affine ? op.d_cellG + (size_t)cb * 8 : nullptr, op.d_skip};
+    a.ncomp = ncomp;
+    a.comp_stride = op.n_local();
     const int qop = op.qop | (affine ? QOP_AFFINE : 0);
     const bool timed = op.timing && op.ev_used + 2 <= op.ev.size();
     if (timed) B200FE_CUDA_TRY(cudaEventRecord(op.ev[op.ev_used], s));
@@ -613,8 +621,11 @@ int op_vmult(Operator &op, double *d_dst, const double *d_src, double *d_dot, bo
         if (int rc = halo_update_ghosts_components(*h, src_mut, ncomp, stride, s)) return rc;
     if (compute_on) {
         if (int rc = op_distribute(op, src_mut, true, s, ncomp)) return rc;
-        for (int c = 0; c < ncomp; ++c)
-            if (int rc = op_apply_cells(op, d_dst + c * stride, d_src + c * stride, 0, op.n_cells, d_dot, s)) return rc;
+        if (ncomp > 1 && op_has_mc_kernel(op)) {  // one launch: the geometric factors of a cell serve all components
+            if (int rc = op_apply_cells(op, d_dst, d_src, 0, op.n_cells, d_dot, s, ncomp)) return rc;
+        } else
+            for (int c = 0; c < ncomp; ++c)
+                if (int rc = op_apply_cells(op, d_dst + c * stride, d_src + c * stride, 0, op.n_cells, d_dot, s)) return rc;
         if (int rc = op_condense(op, d_dst, src_mut, s, ncomp)) return rc;
     }
     if (h && ghost_on) {

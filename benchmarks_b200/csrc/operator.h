@@ -77,8 +77,12 @@ struct Operator {
 };
 
 // dst = 0 on the local vector, cell kernel over cells [cell_begin, cell_end), optional fused dot.
+// ncomp > 1: all components of component-blocked vectors in ONE launch (multi-component kernel; see op_has_mc_kernel)
 int op_apply_cells(Operator &op, double *d_dst, const double *d_src, uint32_t cell_begin, uint32_t cell_end,
-                   double *d_dot, cudaStream_t s);
+                   double *d_dot, cudaStream_t s, int ncomp = 1);
+// vector-valued applies of this operator can use the multi-component kernel (G streamed once): collocated Laplace with
+// stored geometric factors; B200FE_MULTI_COMPONENT=0 falls back to one launch per component
+bool op_has_mc_kernel(const Operator &op);
 // dst[c] = src[c] on owned constrained DoFs; optional dot += sum src[c]^2
 int op_copy_constrained(Operator &op, double *d_dst, const double *d_src, double *d_dot, cudaStream_t s, int ncomp = 1);
 // hanging-node rows: src[h] = sum w src[parents] (old values saved when `save`), and its transpose on dst

@@ -51,6 +51,10 @@ struct KArgs {
     double *dot;            // L-vector only, optional: += sum_e u_e . (A_e u_e)
     const double *cellG;    // affine geometry only: [e][8] = det J * K K^T (rr,rs,rt,ss,st,tt), det J, pad
     const int *skip;        // optional: when *skip != 0 the launch is a no-op (CG iterations replayed after convergence)
+    // vector-valued operators (BP2/4/6 = the scalar operator on every component), multi-component kernels only: the
+    // geometric factors of a batch are fetched once and used for all components; in/out of component c at + c*comp_stride
+    int ncomp = 1;
+    size_t comp_stride = 0;
 };
 
 constexpr __host__ __device__ int odd(int n) { return n | 1; }

@@ -197,10 +197,15 @@ __device__ __forceinline__ void deriv_t(const MatsT &m, const double (&in)[NQ], 
 }  // namespace v2
 
 // ---------------------------------------------------------------------------------------------
-template <int NM, int NQ, bool COLL, int QOP, bool LVEC, int EPB, int MINB, bool EO>
+// MC (multi-component): the batch loop gets an inner loop over the components of a component-blocked vector; the G block of
+// a batch is waited for before the first and re-fetched after the last component, so the geometric factors (75-95 % of the
+// bytes) are streamed once per cell instead of once per cell and component (BP6: 3 components).  Built for the collocated
+// Laplace L-vector kernels; MC = false is the scalar kernel, unchanged.
+template <int NM, int NQ, bool COLL, int QOP, bool LVEC, int EPB, int MINB, bool EO, bool MC = false>
 __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB)), MINB)
     sumfact2_kernel(const __grid_constant__ Mats<NM, NQ, EO> m, const KArgs a)
 {
+    static_assert(!MC || (COLL && LVEC && (QOP & QOP_LAPLACE) && !(QOP & QOP_MASS)), "multi-component kernels: collocated Laplace L-vector operators");
     using L = v2::Layout2<NM, NQ, COLL, QOP>;
     constexpr int N2 = L::N2, N3 = L::N3, M3 = L::M3, RA = L::RA, PA = L::PA, PB = L::PB;
     constexpr int PSQ = L::PSQ, RSR = L::RSR, PSR = L::PSR;
@@ -295,10 +300,11 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
 #pragma unroll
         for (int n = 0; n < NIN; ++n) ix[n] = (ok && in_valid(n)) ? __ldg(a.idx + in_offset(e_, n)) : kInvalidIndex;
     };
-    auto load_val = [&](uint32_t eb_, const uint32_t (&ix)[NIN], double (&val)[NIN]) {
+    auto load_val = [&](uint32_t eb_, const uint32_t (&ix)[NIN], double (&val)[NIN], const double *in_base = nullptr) {
         if constexpr (LVEC) {
+            const double *src = MC ? in_base : a.in;
 #pragma unroll
-            for (int n = 0; n < NIN; ++n) val[n] = ix[n] == kInvalidIndex ? 0.0 : __ldg(a.in + ix[n]);
+            for (int n = 0; n < NIN; ++n) val[n] = ix[n] == kInvalidIndex ? 0.0 : __ldg(src + ix[n]);
         } else {
             const uint32_t e_ = eb_ * EPB + el;
             const bool ok = lane_ok && eb_ < n_batches && e_ < a.n_elems;
@@ -307,7 +313,8 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
         }
     };
     if constexpr (LVEC) load_idx(blockIdx.x, cur_idx);
-    load_val(blockIdx.x, cur_idx, cur_val);
+    load_val(blockIdx.x, cur_idx, cur_val, a.in);
+    const int ncomp = MC ? a.ncomp : 1;
     constexpr bool JW_PIPE = MASS && !LAP && PREFETCH;
     [[maybe_unused]] double jw_cur[NQ];
     auto load_jw = [&](uint32_t eb_, double (&j)[NQ]) {
@@ -323,9 +330,12 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
         const uint32_t e = eb * EPB + el;
         const bool active = lane_ok && e < a.n_elems;
         const uint32_t nb = eb + gridDim.x;
+      for (int comp = 0; comp < ncomp; ++comp) {  // (scalar kernels: one pass)
+        const bool first_c = !MC || comp == 0, last_c = !MC || comp == ncomp - 1;
+        [[maybe_unused]] const size_t coff = MC ? (size_t)comp * a.comp_stride : 0;
         // prefetch: next batch's indices (L-vector) or values (E-vector)
         if constexpr (PREFETCH) {
-            if constexpr (LVEC) load_idx(nb, nxt_idx);
+            if constexpr (LVEC) { if (first_c) load_idx(nb, nxt_idx); }
             else load_val(nb, nxt_idx, nxt_val);
         }
         [[maybe_unused]] double jw[NQ];
@@ -417,8 +427,10 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
             }
             sync_elem();
             if constexpr (STORED_G) {
-                v2::mbar_wait(bar, parity);  // G of this batch has landed
-                parity ^= 1u;
+                if (first_c) {
+                    v2::mbar_wait(bar, parity);  // G of this batch has landed (all components use it)
+                    parity ^= 1u;
+                }
             }
             [[maybe_unused]] double cg[6];
             [[maybe_unused]] double wqr = 0.0;
@@ -455,14 +467,19 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
             if constexpr (STORED_G) __syncthreads();  // CTA-wide: the shared G buffer is about to be refilled
             else sync_elem();
             if constexpr (STORED_G) {
-                if (tid == 0) {  // the G buffer is drained: fetch the next batch's block behind the rest of this one
+                if (tid == 0 && last_c) {  // the G buffer is drained: fetch the next batch's block behind the rest of this one
                     if (nb < n_batches) {
                         v2::fence_proxy_async();
                         issue_g(nb);
                     }
                 }
             }
-            if constexpr (LVEC && PREFETCH) load_val(nb, nxt_idx, nxt_val);  // next batch's gathers (indices arrived long ago)
+            if constexpr (LVEC && PREFETCH) {  // next item's gathers (indices arrived long ago): next component, or next batch
+                if constexpr (MC) {
+                    if (last_c) load_val(nb, nxt_idx, nxt_val, a.in);
+                    else load_val(eb, cur_idx, nxt_val, a.in + coff + a.comp_stride);
+                } else load_val(nb, nxt_idx, nxt_val, a.in);
+            }
             v2::deriv_t<NM, NQ>(m, gr, w);  // w[p'] = sum_p D[p][p'] f_r[p]
             {   // layout Q, transposed derivative along q, in place
                 double c[NQ], o[NQ];
@@ -495,14 +512,14 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
                 if constexpr (LVEC) dot_acc = fma(mv, v[p], dot_acc);  // + u^T M u at the points (jw = 0 on inactive slots)
             }
         }
-        if constexpr (LVEC && !LAP && PREFETCH) load_val(nb, nxt_idx, nxt_val);
+        if constexpr (LVEC && !LAP && PREFETCH) load_val(nb, nxt_idx, nxt_val, a.in);
 
         // ------------------------------------------------------------------ (interpolation +) store
         if constexpr (COLL) {
             if constexpr (LVEC) {
 #pragma unroll
                 for (int p = 0; p < NQ; ++p) {
-                    if (cur_idx[p] != kInvalidIndex) atomicAdd(a.out + cur_idx[p], w[p]);
+                    if (cur_idx[p] != kInvalidIndex) atomicAdd(a.out + coff + cur_idx[p], w[p]);
                 }
             } else {
                 if (active) {
@@ -563,12 +580,14 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
 #pragma unroll
             for (int n = 0; n < NIN; ++n) {
                 cur_val[n] = nxt_val[n];
-                if constexpr (LVEC) cur_idx[n] = nxt_idx[n];
+                if constexpr (LVEC) { if (last_c) cur_idx[n] = nxt_idx[n]; }
             }
         } else {
+            static_assert(!MC || PREFETCH, "multi-component kernels use the software-pipelined inputs");
             if constexpr (LVEC) load_idx(nb, cur_idx);
-            load_val(nb, cur_idx, cur_val);
+            load_val(nb, cur_idx, cur_val, a.in);
         }
+      }  // components
     }
 
     if constexpr (LVEC) {
