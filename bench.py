@@ -517,10 +517,14 @@ def main():
             t6 = c0.elapsed_time(c1) * 1e-4
             # constraints in the face-structured form (default): the index blocks are read by distribute and by condense
             con_bytes = 4 * (hm.face_parents.size + hm.face_children.size)
-            bytes6 = 3 * op6.algorithmic_bytes() + 2 * con_bytes    # G is streamed once per component
+            if op6.multi_component_kernel():   # G and the index table of a cell are read once for the three components
+                bytes6 = op6.algorithmic_bytes() + 2 * 32 * hm.n_owned + 2 * con_bytes
+            else:                              # one cell-kernel launch per component: G streamed three times
+                bytes6 = 3 * op6.algorithmic_bytes() + 2 * con_bytes
             c5 = {"what": "BP6 vector Laplacian apply (3 components, GLL, p=8, deformed MappingQ2 mesh, hanging nodes), 1 GPU",
                   "cells": int(hm.n_cells_global), "n_dofs_3_components": 3 * int(hm.n_dofs_global), "hanging_dofs": int(len(hm.hang_dof)), "constraint_face_blocks": int(len(hm.face_parents)),
                   "ms": 1e3 * t6, "gdofs": 1e-9 * 3 * hm.n_dofs_global / t6, "algorithmic_bytes": int(bytes6),
+                  "multi_component_kernel": bool(op6.multi_component_kernel()),
                   "frac_of_hbm_roofline": 1e-9 * bytes6 / t6 / peak}
             del op6, src6, dst6, hm
             torch.cuda.empty_cache()

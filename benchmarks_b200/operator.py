@@ -214,7 +214,14 @@ class LaplaceOperator:
         keys = ("elems_per_block", "num_blocks", "threads_per_block", "smem_bytes", "blocks_per_sm", "regs_per_thread")
         eo = C.c_int()
         check(lib.b200fe_op_kernel_variant(self._h, C.byref(eo)))
-        return dict(zip(keys, [x.value for x in v]), even_odd=eo.value)
+        return dict(zip(keys, [x.value for x in v]), even_odd=eo.value, multi_component=int(self.multi_component_kernel()))
+
+    def multi_component_kernel(self) -> bool:
+        """Vector-valued applies (vmult_components, n_components CG) run ONE cell-kernel launch that fetches the geometric
+        factors of a cell once for all components (csrc/operator.cu: op_has_mc_kernel): collocated Laplace, stored G."""
+        import os
+        return (self.collocated and self.kind == OP_LAPLACE and self.geometry == "stored"
+                and os.environ.get("B200FE_MULTI_COMPONENT", "1") != "0")
 
     # algorithmic bytes of one apply (SURVEY.md section 8d): G + indices per cell, 32 B per local DoF
     def algorithmic_bytes(self) -> int:
