@@ -633,6 +633,13 @@ static size_t fused_max()
     return n;
 }
 
+// a CTA no larger than the message needs (launch and barrier cost of 32 warps shows at 1 KiB)
+static unsigned ll_threads(uint32_t n, int ncomp)
+{
+    const size_t total = (size_t)n * ncomp;
+    return total <= 512 ? 128u : total <= 2048 ? 256u : 1024u;
+}
+
 static bool ll_enabled()
 {
     static const bool on = [] { const char *e = std::getenv("B200FE_P2P_LL"); return !e || std::atoi(e) != 0; }();
@@ -644,7 +651,7 @@ int p2p_update(Halo &h, double *v, int ncomp, size_t stride, const double *raw_s
     P2P &p = *h.p2p;
     if (ncomp > p.comps) return fail(B200FE_ERR_UNSUPPORTED, "P2P halo: %d components exceed the window (%d)", ncomp, p.comps);
     if (ncomp <= p.ll_max_comps && ll_enabled()) {
-        p2p_round_ll_kernel<<<1, 1024, 0, s>>>(p.d_state, (Ctrl *)p.window, MODE_UPDATE, v, h.n_owned, h.n_send, h.n_ghost, h.d_send_idx, ncomp, stride,
+        p2p_round_ll_kernel<<<1, ll_threads(std::max(h.n_send, h.n_ghost), ncomp), 0, s>>>(p.d_state, (Ctrl *)p.window, MODE_UPDATE, v, h.n_owned, h.n_send, h.n_ghost, h.d_send_idx, ncomp, stride,
                                                raw_send, p.ll_recv, raw_recv);
         B200FE_CUDA_TRY(cudaGetLastError());
         return B200FE_OK;
@@ -664,7 +671,7 @@ int p2p_compress(Halo &h, double *v, int ncomp, size_t stride, cudaStream_t s)
     P2P &p = *h.p2p;
     if (ncomp > p.comps) return fail(B200FE_ERR_UNSUPPORTED, "P2P halo: %d components exceed the window (%d)", ncomp, p.comps);
     if (ncomp <= p.ll_max_comps && ll_enabled()) {
-        p2p_round_ll_kernel<<<1, 1024, 0, s>>>(p.d_state, (Ctrl *)p.window, MODE_COMPRESS, v, h.n_owned, h.n_ghost, h.n_send, h.d_send_idx, ncomp, stride,
+        p2p_round_ll_kernel<<<1, ll_threads(std::max(h.n_send, h.n_ghost), ncomp), 0, s>>>(p.d_state, (Ctrl *)p.window, MODE_COMPRESS, v, h.n_owned, h.n_ghost, h.n_send, h.d_send_idx, ncomp, stride,
                                                nullptr, p.ll_back, nullptr);
         B200FE_CUDA_TRY(cudaGetLastError());
         return B200FE_OK;
