@@ -428,9 +428,10 @@ int b200fe_halo_exchange_raw(b200fe_halo *halo, const double *d_send, double *d_
     Halo &h = *reinterpret_cast<Halo *>(halo);
     if (h.n_ranks == 1) return B200FE_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    if (h.use_p2p) {  // peer stores into the receivers' windows + flags, then wait + copy out (halo_p2p.cu)
-        return p2p_update(h, nullptr, 1, 0, d_send, d_recv, s);
-    }
+    // peer stores into the receivers' windows + flags, then wait + copy out (halo_p2p.cu).  Beyond ~1 GiB per rank and round
+    // the staged copy loses to NCCL's direct receive (r02h, 8 GPUs, 512 MiB messages: 2.7-3.4 vs 4.4-4.8 TB/s aggregate;
+    // at 64 MiB and below P2P is 1.2-2.6x faster): those rounds stay on NCCL.
+    if (h.use_p2p && (size_t)h.n_ghost * sizeof(double) < (size_t)1 << 30) return p2p_update(h, nullptr, 1, 0, d_send, d_recv, s);
     Nccl &n = nccl();
     // one round of p-halox: post all receives, all sends, complete together (phalox.cc:111-125)
     B200FE_NCCL_TRY(n.GroupStart());

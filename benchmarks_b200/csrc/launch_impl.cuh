@@ -77,7 +77,9 @@ struct V2Cfg {
 // Even-odd kernels: built where the B200 sweeps show a gain (profiles/r02a_sweep_{default,eo}.txt): every interpolated
 // operator, and the collocated ones from nq = 9 on (below that the collocated kernels are at 0.87-0.93 of the HBM roofline
 // either way and the plain contraction is as fast or faster: BP5 p = 7 0.92 vs 0.87).
-constexpr bool eo_built(int nq, bool coll) { return coll ? nq >= 9 : true; }
+// The on-the-fly (affine) geometry kernels keep six per-cell constants and the weights live on top of the contractions and
+// spilled 424-1208 B/thread with plain contractions (profiles/r01k_static_resource_usage.txt): always even-odd.
+constexpr bool eo_built(int nq, bool coll, int qop = 0) { return (qop & QOP_AFFINE) ? true : (coll ? nq >= 9 : true); }
 
 inline bool eo_enabled()
 {
@@ -137,7 +139,7 @@ template <int NM, int NQ, bool COLL, int QOP, bool LVEC>
 cudaError_t launch_t(const double *hB, const double *hD, const double *hW, const KArgs &a, cudaStream_t s,
                      LaunchInfo *info, bool dry_run)
 {
-    if constexpr (eo_built(NQ, COLL)) {
+    if constexpr (eo_built(NQ, COLL, QOP)) {
         if (eo_enabled()) {
             // the symmetric 1-D matrices of a real basis (not the reference drivers' cos() test matrices): even-odd kernel
             double Bsym[NQ * NM], Dsym[NQ * NQ];
