@@ -5,6 +5,7 @@
 
 #include "kernels.h"
 #include "sumfact2.cuh"
+#include "sumfact_tpe.cuh"
 
 namespace b200fe {
 
@@ -135,10 +136,70 @@ cudaError_t launch_variant(const Mats<NM, NQ, EO> &m, const KArgs &a, cudaStream
     return cudaGetLastError();
 }
 
+// tiny elements (nq <= 3): one thread per element, everything in registers (sumfact_tpe.cuh); B200FE_TPE=0 keeps the
+// plane-per-thread kernel for A/B runs
+constexpr bool tpe_built(int nq, int qop) { return nq <= 3 && !(qop & QOP_AFFINE); }
+inline bool tpe_enabled()
+{
+    static const bool on = [] { const char *e = std::getenv("B200FE_TPE"); return !e || std::atoi(e) != 0; }();
+    return on;
+}
+
+template <int NM, int NQ, bool COLL, int QOP, bool LVEC>
+cudaError_t launch_tpe(const double *hB, const double *hD, const KArgs &a, cudaStream_t s, LaunchInfo *info, bool dry_run)
+{
+    constexpr int TPB = NQ == 2 ? 64 : 32;
+    constexpr int MINB = NQ == 2 ? 6 : 1;
+    using L = tpe::LayoutT<NM, NQ, COLL, QOP, TPB>;
+    auto kern = sumfact_tpe_kernel<NM, NQ, COLL, QOP, LVEC, TPB, MINB>;
+    const size_t smem = L::smem_bytes();
+    if ((QOP & QOP_LAPLACE) && !dry_run && (reinterpret_cast<uintptr_t>(a.G) & 15u) != 0) return cudaErrorMisalignedAddress;
+    struct Cfg {
+        bool ready = false;
+        int blocks_per_sm = 0, sms = 0, regs = 0;
+    };
+    static Cfg cfg[64];
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return err;
+    Cfg &c = cfg[dev & 63];
+    if (!c.ready) {
+        err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+        err = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (err != cudaSuccess) return err;
+        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.blocks_per_sm, kern, TPB, smem);
+        if (err != cudaSuccess) return err;
+        err = cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, dev);
+        if (err != cudaSuccess) return err;
+        cudaFuncAttributes fa;
+        err = cudaFuncGetAttributes(&fa, kern);
+        if (err != cudaSuccess) return err;
+        c.regs = fa.numRegs;
+        if (c.blocks_per_sm < 1) return cudaErrorLaunchOutOfResources;
+        c.ready = true;
+    }
+    const uint32_t n_batches = (a.n_elems + TPB - 1) / TPB;
+    const long long resident = (long long)c.sms * c.blocks_per_sm * grid_multiplier();
+    const int grid = (int)(n_batches < (uint32_t)resident ? n_batches : resident);
+    if (info) *info = LaunchInfo{TPB, grid, TPB, (int)smem, c.blocks_per_sm, c.regs, 0};
+    if (dry_run || a.n_elems == 0) return cudaSuccess;
+    Mats<NM, NQ, false> m;
+    if (hB) std::memcpy(m.B, hB, sizeof(m.B));
+    else for (int q = 0; q < NQ; ++q) for (int i = 0; i < NM; ++i) m.B[q * NM + i] = (COLL && q == i) ? 1.0 : 0.0;
+    if (hD) std::memcpy(m.D, hD, sizeof(m.D)); else std::memset(m.D, 0, sizeof(m.D));
+    std::memset(m.W, 0, sizeof(m.W));
+    kern<<<grid, TPB, smem, s>>>(m, a);
+    return cudaGetLastError();
+}
+
 template <int NM, int NQ, bool COLL, int QOP, bool LVEC>
 cudaError_t launch_t(const double *hB, const double *hD, const double *hW, const KArgs &a, cudaStream_t s,
                      LaunchInfo *info, bool dry_run)
 {
+    if constexpr (tpe_built(NQ, QOP)) {
+        if (tpe_enabled() && a.ncomp <= 1) return launch_tpe<NM, NQ, COLL, QOP, LVEC>(hB, hD, a, s, info, dry_run);
+    }
     if constexpr (eo_built(NQ, COLL, QOP)) {
         if (eo_enabled()) {
             // the symmetric 1-D matrices of a real basis (not the reference drivers' cos() test matrices): even-odd kernel
