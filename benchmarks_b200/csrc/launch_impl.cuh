@@ -137,8 +137,11 @@ cudaError_t launch_variant(const Mats<NM, NQ, EO> &m, const KArgs &a, cudaStream
 }
 
 // tiny elements (nq <= 3): one thread per element, everything in registers (sumfact_tpe.cuh); B200FE_TPE=0 keeps the
-// plane-per-thread kernel for A/B runs
-constexpr bool tpe_built(int nq, int qop) { return nq <= 3 && !(qop & QOP_AFFINE); }
+// plane-per-thread kernel for A/B runs.  Measured (profiles/r02k_tpe_ab.txt, fraction of the HBM roofline, plane-per-thread
+// -> thread-per-element): BP5 p=1 0.61 -> 0.95, BP3 p=1 0.60 -> 0.93, BK3 p=1 0.58 -> 0.92, BK5 p=1 0.65 -> 0.83, BP5 p=2
+// 0.71 -> 0.75, "bp35" p=2 0.58 -> 0.74.  Operators with geometric factors only: the pure mass kernels read JxW straight
+// from global memory per thread and lose (BK1 p=1 0.42 -> 0.36), they keep the plane-per-thread kernel.
+constexpr bool tpe_built(int nq, int qop) { return nq <= 3 && (qop & QOP_LAPLACE) && !(qop & QOP_AFFINE); }
 inline bool tpe_enabled()
 {
     static const bool on = [] { const char *e = std::getenv("B200FE_TPE"); return !e || std::atoi(e) != 0; }();
