@@ -141,7 +141,7 @@ cudaError_t launch_variant(const Mats<NM, NQ, EO> &m, const KArgs &a, cudaStream
 // -> thread-per-element): BP5 p=1 0.61 -> 0.95, BP3 p=1 0.60 -> 0.93, BK3 p=1 0.58 -> 0.92, BK5 p=1 0.65 -> 0.83, BP5 p=2
 // 0.71 -> 0.75, "bp35" p=2 0.58 -> 0.74.  Operators with geometric factors only: the pure mass kernels read JxW straight
 // from global memory per thread and lose (BK1 p=1 0.42 -> 0.36), they keep the plane-per-thread kernel.
-constexpr bool tpe_built(int nq, int qop) { return nq <= 3 && (qop & QOP_LAPLACE) && !(qop & QOP_AFFINE); }
+constexpr bool tpe_built(int nq, int qop) { return nq <= 3 && !(qop & QOP_AFFINE); }
 inline bool tpe_enabled()
 {
     static const bool on = [] { const char *e = std::getenv("B200FE_TPE"); return !e || std::atoi(e) != 0; }();
@@ -201,7 +201,10 @@ cudaError_t launch_t(const double *hB, const double *hD, const double *hW, const
                      LaunchInfo *info, bool dry_run)
 {
     if constexpr (tpe_built(NQ, QOP)) {
-        if (tpe_enabled() && a.ncomp <= 1) return launch_tpe<NM, NQ, COLL, QOP, LVEC>(hB, hD, a, s, info, dry_run);
+        // (the staged JxW batch copy needs a 16-byte aligned source: a cell range that starts at an odd cell of an nq = 3
+        //  mass-type operator falls back to the plane-per-thread kernel)
+        const bool jxw_ok = !(QOP & QOP_MASS) || dry_run || (reinterpret_cast<uintptr_t>(a.JxW) & 15u) == 0;
+        if (tpe_enabled() && a.ncomp <= 1 && jxw_ok) return launch_tpe<NM, NQ, COLL, QOP, LVEC>(hB, hD, a, s, info, dry_run);
     }
     if constexpr (eo_built(NQ, COLL, QOP)) {
         if (eo_enabled()) {

@@ -14,6 +14,8 @@
 //     doubles apart, so the 16 lanes of a half-warp read 8 distinct banks (2-way instead of 16-way);
 //   * the next batch's indices / values and the next batch's G copy are in flight behind the current element's arithmetic
 //     (same software pipeline as sumfact2.cuh).
+//   * JxW (mass, Helmholtz) is staged the same way: one contiguous bulk copy per batch when nq^3 is odd (slot stride 27:
+//     conflict-free), per-thread copies into padded slots when it is even; a partial tail batch copies with plain loads.
 // Same KArgs, same numerics contract (<= 1e-12 against the oracle) and the same fused epilogues (RED scatter, p.Ap) as the
 // plane-per-thread kernel; stored geometric factors and / or JxW (Laplace, mass, Helmholtz).
 #pragma once
@@ -34,12 +36,24 @@ constexpr int g_slot(int nq)
     return s;
 }
 
+constexpr int j_slot(int n3)
+{
+    int s = n3;
+    while (s % 16 != 2) ++s;
+    return s;
+}
+
 template <int NM, int NQ, bool COLL, int QOP, int TPB>
 struct LayoutT {
     static constexpr int N3 = NQ * NQ * NQ, M3 = NM * NM * NM;
     static constexpr bool LAP = (QOP & QOP_LAPLACE) != 0;
+    static constexpr bool MASS = (QOP & QOP_MASS) != 0;
     static constexpr int SLOT = LAP ? g_slot(NQ) : 0;
-    static constexpr size_t smem_bytes() { return 16 + sizeof(double) * (size_t)TPB * SLOT; }
+    // JxW: nq^3 odd -> the batch is one contiguous bulk copy and the odd slot stride is conflict-free as it is;
+    //      nq^3 even -> per-thread copies into slots 2 (mod 16) apart, like G
+    static constexpr bool J_BATCH_COPY = (N3 % 2) == 1;
+    static constexpr int SLOT_J = !MASS ? 0 : (J_BATCH_COPY ? N3 : j_slot(N3));
+    static constexpr size_t smem_bytes() { return 16 + sizeof(double) * (size_t)TPB * (SLOT + SLOT_J); }
 };
 
 }  // namespace tpe
@@ -48,8 +62,9 @@ template <int NM, int NQ, bool COLL, int QOP, bool LVEC, int TPB, int MINB>
 __global__ void __launch_bounds__(TPB, MINB) sumfact_tpe_kernel(const __grid_constant__ Mats<NM, NQ, false> m, const KArgs a)
 {
     using L = tpe::LayoutT<NM, NQ, COLL, QOP, TPB>;
-    constexpr int N3 = L::N3, M3 = L::M3, SLOT = L::SLOT;
-    constexpr bool LAP = L::LAP, MASS = (QOP & QOP_MASS) != 0;
+    constexpr int N3 = L::N3, M3 = L::M3, SLOT = L::SLOT, SLOT_J = L::SLOT_J;
+    constexpr bool LAP = L::LAP, MASS = L::MASS, STAGED = LAP || MASS;
+    static_assert(TPB % 2 == 0, "even CTA size: a full batch of JxW is a multiple of 16 bytes");
     static_assert(!COLL || NM == NQ, "collocated operators need nm == nq");
     static_assert(NQ <= 3, "thread-per-element kernel: nq <= 3");
     static_assert(!(QOP & QOP_AFFINE), "thread-per-element kernel: stored geometric factors");
@@ -60,20 +75,36 @@ __global__ void __launch_bounds__(TPB, MINB) sumfact_tpe_kernel(const __grid_con
     double *Gs = reinterpret_cast<double *>(smem_raw + 16);
     const int tid = threadIdx.x;
     const double *Ge = Gs + tid * SLOT;
+    double *Js = Gs + TPB * SLOT;
+    const double *Je = Js + tid * SLOT_J;
     const uint32_t n_batches = (a.n_elems + TPB - 1) / TPB;
 
-    auto issue_g = [&](uint32_t eb) {  // every thread fetches its own element's block; thread 0 announces the total
+    auto issue_g = [&](uint32_t eb) {  // every thread fetches its own element's block(s); thread 0 announces the total
         const uint32_t first = eb * TPB;
         const uint32_t cnt = (a.n_elems - first) < (uint32_t)TPB ? (a.n_elems - first) : (uint32_t)TPB;
-        if (tid == 0) v2::mbar_expect_tx(bar, cnt * (uint32_t)(6 * N3 * sizeof(double)));
-        if ((uint32_t)tid < cnt) v2::bulk_g2s(Gs + tid * SLOT, a.G + (size_t)(first + tid) * 6 * N3, (uint32_t)(6 * N3 * sizeof(double)), bar);
+        constexpr uint32_t GB = 6 * N3 * sizeof(double), JB = N3 * sizeof(double);
+        const bool j_tma = MASS && (!L::J_BATCH_COPY || cnt == (uint32_t)TPB);
+        if (tid == 0) v2::mbar_expect_tx(bar, (LAP ? cnt * GB : 0u) + (j_tma ? cnt * JB : 0u));
+        if constexpr (LAP)
+            if ((uint32_t)tid < cnt) v2::bulk_g2s(Gs + tid * SLOT, a.G + (size_t)(first + tid) * 6 * N3, GB, bar);
+        if constexpr (MASS) {
+            if constexpr (L::J_BATCH_COPY) {
+                if (j_tma) {
+                    if (tid == 0) v2::bulk_g2s(Js, a.JxW + (size_t)first * N3, (uint32_t)TPB * JB, bar);
+                } else if ((uint32_t)tid < cnt) {  // partial tail batch (its byte count need not be a multiple of 16): plain copy
+                    for (int l = 0; l < N3; ++l) Js[tid * SLOT_J + l] = __ldg(a.JxW + (size_t)(first + tid) * N3 + l);
+                }
+            } else if ((uint32_t)tid < cnt)
+                v2::bulk_g2s(Js + tid * SLOT_J, a.JxW + (size_t)(first + tid) * N3, JB, bar);
+        }
     };
-    if constexpr (LAP) {
+    if constexpr (STAGED) {
         if (tid == 0) {
             v2::mbar_init(bar, 1);
             v2::fence_mbar_init();
         }
-        for (int i = tid; i < TPB * SLOT; i += TPB) Gs[i] = 0.0;  // unused slots of a tail batch: zeros, never NaNs (0 * stale in p.Ap)
+        // unused slots of a tail batch: zeros, never NaNs (0 * stale in p.Ap)
+        for (int i = tid; i < TPB * (SLOT + SLOT_J); i += TPB) Gs[i] = 0.0;
         v2::fence_proxy_async();
         __syncthreads();
         if (blockIdx.x < n_batches) issue_g(blockIdx.x);
@@ -155,9 +186,11 @@ __global__ void __launch_bounds__(TPB, MINB) sumfact_tpe_kernel(const __grid_con
         double w[N3];
 #pragma unroll
         for (int l = 0; l < N3; ++l) w[l] = 0.0;
-        if constexpr (LAP) {
-            v2::mbar_wait(bar, parity);  // this batch's geometric factors have landed
+        if constexpr (STAGED) {
+            v2::mbar_wait(bar, parity);  // this batch's geometric factors / JxW have landed
             parity ^= 1u;
+        }
+        if constexpr (LAP) {
 #pragma unroll
             for (int p = 0; p < NQ; ++p)
 #pragma unroll
@@ -185,19 +218,20 @@ __global__ void __launch_bounds__(TPB, MINB) sumfact_tpe_kernel(const __grid_con
                             w[(p * NQ + q) * NQ + n] = fma(m.D[r * NQ + n], ft, w[(p * NQ + q) * NQ + n]);
                         }
                     }
-            __syncthreads();  // every thread has drained its slot: the buffer may be refilled
+        }
+        if constexpr (MASS) {
+#pragma unroll
+            for (int l = 0; l < N3; ++l) {
+                const double mv = (active ? Je[l] : 0.0) * v[l];
+                w[l] += mv;
+                if constexpr (LVEC) dot_acc = fma(mv, v[l], dot_acc);
+            }
+        }
+        if constexpr (STAGED) {
+            __syncthreads();  // every thread has drained its slots: the buffers may be refilled
             if (nb < n_batches) {
                 v2::fence_proxy_async();
                 issue_g(nb);
-            }
-        }
-        if constexpr (MASS) {
-            const double *Je = a.JxW + (size_t)(active ? e : 0) * N3;
-#pragma unroll
-            for (int l = 0; l < N3; ++l) {
-                const double mv = (active ? __ldg(Je + l) : 0.0) * v[l];
-                w[l] += mv;
-                if constexpr (LVEC) dot_acc = fma(mv, v[l], dot_acc);
             }
         }
         if constexpr (LVEC && PREFETCH_VAL) load_val(nb, nxt_idx, nxt);  // next batch's gathers behind the rest of this element

@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--degrees", default="1,2,3,4,5,6,7,8")
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--json", default=None)
+    ap.add_argument("--mass", action="store_true", help="also BP1 (mass, QGauss(p+2)) and the bp5_kokkos Helmholtz operator")
     args = ap.parse_args()
     try:
         peak = float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"])
@@ -31,8 +32,11 @@ def main():
             return float(np.prod([((2 if d < rem else 1) << n) * p + 1 for d in range(3)]))
         best = min(range(0, 27), key=lambda c: abs(np.log(ndofs(c) / 1.2e7)))
         mesh = b.BoxMesh.bp3_cycle(best, p)
-        for name, kw in (("bp5", dict(quad="gll")), ("bp3", dict(quad="gauss", nq=p + 2)), ("bp35", dict(quad="gauss", nq=p + 1))):
-            op = b.LaplaceOperator(mesh, with_jxw=False, **kw)
+        for name, kw in (("bp5", dict(quad="gll")), ("bp3", dict(quad="gauss", nq=p + 2)), ("bp35", dict(quad="gauss", nq=p + 1)),
+                         ("bp1", dict(quad="gauss", nq=p + 2, kind="mass")), ("helm", dict(quad="gauss", nq=p + 1, kind="helmholtz"))):
+            if name in ("bp1", "helm") and not args.mass:
+                continue
+            op = b.LaplaceOperator(mesh, with_jxw=name in ("bp1", "helm"), **kw)
             src = torch.rand(mesh.n_owned, dtype=torch.float64, device="cuda")
             dst = torch.empty_like(src)
             for _ in range(3):
