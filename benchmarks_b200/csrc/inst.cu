@@ -26,4 +26,8 @@ INST(NM, NM, false, QOP_HELMHOLTZ, true)     // bp5_kokkos Helmholtz (QGauss(p+1
 INST(NM, NM + 1, false, QOP_LAPLACE | QOP_AFFINE, true)
 INST(NM, NM, false, QOP_LAPLACE | QOP_AFFINE, true)
 INST(NM, NM, true, QOP_LAPLACE | QOP_AFFINE, true)
+// ... and for trilinear cells (8 vertices per cell, G rebuilt at every quadrature point)
+INST(NM, NM + 1, false, QOP_LAPLACE | QOP_TRILINEAR, true)
+INST(NM, NM, false, QOP_LAPLACE | QOP_TRILINEAR, true)
+INST(NM, NM, true, QOP_LAPLACE | QOP_TRILINEAR, true)
 }  // namespace b200fe

@@ -41,7 +41,7 @@ constexpr int v2_rmin(int nq, bool coll, int qop, bool eo = false)
     return B200FE_V2_RMIN_FIXED;
 #else
     if (!(qop & QOP_LAPLACE)) return 64 + 12 * nq;  // mass only: no G buffer, registers are the limit
-    if (nq <= 6) return (qop & QOP_AFFINE) ? 128 : 96;  // affine kernels keep six more constants + weights live
+    if (nq <= 6) return (qop & (QOP_AFFINE | QOP_TRILINEAR)) ? 128 : 96;  // on-the-fly kernels keep the cell constants + weights live
 #ifdef B200FE_V2_RMIN_HI
     return B200FE_V2_RMIN_HI;
 #else
@@ -80,7 +80,7 @@ struct V2Cfg {
 // either way and the plain contraction is as fast or faster: BP5 p = 7 0.92 vs 0.87).
 // The on-the-fly (affine) geometry kernels keep six per-cell constants and the weights live on top of the contractions and
 // spilled 424-1208 B/thread with plain contractions (profiles/r01k_static_resource_usage.txt): always even-odd.
-constexpr bool eo_built(int nq, bool coll, int qop = 0) { return (qop & QOP_AFFINE) ? true : (coll ? nq >= 9 : true); }
+constexpr bool eo_built(int nq, bool coll, int qop = 0) { return (qop & (QOP_AFFINE | QOP_TRILINEAR)) ? true : (coll ? nq >= 9 : true); }
 
 inline bool eo_enabled()
 {
@@ -100,7 +100,7 @@ cudaError_t launch_variant(const Mats<NM, NQ, EO> &m, const KArgs &a, cudaStream
     auto kern = sumfact2_kernel<NM, NQ, COLL, QOP, LVEC, EPB, C::MINB, EO, MC>;
     const size_t smem = C::SMEM;
     // TMA bulk copies need a 16-byte aligned source (the batch block offset is a multiple of 48 nq^3 bytes)
-    if ((QOP & QOP_LAPLACE) && !(QOP & QOP_AFFINE) && !dry_run && (reinterpret_cast<uintptr_t>(a.G) & 15u) != 0) return cudaErrorMisalignedAddress;
+    if ((QOP & QOP_LAPLACE) && !(QOP & (QOP_AFFINE | QOP_TRILINEAR)) && !dry_run && (reinterpret_cast<uintptr_t>(a.G) & 15u) != 0) return cudaErrorMisalignedAddress;
 
     struct Cfg {
         bool ready = false;
@@ -141,7 +141,7 @@ cudaError_t launch_variant(const Mats<NM, NQ, EO> &m, const KArgs &a, cudaStream
 // -> thread-per-element): BP5 p=1 0.61 -> 0.95, BP3 p=1 0.60 -> 0.93, BK3 p=1 0.58 -> 0.92, BK5 p=1 0.65 -> 0.83, BP5 p=2
 // 0.71 -> 0.75, "bp35" p=2 0.58 -> 0.74.  Operators with geometric factors only: the pure mass kernels read JxW straight
 // from global memory per thread and lose (BK1 p=1 0.42 -> 0.36), they keep the plane-per-thread kernel.
-constexpr bool tpe_built(int nq, int qop) { return nq <= 3 && !(qop & QOP_AFFINE); }
+constexpr bool tpe_built(int nq, int qop) { return nq <= 3 && !(qop & (QOP_AFFINE | QOP_TRILINEAR)); }
 inline bool tpe_enabled()
 {
     static const bool on = [] { const char *e = std::getenv("B200FE_TPE"); return !e || std::atoi(e) != 0; }();
@@ -192,6 +192,7 @@ cudaError_t launch_tpe(const double *hB, const double *hD, const KArgs &a, cudaS
     else for (int q = 0; q < NQ; ++q) for (int i = 0; i < NM; ++i) m.B[q * NM + i] = (COLL && q == i) ? 1.0 : 0.0;
     if (hD) std::memcpy(m.D, hD, sizeof(m.D)); else std::memset(m.D, 0, sizeof(m.D));
     std::memset(m.W, 0, sizeof(m.W));
+    std::memset(m.X, 0, sizeof(m.X));
     kern<<<grid, TPB, smem, s>>>(m, a);
     return cudaGetLastError();
 }
@@ -216,6 +217,7 @@ cudaError_t launch_t(const double *hB, const double *hD, const double *hW, const
             Mats<NM, NQ, true> me;
             if (eo::fill<NM, NQ>(Bsym, Dsym, me.E) <= 1e-10) {
                 if (hW) std::memcpy(me.W, hW, sizeof(me.W)); else std::memset(me.W, 0, sizeof(me.W));
+                if (hW && (QOP & QOP_TRILINEAR)) std::memcpy(me.X, hW + NQ, sizeof(me.X)); else std::memset(me.X, 0, sizeof(me.X));  // hW = weights | points
                 if (a.ncomp > 1) {
                     if constexpr (mc_built(COLL, QOP, LVEC)) return launch_variant<NM, NQ, COLL, QOP, LVEC, true, true>(me, a, s, info, dry_run);
                     else return cudaErrorNotSupported;
@@ -224,15 +226,20 @@ cudaError_t launch_t(const double *hB, const double *hD, const double *hW, const
             }
         }
     }
+    if constexpr ((QOP & QOP_TRILINEAR) != 0) {
+        return cudaErrorNotSupported;  // trilinear on-the-fly geometry is built with the even-odd contractions only (real bases)
+    } else {
     Mats<NM, NQ, false> m;
     if (hB) std::memcpy(m.B, hB, sizeof(m.B)); else std::memset(m.B, 0, sizeof(m.B));
     if (hD) std::memcpy(m.D, hD, sizeof(m.D)); else std::memset(m.D, 0, sizeof(m.D));
     if (hW) std::memcpy(m.W, hW, sizeof(m.W)); else std::memset(m.W, 0, sizeof(m.W));
+    std::memset(m.X, 0, sizeof(m.X));
     if (a.ncomp > 1) {
         if constexpr (mc_built(COLL, QOP, LVEC)) return launch_variant<NM, NQ, COLL, QOP, LVEC, false, true>(m, a, s, info, dry_run);
         else return cudaErrorNotSupported;
     }
     return launch_variant<NM, NQ, COLL, QOP, LVEC, false>(m, a, s, info, dry_run);
+    }
 }
 
 }  // namespace b200fe

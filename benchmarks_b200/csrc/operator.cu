@@ -482,7 +482,7 @@ __global__ void condense_faces_kernel(uint32_t n_blocks, int nm, int nf, const d
 bool op_has_mc_kernel(const Operator &op)
 {
     static const bool on = [] { const char *e = std::getenv("B200FE_MULTI_COMPONENT"); return !e || std::atoi(e) != 0; }();
-    return on && op.collocated && op.qop == QOP_LAPLACE && op.d_cellG == nullptr;
+    return on && op.collocated && op.qop == QOP_LAPLACE && op.otf_flag() == 0;
 }
 
 int op_apply_cells(Operator &op, double *d_dst, const double *d_src, uint32_t cb, uint32_t ce,
@@ -490,12 +490,12 @@ int op_apply_cells(Operator &op, double *d_dst, const double *d_src, uint32_t cb
 {
     if (ce <= cb) return B200FE_OK;
     const size_t nm3 = (size_t)op.nm * op.nm * op.nm, nq3 = (size_t)op.nq * op.nq * op.nq;
-    const bool affine = op.d_cellG != nullptr;
+    const bool affine = op.otf_flag() != 0;  // geometric factors evaluated on the fly (affine or trilinear cells)
     KArgs a{ce - cb, (op.d_G && !affine) ? op.d_G + cb * 6 * nq3 : nullptr, op.d_JxW ? op.d_JxW + cb * nq3 : nullptr,
-            d_src, d_dst, op.d_idx + cb * nm3, d_dot, affine ? op.d_cellG + (size_t)cb * 8 : nullptr, op.d_skip};
+            d_src, d_dst, op.d_idx + cb * nm3, d_dot, affine ? op.otf_data() + (size_t)cb * op.otf_stride() : nullptr, op.d_skip};
     a.ncomp = ncomp;
     a.comp_stride = op.n_local();
-    const int qop = op.qop | (affine ? QOP_AFFINE : 0);
+    const int qop = op.qop | op.otf_flag();
     const bool timed = op.timing && op.ev_used + 2 <= op.ev.size();
     if (timed) B200FE_CUDA_TRY(cudaEventRecord(op.ev[op.ev_used], s));
     B200FE_CUDA_TRY(launch_sumfact(op.nm, op.nq, op.collocated, qop, true, op.B.data(), op.D.data(), a, s,
@@ -908,10 +908,13 @@ int b200fe_op_create(const b200fe_op_desc *d, b200fe_op **out)
     if (!ok) return fail(B200FE_ERR_UNSUPPORTED, "b200fe_op_create: no kernel for op_kind=%d p=%d nq=%d collocated=%d", d->op_kind, d->p, d->nq, (int)coll);
     B200FE_REQUIRE(d->h_co_shape_gradients && (coll || d->h_shape_values), "b200fe_op_create: 1-D matrices missing");
     B200FE_REQUIRE(d->n_cells == 0 || d->d_dof_indices, "b200fe_op_create: dof_indices missing");
-    const bool affine = d->d_cell_G != nullptr;
+    const bool trilinear = d->d_cell_vertices != nullptr;
+    const bool affine = d->d_cell_G != nullptr || trilinear;  // on-the-fly geometry of either kind
+    B200FE_REQUIRE(!(d->d_cell_G && trilinear), "b200fe_op_create: d_cell_G and d_cell_vertices are mutually exclusive");
     if (affine && d->op_kind != B200FE_OP_LAPLACE)
-        return fail(B200FE_ERR_UNSUPPORTED, "b200fe_op_create: on-the-fly (affine) geometry is built for the Laplace operators only");
-    B200FE_REQUIRE(!affine || d->h_weights, "b200fe_op_create: affine geometry needs the 1-D quadrature weights");
+        return fail(B200FE_ERR_UNSUPPORTED, "b200fe_op_create: on-the-fly geometry is built for the Laplace operators only");
+    B200FE_REQUIRE(!affine || d->h_weights, "b200fe_op_create: on-the-fly geometry needs the 1-D quadrature weights");
+    B200FE_REQUIRE(!trilinear || d->h_points, "b200fe_op_create: trilinear geometry needs the 1-D quadrature points");
     B200FE_REQUIRE(!(d->op_kind & B200FE_OP_LAPLACE) || d->n_cells == 0 || d->d_G || affine, "b200fe_op_create: G missing");
     B200FE_REQUIRE(!(d->op_kind & B200FE_OP_MASS) || d->n_cells == 0 || d->d_JxW, "b200fe_op_create: JxW missing");
     B200FE_REQUIRE(d->n_constrained == 0 || d->h_constrained, "b200fe_op_create: constrained list missing");
@@ -921,8 +924,9 @@ int b200fe_op_create(const b200fe_op_desc *d, b200fe_op **out)
     op->p = d->p; op->nm = nm; op->nq = d->nq; op->qop = d->op_kind; op->collocated = coll;
     op->n_cells = d->n_cells; op->n_owned = d->n_owned; op->n_ghost = d->n_ghost; op->n_constrained = d->n_constrained;
     op->n_phase0 = d->n_phase0; op->n_phase1 = d->n_phase1;
-    op->d_idx = d->d_dof_indices; op->d_G = d->d_G; op->d_JxW = d->d_JxW; op->d_cellG = d->d_cell_G;
+    op->d_idx = d->d_dof_indices; op->d_G = d->d_G; op->d_JxW = d->d_JxW; op->d_cellG = d->d_cell_G; op->d_cellX = d->d_cell_vertices;
     if (affine) op->W.assign(d->h_weights, d->h_weights + d->nq);
+    if (trilinear) op->W.insert(op->W.end(), d->h_points, d->h_points + d->nq);
     const int nq = d->nq;
     op->shape_values.assign(nm * nq, 0.0);
     if (coll) for (int i = 0; i < nm; ++i) op->shape_values[i * nq + i] = 1.0;
@@ -1179,7 +1183,7 @@ int b200fe_op_launch_info(b200fe_op *o, int *elems_per_block, int *num_blocks, i
     Operator &op = *reinterpret_cast<Operator *>(o);
     KArgs a{op.n_cells, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     LaunchInfo li{};
-    B200FE_CUDA_TRY(launch_sumfact(op.nm, op.nq, op.collocated, op.qop | (op.d_cellG ? QOP_AFFINE : 0), true, op.B.data(), op.D.data(), a, nullptr, &li, true));
+    B200FE_CUDA_TRY(launch_sumfact(op.nm, op.nq, op.collocated, op.qop | op.otf_flag(), true, op.B.data(), op.D.data(), a, nullptr, &li, true));
     if (elems_per_block) *elems_per_block = li.elems_per_block;
     if (num_blocks) *num_blocks = li.num_blocks;
     if (threads_per_block) *threads_per_block = li.threads_per_block;
@@ -1195,7 +1199,7 @@ int b200fe_op_kernel_variant(b200fe_op *o, int *even_odd)
     Operator &op = *reinterpret_cast<Operator *>(o);
     KArgs a{op.n_cells, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     LaunchInfo li{};
-    B200FE_CUDA_TRY(launch_sumfact(op.nm, op.nq, op.collocated, op.qop | (op.d_cellG ? QOP_AFFINE : 0), true, op.B.data(), op.D.data(), a, nullptr, &li, true));
+    B200FE_CUDA_TRY(launch_sumfact(op.nm, op.nq, op.collocated, op.qop | op.otf_flag(), true, op.B.data(), op.D.data(), a, nullptr, &li, true));
     *even_odd = li.even_odd;
     return B200FE_OK;
 }

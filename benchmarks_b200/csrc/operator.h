@@ -19,7 +19,11 @@ struct Operator {
     const double *d_G = nullptr;      // borrowed
     const double *d_JxW = nullptr;    // borrowed
     const double *d_cellG = nullptr;  // borrowed; affine on-the-fly geometry: [cell][8]
-    std::vector<double> W;            // 1-D quadrature weights (affine geometry)
+    const double *d_cellX = nullptr;  // borrowed; trilinear on-the-fly geometry: [cell][3][2][2][2] vertex coordinates
+    std::vector<double> W;            // 1-D quadrature weights (on-the-fly geometry), followed by the points (trilinear)
+    int otf_flag() const { return d_cellG ? QOP_AFFINE : d_cellX ? QOP_TRILINEAR : 0; }
+    const double *otf_data() const { return d_cellG ? d_cellG : d_cellX; }
+    int otf_stride() const { return d_cellG ? 8 : 24; }
     uint32_t *d_constrained = nullptr;  // owned
     double *d_mats = nullptr;           // owned: shape_values | co_shape_gradients | shape_gradients (setup kernels)
     // the same constraints grouped by coarse face (b200fe_op_set_face_constraints); takes precedence when set

@@ -21,7 +21,10 @@ constexpr uint32_t kInvalidIndex = 0xFFFFFFFFu;  // numbers::invalid_unsigned_in
 enum : int { QOP_LAPLACE = 1, QOP_MASS = 2, QOP_HELMHOLTZ = 3,
              // geometry evaluated on the fly for affine cells: G(q) = cellG * w_p w_q w_r with six
              // per-cell constants instead of the streamed 6 nq^3 factors; sumfact2 kernel, L-vector operators only
-             QOP_AFFINE = 4 };
+             QOP_AFFINE = 4,
+             // geometry evaluated on the fly for TRILINEAR cells (general hexahedra given by their 8 vertices): the Jacobian
+             // at a quadrature point is rebuilt from 24 vertex coordinates per cell and G = JxW K K^T formed in registers
+             QOP_TRILINEAR = 8 };
 
 // 1-D matrices in the BK layout: B[q*NM+i] (CEED_BK BK1 serial_kernels.hpp:39),
 // D[p*NQ+n] = derivative of collocation function n at point p (BK3 serial_kernels.hpp:98).
@@ -32,13 +35,15 @@ struct Mats {
     static constexpr bool kEvenOdd = false;
     double B[NQ * NM];
     double D[NQ * NQ];
-    double W[NQ];  // 1-D quadrature weights (affine on-the-fly geometry only)
+    double W[NQ];  // 1-D quadrature weights (on-the-fly geometry only)
+    double X[NQ];  // 1-D quadrature points on [0,1] (trilinear on-the-fly geometry only)
 };
 template <int NM, int NQ>
 struct Mats<NM, NQ, true> {
     static constexpr bool kEvenOdd = true;
     eo::EoMats<NM, NQ> E;
     double W[NQ];
+    double X[NQ];
 };
 
 struct KArgs {
@@ -49,7 +54,8 @@ struct KArgs {
     double *out;            // E-vector [e][NM^3]  | L-vector dst
     const uint32_t *idx;    // L-vector only: [e][NM^3], kInvalidIndex = constrained
     double *dot;            // L-vector only, optional: += sum_e u_e . (A_e u_e)
-    const double *cellG;    // affine geometry only: [e][8] = det J * K K^T (rr,rs,rt,ss,st,tt), det J, pad
+    const double *cellG;    // affine geometry: [e][8] = det J * K K^T (rr,rs,rt,ss,st,tt), det J, pad;
+                            // trilinear geometry: [e][3][2][2][2] vertex coordinates (x fastest), 24 doubles per cell
     const int *skip;        // optional: when *skip != 0 the launch is a no-op (CG iterations replayed after convergence)
     // vector-valued operators (BP2/4/6 = the scalar operator on every component), multi-component kernels only: the
     // geometric factors of a batch are fetched once and used for all components; in/out of component c at + c*comp_stride

@@ -98,7 +98,8 @@ struct Layout2 {
     static constexpr int pad_elem(int w) { while ((w - N2) % 16 != 0) ++w; return w; }
     static constexpr int WORK_PER_ELEM = N_REGIONS == 0 ? 0 : pad_elem(N_REGIONS * REGION);
     static constexpr bool AFFINE = (QOP & QOP_AFFINE) != 0;  // no streamed G: nothing to stage
-    static constexpr int G_PER_ELEM = (LAP && !AFFINE) ? 6 * N3 : 0;
+    static constexpr bool TRILIN = (QOP & QOP_TRILINEAR) != 0;
+    static constexpr int G_PER_ELEM = (LAP && !AFFINE && !TRILIN) ? 6 * N3 : 0;
     // warp-local mode (nq <= 5): an element's nq^2 threads sit inside one warp, EPW elements per warp;
     // every intra-element barrier becomes __syncwarp().  Idle lanes of a warp work on a dummy slot.
     // Measured (profiles/r01d_warp_local.txt): a win only when the planes tile the warp exactly (nq = 2, 4:
@@ -209,7 +210,8 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
     using L = v2::Layout2<NM, NQ, COLL, QOP>;
     constexpr int N2 = L::N2, N3 = L::N3, M3 = L::M3, RA = L::RA, PA = L::PA, PB = L::PB;
     constexpr int PSQ = L::PSQ, RSR = L::RSR, PSR = L::PSR;
-    constexpr bool LAP = L::LAP, MASS = (QOP & QOP_MASS) != 0, AFFINE = L::AFFINE, STORED_G = LAP && !AFFINE;
+    constexpr bool LAP = L::LAP, MASS = (QOP & QOP_MASS) != 0, AFFINE = L::AFFINE, TRILIN = L::TRILIN, STORED_G = LAP && !AFFINE && !TRILIN;
+    static_assert(!(AFFINE && TRILIN), "one on-the-fly geometry at a time");
     static_assert(!COLL || NM == NQ, "collocated operators need nm == nq");
 
     if (a.skip != nullptr && *a.skip != 0) return;  // uniform across the grid: decided before any barrier
@@ -434,6 +436,31 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
             }
             [[maybe_unused]] double cg[6];
             [[maybe_unused]] double wqr = 0.0;
+            // trilinear cells: the columns of J at this thread's (x^, y^) as linear functions of z^ (J[.][2] is constant in z^)
+            [[maybe_unused]] double j0a[3], j0b[3], j1a[3], j1b[3], j2c[3];
+            if constexpr (TRILIN) {
+                const double *X = a.cellG + (size_t)(active ? e : 0) * 24;
+                const double xx = m.X[tb], xy = m.X[ta];  // x^ = fastest local index (tb), y^ = middle (ta)
+                wqr = m.W[ta] * m.W[tb];
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    double v8[8];  // vertex index c*4 + b*2 + a  (a <-> x^)
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) v8[k] = active ? __ldg(X + d * 8 + k) : (((k >> d) & 1) ? 1.0 : 0.0);  // idle slots: unit cube
+                    // d/dx^: differences along a, bilinear in (y^, z^)
+                    const double dx0 = fma(xy, (v8[3] - v8[2]) - (v8[1] - v8[0]), v8[1] - v8[0]);   // z^ = 0
+                    const double dx1 = fma(xy, (v8[7] - v8[6]) - (v8[5] - v8[4]), v8[5] - v8[4]);   // z^ = 1
+                    j0a[d] = dx0; j0b[d] = dx1 - dx0;
+                    // d/dy^: differences along b, bilinear in (x^, z^)
+                    const double dy0 = fma(xx, (v8[3] - v8[1]) - (v8[2] - v8[0]), v8[2] - v8[0]);
+                    const double dy1 = fma(xx, (v8[7] - v8[5]) - (v8[6] - v8[4]), v8[6] - v8[4]);
+                    j1a[d] = dy0; j1b[d] = dy1 - dy0;
+                    // d/dz^: differences along c, bilinear in (x^, y^): constant along the column
+                    const double dz0 = fma(xx, (v8[5] - v8[1]) - (v8[4] - v8[0]), v8[4] - v8[0]);   // y^ = 0
+                    const double dz1 = fma(xx, (v8[7] - v8[3]) - (v8[6] - v8[2]), v8[6] - v8[2]);   // y^ = 1
+                    j2c[d] = fma(xy, dz1 - dz0, dz0);
+                }
+            }
             if constexpr (AFFINE) {  // six constants per cell, scaled by the tensor-product quadrature weight
                 const double *c8 = a.cellG + (size_t)(active ? e : 0) * 8;
 #pragma unroll
@@ -446,7 +473,38 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
                 const double qs = RQ[p * PSQ + t2];
                 const double qt = RR[p * PSR + ta * RSR + tb];
                 double g0, g1, g2, g3, g4, g5;
-                if constexpr (AFFINE) {
+                if constexpr (TRILIN) {
+                    // J[d][b] = d x_d / d xi_b at (x^, y^, z^ = X[p]); adj = det * J^-1; G = w / det * adj adj^T with the kernel's
+                    // directions (r,s,t) = (z^, y^, x^)  (geometry_kernel of operator.cu, the same arithmetic per point)
+                    const double xz = m.X[p];
+                    double J[3][3];
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        J[d][0] = fma(xz, j0b[d], j0a[d]);
+                        J[d][1] = fma(xz, j1b[d], j1a[d]);
+                        J[d][2] = j2c[d];
+                    }
+                    // rows of adj: A[b][a] = cofactor, so that K[b][a] = A[b][a] / det = d xi_b / d x_a
+                    double A[3][3];
+                    A[0][0] = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+                    A[0][1] = J[0][2] * J[2][1] - J[0][1] * J[2][2];
+                    A[0][2] = J[0][1] * J[1][2] - J[0][2] * J[1][1];
+                    A[1][0] = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+                    A[1][1] = J[0][0] * J[2][2] - J[0][2] * J[2][0];
+                    A[1][2] = J[0][2] * J[1][0] - J[0][0] * J[1][2];
+                    A[2][0] = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+                    A[2][1] = J[0][1] * J[2][0] - J[0][0] * J[2][1];
+                    A[2][2] = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+                    const double det = J[0][0] * A[0][0] + J[0][1] * A[1][0] + J[0][2] * A[2][0];
+                    const double sc = wqr * m.W[p] / det;
+                    // (r,s,t) = rows 2,1,0 of K
+                    g0 = sc * (A[2][0] * A[2][0] + A[2][1] * A[2][1] + A[2][2] * A[2][2]);
+                    g1 = sc * (A[2][0] * A[1][0] + A[2][1] * A[1][1] + A[2][2] * A[1][2]);
+                    g2 = sc * (A[2][0] * A[0][0] + A[2][1] * A[0][1] + A[2][2] * A[0][2]);
+                    g3 = sc * (A[1][0] * A[1][0] + A[1][1] * A[1][1] + A[1][2] * A[1][2]);
+                    g4 = sc * (A[1][0] * A[0][0] + A[1][1] * A[0][1] + A[1][2] * A[0][2]);
+                    g5 = sc * (A[0][0] * A[0][0] + A[0][1] * A[0][1] + A[0][2] * A[0][2]);
+                } else if constexpr (AFFINE) {
                     const double wt = wqr * m.W[p];
                     g0 = cg[0] * wt; g1 = cg[1] * wt; g2 = cg[2] * wt; g3 = cg[3] * wt; g4 = cg[4] * wt; g5 = cg[5] * wt;
                 } else {

@@ -29,7 +29,7 @@ class _OpDesc(C.Structure):
                 ("d_dof_indices", C.c_void_p), ("d_G", C.c_void_p), ("d_JxW", C.c_void_p),
                 ("h_constrained", C.c_void_p), ("n_constrained", C.c_uint32),
                 ("n_phase0", C.c_uint32), ("n_phase1", C.c_uint32),
-                ("d_cell_G", C.c_void_p), ("h_weights", C.c_void_p)]
+                ("d_cell_G", C.c_void_p), ("h_weights", C.c_void_p), ("d_cell_vertices", C.c_void_p), ("h_points", C.c_void_p)]
 
 
 class _CgResult(C.Structure):
@@ -95,11 +95,16 @@ class LaplaceOperator:
         nq3 = self.nq ** 3
         self.geometry = geometry
         self.cell_G = None
+        self.cell_vertices = None
         if geometry == "affine":  # on-the-fly geometric factors from six per-cell constants
             if p_geo != 1 or deform is not None or self.kind != OP_LAPLACE:
                 raise ValueError("geometry='affine' needs p_geo=1, no deformation and the Laplace operator")
             self.cell_G = torch.empty(mesh.n_cells * 8, dtype=torch.float64, device=self.device)
             check(lib.b200fe_geometry_affine_from_nodes(mesh.n_cells, _dp(nodes), _dp(self.cell_G), _sp()))
+        elif geometry == "trilinear":  # general hexahedra: the 8 vertices per cell ARE the geometry (MappingQ1), G rebuilt per point
+            if p_geo != 1 or self.kind != OP_LAPLACE:
+                raise ValueError("geometry='trilinear' needs p_geo=1 and the Laplace operator")
+            self.cell_vertices = nodes   # [cell][3][2][2][2], kept alive: borrowed by the operator
         elif geometry != "stored":
             raise ValueError(geometry)
         need_G = bool(self.kind & OP_LAPLACE) and geometry == "stored"
@@ -127,6 +132,9 @@ class LaplaceOperator:
         self._w = np.ascontiguousarray(self.basis["weights"])
         d.d_cell_G = self.cell_G.data_ptr() if self.cell_G is not None else None
         d.h_weights = self._w.ctypes.data
+        self._x = np.ascontiguousarray(self.basis["points"])
+        d.d_cell_vertices = self.cell_vertices.data_ptr() if self.cell_vertices is not None else None
+        d.h_points = self._x.ctypes.data
         self._h = C.c_void_p()
         check(lib.b200fe_op_create(C.byref(d), C.byref(self._h)))
         self.halo = halo
@@ -226,7 +234,7 @@ class LaplaceOperator:
     # algorithmic bytes of one apply: G + indices per cell, 32 B per local DoF
     def algorithmic_bytes(self) -> int:
         nq3, nm3 = self.nq ** 3, self.nm ** 3
-        g_bytes = 64 if self.geometry == "affine" else 48 * nq3
+        g_bytes = 64 if self.geometry == "affine" else 192 if self.geometry == "trilinear" else 48 * nq3
         per_cell = 4 * nm3 + (g_bytes if self.kind & OP_LAPLACE else 0) + (8 * nq3 if self.kind & OP_MASS else 0)
         return self.mesh.n_cells * per_cell + 32 * self.mesh.n_owned
 

@@ -264,6 +264,14 @@ typedef struct {
      * d_G may still be given (needed by b200fe_op_diagonal).  BORROWED. */
     const double *d_cell_G;
     const double *h_weights;
+    /* Optional: geometry evaluated on the fly for TRILINEAR cells (general hexahedra, the MappingQ1 case of SURVEY.md 8f.1):
+     * when d_cell_vertices != NULL the Laplace kernels rebuild the Jacobian at every quadrature point from the DEVICE array
+     * d_cell_vertices[cell][3][2][2][2] (coordinate d, then the vertex index z, y, x with x fastest -- b200fe_boxmesh_nodes
+     * with p_geo = 1) and form G = JxW J^-1 J^-T in registers; needs h_weights and the HOST 1-D points h_points[nq].
+     * 192 bytes per cell instead of 48 nq^3; results equal the stored-G operator of the same MappingQ1 mesh to rounding.
+     * Built for operators with the symmetric 1-D matrices of a real basis (b200fe_basis_1d).  BORROWED. */
+    const double *d_cell_vertices;
+    const double *h_points;
 } b200fe_op_desc;
 
 typedef struct b200fe_op b200fe_op;

@@ -120,3 +120,16 @@ def test_check_bk3_deformed_strip_matches_oracle(oracle_mod, degree):
     assert rel_max(out, ref) <= TOL
     # the deformation is really there: first cell is not a cube (off-diagonal geometric factors present)
     assert np.abs(Go[0, 1]).max() > 1e-3 * np.abs(Go[0, 0]).max()
+
+
+def test_matches_the_reference_cuda_kernels_elementwise():
+    """The reference's OWN CUDA kernels (CEED_BK/include/kernels/BK{1,3,5}/templated_cuda_kernels.cuh, T = double, compiled in
+    place into oracle/_ref/libref_gpu_ceedbk.so, the drivers' launch shape) on the same device arrays: every degree, <= 1e-13."""
+    import benchmarks_b200 as b
+    from oracle import ref_gpu
+    if not ref_gpu.available():
+        pytest.skip("oracle/_ref/libref_gpu_*.so not built in this checkout")
+    rows = ref_gpu.kernel_to_beat(b, dofs=3e5, ntests=1)
+    assert len(rows) == 24
+    for r in rows:
+        assert r["max_rel_diff"] <= 1e-13, (r["kind"], r["p"], r["max_rel_diff"])

@@ -91,6 +91,34 @@ def test_diagonal_rhs_and_dummy(oracle_mod, p):
     assert torch.equal(ghost_only[con], src[con]) and (ghost_only[free] == 3.0).all()  # no dst = 0 without computation
 
 
+@pytest.mark.parametrize("p", [1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("name,dq,quad", [("bp3", 2, "gauss"), ("bp35", 1, "gauss"), ("bp5", 1, "gll")])
+def test_trilinear_on_the_fly_geometry_matches_oracle(oracle_mod, p, name, dq, quad):
+    """geometry='trilinear' (SURVEY 8f.1): general hexahedra given by their 8 vertices, the Jacobian rebuilt at every
+    quadrature point inside the kernel instead of streaming 48 nq^3 bytes of G per cell.  Against the oracle's operator with
+    G from the same MappingQ1 cells (vertices displaced by the smooth map), <= 1e-12; same CG iteration count as stored G."""
+    import benchmarks_b200 as b
+    fe = oracle_mod.fe
+    sub, nref, nq = (2, 1, 1), 1, p + dq
+    om, od, rd, bas, G, JxW = _oracle_setup(fe, sub, nref, p, nq, quad, 1, DEFORM)
+    mesh = b.BoxMesh(sub, nref, p)
+    A = b.LaplaceOperator(mesh, nq=nq, quad=quad, p_geo=1, deform=DEFORM, geometry="trilinear", with_jxw=True)
+    rng = np.random.default_rng(300 + p)
+    src = rng.standard_normal(mesh.n_owned)
+    ref = fe.op_apply(src, rd, bas, G)
+    dst = A.initialize_dof_vector()
+    dot = A.vmult_dot(dst, torch.from_numpy(src).cuda())
+    assert rel(dst.cpu().numpy(), ref) <= TOL, name
+    assert abs(dot.item() - float(src @ ref)) <= 1e-11 * np.abs(src).dot(np.abs(ref))
+    A2 = b.LaplaceOperator(mesh, nq=nq, quad=quad, p_geo=1, deform=DEFORM)
+    its = []
+    for op in (A, A2):
+        ctl = b.ReductionControl(5000, 1e-16, 1e-9)
+        b.SolverCG(ctl).solve(op, op.initialize_dof_vector(), A2.compute_rhs())
+        its.append(ctl.last_step())
+    assert abs(its[0] - its[1]) <= 1
+
+
 @pytest.mark.parametrize("p,name,dq,quad,kind", [(2, "bp3", 2, "gauss", "laplace"), (4, "bp5", 1, "gll", "laplace"), (3, "helmholtz", 1, "gauss", "helmholtz")])
 def test_chebyshev_preconditioned_cg_matches_oracle(oracle_mod, p, name, dq, quad, kind):
     """PreconditionChebyshev (degree 4 polynomial in D^-1 A) inside SolverCG: eigenvalue estimate and iteration count

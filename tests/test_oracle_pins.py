@@ -233,3 +233,29 @@ def test_chebyshev_preconditioner_algebra():
     assert np.allclose(1.0 - lam * z, Tk((theta - lam) / delta) / Tk(theta / delta), rtol=1e-10, atol=1e-12)
     est = fe.estimate_max_eigenvalue(apply, inv_diag, len(lam), 200)
     assert est == pytest.approx(1.2 * 2.0, rel=1e-3)
+
+
+def test_fast_single_rank_numbering_equals_literal_first_touch():
+    """oracle.fe.rank_data_single_fast (what bench.py's CPU arm builds its mesh with) == the literal first-touch simulation."""
+    import numpy as np
+    import oracle
+    fe = oracle.fe
+    for sub, nref, p in [((1, 1, 1), 1, 1), ((2, 1, 1), 1, 2), ((2, 2, 1), 1, 3), ((1, 1, 1), 2, 2), ((1, 2, 1), 1, 4)]:
+        m = fe.BoxMesh(sub, nref)
+        a = fe.rank_data(m, fe.distribute_dofs(m, p, 1), 0)
+        b = fe.rank_data_single_fast(m, p)
+        assert np.array_equal(a["dof_indices"], b["dof_indices"]) and np.array_equal(a["constrained"], b["constrained"])
+        assert a["n_owned"] == b["n_owned"] and b["n_ghost"] == 0
+
+
+def test_reference_gpu_kernel_shims_export_their_entry_points():
+    """oracle/_ref/libref_gpu_*.so (the reference's own CUDA kernels, compiled in place): present when /root/reference was
+    there at build time, and exporting the entry points oracle/ref_gpu.py binds (no GPU call here)."""
+    import ctypes
+    import os
+    from oracle import ref_gpu
+    if not ref_gpu.available():
+        pytest.skip("oracle/_ref/libref_gpu_*.so not built in this checkout")
+    here = os.path.dirname(os.path.abspath(ref_gpu.__file__))
+    assert hasattr(ctypes.CDLL(os.path.join(here, "_ref", "libref_gpu_ceedbk.so")), "ref_gpu_ceedbk")
+    assert hasattr(ctypes.CDLL(os.path.join(here, "_ref", "libref_gpu_sumfact.so")), "ref_gpu_sumfact_bk1")
