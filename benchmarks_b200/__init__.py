@@ -7,7 +7,7 @@ package without the built library raises, and every compute call needs a CUDA de
 """
 from ._lib import lib, LIB_PATH, B200feError, check  # noqa: F401
 from .mesh import BoxMesh, HangingBoxMesh, basis_1d, QUAD_GAUSS, QUAD_GLL, PARTITION_P4EST, PARTITION_BLOCKS, GHOSTS_MINIMAL, GHOSTS_RELEVANT  # noqa: F401
-from .operator import (LaplaceOperator, ReductionControl, SolverCG, NoConvergence, PreconditionChebyshev,  # noqa: F401
+from .operator import (LaplaceOperator, ReductionControl, SolverCG, NoConvergence, PreconditionChebyshev, PreconditionPMG, PTransfer,  # noqa: F401
                        OP_LAPLACE, OP_MASS, OP_HELMHOLTZ, overlap_permutation)
 from .bk import bk1_apply, bk3_apply, bk5_apply, sum_squares, bk_launch_info  # noqa: F401
 

@@ -75,6 +75,14 @@ _SIGNATURES = {
     "b200fe_cg_solve_host": (_i, [_vp, _vp, _vp, _vp, C.c_double, C.c_double, _i, _i, _vp, _vp]),
     "b200fe_cg_solve_chebyshev": (_i, [_vp, _vp, _vp, _vp, _i, C.c_double, C.c_double, C.c_double, C.c_double, _i, _i, _vp, _vp]),
     "b200fe_op_estimate_max_eigenvalue": (_i, [_vp, _vp, _i, _pd, _vp]),
+    "b200fe_ptransfer_create": (_i, [_i, _i, _u32, _vp, _vp, _u32, _u32, _vp]),
+    "b200fe_ptransfer_destroy": (None, [_vp]),
+    "b200fe_ptransfer_prolongate_add": (_i, [_vp, _vp, _vp, _vp]),
+    "b200fe_ptransfer_restrict_add": (_i, [_vp, _vp, _vp, _vp]),
+    "b200fe_pmg_create": (_i, [_i, _vp, _vp, _vp, _vp, _i, C.c_double, _i, _vp]),
+    "b200fe_pmg_destroy": (None, [_vp]),
+    "b200fe_pmg_vcycle": (_i, [_vp, _vp, _vp, _vp]),
+    "b200fe_cg_solve_pmg": (_i, [_vp, _vp, _vp, C.c_double, C.c_double, _i, _i, _vp, _vp]),
     "b200fe_exchange_create_box": (_i, [_vp, C.POINTER(_vp)]),
     "b200fe_exchange_create_hang": (_i, [_vp, C.POINTER(_vp)]),
     "b200fe_exchange_destroy": (None, [_vp]),

@@ -18,9 +18,11 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <list>
 #include <memory>
 #include <mutex>
+#include <vector>
 
 #include "halo.h"
 #include "operator.h"
@@ -207,6 +209,105 @@ __global__ void scale_diag_kernel(uint32_t n, const double *__restrict__ x, cons
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) y[i] = f * (inv_diag ? inv_diag[i] * x[i] : x[i]);
 }
 
+// ---- p-multigrid (polynomial global coarsening on the same cells; deal.II MGTransferGlobalCoarsening, the header the
+//      reference already includes: CEED_bp/src/bp3.cc:27) ---------------------------------------------------------------
+// One CTA per cell: the embedding of FE_Q(p_coarse) into FE_Q(p_fine) is the tensor product of the 1-D matrix
+// P[jf][ic] = coarse Lagrange function ic at fine GLL node jf; continuous elements make every cell produce the same value at
+// a shared fine DoF, so the cell contributions are weighted by 1 / valence (prolongate_and_add) and the restriction is the
+// exact transpose (restrict_and_add).  Runtime sizes (nf, nc <= 9), shared-memory sweeps: a transfer moves ~2 vectors, the
+// smoothers around it dozens.
+__global__ void ptransfer_kernel(uint32_t n_cells, int nf, int nc, int transpose, const double *__restrict__ P, const double *__restrict__ wgt,
+                                 const uint32_t *__restrict__ idx_f, const uint32_t *__restrict__ idx_c, double *fine, double *coarse,
+                                 const CgScalars *sc)
+{
+    if (sc != nullptr && sc->done) return;
+    extern __shared__ double psm[];
+    const int nf3 = nf * nf * nf, nc3 = nc * nc * nc;
+    double *sP = psm, *a0 = sP + nf * nc, *a1 = a0 + nf3;  // two ping-pong arrays of nf^3
+    for (int t = threadIdx.x; t < nf * nc; t += blockDim.x) sP[t] = P[t];
+    for (uint32_t cell = blockIdx.x; cell < n_cells; cell += gridDim.x) {
+        __syncthreads();
+        if (!transpose) {
+            // coarse values [kc][jc][ic] -> a0
+            for (int t = threadIdx.x; t < nc3; t += blockDim.x) {
+                const uint32_t id = idx_c[(size_t)cell * nc3 + t];
+                a0[t] = id == kInvalidIndex ? 0.0 : coarse[id];
+            }
+            __syncthreads();
+            for (int t = threadIdx.x; t < nc * nc * nf; t += blockDim.x) {  // x: a1[kc][jc][if]
+                const int i = t % nf, r = t / nf;
+                double v = 0.0;
+                for (int ic = 0; ic < nc; ++ic) v = fma(sP[i * nc + ic], a0[r * nc + ic], v);
+                a1[t] = v;
+            }
+            __syncthreads();
+            for (int t = threadIdx.x; t < nc * nf * nf; t += blockDim.x) {  // y: a0[kc][jf][if]
+                const int i = t % nf, j = (t / nf) % nf, k = t / (nf * nf);
+                double v = 0.0;
+                for (int jc = 0; jc < nc; ++jc) v = fma(sP[j * nc + jc], a1[(k * nc + jc) * nf + i], v);
+                a0[t] = v;
+            }
+            __syncthreads();
+            for (int t = threadIdx.x; t < nf3; t += blockDim.x) {  // z, weight, add
+                const uint32_t id = idx_f[(size_t)cell * nf3 + t];
+                if (id == kInvalidIndex) continue;
+                const int ij = t % (nf * nf), k = t / (nf * nf);
+                double v = 0.0;
+                for (int kc = 0; kc < nc; ++kc) v = fma(sP[k * nc + kc], a0[kc * nf * nf + ij], v);
+                atomicAdd(fine + id, wgt[id] * v);
+            }
+        } else {
+            for (int t = threadIdx.x; t < nf3; t += blockDim.x) {  // weighted fine values -> a0[kf][jf][if]
+                const uint32_t id = idx_f[(size_t)cell * nf3 + t];
+                a0[t] = id == kInvalidIndex ? 0.0 : wgt[id] * fine[id];
+            }
+            __syncthreads();
+            for (int t = threadIdx.x; t < nc * nf * nf; t += blockDim.x) {  // z^T: a1[kc][jf][if]
+                const int ij = t % (nf * nf), kc = t / (nf * nf);
+                double v = 0.0;
+                for (int k = 0; k < nf; ++k) v = fma(sP[k * nc + kc], a0[k * nf * nf + ij], v);
+                a1[t] = v;
+            }
+            __syncthreads();
+            for (int t = threadIdx.x; t < nc * nc * nf; t += blockDim.x) {  // y^T: a0[kc][jc][if]
+                const int i = t % nf, jc = (t / nf) % nc, kc = t / (nf * nc);
+                double v = 0.0;
+                for (int j = 0; j < nf; ++j) v = fma(sP[j * nc + jc], a1[(kc * nf + j) * nf + i], v);
+                a0[t] = v;
+            }
+            __syncthreads();
+            for (int t = threadIdx.x; t < nc3; t += blockDim.x) {  // x^T, add
+                const uint32_t id = idx_c[(size_t)cell * nc3 + t];
+                if (id == kInvalidIndex) continue;
+                const int ic = t % nc, r = t / nc;
+                double v = 0.0;
+                for (int i = 0; i < nf; ++i) v = fma(sP[i * nc + ic], a0[r * nf + i], v);
+                atomicAdd(coarse + id, v);
+            }
+        }
+    }
+}
+__global__ void valence_kernel(size_t n, const uint32_t *__restrict__ idx, double *cnt)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        if (idx[i] != kInvalidIndex) atomicAdd(cnt + idx[i], 1.0);
+}
+__global__ void reciprocal_kernel(uint32_t n, double *v)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v[i] = v[i] > 0.0 ? 1.0 / v[i] : 0.0;
+}
+// r = b - t ; x += e
+__global__ void residual_kernel(uint32_t n, const double *__restrict__ b, const double *__restrict__ t, double *__restrict__ r, const CgScalars *sc)
+{
+    if (sc != nullptr && sc->done) return;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) r[i] = b[i] - t[i];
+}
+__global__ void add_kernel(uint32_t n, const double *__restrict__ e, double *__restrict__ x, const CgScalars *sc)
+{
+    if (sc != nullptr && sc->done) return;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) x[i] += e[i];
+}
+
 }  // namespace
 
 struct CgWork {
@@ -268,21 +369,20 @@ struct ChebSpec {  // degree >= 1 terms of the polynomial in D^-1 A on [lambda_m
 };
 
 // z = p_k(D^-1 A) D^-1 r  (three-term recurrence, Saad Alg. 12.1; k - 1 operator applications)
-static int cheb_apply(Operator &op, CgWork &w, const ChebSpec &c, const double *d_inv_diag, const double *d_r, dim3 blocks, cudaStream_t s)
+static int cheb_apply(Operator &op, double *z, double *d, double *t, const CgScalars *sc, const ChebSpec &c, const double *d_inv_diag,
+                      const double *d_r, dim3 blocks, cudaStream_t s)
 {
     const uint32_t n = op.n_owned;
-    const size_t nl = op.n_local();
-    double *z = w.cheb, *d = w.cheb + nl, *t = w.cheb + 2 * nl;
     const double lmax = c.lambda_max, lmin = c.lambda_max / c.smoothing_range;
     const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma1 = theta / delta;
     double rho = 1.0 / sigma1;
-    cheb_first_kernel<<<blocks, 256, 0, s>>>(n, 1.0 / theta, d_r, d_inv_diag, d, z, w.sc);
+    cheb_first_kernel<<<blocks, 256, 0, s>>>(n, 1.0 / theta, d_r, d_inv_diag, d, z, sc);
     B200FE_CUDA_TRY(cudaGetLastError());
     ++g_launch_count;
     for (int k = 1; k < c.degree; ++k) {
         if (int rc = op_vmult(op, t, z, nullptr, true, true, s, 1)) return rc;
         const double rho_new = 1.0 / (2.0 * sigma1 - rho);
-        cheb_step_kernel<<<blocks, 256, 0, s>>>(n, rho_new * rho, 2.0 * rho_new / delta, d_r, t, d_inv_diag, d, z, w.sc);
+        cheb_step_kernel<<<blocks, 256, 0, s>>>(n, rho_new * rho, 2.0 * rho_new / delta, d_r, t, d_inv_diag, d, z, sc);
         B200FE_CUDA_TRY(cudaGetLastError());
         ++g_launch_count;
         rho = rho_new;
@@ -290,8 +390,11 @@ static int cheb_apply(Operator &op, CgWork &w, const ChebSpec &c, const double *
     return B200FE_OK;
 }
 
+// general preconditioner of the CG loop: z = M^-1 r into w.cheb (first n_local doubles); `sc` lets its kernels skip once done
+using PrecondFn = std::function<int(const double *d_r, double *d_z, const CgScalars *sc, cudaStream_t s)>;
+
 static int cg_run(Operator &op, int ncomp, CgWork &w, double *d_x, const double *d_b, const double *d_inv_diag, double abs_tol,
-                  double rel_tol, int max_it, int check_every, b200fe_cg_result *res, cudaStream_t s, const ChebSpec *cheb = nullptr)
+                  double rel_tol, int max_it, int check_every, b200fe_cg_result *res, cudaStream_t s, const PrecondFn *cheb = nullptr)
 {
     NvtxRange range("cg_solver");
     const uint32_t n = op.n_owned;
@@ -299,7 +402,7 @@ static int cg_run(Operator &op, int ncomp, CgWork &w, double *d_x, const double 
     const unsigned bx = n == 0 ? 1u : std::min<unsigned>((n + 1023) / 1024, std::max(148u * 8u / (unsigned)ncomp, 148u));
     const dim3 blocks(bx, (unsigned)ncomp);
     const dim3 blocks_local(stride == 0 ? 1u : std::min<unsigned>((unsigned)((stride + 1023) / 1024), std::max(148u * 8u / (unsigned)ncomp, 148u)), (unsigned)ncomp);
-    const int jacobi = d_inv_diag != nullptr;  // (Chebyshev: rho = r.z as well, z = w.cheb)
+    const int jacobi = d_inv_diag != nullptr || cheb != nullptr;  // (general preconditioner: rho = r.z as well, z = w.cheb)
     // the vector kernels fuse z = D^-1 r for Jacobi; with the polynomial preconditioner z is a vector of its own
     const double *fused_diag = cheb ? nullptr : d_inv_diag;
     if (check_every < 1) check_every = 1;
@@ -310,7 +413,7 @@ static int cg_run(Operator &op, int ncomp, CgWork &w, double *d_x, const double 
     B200FE_CUDA_TRY(cudaGetLastError());
     ++g_launch_count;
     auto precondition = [&]() -> int {  // Chebyshev only: z = M^-1 r, acc[2] = r.z
-        if (int rc = cheb_apply(op, w, *cheb, d_inv_diag, w.r, blocks, s)) return rc;
+        if (int rc = (*cheb)(w.r, w.cheb, w.sc, s)) return rc;
         dot_kernel<<<blocks, 256, 0, s>>>(n, w.r, w.cheb, &w.sc->acc[2], w.sc);
         B200FE_CUDA_TRY(cudaGetLastError());
         ++g_launch_count;
@@ -416,6 +519,85 @@ static int cg_run(Operator &op, int ncomp, CgWork &w, double *d_x, const double 
     return w.h_sc->converged ? B200FE_OK : B200FE_ERR_NO_CONVERGENCE;
 }
 
+// ---- p-multigrid objects ------------------------------------------------------------------------------------------------
+struct PTransfer {
+    int nf = 0, nc = 0;
+    uint32_t n_cells = 0, n_fine = 0, n_coarse = 0;
+    const uint32_t *d_idx_f = nullptr, *d_idx_c = nullptr;  // borrowed index tables of the two levels
+    double *d_P = nullptr, *d_w = nullptr;                  // owned: 1-D embedding matrix, 1 / valence of the fine DoFs
+    ~PTransfer() { cudaFree(d_P); cudaFree(d_w); }
+};
+
+static int ptransfer_apply(const PTransfer &t, bool transpose, double *fine, double *coarse, const CgScalars *sc, cudaStream_t s)
+{
+    if (t.n_cells == 0) return B200FE_OK;
+    const size_t smem = sizeof(double) * ((size_t)t.nf * t.nc + 2 * (size_t)t.nf * t.nf * t.nf);
+    ptransfer_kernel<<<std::min<uint32_t>(t.n_cells, 148u * 8u), 128, smem, s>>>(t.n_cells, t.nf, t.nc, transpose ? 1 : 0, t.d_P, t.d_w, t.d_idx_f,
+                                                                              t.d_idx_c, fine, coarse, sc);
+    B200FE_CUDA_TRY(cudaGetLastError());
+    ++g_launch_count;
+    return B200FE_OK;
+}
+
+struct PmgLevel {
+    Operator *op = nullptr;
+    const double *inv_diag = nullptr;  // borrowed
+    double lambda_max = 0.0;
+    double *buf = nullptr;  // x | b | r | z | d | t, n_local each (owned)
+    ~PmgLevel() { cudaFree(buf); }
+};
+struct Pmg {
+    std::vector<std::unique_ptr<PmgLevel>> level;  // 0 = finest
+    std::vector<const PTransfer *> transfer;       // transfer[l]: level l (fine) <-> level l + 1 (coarse); borrowed
+    int degree = 3, coarse_degree = 8;
+    double range = 20.0;
+};
+
+// x_l = V(b_l), x_l = 0 on entry: Chebyshev pre-smoothing, coarse correction, Chebyshev post-smoothing (symmetric)
+static int pmg_vcycle_level(Pmg &m, size_t l, const CgScalars *sc, cudaStream_t s)
+{
+    PmgLevel &L = *m.level[l];
+    Operator &op = *L.op;
+    const uint32_t n = op.n_owned;
+    const size_t nl = op.n_local();
+    double *x = L.buf, *b = x + nl, *r = b + nl, *z = r + nl, *d = z + nl, *t = d + nl;
+    const dim3 blocks(n == 0 ? 1u : std::min<unsigned>((n + 1023) / 1024, 148u * 8u));
+    const bool coarsest = l + 1 == m.level.size();
+    const ChebSpec spec{coarsest ? m.coarse_degree : m.degree, L.lambda_max, m.range};
+    // pre-smoothing from x = 0: x = p(D^-1 A) D^-1 b
+    if (int rc = cheb_apply(op, x, d, t, sc, spec, L.inv_diag, b, blocks, s)) return rc;
+    if (coarsest) return B200FE_OK;
+    PmgLevel &C = *m.level[l + 1];
+    const size_t nlc = C.op->n_local();
+    double *xc = C.buf, *bc = xc + nlc;
+    // r = b - A x ; b_coarse = P^T r
+    if (int rc = op_vmult(op, t, x, nullptr, true, true, s, 1)) return rc;
+    residual_kernel<<<blocks, 256, 0, s>>>(n, b, t, r, sc);
+    B200FE_CUDA_TRY(cudaMemsetAsync(bc, 0, sizeof(double) * nlc, s));
+    if (int rc = ptransfer_apply(*m.transfer[l], true, r, bc, sc, s)) return rc;
+    if (int rc = pmg_vcycle_level(m, l + 1, sc, s)) return rc;
+    // x += P x_coarse
+    if (int rc = ptransfer_apply(*m.transfer[l], false, x, xc, sc, s)) return rc;
+    // post-smoothing: x += p(D^-1 A) D^-1 (b - A x)
+    if (int rc = op_vmult(op, t, x, nullptr, true, true, s, 1)) return rc;
+    residual_kernel<<<blocks, 256, 0, s>>>(n, b, t, r, sc);
+    if (int rc = cheb_apply(op, z, d, t, sc, spec, L.inv_diag, r, blocks, s)) return rc;
+    add_kernel<<<blocks, 256, 0, s>>>(n, z, x, sc);
+    B200FE_CUDA_TRY(cudaGetLastError());
+    g_launch_count += 3;
+    return B200FE_OK;
+}
+
+static int pmg_apply(Pmg &m, const double *d_r, double *d_z, const CgScalars *sc, cudaStream_t s)
+{
+    PmgLevel &L = *m.level[0];
+    const size_t nl = L.op->n_local();
+    B200FE_CUDA_TRY(cudaMemcpyAsync(L.buf + nl, d_r, sizeof(double) * L.op->n_owned, cudaMemcpyDeviceToDevice, s));
+    if (int rc = pmg_vcycle_level(m, 0, sc, s)) return rc;
+    B200FE_CUDA_TRY(cudaMemcpyAsync(d_z, L.buf, sizeof(double) * L.op->n_owned, cudaMemcpyDeviceToDevice, s));
+    return B200FE_OK;
+}
+
 }  // namespace b200fe
 
 using namespace b200fe;
@@ -456,7 +638,113 @@ int b200fe_cg_solve_chebyshev(b200fe_op *o, double *d_x, const double *d_b, cons
     if (int rc = ensure_work(w, op.n_local(), false)) return rc;
     if (int rc = ensure_cheb(*w, op.n_local(), (cudaStream_t)stream)) return rc;
     const ChebSpec spec{degree, lambda_max, smoothing_range};
-    int rc = cg_run(op, 1, *w, d_x, d_b, d_inv_diag, abs_tol, rel_tol, max_it, check_every, result, (cudaStream_t)stream, &spec);
+    const uint32_t n = op.n_owned;
+    const size_t nl = op.n_local();
+    const dim3 blocks(n == 0 ? 1u : std::min<unsigned>((n + 1023) / 1024, 148u * 8u));
+    CgWork *wk = w.get();
+    const PrecondFn pre = [&, wk](const double *r, double *z, const CgScalars *sc, cudaStream_t st) -> int {
+        return cheb_apply(op, z, wk->cheb + nl, wk->cheb + 2 * nl, sc, spec, d_inv_diag, r, blocks, st);
+    };
+    int rc = cg_run(op, 1, *w, d_x, d_b, d_inv_diag, abs_tol, rel_tol, max_it, check_every, result, (cudaStream_t)stream, &pre);
+    if (rc == B200FE_ERR_NO_CONVERGENCE) fail(rc, "CG did not converge in %d iterations", max_it);
+    return rc;
+}
+
+int b200fe_ptransfer_create(int p_fine, int p_coarse, uint32_t n_cells, const uint32_t *d_idx_fine, const uint32_t *d_idx_coarse,
+                            uint32_t n_local_fine, uint32_t n_local_coarse, b200fe_ptransfer **out)
+{
+    B200FE_REQUIRE(out && (n_cells == 0 || (d_idx_fine && d_idx_coarse)), "b200fe_ptransfer_create: null pointer");
+    B200FE_REQUIRE(p_coarse >= 1 && p_coarse < p_fine && p_fine <= 8, "b200fe_ptransfer_create: need 1 <= p_coarse < p_fine <= 8");
+    auto t = std::make_unique<PTransfer>();
+    t->nf = p_fine + 1; t->nc = p_coarse + 1; t->n_cells = n_cells; t->n_fine = n_local_fine; t->n_coarse = n_local_coarse;
+    t->d_idx_f = d_idx_fine; t->d_idx_c = d_idx_coarse;
+    // P[jf][ic] = coarse shape function ic at fine node jf = shape_values[ic*nf + jf] of FE_Q(p_coarse) on the GLL points of p_fine
+    std::vector<double> sv((size_t)t->nc * t->nf), P((size_t)t->nf * t->nc);
+    if (int rc = b200fe_basis_1d(p_coarse, t->nf, B200FE_QUAD_GLL, sv.data(), nullptr, nullptr, nullptr, nullptr)) return rc;
+    for (int j = 0; j < t->nf; ++j)
+        for (int i = 0; i < t->nc; ++i) P[(size_t)j * t->nc + i] = sv[(size_t)i * t->nf + j];
+    B200FE_CUDA_TRY(cudaMalloc(&t->d_P, P.size() * sizeof(double)));
+    B200FE_CUDA_TRY(cudaMemcpy(t->d_P, P.data(), P.size() * sizeof(double), cudaMemcpyHostToDevice));
+    B200FE_CUDA_TRY(cudaMalloc(&t->d_w, std::max<size_t>(n_local_fine, 1) * sizeof(double)));
+    B200FE_CUDA_TRY(cudaMemset(t->d_w, 0, std::max<size_t>(n_local_fine, 1) * sizeof(double)));
+    const size_t n_idx = (size_t)n_cells * t->nf * t->nf * t->nf;
+    if (n_idx) {
+        valence_kernel<<<(unsigned)std::min<size_t>((n_idx + 255) / 256, 148u * 16u), 256>>>(n_idx, d_idx_fine, t->d_w);
+        reciprocal_kernel<<<std::min<unsigned>((n_local_fine + 255) / 256, 148u * 16u), 256>>>(n_local_fine, t->d_w);
+        B200FE_CUDA_TRY(cudaGetLastError());
+        B200FE_CUDA_TRY(cudaDeviceSynchronize());
+    }
+    *out = reinterpret_cast<b200fe_ptransfer *>(t.release());
+    return B200FE_OK;
+}
+
+void b200fe_ptransfer_destroy(b200fe_ptransfer *t) { delete reinterpret_cast<PTransfer *>(t); }
+
+int b200fe_ptransfer_prolongate_add(b200fe_ptransfer *t, double *d_fine, const double *d_coarse, void *stream)
+{
+    B200FE_REQUIRE(t && d_fine && d_coarse, "b200fe_ptransfer_prolongate_add: null pointer");
+    return ptransfer_apply(*reinterpret_cast<PTransfer *>(t), false, d_fine, const_cast<double *>(d_coarse), nullptr, (cudaStream_t)stream);
+}
+
+int b200fe_ptransfer_restrict_add(b200fe_ptransfer *t, double *d_coarse, const double *d_fine, void *stream)
+{
+    B200FE_REQUIRE(t && d_fine && d_coarse, "b200fe_ptransfer_restrict_add: null pointer");
+    return ptransfer_apply(*reinterpret_cast<PTransfer *>(t), true, const_cast<double *>(d_fine), d_coarse, nullptr, (cudaStream_t)stream);
+}
+
+int b200fe_pmg_create(int n_levels, b200fe_op *const *ops, const double *const *d_inv_diag, const double *lambda_max,
+                      b200fe_ptransfer *const *transfers, int smoother_degree, double smoothing_range, int coarse_degree, b200fe_pmg **out)
+{
+    B200FE_REQUIRE(out && ops && d_inv_diag && lambda_max && (n_levels == 1 || transfers), "b200fe_pmg_create: null pointer");
+    B200FE_REQUIRE(n_levels >= 1 && n_levels <= 8, "b200fe_pmg_create: n_levels outside 1..8");
+    B200FE_REQUIRE(smoother_degree >= 1 && coarse_degree >= 1 && smoothing_range > 1.0, "b200fe_pmg_create: bad smoother parameters");
+    auto m = std::make_unique<Pmg>();
+    m->degree = smoother_degree; m->coarse_degree = coarse_degree; m->range = smoothing_range;
+    for (int l = 0; l < n_levels; ++l) {
+        B200FE_REQUIRE(ops[l] && d_inv_diag[l] && lambda_max[l] > 0.0, "b200fe_pmg_create: level %d incomplete", l);
+        auto L = std::make_unique<PmgLevel>();
+        L->op = reinterpret_cast<Operator *>(ops[l]);
+        B200FE_REQUIRE(L->op->halo == nullptr, "b200fe_pmg_create: single-rank operators only (the transfer weights are local valences)");
+        L->inv_diag = d_inv_diag[l]; L->lambda_max = lambda_max[l];
+        const size_t bytes = 6 * sizeof(double) * std::max<size_t>(L->op->n_local(), 1);
+        B200FE_CUDA_TRY(cudaMalloc(&L->buf, bytes));
+        B200FE_CUDA_TRY(cudaMemset(L->buf, 0, bytes));
+        m->level.push_back(std::move(L));
+        if (l + 1 < n_levels) {
+            B200FE_REQUIRE(transfers[l], "b200fe_pmg_create: transfer %d missing", l);
+            m->transfer.push_back(reinterpret_cast<const PTransfer *>(transfers[l]));
+        }
+    }
+    for (int l = 0; l + 1 < n_levels; ++l) {
+        const PTransfer &t = *m->transfer[l];
+        B200FE_REQUIRE(t.nf == m->level[l]->op->nm && t.nc == m->level[l + 1]->op->nm && t.n_fine == m->level[l]->op->n_local() &&
+                           t.n_coarse == m->level[l + 1]->op->n_local() && t.n_cells == m->level[l]->op->n_cells,
+                       "b200fe_pmg_create: transfer %d does not fit levels %d and %d", l, l, l + 1);
+    }
+    *out = reinterpret_cast<b200fe_pmg *>(m.release());
+    return B200FE_OK;
+}
+
+void b200fe_pmg_destroy(b200fe_pmg *m) { delete reinterpret_cast<Pmg *>(m); }
+
+int b200fe_pmg_vcycle(b200fe_pmg *pm, double *d_z, const double *d_r, void *stream)
+{
+    B200FE_REQUIRE(pm && d_z && d_r, "b200fe_pmg_vcycle: null pointer");
+    return pmg_apply(*reinterpret_cast<Pmg *>(pm), d_r, d_z, nullptr, (cudaStream_t)stream);
+}
+
+int b200fe_cg_solve_pmg(b200fe_pmg *pm, double *d_x, const double *d_b, double abs_tol, double rel_tol, int max_it, int check_every,
+                        b200fe_cg_result *result, void *stream)
+{
+    B200FE_REQUIRE(pm && d_x && d_b, "b200fe_cg_solve_pmg: null pointer");
+    B200FE_REQUIRE(max_it >= 0, "b200fe_cg_solve_pmg: max_it < 0");
+    Pmg &m = *reinterpret_cast<Pmg *>(pm);
+    Operator &op = *m.level[0]->op;
+    auto &w = work_of(&op);
+    if (int rc = ensure_work(w, op.n_local(), false)) return rc;
+    if (int rc = ensure_cheb(*w, op.n_local(), (cudaStream_t)stream)) return rc;
+    const PrecondFn pre = [&m](const double *r, double *z, const CgScalars *sc, cudaStream_t st) -> int { return pmg_apply(m, r, z, sc, st); };
+    int rc = cg_run(op, 1, *w, d_x, d_b, m.level[0]->inv_diag, abs_tol, rel_tol, max_it, check_every, result, (cudaStream_t)stream, &pre);
     if (rc == B200FE_ERR_NO_CONVERGENCE) fail(rc, "CG did not converge in %d iterations", max_it);
     return rc;
 }

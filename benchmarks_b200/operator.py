@@ -282,9 +282,66 @@ class PreconditionChebyshev:
         self.max_eigenvalue = float(max_eigenvalue)
 
 
+class PTransfer:
+    """deal.II MGTransferGlobalCoarsening between FE_Q(p_fine) and FE_Q(p_coarse) on the same cells (polynomial coarsening):
+    prolongate_and_add / restrict_and_add on L-vectors of the two operators (same mesh cells, different degree)."""
+
+    def __init__(self, A_fine: "LaplaceOperator", A_coarse: "LaplaceOperator"):
+        if A_fine.mesh.n_cells != A_coarse.mesh.n_cells or A_fine.perm is not None or A_coarse.perm is not None:
+            raise ValueError("PTransfer: the two operators must live on the same cells in the same order")
+        self.fine, self.coarse = A_fine, A_coarse
+        self._h = C.c_void_p()
+        check(lib.b200fe_ptransfer_create(A_fine.p, A_coarse.p, A_fine.mesh.n_cells, _dp(A_fine.dof_indices), _dp(A_coarse.dof_indices),
+                                          A_fine.mesh.n_owned + A_fine.mesh.n_ghost, A_coarse.mesh.n_owned + A_coarse.mesh.n_ghost,
+                                          C.byref(self._h)))
+
+    def prolongate_and_add(self, fine: torch.Tensor, coarse: torch.Tensor, stream=None):
+        check(lib.b200fe_ptransfer_prolongate_add(self._h, _dp(fine), _dp(coarse), _sp(stream)))
+
+    def restrict_and_add(self, coarse: torch.Tensor, fine: torch.Tensor, stream=None):
+        check(lib.b200fe_ptransfer_restrict_add(self._h, _dp(coarse), _dp(fine), _sp(stream)))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            lib.b200fe_ptransfer_destroy(h)
+            self._h = None
+
+
+class PreconditionPMG:
+    """p-multigrid V-cycle (Chebyshev smoothers on every level, polynomial coarsening on the same cells) as a SolverCG
+    preconditioner: operators from fine to coarse, e.g. degrees 8, 4, 2, 1 on one BoxMesh geometry."""
+
+    def __init__(self, operators, smoother_degree: int = 3, smoothing_range: float = 20.0, coarse_degree: int = 8, eig_iterations: int = 12):
+        self.operators = list(operators)
+        self.transfers = [PTransfer(a, c) for a, c in zip(self.operators[:-1], self.operators[1:])]
+        self.inv_diags = [A.get_matrix_diagonal_inverse() for A in self.operators]
+        self.lambdas = []
+        for A, d in zip(self.operators, self.inv_diags):
+            lam = C.c_double()
+            check(lib.b200fe_op_estimate_max_eigenvalue(A._h, _dp(d), int(eig_iterations), C.byref(lam), _sp()))
+            self.lambdas.append(lam.value)
+        n = len(self.operators)
+        ops = (C.c_void_p * n)(*[A._h for A in self.operators])
+        diags = (C.c_void_p * n)(*[d.data_ptr() for d in self.inv_diags])
+        lams = (C.c_double * n)(*self.lambdas)
+        trs = (C.c_void_p * max(n - 1, 1))(*[t._h for t in self.transfers])
+        self._h = C.c_void_p()
+        check(lib.b200fe_pmg_create(n, ops, diags, lams, trs, int(smoother_degree), float(smoothing_range), int(coarse_degree), C.byref(self._h)))
+
+    def vmult(self, z: torch.Tensor, r: torch.Tensor, stream=None):
+        check(lib.b200fe_pmg_vcycle(self._h, _dp(z), _dp(r), _sp(stream)))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            lib.b200fe_pmg_destroy(h)
+            self._h = None
+
+
 class SolverCG:
     """dealii::SolverCG: solve(A, x, b, preconditioner); preconditioner None = PreconditionIdentity,
-    a tensor holding the inverse diagonal (DiagonalMatrix / Jacobi), or a PreconditionChebyshev."""
+    a tensor holding the inverse diagonal (DiagonalMatrix / Jacobi), a PreconditionChebyshev or a PreconditionPMG."""
 
     def __init__(self, control: ReductionControl, check_every: int = 8):
         self.control = control
@@ -295,7 +352,12 @@ class SolverCG:
         """n_components > 1: vector-valued problem (BP2/BP4/BP6), x and b component-blocked
         [component][n_owned + n_ghost]."""
         res = _CgResult()
-        if isinstance(preconditioner, PreconditionChebyshev):
+        if isinstance(preconditioner, PreconditionPMG):
+            if n_components != 1 or preconditioner.operators[0] is not A:
+                raise ValueError("PreconditionPMG: scalar problems, built on the operator being solved")
+            rc = lib.b200fe_cg_solve_pmg(preconditioner._h, _dp(x), _dp(b), self.control.tolerance, self.control.reduction,
+                                         self.control.max_steps, self.check_every, C.byref(res), _sp(stream))
+        elif isinstance(preconditioner, PreconditionChebyshev):
             if n_components != 1:
                 raise ValueError("PreconditionChebyshev: scalar problems only")
             c = preconditioner

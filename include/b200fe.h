@@ -376,6 +376,29 @@ int b200fe_cg_solve_components(b200fe_op *op, int n_components, double *d_x, con
 int b200fe_cg_solve_chebyshev(b200fe_op *op, double *d_x, const double *d_b, const double *d_inv_diag, int degree, double lambda_max,
                               double smoothing_range, double abs_tol, double rel_tol, int max_it, int check_every,
                               b200fe_cg_result *result, void *stream);
+/* p-multigrid (polynomial global coarsening on the same cells): deal.II's MGTransferGlobalCoarsening between FE_Q(p_fine) and
+ * FE_Q(p_coarse) -- the header the reference already includes for this step (CEED_bp/src/bp3.cc:27) -- and a V-cycle with
+ * PreconditionChebyshev smoothers as a SolverCG preconditioner.
+ *   ptransfer: the two levels' index tables [cell][(p+1)^3] (BORROWED; Dirichlet DoFs masked on both) and local vector lengths;
+ *     prolongate_add: fine += P coarse (cell contributions weighted by 1 / valence); restrict_add: coarse += P^T fine.
+ *   pmg: n_levels operators from fine to coarse on the SAME cells (single rank), their inverse diagonals and
+ *     b200fe_op_estimate_max_eigenvalue values, the n_levels - 1 transfers; smoother_degree terms of the Chebyshev polynomial
+ *     before and after the coarse correction, coarse_degree terms on the coarsest level.  vcycle: z = V(r) from a zero start
+ *     (n_owned entries of the finest level); cg_solve_pmg: SolverCG on the finest operator with that preconditioner. */
+typedef struct b200fe_ptransfer b200fe_ptransfer;
+typedef struct b200fe_pmg b200fe_pmg;
+int b200fe_ptransfer_create(int p_fine, int p_coarse, uint32_t n_cells, const uint32_t *d_idx_fine, const uint32_t *d_idx_coarse,
+                            uint32_t n_local_fine, uint32_t n_local_coarse, b200fe_ptransfer **out);
+void b200fe_ptransfer_destroy(b200fe_ptransfer *t);
+int b200fe_ptransfer_prolongate_add(b200fe_ptransfer *t, double *d_fine, const double *d_coarse, void *stream);
+int b200fe_ptransfer_restrict_add(b200fe_ptransfer *t, double *d_coarse, const double *d_fine, void *stream);
+int b200fe_pmg_create(int n_levels, b200fe_op *const *ops, const double *const *d_inv_diag, const double *lambda_max,
+                      b200fe_ptransfer *const *transfers, int smoother_degree, double smoothing_range, int coarse_degree,
+                      b200fe_pmg **out);
+void b200fe_pmg_destroy(b200fe_pmg *pmg);
+int b200fe_pmg_vcycle(b200fe_pmg *pmg, double *d_z, const double *d_r, void *stream);
+int b200fe_cg_solve_pmg(b200fe_pmg *pmg, double *d_x, const double *d_b, double abs_tol, double rel_tol, int max_it, int check_every,
+                        b200fe_cg_result *result, void *stream);
 /* Largest eigenvalue of D^-1 A by n_iterations power iterations from a fixed pseudo-random start vector, times deal.II's
  * safety factor 1.2 (PreconditionChebyshev::estimate_eigenvalues).  d_inv_diag = NULL: of A itself.  Synchronises. */
 int b200fe_op_estimate_max_eigenvalue(b200fe_op *op, const double *d_inv_diag, int n_iterations, double *lambda_max, void *stream);

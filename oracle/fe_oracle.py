@@ -586,6 +586,45 @@ def chebyshev_preconditioner(apply, inv_diag, degree, lambda_max, smoothing_rang
     return M
 
 
+def p_transfer(idx_fine, idx_coarse, p_fine, p_coarse, n_fine, n_coarse):
+    """MGTransferGlobalCoarsening for polynomial coarsening on the same cells: returns (prolongate, restrict) with
+    prolongate(u_c) = P u_c (cell-wise tensor-product embedding, contributions weighted by 1 / valence of the fine DoF) and
+    restrict(r_f) = P^T r_f.  Index tables [cell][(p+1)^3] lexicographic, INVALID = masked."""
+    nf, nc = p_fine + 1, p_coarse + 1
+    P1 = lagrange_values(gll_01(nc)[0], gll_01(nf)[0])  # [jf, ic]
+    vf, vc = idx_fine != INVALID, idx_coarse != INVALID
+    sf, sc = np.where(vf, idx_fine, 0).astype(np.int64), np.where(vc, idx_coarse, 0).astype(np.int64)
+    w = np.bincount(sf[vf], minlength=n_fine).astype(np.float64)
+    w = np.where(w > 0, 1.0 / np.maximum(w, 1), 0.0)
+
+    def prolongate(uc):
+        loc = np.where(vc, uc[sc], 0.0).reshape(-1, nc, nc, nc)
+        uf = np.einsum("ck,bj,ai,zkji->zcba", P1, P1, P1, loc, optimize=True).reshape(idx_fine.shape)
+        return np.bincount(sf[vf], weights=(w[sf] * uf)[vf], minlength=n_fine)
+
+    def restrict(rf):
+        loc = np.where(vf, w[sf] * rf[sf], 0.0).reshape(-1, nf, nf, nf)
+        rc = np.einsum("ck,bj,ai,zcba->zkji", P1, P1, P1, loc, optimize=True).reshape(idx_coarse.shape)
+        return np.bincount(sc[vc], weights=rc[vc], minlength=n_coarse)
+    return prolongate, restrict
+
+
+def pmg_vcycle(levels, transfers, degree, smoothing_range, coarse_degree):
+    """z = V(r): levels = [(apply, inv_diag, lambda_max), ...] fine to coarse, transfers = [(prolongate, restrict), ...];
+    Chebyshev pre- and post-smoothing with `degree` terms, `coarse_degree` terms on the coarsest level."""
+    def cycle(l, b):
+        apply, inv_diag, lam = levels[l]
+        last = l + 1 == len(levels)
+        S = chebyshev_preconditioner(apply, inv_diag, coarse_degree if last else degree, lam, smoothing_range)
+        x = S(b)
+        if last:
+            return x
+        prolongate, restrict = transfers[l]
+        x = x + prolongate(cycle(l + 1, restrict(b - apply(x))))
+        return x + S(b - apply(x))
+    return lambda r: cycle(0, r)
+
+
 def solver_cg(apply, b, max_it, abs_tol, rel_tol, precond_inv_diag=None, dot=np.dot, precond=None):
     """Returns (x, its, res0, resn, converged).  x0 = 0.  precond: callable z = M(r) (overrides precond_inv_diag)."""
     x = np.zeros_like(b)

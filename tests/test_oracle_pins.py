@@ -259,3 +259,31 @@ def test_reference_gpu_kernel_shims_export_their_entry_points():
     here = os.path.dirname(os.path.abspath(ref_gpu.__file__))
     assert hasattr(ctypes.CDLL(os.path.join(here, "_ref", "libref_gpu_ceedbk.so")), "ref_gpu_ceedbk")
     assert hasattr(ctypes.CDLL(os.path.join(here, "_ref", "libref_gpu_sumfact.so")), "ref_gpu_sumfact_bk1")
+
+
+def test_p_transfer_oracle_is_exact_for_coarse_polynomials_and_adjoint():
+    """oracle.fe.p_transfer: the prolongation reproduces every polynomial of the coarse degree at the fine nodes (an
+    implementation-independent property of the FE_Q embedding), and the restriction is its exact transpose."""
+    import numpy as np
+    import oracle
+    fe = oracle.fe
+    m = fe.BoxMesh((2, 1, 1), 1)
+    for pf, pc in ((4, 2), (3, 1), (8, 4)):
+        rf, rc = fe.rank_data_single_fast(m, pf, dirichlet=False), fe.rank_data_single_fast(m, pc, dirichlet=False)
+        P, R = fe.p_transfer(rf["dof_indices"], rc["dof_indices"], pf, pc, rf["n_owned"], rc["n_owned"])
+
+        def coords(rd, p):
+            t, _ = fe.gll_01(p + 1)
+            n = p + 1
+            X = np.zeros((rd["n_owned"], 3))
+            l = np.arange(n ** 3)
+            a, b, c = l % n, (l // n) % n, l // (n * n)
+            for ci in range(m.n_cells):
+                x, y, z = m.cell_xyz[ci]
+                X[rd["dof_indices"][ci]] = np.stack([(x + t[a]) * m.h[0], (y + t[b]) * m.h[1], (z + t[c]) * m.h[2]], 1)
+            return X
+        f = lambda X: 1 + X[:, 0] ** pc * X[:, 1] - 0.5 * X[:, 2] ** pc * X[:, 0] + X[:, 1] * X[:, 2]
+        assert np.abs(P(f(coords(rc, pc))) - f(coords(rf, pf))).max() <= 1e-12
+        rng = np.random.default_rng(pf)
+        u, r = rng.standard_normal(rc["n_owned"]), rng.standard_normal(rf["n_owned"])
+        assert abs(P(u) @ r - u @ R(r)) <= 1e-11 * np.abs(P(u)).dot(np.abs(r))
