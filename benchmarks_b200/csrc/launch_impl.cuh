@@ -35,6 +35,14 @@ constexpr int v2_rmin(int nq, bool coll, int qop, bool eo = false)
 #ifdef B200FE_V2_RMIN_EO9
     if (eo && !coll && nq == 9 && (qop & QOP_LAPLACE)) return B200FE_V2_RMIN_EO9;
 #endif
+    // plain contractions at nq = 9, 10 (only reached with non-symmetric 1-D matrices, i.e. the reference drivers' cos() test
+    // matrices on the E-vector kernels): tuning knobs for the same 2 x 255 vs 3-4 x 168 question
+#ifdef B200FE_V2_RMIN_GEN9
+    if (!eo && !coll && nq == 9 && (qop & QOP_LAPLACE)) return B200FE_V2_RMIN_GEN9;
+#endif
+#ifdef B200FE_V2_RMIN_GEN10
+    if (!eo && !coll && nq == 10 && (qop & QOP_LAPLACE)) return B200FE_V2_RMIN_GEN10;
+#endif
     if (eo && !coll && nq == 10 && (qop & QOP_LAPLACE)) return B200FE_V2_RMIN_EO10;
     if (!(qop & QOP_LAPLACE) && nq == 9) return B200FE_V2_RMIN_MASS9;
 #ifdef B200FE_V2_RMIN_FIXED
