@@ -6,7 +6,6 @@
 #include "kernels.h"
 #include "sumfact2.cuh"
 #include "sumfact_tpe.cuh"
-#include "sumfact_mass.cuh"
 
 namespace b200fe {
 
@@ -206,56 +205,6 @@ cudaError_t launch_tpe(const double *hB, const double *hD, const KArgs &a, cudaS
     return cudaGetLastError();
 }
 
-// interpolated mass operator (BK1 / BP1) at p = 2 ... 6: plane-per-thread kernel with one shared-memory round trip per
-// direction (sumfact_mass.cuh); B200FE_MASS_KERNEL=0 keeps the generic kernel for A/B runs
-constexpr bool mass_built(int nm, int nq, bool coll, int qop) { return qop == QOP_MASS && !coll && nq == nm + 1 && nm >= 3 && nm <= 7; }
-inline bool mass_enabled()
-{
-    static const bool on = [] { const char *e = std::getenv("B200FE_MASS_KERNEL"); return !e || std::atoi(e) != 0; }();
-    return on;
-}
-
-template <int NM, int NQ, bool LVEC, bool EO>
-cudaError_t launch_mass(const Mats<NM, NQ, EO> &m, const KArgs &a, cudaStream_t s, LaunchInfo *info, bool dry_run)
-{
-    // elements per CTA: ~256 threads while the plane threads' registers fit a 128-register cap (nm <= 4), fewer threads and a
-    // higher cap above (two resident CTAs: 170 registers at nm = 5, 255 at nm = 6, 7)
-    constexpr int EPB = NM <= 4 ? 256 / (NQ * NQ) : NM == 5 ? 5 : 2;
-    using L = MassLayout<NM, NQ, EPB>;
-    auto kern = sumfact_mass_kernel<NM, NQ, LVEC, EPB, 2, EO>;
-    const size_t smem = L::smem_bytes();
-    struct Cfg {
-        bool ready = false;
-        int blocks_per_sm = 0, sms = 0, regs = 0;
-    };
-    static Cfg cfg[64];
-    int dev = 0;
-    cudaError_t err = cudaGetDevice(&dev);
-    if (err != cudaSuccess) return err;
-    Cfg &c = cfg[dev & 63];
-    if (!c.ready) {
-        err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (err != cudaSuccess) return err;
-        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.blocks_per_sm, kern, L::THREADS, smem);
-        if (err != cudaSuccess) return err;
-        err = cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, dev);
-        if (err != cudaSuccess) return err;
-        cudaFuncAttributes fa;
-        err = cudaFuncGetAttributes(&fa, kern);
-        if (err != cudaSuccess) return err;
-        c.regs = fa.numRegs;
-        if (c.blocks_per_sm < 1) return cudaErrorLaunchOutOfResources;
-        c.ready = true;
-    }
-    const uint32_t n_batches = (a.n_elems + EPB - 1) / EPB;
-    const long long resident = (long long)c.sms * c.blocks_per_sm * grid_multiplier();
-    const int grid = (int)(n_batches < (uint32_t)resident ? n_batches : resident);
-    if (info) *info = LaunchInfo{EPB, grid, L::THREADS, (int)smem, c.blocks_per_sm, c.regs, EO ? 1 : 0};
-    if (dry_run || a.n_elems == 0) return cudaSuccess;
-    kern<<<grid, L::THREADS, smem, s>>>(m, a);
-    return cudaGetLastError();
-}
-
 template <int NM, int NQ, bool COLL, int QOP, bool LVEC>
 cudaError_t launch_t(const double *hB, const double *hD, const double *hW, const KArgs &a, cudaStream_t s,
                      LaunchInfo *info, bool dry_run)
@@ -277,9 +226,6 @@ cudaError_t launch_t(const double *hB, const double *hD, const double *hW, const
             if (eo::fill<NM, NQ>(Bsym, Dsym, me.E) <= 1e-10) {
                 if (hW) std::memcpy(me.W, hW, sizeof(me.W)); else std::memset(me.W, 0, sizeof(me.W));
                 if (hW && (QOP & QOP_TRILINEAR)) std::memcpy(me.X, hW + NQ, sizeof(me.X)); else std::memset(me.X, 0, sizeof(me.X));  // hW = weights | points
-                if constexpr (mass_built(NM, NQ, COLL, QOP)) {
-                    if (mass_enabled() && a.ncomp <= 1) return launch_mass<NM, NQ, LVEC, true>(me, a, s, info, dry_run);
-                }
                 if (a.ncomp > 1) {
                     if constexpr (mc_built(COLL, QOP, LVEC)) return launch_variant<NM, NQ, COLL, QOP, LVEC, true, true>(me, a, s, info, dry_run);
                     else return cudaErrorNotSupported;
@@ -296,9 +242,6 @@ cudaError_t launch_t(const double *hB, const double *hD, const double *hW, const
     if (hD) std::memcpy(m.D, hD, sizeof(m.D)); else std::memset(m.D, 0, sizeof(m.D));
     if (hW) std::memcpy(m.W, hW, sizeof(m.W)); else std::memset(m.W, 0, sizeof(m.W));
     std::memset(m.X, 0, sizeof(m.X));
-    if constexpr (mass_built(NM, NQ, COLL, QOP)) {
-        if (mass_enabled() && a.ncomp <= 1) return launch_mass<NM, NQ, LVEC, false>(m, a, s, info, dry_run);
-    }
     if (a.ncomp > 1) {
         if constexpr (mc_built(COLL, QOP, LVEC)) return launch_variant<NM, NQ, COLL, QOP, LVEC, false, true>(m, a, s, info, dry_run);
         else return cudaErrorNotSupported;
