@@ -1,10 +1,16 @@
 #!/bin/bash
-# round-end evidence on 1 GPU: bench line + reference arm + ncu launch list + one full capture of the cell kernel
-tag=${1:-r01c}
+# round-end evidence on 1 GPU: full parity suite, smoke(), default bench line + reference arm.  usage: bash tools/gpu_final.sh <tag>
+tag=${1:-r02r}
 mkdir -p gpurun_out
-python bench.py > gpurun_out/${tag}_bench_1gpu.json 2> gpurun_out/${tag}_bench_1gpu.err
-python bench.py --impl reference --steps 2 --warmup 3 > gpurun_out/${tag}_bench_reference.json 2> gpurun_out/${tag}_bench_reference.err
-CMD="python bench.py --steps 2 --warmup 3 --its 10 --no-sweep --no-cpu-baseline"
-ncu --metrics gpu__time_duration.sum --clock-control none -s 250 -c 200 --csv --log-file gpurun_out/${tag}_launches.csv $CMD > gpurun_out/${tag}_launches.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:sumfact -s 40 -c 1 -f -o gpurun_out/${tag}_bp5_p6_kernel $CMD > gpurun_out/${tag}_full.log 2>&1
-head -c 400 gpurun_out/${tag}_bench_1gpu.json; echo; cat gpurun_out/${tag}_bench_reference.json | head -c 300
+python -m pytest tests -m gpu -q 2>&1 | tail -4 | tee gpurun_out/${tag}_pytest_gpu.txt
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 | tee gpurun_out/${tag}_smoke.txt
+( time python bench.py > gpurun_out/${tag}_bench_1gpu.json 2> gpurun_out/${tag}_bench_1gpu.err ) 2>&1 | grep real
+( time python bench.py --impl reference > gpurun_out/${tag}_bench_reference.json 2> gpurun_out/${tag}_bench_reference.err ) 2>&1 | grep real
+python -c "
+import json
+d = json.loads(open('gpurun_out/${tag}_bench_1gpu.json').read().strip().splitlines()[-1])
+print('headline', d['value'], 'frac', d['roofline']['frac'], 'e2e', d['e2e']['value'], 'launches', d['gpu_launches'], 'clocks', d['clocks'])
+print('parity', d['parity']['its'], d['parity']['golden'], 'cpu', d['cpu_baseline']['value'], d['cpu_baseline']['cores'])
+print('c5', d['bp6_hanging_nodes_p8']['gdofs'], d['bp6_hanging_nodes_p8']['frac_of_hbm_roofline'])
+r = json.loads(open('gpurun_out/${tag}_bench_reference.json').read().strip().splitlines()[-1]); print('reference arm', r['value'], r['cpu_baseline']['cores'])
+"
