@@ -284,6 +284,7 @@ def main():
         if args.transport != "auto":
             halo.set_transport(args.transport)
     A = b.LaplaceOperator(mesh, quad="gll", halo=halo, overlap=bool(args.overlap))
+    exclusive_interior = A.launch_info()["exclusive_interior"]
     rhs = A.compute_rhs()
     x = A.initialize_dof_vector()
     t_setup = time.perf_counter() - t_setup
@@ -648,7 +649,8 @@ def main():
             "roofline": {"bound": "hbm", "kernel": f"sumfact2_kernel<{p+1},{p+1},collocated,laplace,lvec> (BP5 cell kernel: gather + D^T G D + atomic scatter + fused p.Ap)",
                          "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak if peak else None,
                          "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": 1e3 * k_avg_s,
-                         "launches_timed": k_n, "launches_per_apply": launches_per_apply, "kernel_share_of_step": (1e-3 * k_ms) / t_dev if t_dev else None},
+                         "launches_timed": k_n, "launches_per_apply": launches_per_apply,
+                         "exclusive_interior_stores": exclusive_interior, "kernel_share_of_step": (1e-3 * k_ms) / t_dev if t_dev else None},
             "apply_only": apply_info,
             "clocks": clocks,
         }

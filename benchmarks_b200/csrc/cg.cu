@@ -94,7 +94,8 @@ __global__ void cg_scalar_kernel(CgScalars *sc, int jacobi, int max_it, double a
 // previous iteration (p_old is read here anyway: 8 B/DoF less than updating x together with r); v = 0 for the scatter of
 // the coming apply (owned and ghost entries; replaces a separate memset launch).
 __global__ void cg_update_p_kernel(uint32_t n, uint32_t n_local, size_t stride, const double *__restrict__ r, const double *__restrict__ inv_diag,
-                                   double *__restrict__ p, double *__restrict__ x, double *__restrict__ v, const CgScalars *sc)
+                                   double *__restrict__ p, double *__restrict__ x, double *__restrict__ v, const CgScalars *sc,
+                                   const uint32_t *__restrict__ excl_mask)
 {
     if (sc->done) return;
     r += blockIdx.y * stride; p += blockIdx.y * stride; x += blockIdx.y * stride; v += blockIdx.y * stride;
@@ -103,7 +104,8 @@ __global__ void cg_update_p_kernel(uint32_t n, uint32_t n_local, size_t stride, 
     const bool pending = sc->has_pending != 0;
     const double alpha = sc->alpha_pending;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += gridDim.x * blockDim.x) {
-        v[i] = 0.0;
+        // (cell-interior DoFs are overwritten by the apply with plain stores: no zero-fill, Operator::d_excl_mask)
+        if (excl_mask == nullptr || !((__ldg(excl_mask + (i >> 5)) >> (i & 31)) & 1u)) v[i] = 0.0;
         if (i < n) {
             const double z = inv_diag ? inv_diag[i] * r[i] : r[i];
             const double pi = first ? 0.0 : p[i];
@@ -440,7 +442,7 @@ static int cg_run(Operator &op, int ncomp, CgWork &w, double *d_x, const double 
         return B200FE_OK;
     };
     auto iteration = [&]() -> int {
-        cg_update_p_kernel<<<blocks_local, 256, 0, s>>>(n, (uint32_t)stride, stride, cheb ? w.cheb : w.r, fused_diag, w.p, d_x, w.v, w.sc);
+        cg_update_p_kernel<<<blocks_local, 256, 0, s>>>(n, (uint32_t)stride, stride, cheb ? w.cheb : w.r, fused_diag, w.p, d_x, w.v, w.sc, op.d_excl_mask);
         B200FE_CUDA_TRY(cudaGetLastError());
         ++g_launch_count;
         // block-diagonal operator: the fused p.Ap of every component lands in acc[0]; v was cleared by the p pass

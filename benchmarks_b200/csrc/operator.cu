@@ -306,6 +306,27 @@ __global__ void rhs_one_kernel(uint32_t n_cells, int nm, int nq, const double *_
         }
 }
 
+// Setup of KArgs::excl_interior.  Pass 1 over the index table: `seen` / `multi` = DoF referenced at least once / twice,
+// `inter` = DoF referenced from an interior position of a cell (all three local indices in 1..nm-2).
+__global__ void excl_scan_kernel(size_t n_entries, int nm, const uint32_t *__restrict__ idx, uint32_t *seen, uint32_t *multi, uint32_t *inter)
+{
+    const int nm3 = nm * nm * nm;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n_entries; t += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t id = idx[t];
+        if (id == kInvalidIndex) continue;
+        const int l = (int)(t % nm3), k = l % nm, j = (l / nm) % nm, i = l / (nm * nm);
+        const uint32_t bit = 1u << (id & 31);
+        if (atomicOr(seen + (id >> 5), bit) & bit) atomicOr(multi + (id >> 5), bit);
+        if (i >= 1 && i <= nm - 2 && j >= 1 && j <= nm - 2 && k >= 1 && k <= nm - 2) atomicOr(inter + (id >> 5), bit);
+    }
+}
+// Pass 2: the property holds iff no DoF is both interior somewhere and referenced twice
+__global__ void excl_check_kernel(uint32_t n_words, const uint32_t *__restrict__ multi, const uint32_t *__restrict__ inter, int *violation)
+{
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += gridDim.x * blockDim.x)
+        if (multi[w] & inter[w]) *violation = 1;
+}
+
 __global__ void set_constrained_kernel(uint32_t n, const uint32_t *__restrict__ list, double value, double *__restrict__ v)
 {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v[list[i]] = value;
@@ -485,6 +506,32 @@ bool op_has_mc_kernel(const Operator &op)
     return on && op.collocated && op.qop == QOP_LAPLACE && op.otf_flag() == 0;
 }
 
+// Exclusive cell-interior DoFs: verified on the caller's index table, not assumed (a table that maps two cells' interior
+// positions to one DoF keeps the atomic scatter everywhere).  Best effort: without the scratch memory the feature stays off.
+static void op_prepare_exclusive(Operator &op)
+{
+    static const bool on = [] { const char *e = std::getenv("B200FE_EXCL_INTERIOR"); return !e || std::atoi(e) != 0; }();
+    if (!on || op.nm < 4 || op.n_cells == 0 || op.n_local() == 0) return;  // p <= 2: thread-per-element kernels / no interior to speak of
+    const uint32_t n_words = (op.n_local() + 31) / 32;
+    uint32_t *d_bits = nullptr;  // seen | multi | violation word, then the mask that stays
+    int h_violation = 1;
+    if (cudaMalloc(&d_bits, (2 * (size_t)n_words + 1) * sizeof(uint32_t)) != cudaSuccess) { cudaGetLastError(); return; }
+    if (cudaMalloc(&op.d_excl_mask, (size_t)n_words * sizeof(uint32_t)) != cudaSuccess) { cudaGetLastError(); cudaFree(d_bits); op.d_excl_mask = nullptr; return; }
+    cudaMemset(d_bits, 0, (2 * (size_t)n_words + 1) * sizeof(uint32_t));
+    cudaMemset(op.d_excl_mask, 0, (size_t)n_words * sizeof(uint32_t));
+    const size_t n_entries = (size_t)op.n_cells * op.nm * op.nm * op.nm;
+    excl_scan_kernel<<<148 * 16, 256>>>(n_entries, op.nm, op.d_idx, d_bits, d_bits + n_words, op.d_excl_mask);
+    excl_check_kernel<<<148 * 4, 256>>>(n_words, d_bits + n_words, op.d_excl_mask, reinterpret_cast<int *>(d_bits + 2 * (size_t)n_words));
+    g_launch_count += 2;
+    const cudaError_t e = cudaMemcpy(&h_violation, d_bits + 2 * (size_t)n_words, sizeof(int), cudaMemcpyDeviceToHost);
+    cudaFree(d_bits);
+    if (e != cudaSuccess || h_violation != 0) {
+        cudaGetLastError();
+        cudaFree(op.d_excl_mask);
+        op.d_excl_mask = nullptr;
+    }
+}
+
 int op_apply_cells(Operator &op, double *d_dst, const double *d_src, uint32_t cb, uint32_t ce,
                    double *d_dot, cudaStream_t s, int ncomp)
 {
@@ -495,6 +542,7 @@ int op_apply_cells(Operator &op, double *d_dst, const double *d_src, uint32_t cb
             d_src, d_dst, op.d_idx + cb * nm3, d_dot, affine ? op.otf_data() + (size_t)cb * op.otf_stride() : nullptr, op.d_skip};
     a.ncomp = ncomp;
     a.comp_stride = op.n_local();
+    a.excl_interior = op.d_excl_mask != nullptr;
     const int qop = op.qop | op.otf_flag();
     const bool timed = op.timing && op.ev_used + 2 <= op.ev.size();
     if (timed) B200FE_CUDA_TRY(cudaEventRecord(op.ev[op.ev_used], s));
@@ -954,6 +1002,7 @@ int b200fe_op_create(const b200fe_op_desc *d, b200fe_op **out)
         B200FE_CUDA_TRY(cudaMalloc(&op->d_constrained, d->n_constrained * sizeof(uint32_t)));
         B200FE_CUDA_TRY(cudaMemcpy(op->d_constrained, d->h_constrained, d->n_constrained * sizeof(uint32_t), cudaMemcpyHostToDevice));
     }
+    op_prepare_exclusive(*op);
     *out = reinterpret_cast<b200fe_op *>(op.release());
     return B200FE_OK;
 }
@@ -1201,6 +1250,14 @@ int b200fe_op_kernel_variant(b200fe_op *o, int *even_odd)
     LaunchInfo li{};
     B200FE_CUDA_TRY(launch_sumfact(op.nm, op.nq, op.collocated, op.qop | op.otf_flag(), true, op.B.data(), op.D.data(), a, nullptr, &li, true));
     *even_odd = li.even_odd;
+    return B200FE_OK;
+}
+
+int b200fe_op_exclusive_interior(b200fe_op *o, int *on)
+{
+    Operator *op = reinterpret_cast<Operator *>(o);
+    B200FE_REQUIRE(op && on, "b200fe_op_exclusive_interior: null pointer");
+    *on = op->d_excl_mask != nullptr;
     return B200FE_OK;
 }
 

@@ -40,6 +40,10 @@ struct Operator {
     int hang_save_comps = 0;                              // components the save buffer has room for
     std::vector<uint32_t> h_hang_dof, h_hang_ptr, h_hang_col;  // host copies of the rows (compute_diagonal with constraints)
     std::vector<double> h_hang_w;
+    // exclusive cell-interior DoFs (KArgs::excl_interior): bit i set = local DoF i sits at an interior position of exactly one
+    // cell -- the cell kernel writes it with a plain store, so the zero-fill before an apply may skip it.  Owned; null when
+    // the property does not hold on this index table (or p <= 2, or B200FE_EXCL_INTERIOR=0).
+    uint32_t *d_excl_mask = nullptr;
     const int *d_skip = nullptr;        // set by the CG driver for the duration of a solve (see KArgs::skip)
     // overlap split: cells [0, n_phase0) and [n_phase0+n_phase1, n_cells) touch no ghost DoF
     uint32_t n_phase0 = 0, n_phase1 = 0;
@@ -58,6 +62,7 @@ struct Operator {
         for (cudaEvent_t e : ev) cudaEventDestroy(e);
         cudaFree(d_constrained);
         cudaFree(d_mats);
+        cudaFree(d_excl_mask);
         free_constraints();
         free_face_constraints();
     }

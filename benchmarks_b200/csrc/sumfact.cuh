@@ -61,6 +61,10 @@ struct KArgs {
     // geometric factors of a batch are fetched once and used for all components; in/out of component c at + c*comp_stride
     int ncomp = 1;
     size_t comp_stride = 0;
+    // L-vector only: the DoFs at the interior positions of a cell (all three local indices in 1..nm-2) belong to that cell
+    // alone (FE_Q; verified on the index table at operator creation).  When set, they are written with plain stores -- no
+    // zero-fill before the launch and no read-modify-write in L2 for (p-1)^3 / p^3 of the result vector.
+    int excl_interior = 0;
 };
 
 constexpr __host__ __device__ int odd(int n) { return n | 1; }

@@ -316,6 +316,12 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
     };
     if constexpr (LVEC) load_idx(blockIdx.x, cur_idx);
     load_val(blockIdx.x, cur_idx, cur_val, a.in);
+    // KArgs::excl_interior: this thread's two fixed local indices are interior ones (the third runs over the register column)
+    [[maybe_unused]] bool excl_t2 = false;
+    if constexpr (LVEC) {
+        const int t_hi = COLL ? ta : t2 / NM, t_lo = COLL ? tb : t2 % NM;
+        excl_t2 = a.excl_interior != 0 && t_hi >= 1 && t_hi <= NM - 2 && t_lo >= 1 && t_lo <= NM - 2;
+    }
     const int ncomp = MC ? a.ncomp : 1;
     constexpr bool JW_PIPE = MASS && !LAP && PREFETCH;
     [[maybe_unused]] double jw_cur[NQ];
@@ -577,7 +583,10 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
             if constexpr (LVEC) {
 #pragma unroll
                 for (int p = 0; p < NQ; ++p) {
-                    if (cur_idx[p] != kInvalidIndex) atomicAdd(a.out + coff + cur_idx[p], w[p]);
+                    if (cur_idx[p] != kInvalidIndex) {
+                        if (excl_t2 && p >= 1 && p <= NQ - 2) a.out[coff + cur_idx[p]] = w[p];  // cell-interior DoF: sole writer
+                        else atomicAdd(a.out + coff + cur_idx[p], w[p]);
+                    }
                 }
             } else {
                 if (active) {
@@ -611,7 +620,10 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
                 if constexpr (ROW_IO) {  // scatter the row straight from registers
 #pragma unroll
                     for (int k = 0; k < NM; ++k)
-                        if (cur_idx[k] != kInvalidIndex) atomicAdd(a.out + cur_idx[k], z[k]);
+                        if (cur_idx[k] != kInvalidIndex) {
+                            if (excl_t2 && k >= 1 && k <= NM - 2) a.out[cur_idx[k]] = z[k];  // cell-interior DoF: sole writer
+                            else atomicAdd(a.out + cur_idx[k], z[k]);
+                        }
                 } else {
 #pragma unroll
                     for (int k = 0; k < NM; ++k) R1[t2 * RU + k] = z[k];  // odd row stride

@@ -222,7 +222,10 @@ class LaplaceOperator:
         keys = ("elems_per_block", "num_blocks", "threads_per_block", "smem_bytes", "blocks_per_sm", "regs_per_thread")
         eo = C.c_int()
         check(lib.b200fe_op_kernel_variant(self._h, C.byref(eo)))
-        return dict(zip(keys, [x.value for x in v]), even_odd=eo.value, multi_component=int(self.multi_component_kernel()))
+        ex = C.c_int()
+        check(lib.b200fe_op_exclusive_interior(self._h, C.byref(ex)))
+        return dict(zip(keys, [x.value for x in v]), even_odd=eo.value, multi_component=int(self.multi_component_kernel()),
+                    exclusive_interior=ex.value)
 
     def multi_component_kernel(self) -> bool:
         """Vector-valued applies (vmult_components, n_components CG) run ONE cell-kernel launch that fetches the geometric

@@ -345,6 +345,14 @@ int b200fe_op_launch_info(b200fe_op *op, int *elems_per_block, int *num_blocks, 
  * reference drivers' cos() test matrices, CEED_BK/src/BK3/templated_cuda_benchmark.cc:50-66).  B200FE_EVEN_ODD=0 in the
  * environment forces 0. */
 int b200fe_op_kernel_variant(b200fe_op *op, int *even_odd);
+/* *on = 1 when the scatter of this operator writes the DoFs at the interior positions of a cell (all three local indices in
+ * 1..p-1) with plain stores instead of atomic adds: for FE_Q those DoFs belong to one cell only, which b200fe_op_create
+ * VERIFIES on the dof_indices table it is given (one device pass; a table that breaks the property keeps atomics
+ * everywhere, *on = 0).  The CG loop then skips their zero-fill as well: (p-1)^3 / p^3 of the result vector is written
+ * once per apply instead of zeroed, fetched into L2 and added to.  p >= 3 only; B200FE_EXCL_INTERIOR=0 forces 0.
+ * (deal.II's matrix-free loops get the same effect from their cell-interior "pre/post" ranges; no reference file -- the
+ * reference kernels scatter everything with Kokkos::atomic_add, CEED_bp/include/bk3_kokkos_kernel.h:372-386.) */
+int b200fe_op_exclusive_interior(b200fe_op *op, int *on);
 
 /* ------------------------------------------------------------------------------------------
  * 5. Conjugate gradients (dealii::SolverCG + ReductionControl as called at CEED_bp/src/bp3.cc:266-285

@@ -63,6 +63,36 @@ def test_vmult_matches_oracle_on_deformed_mesh(oracle_mod, p, name, dq, quad, ki
     assert abs(dot.item() - float(src @ ref)) <= 1e-11 * np.abs(src).dot(np.abs(ref))
 
 
+@pytest.mark.parametrize("name,dq,quad,kind", [VARIANTS[0], VARIANTS[2], VARIANTS[3]])
+@pytest.mark.parametrize("p", [2, 3, 6])
+def test_exclusive_interior_is_verified_on_the_index_table(oracle_mod, p, name, dq, quad, kind):
+    """Plain stores for cell-interior DoFs (b200fe_op_exclusive_interior): on from p = 3 on an FE_Q table; an index table
+    that maps the interior positions of two cells to the same DoFs must keep the atomic scatter -- and stay correct."""
+    import benchmarks_b200 as b
+    fe = oracle_mod.fe
+    sub, nref, nq = (2, 1, 1), 1, p + dq
+    om, od, rd, bas, G, JxW = _oracle_setup(fe, sub, nref, p, nq, quad, 1, DEFORM)
+    mesh = b.BoxMesh(sub, nref, p)
+    A = b.LaplaceOperator(mesh, nq=nq, quad=quad, kind=kind, deform=DEFORM)
+    assert A.launch_info()["exclusive_interior"] == (1 if p >= 3 else 0)
+    # cell 1 now writes to the DoFs of cell 0: every interior DoF of cell 0 has two writers
+    mesh.dof_indices[1] = mesh.dof_indices[0]
+    idx = rd["dof_indices"].copy()
+    idx[1] = idx[0]
+    assert np.array_equal(idx, mesh.dof_indices)
+    A2 = b.LaplaceOperator(mesh, nq=nq, quad=quad, kind=kind, deform=DEFORM)
+    assert A2.launch_info()["exclusive_interior"] == 0
+    src = np.random.default_rng(10 + p).standard_normal(mesh.n_owned)
+    ref = fe.op_apply(src, idx, bas, G, JxW, laplace=kind != "mass", mass=kind != "laplace", constrained=rd["constrained"])
+    dst = torch.full((mesh.n_owned,), -3.0, dtype=torch.float64, device="cuda")
+    A2.vmult(dst, torch.from_numpy(src).cuda())
+    assert rel(dst.cpu().numpy(), ref) <= TOL
+    # and the verified operator agrees with the oracle on the untouched table (plain stores on, dst pre-filled with garbage)
+    ref1 = fe.op_apply(src, rd, bas, G, JxW, laplace=kind != "mass", mass=kind != "laplace")
+    A.vmult(dst, torch.from_numpy(src).cuda())
+    assert rel(dst.cpu().numpy(), ref1) <= TOL
+
+
 @pytest.mark.parametrize("p", [1, 2, 4, 7])
 def test_diagonal_rhs_and_dummy(oracle_mod, p):
     import benchmarks_b200 as b
