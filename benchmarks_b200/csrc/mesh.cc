@@ -22,6 +22,7 @@
 #endif
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -70,7 +71,7 @@ struct BoxMesh {
     // local data of `rank`
     int64_t cell_begin = 0, cell_end = 0;
     uint64_t owned_begin = 0, owned_end = 0;
-    std::vector<uint32_t> dof_indices;   // [n_local_cells][nm^3] lexicographic, local numbering
+    std::vector<uint32_t> lbase;         // [n_local_cells][27] local index of the first DoF of each entity of the cell
     std::vector<uint64_t> ghost_global;  // sorted
     std::vector<int32_t> ghost_owner;
     std::vector<uint32_t> constrained;   // owned local indices on the Dirichlet boundary
@@ -158,6 +159,84 @@ struct BoxMesh {
         }
     }
 
+    // 3x3x3 neighbourhood of cell c: active index of every neighbour, ~0 where the mesh ends; slot = (dx+1) + 3 (dy+1) + 9 (dz+1)
+    void neighbourhood(const int64_t c[3], uint64_t nb[27]) const
+    {
+        for (int dz = -1; dz <= 1; ++dz)
+            for (int dy = -1; dy <= 1; ++dy)
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int64_t x = c[0] + dx, y = c[1] + dy, z = c[2] + dz;
+                    const bool in = x >= 0 && y >= 0 && z >= 0 && x < cells[0] && y < cells[1] && z < cells[2];
+                    nb[(dx + 1) + 3 * (dy + 1) + 9 * (dz + 1)] = in ? pos_of(x, y, z) : ~0ull;
+                }
+    }
+    // per entity: the neighbourhood slots of the cells sharing it, and the entity's id as seen from each of them
+    struct NbTables {
+        uint32_t sharers[27];
+        int n_sharers[27], sharer_slot[27][8], ef_of[27][27];
+        NbTables()
+        {
+            for (int e = 0; e < 27; ++e) {
+                sharers[e] = 0;
+                n_sharers[e] = 0;
+                for (int k = 0; k < 27; ++k) ef_of[e][k] = -1;
+                int lo[3], hi[3];
+                for (int d = 0; d < 3; ++d) {
+                    const int t = kEnt.code[e][d];
+                    lo[d] = t == 0 ? -1 : 0;
+                    hi[d] = t == 2 ? 1 : 0;
+                }
+                for (int dz = lo[2]; dz <= hi[2]; ++dz)
+                    for (int dy = lo[1]; dy <= hi[1]; ++dy)
+                        for (int dx = lo[0]; dx <= hi[0]; ++dx) {
+                            const int slot = (dx + 1) + 3 * (dy + 1) + 9 * (dz + 1), off[3] = {dx, dy, dz};
+                            int rc[3];
+                            for (int d = 0; d < 3; ++d) {
+                                const int t = kEnt.code[e][d];
+                                rc[d] = t == 1 ? 1 : (off[d] == (t == 2 ? 1 : 0) ? 0 : 2);  // the entity's plane as seen from that cell
+                            }
+                            sharers[e] |= 1u << slot;
+                            sharer_slot[e][n_sharers[e]++] = slot;
+                            ef_of[e][slot] = kEnt.id_of_code[rc[0]][rc[1]][rc[2]];
+                        }
+            }
+        }
+    };
+    static const NbTables &nb_tables()
+    {
+        static const NbTables t;
+        return t;
+    }
+
+    bool cell_at_boundary(const int32_t *c) const
+    {
+        bool at = false;
+        for (int d = 0; d < 3; ++d) at |= c[d] == 0 || c[d] == cells[d] - 1;
+        return at;
+    }
+    // the index table [n_local_cells][nm^3] (lexicographic, local numbering, invalid on the Dirichlet boundary), written
+    // straight into the caller's buffer: its pages are first touched by the threads that fill them
+    void expand_indices(uint32_t *out) const
+    {
+        meshdetail::use_setup_threads();
+        const int nm = p + 1, nm3 = nm * nm * nm;
+        const int64_t nloc = n_local_cells();
+        const int64_t dimsL[3] = {cells[0] * p, cells[1] * p, cells[2] * p};
+#pragma omp parallel for schedule(static)
+        for (int64_t ci = 0; ci < nloc; ++ci) {
+            const uint32_t *lb = &lbase[(size_t)ci * 27];
+            const int32_t *c = &cell_xyz[ci * 3];
+            uint32_t *row = out + (size_t)ci * nm3;
+            for (int l = 0; l < nm3; ++l) row[l] = lb[l_ent[l]] + (uint32_t)l_idx[l];
+            if (!(dirichlet && cell_at_boundary(c))) continue;
+            for (int l = 0; l < nm3; ++l) {
+                const int a = l % nm, b = (l / nm) % nm, cc = l / (nm * nm);
+                const int64_t X = (int64_t)c[0] * p + a, Y = (int64_t)c[1] * p + b, Z = (int64_t)c[2] * p + cc;
+                if (X == 0 || Y == 0 || Z == 0 || X == dimsL[0] || Y == dimsL[1] || Z == dimsL[2]) row[l] = B200FE_INVALID_INDEX;
+            }
+        }
+    }
+
     uint64_t within_prefix(uint32_t mask, int e) const
     {
         uint64_t s = 0;
@@ -172,6 +251,15 @@ struct BoxMesh {
 int BoxMesh::build()
 {
     meshdetail::use_setup_threads();
+    // B200FE_SETUP_TRACE=1: wall time of the build phases on stderr
+    static const bool trace = [] { const char *e = std::getenv("B200FE_SETUP_TRACE"); return e && std::atoi(e) != 0; }();
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!trace) return;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[b200fe setup] box mesh rank %d: %-28s %7.1f ms\n", rank, what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
     const int nm = p + 1, nm3 = nm * nm * nm;
     for (int e = 0; e < 27; ++e) ent_size[e] = meshdetail::entity_size(p, e);
     for (int d = 0; d < 3; ++d) {
@@ -194,29 +282,36 @@ int BoxMesh::build()
         pos_tab.swap(tab);
     }
 
-    // pass 1 over ALL cells: which entities does each cell number, and how many DoFs
+    lap("position table");
+    // pass 1 over ALL cells: which entities does each cell number, and how many DoFs.  One look-up per neighbour (26 per
+    // cell) instead of one per (entity, sharing cell) pair (up to 216): a cell numbers an entity iff none of the cells
+    // sharing it comes earlier in the active order.
+    const NbTables &nt = nb_tables();
     newmask.assign(n_cells_global, 0);
     gprefix.assign(n_cells_global + 1, 0);
+    lap("pass 1 allocation");
 #pragma omp parallel for schedule(static)
     for (int64_t ps = 0; ps < n_cells_global; ++ps) {
         int64_t c[3];
         xyz_of((uint64_t)ps, c[0], c[1], c[2]);
+        uint64_t nb[27];
+        neighbourhood(c, nb);
+        uint32_t lower = 0;  // neighbours that exist and come before this cell
+        for (int k = 0; k < 27; ++k) lower |= (uint32_t)(nb[k] < (uint64_t)ps) << k;
         uint32_t mask = 0;
         uint64_t cnt = 0;
-        for (int e = 0; e < 27; ++e) {
-            if (ent_size[e] == 0) continue;
-            int owner; uint64_t first;
-            entity_owner(c, e, owner, first, nullptr, false);
-            if (first == (uint64_t)ps) { mask |= 1u << e; cnt += ent_size[e]; }
-        }
+        for (int e = 0; e < 27; ++e)
+            if (ent_size[e] != 0 && (lower & nt.sharers[e]) == 0) { mask |= 1u << e; cnt += ent_size[e]; }
         newmask[ps] = mask;
         gprefix[ps + 1] = cnt;
     }
+    lap("pass 1 (all cells)");
     for (int64_t ps = 0; ps < n_cells_global; ++ps) gprefix[ps + 1] += gprefix[ps];
     if (gprefix[n_cells_global] != n_dofs_global)
         return fail(B200FE_ERR_INVALID_ARG, "box mesh: internal numbering error (%llu != %llu)",
                     (unsigned long long)gprefix[n_cells_global], (unsigned long long)n_dofs_global);
 
+    lap("pass 1 (all cells) + prefix");
     rank_cell_begin.resize(nranks + 1);
     rank_dof_begin.resize(nranks + 1);
     {
@@ -225,7 +320,6 @@ int BoxMesh::build()
             while (ps < n_cells_global && rank_of_pos((uint64_t)ps) < r) ++ps;  // monotone
             rank_cell_begin[r] = r == nranks ? n_cells_global : ps;
         }
-        // ranks own contiguous cell ranges => binary search instead of the linear scan
         for (int r = 0; r <= nranks; ++r) rank_dof_begin[r] = gprefix[rank_cell_begin[r]];
     }
     cell_begin = rank_cell_begin[rank];
@@ -233,37 +327,44 @@ int BoxMesh::build()
     owned_begin = rank_dof_begin[rank];
     owned_end = rank_dof_begin[rank + 1];
     const int64_t nloc = n_local_cells();
-    if (owned_end - owned_begin >= 0xFFFFFFFFull) return fail(B200FE_ERR_UNSUPPORTED, "box mesh: more than 2^32-2 owned DoFs on one rank");
+    const uint64_t n_owned = owned_end - owned_begin;
+    if (n_owned >= 0xFFFFFFFFull) return fail(B200FE_ERR_UNSUPPORTED, "box mesh: more than 2^32-2 owned DoFs on one rank");
 
-    // pass 2 over own cells: global index of every local DoF
-    std::vector<uint64_t> gidx((size_t)nloc * nm3);
+    // pass 2 over own cells: global index of the first DoF of each of the cell's 27 entities (the DoFs of an entity are
+    // contiguous in the global numbering, so everything below works per entity, not per DoF); entities of other ranks
+    // are the ghost candidates
+    std::vector<uint64_t> gbase((size_t)nloc * 27);
     cell_xyz.resize((size_t)nloc * 3);
-    const int64_t dimsL[3] = {cells[0] * p, cells[1] * p, cells[2] * p};
-    std::vector<uint8_t> on_boundary((size_t)nloc * nm3);
-#pragma omp parallel for schedule(static)
-    for (int64_t ci = 0; ci < nloc; ++ci) {
-        int64_t c[3];
-        xyz_of((uint64_t)(cell_begin + ci), c[0], c[1], c[2]);
-        for (int d = 0; d < 3; ++d) cell_xyz[ci * 3 + d] = (int32_t)c[d];
-        uint64_t base[27];
-        for (int e = 0; e < 27; ++e) {
-            if (ent_size[e] == 0) { base[e] = 0; continue; }
-            int owner, ef; uint64_t first;
-            entity_owner(c, e, owner, first, &ef, false);
-            base[e] = gprefix[first] + within_prefix(newmask[first], ef);
+    struct Ent { uint64_t base; uint32_t size; };
+    std::vector<Ent> cand;
+#pragma omp parallel
+    {
+        std::vector<Ent> mine;
+#pragma omp for schedule(static) nowait
+        for (int64_t ci = 0; ci < nloc; ++ci) {
+            int64_t c[3];
+            xyz_of((uint64_t)(cell_begin + ci), c[0], c[1], c[2]);
+            for (int d = 0; d < 3; ++d) cell_xyz[ci * 3 + d] = (int32_t)c[d];
+            uint64_t nb[27];
+            neighbourhood(c, nb);
+            for (int e = 0; e < 27; ++e) {
+                if (ent_size[e] == 0) { gbase[ci * 27 + e] = 0; continue; }
+                uint64_t first = ~0ull;
+                int slot = 13;
+                for (int k = 0; k < nt.n_sharers[e]; ++k) {
+                    const int sl = nt.sharer_slot[e][k];
+                    if (nb[sl] < first) { first = nb[sl]; slot = sl; }
+                }
+                const uint64_t b0 = gprefix[first] + within_prefix(newmask[first], nt.ef_of[e][slot]);
+                gbase[ci * 27 + e] = b0;
+                if (b0 < owned_begin || b0 >= owned_end) mine.push_back(Ent{b0, (uint32_t)ent_size[e]});
+            }
         }
-        for (int l = 0; l < nm3; ++l) {
-            gidx[ci * nm3 + l] = base[l_ent[l]] + (uint64_t)l_idx[l];
-            const int a = l % nm, b = (l / nm) % nm, cc = l / (nm * nm);
-            const int64_t X = c[0] * p + a, Y = c[1] * p + b, Z = c[2] * p + cc;
-            on_boundary[ci * nm3 + l] = dirichlet && (X == 0 || Y == 0 || Z == 0 || X == dimsL[0] || Y == dimsL[1] || Z == dimsL[2]);
-        }
+#pragma omp critical
+        cand.insert(cand.end(), mine.begin(), mine.end());
     }
-
-    // ghost set: DoFs on own cells (minimal) or on own + vertex-neighbour cells (deal.II "relevant")
-    std::vector<uint64_t> cand;
-    for (size_t i = 0; i < gidx.size(); ++i)
-        if (gidx[i] < owned_begin || gidx[i] >= owned_end) cand.push_back(gidx[i]);
+    lap("pass 2 (own cells)");
+    // deal.II "relevant" ghosts: also the DoFs on the vertex-neighbour cells of own cells
     if (ghost_mode == B200FE_GHOSTS_RELEVANT && nranks > 1) {
         std::vector<uint64_t> layer;
         for (int64_t ci = 0; ci < nloc; ++ci) {
@@ -287,44 +388,73 @@ int BoxMesh::build()
                 int owner, ef; uint64_t first;
                 entity_owner(c, e, owner, first, &ef);
                 if (owner == rank) continue;
-                const uint64_t b0 = gprefix[first] + within_prefix(newmask[first], ef);
-                for (int k = 0; k < ent_size[e]; ++k) cand.push_back(b0 + k);
+                cand.push_back(Ent{gprefix[first] + within_prefix(newmask[first], ef), (uint32_t)ent_size[e]});
             }
         }
     }
-    std::sort(cand.begin(), cand.end());
-    cand.erase(std::unique(cand.begin(), cand.end()), cand.end());
-    ghost_global.swap(cand);
-    ghost_owner.resize(ghost_global.size());
-    for (size_t i = 0; i < ghost_global.size(); ++i)
-        ghost_owner[i] = (int32_t)(std::upper_bound(rank_dof_begin.begin(), rank_dof_begin.end(), ghost_global[i]) - rank_dof_begin.begin() - 1);
-    const uint64_t n_owned = owned_end - owned_begin;
-    if (n_owned + ghost_global.size() >= 0xFFFFFFFFull) return fail(B200FE_ERR_UNSUPPORTED, "box mesh: local vector too long for 32-bit indices");
-
-    // local index table with the Dirichlet mask, and the owned constrained list
-    dof_indices.resize(gidx.size());
-    std::vector<uint32_t> cons;
-#pragma omp parallel
-    {
-        std::vector<uint32_t> mine;
-#pragma omp for schedule(static) nowait
-        for (int64_t i = 0; i < (int64_t)gidx.size(); ++i) {
-            const uint64_t g = gidx[i];
-            uint32_t loc;
-            if (g >= owned_begin && g < owned_end) loc = (uint32_t)(g - owned_begin);
-            else loc = (uint32_t)(n_owned + (std::lower_bound(ghost_global.begin(), ghost_global.end(), g) - ghost_global.begin()));
-            if (on_boundary[i]) {
-                if (loc < n_owned) mine.push_back(loc);
-                dof_indices[i] = B200FE_INVALID_INDEX;
-            } else
-                dof_indices[i] = loc;
+    std::sort(cand.begin(), cand.end(), [](const Ent &a, const Ent &b) { return a.base < b.base; });
+    cand.erase(std::unique(cand.begin(), cand.end(), [](const Ent &a, const Ent &b) { return a.base == b.base; }), cand.end());
+    // ghost entities sorted by global index: their DoFs in that order are the (sorted) ghost list
+    std::vector<uint64_t> gent_base(cand.size());
+    std::vector<uint32_t> gent_local(cand.size() + 1, 0);  // position of the entity's first DoF in the ghost segment
+    for (size_t i = 0; i < cand.size(); ++i) {
+        gent_base[i] = cand[i].base;
+        gent_local[i + 1] = gent_local[i] + cand[i].size;
+    }
+    const size_t n_ghost = gent_local[cand.size()];
+    if (n_owned + n_ghost >= 0xFFFFFFFFull) return fail(B200FE_ERR_UNSUPPORTED, "box mesh: local vector too long for 32-bit indices");
+    ghost_global.resize(n_ghost);
+    ghost_owner.resize(n_ghost);
+    for (size_t i = 0; i < cand.size(); ++i) {
+        const int32_t owner = (int32_t)(std::upper_bound(rank_dof_begin.begin(), rank_dof_begin.end(), cand[i].base) - rank_dof_begin.begin() - 1);
+        for (uint32_t k = 0; k < cand[i].size; ++k) {
+            ghost_global[gent_local[i] + k] = cand[i].base + k;
+            ghost_owner[gent_local[i] + k] = owner;
         }
+    }
+
+    lap("ghost list");
+    // local index of the first DoF of every entity of every own cell (the index table itself -- nm^3 entries per cell, 360 MB
+    // for the 64^3-cell headline mesh -- is expanded from this straight into the caller's buffer by b200fe_boxmesh_fill)
+    lbase.resize((size_t)nloc * 27);
+#pragma omp parallel for schedule(static)
+    for (int64_t ci = 0; ci < nloc; ++ci)
+        for (int e = 0; e < 27; ++e) {
+            const uint64_t g = gbase[ci * 27 + e];
+            uint32_t lb;
+            if (ent_size[e] == 0) lb = 0;
+            else if (g >= owned_begin && g < owned_end) lb = (uint32_t)(g - owned_begin);
+            else lb = (uint32_t)(n_owned + gent_local[std::lower_bound(gent_base.begin(), gent_base.end(), g) - gent_base.begin()]);
+            lbase[ci * 27 + e] = lb;
+        }
+    // owned constrained list: DoFs of own boundary cells on the Dirichlet boundary
+    std::vector<uint32_t> cons;
+    if (dirichlet) {
+        const int64_t dimsL[3] = {cells[0] * p, cells[1] * p, cells[2] * p};
+#pragma omp parallel
+        {
+            std::vector<uint32_t> mine;
+#pragma omp for schedule(static) nowait
+            for (int64_t ci = 0; ci < nloc; ++ci) {
+                const int32_t *c = &cell_xyz[ci * 3];
+                if (!cell_at_boundary(c)) continue;
+                for (int l = 0; l < nm3; ++l) {
+                    const int a = l % nm, b = (l / nm) % nm, cc = l / (nm * nm);
+                    const int64_t X = (int64_t)c[0] * p + a, Y = (int64_t)c[1] * p + b, Z = (int64_t)c[2] * p + cc;
+                    if (X == 0 || Y == 0 || Z == 0 || X == dimsL[0] || Y == dimsL[1] || Z == dimsL[2]) {
+                        const uint32_t loc = lbase[ci * 27 + l_ent[l]] + (uint32_t)l_idx[l];
+                        if (loc < n_owned) mine.push_back(loc);
+                    }
+                }
+            }
 #pragma omp critical
-        cons.insert(cons.end(), mine.begin(), mine.end());
+            cons.insert(cons.end(), mine.begin(), mine.end());
+        }
     }
     std::sort(cons.begin(), cons.end());
     cons.erase(std::unique(cons.begin(), cons.end()), cons.end());
     constrained.swap(cons);
+    lap("local entity bases, constrained");
     // owned boundary DoFs that only OTHER ranks' cells touch cannot exist: the owner is the lowest
     // rank among the cells sharing the entity, so it has a cell there.
     return B200FE_OK;
@@ -441,7 +571,7 @@ int b200fe_boxmesh_fill(const b200fe_boxmesh *mesh, uint32_t *h_dof_indices, uin
 {
     B200FE_REQUIRE(mesh, "b200fe_boxmesh_fill: null mesh");
     const BoxMesh *m = reinterpret_cast<const BoxMesh *>(mesh);
-    if (h_dof_indices) std::memcpy(h_dof_indices, m->dof_indices.data(), m->dof_indices.size() * sizeof(uint32_t));
+    if (h_dof_indices) m->expand_indices(h_dof_indices);
     if (h_constrained) std::memcpy(h_constrained, m->constrained.data(), m->constrained.size() * sizeof(uint32_t));
     if (h_ghost_global) std::memcpy(h_ghost_global, m->ghost_global.data(), m->ghost_global.size() * sizeof(uint64_t));
     if (h_ghost_owner) std::memcpy(h_ghost_owner, m->ghost_owner.data(), m->ghost_owner.size() * sizeof(int32_t));
