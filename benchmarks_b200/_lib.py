@@ -41,6 +41,7 @@ _SIGNATURES = {
     "b200fe_boxmesh_destroy": (None, [_vp]),
     "b200fe_boxmesh_info": (_i, [_vp, _vp]),
     "b200fe_boxmesh_fill": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200fe_boxmesh_dof_indices_device": (_i, [_vp, _vp, _vp]),
     "b200fe_boxmesh_nodes": (_i, [_vp, _i, _i, C.c_double, C.c_double, _vp, _vp]),
     "b200fe_hangmesh_create": (_i, [_vp, C.POINTER(_vp)]),
     "b200fe_hangmesh_destroy": (None, [_vp]),

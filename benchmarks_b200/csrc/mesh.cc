@@ -518,6 +518,17 @@ int boxmesh_send_lists(const b200fe_boxmesh *mesh, std::vector<std::vector<uint3
     return B200FE_OK;
 }
 
+int boxmesh_tables(const b200fe_boxmesh *mesh, BoxMeshTables *t)
+{
+    const BoxMesh &m = *reinterpret_cast<const BoxMesh *>(mesh);
+    t->p = m.p; t->dirichlet = m.dirichlet;
+    t->n_cells_local = m.n_local_cells();
+    for (int d = 0; d < 3; ++d) t->cells[d] = m.cells[d];
+    t->lbase = m.lbase.data(); t->cell_xyz = m.cell_xyz.data();
+    t->l_ent = m.l_ent.data(); t->l_idx = m.l_idx.data();
+    return B200FE_OK;
+}
+
 }  // namespace b200fe
 
 using namespace b200fe;

@@ -10,6 +10,18 @@ namespace b200fe {
 // mesh.cc: owned local indices every other rank ghosts (ascending), from this rank's own view (minimal ghost sets)
 int boxmesh_send_lists(const b200fe_boxmesh *mesh, std::vector<std::vector<uint32_t>> &send);
 
+// mesh.cc: what the device-side expansion of the index table needs (operator.cu: b200fe_boxmesh_dof_indices_device) --
+// per own cell the local index of the first DoF of each of its 27 entities and the cell coordinates, per lexicographic
+// local DoF its (entity, index in entity); all pointers into the mesh object
+struct BoxMeshTables {
+    int p, dirichlet;
+    int64_t n_cells_local, cells[3];
+    const uint32_t *lbase;   // [n_cells_local][27]
+    const int32_t *cell_xyz; // [n_cells_local][3]
+    const int *l_ent, *l_idx;  // [(p+1)^3]
+};
+int boxmesh_tables(const b200fe_boxmesh *mesh, BoxMeshTables *t);
+
 namespace meshdetail {
 
 // OpenMP team of the host-side mesh builders.  Launchers export OMP_NUM_THREADS=1 to every rank (torchrun does), which

@@ -13,6 +13,7 @@
 
 #include "halo.h"
 #include "operator.h"
+#include "mesh_common.h"
 
 namespace b200fe {
 
@@ -325,6 +326,28 @@ __global__ void excl_check_kernel(uint32_t n_words, const uint32_t *__restrict__
 {
     for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += gridDim.x * blockDim.x)
         if (multi[w] & inter[w]) *violation = 1;
+}
+
+// Index table of a box mesh on the device (the device twin of BoxMesh::expand_indices, mesh.cc): entry (cell, l) = local
+// index of the first DoF of the entity local DoF l sits on + its index inside the entity; invalid on the Dirichlet boundary.
+// ent_idx[l] = entity << 16 | index in entity.
+__global__ void expand_indices_kernel(size_t n_entries, int nm, int p, int dirichlet, int64_t dx, int64_t dy, int64_t dz,
+                                      const uint32_t *__restrict__ lbase, const int32_t *__restrict__ cell_xyz,
+                                      const uint32_t *__restrict__ ent_idx, uint32_t *__restrict__ out)
+{
+    const int nm3 = nm * nm * nm;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n_entries; t += (size_t)gridDim.x * blockDim.x) {
+        const size_t cell = t / nm3;
+        const int l = (int)(t - cell * nm3);
+        const uint32_t ei = ent_idx[l];
+        uint32_t loc = lbase[cell * 27 + (ei >> 16)] + (ei & 0xFFFFu);
+        if (dirichlet) {
+            const int a = l % nm, b = (l / nm) % nm, c = l / (nm * nm);
+            const int64_t X = (int64_t)cell_xyz[cell * 3] * p + a, Y = (int64_t)cell_xyz[cell * 3 + 1] * p + b, Z = (int64_t)cell_xyz[cell * 3 + 2] * p + c;
+            if (X == 0 || Y == 0 || Z == 0 || X == dx || Y == dy || Z == dz) loc = kInvalidIndex;
+        }
+        out[t] = loc;
+    }
 }
 
 __global__ void set_constrained_kernel(uint32_t n, const uint32_t *__restrict__ list, double value, double *__restrict__ v)
@@ -863,6 +886,34 @@ int b200fe_boxmesh_nodes(const b200fe_boxmesh *mesh, int p_geo, int deform_kind,
     if (int rc = b200fe_boxmesh_fill(mesh, nullptr, nullptr, nullptr, nullptr, xyz.data(), nullptr)) return rc;
     return nodes_from_cell_table(xyz, 3, info.n_cells_local, info.origin, info.h, p_geo, deform_kind, amplitude, frequency, d_nodes,
                                  (cudaStream_t)stream);
+}
+
+int b200fe_boxmesh_dof_indices_device(const b200fe_boxmesh *mesh, uint32_t *d_dof_indices, void *stream)
+{
+    B200FE_REQUIRE(mesh && d_dof_indices, "b200fe_boxmesh_dof_indices_device: null pointer");
+    BoxMeshTables t;
+    if (int rc = boxmesh_tables(mesh, &t)) return rc;
+    if (t.n_cells_local == 0) return B200FE_OK;
+    const int nm = t.p + 1, nm3 = nm * nm * nm;
+    std::vector<uint32_t> ent_idx(nm3);
+    for (int l = 0; l < nm3; ++l) ent_idx[l] = (uint32_t)t.l_ent[l] << 16 | (uint32_t)t.l_idx[l];
+    cudaStream_t s = (cudaStream_t)stream;
+    SetupScratch scratch;
+    uint32_t *d_lbase = nullptr, *d_ei = nullptr;
+    int32_t *d_xyz = nullptr;
+    B200FE_CUDA_TRY(scratch.make(&d_lbase, (size_t)t.n_cells_local * 27));
+    B200FE_CUDA_TRY(scratch.make(&d_xyz, (size_t)t.n_cells_local * 3));
+    B200FE_CUDA_TRY(scratch.make(&d_ei, (size_t)nm3));
+    B200FE_CUDA_TRY(cudaMemcpyAsync(d_lbase, t.lbase, (size_t)t.n_cells_local * 27 * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    B200FE_CUDA_TRY(cudaMemcpyAsync(d_xyz, t.cell_xyz, (size_t)t.n_cells_local * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    B200FE_CUDA_TRY(cudaMemcpyAsync(d_ei, ent_idx.data(), (size_t)nm3 * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    const size_t n_entries = (size_t)t.n_cells_local * nm3;
+    expand_indices_kernel<<<(unsigned)std::min<size_t>((n_entries + 255) / 256, 148u * 32u), 256, 0, s>>>(
+        n_entries, nm, t.p, t.dirichlet, t.cells[0] * t.p, t.cells[1] * t.p, t.cells[2] * t.p, d_lbase, d_xyz, d_ei, d_dof_indices);
+    B200FE_CUDA_TRY(cudaGetLastError());
+    ++g_launch_count;
+    B200FE_CUDA_TRY(cudaStreamSynchronize(s));  // setup call: the temporaries are freed on return
+    return B200FE_OK;
 }
 
 int b200fe_hangmesh_nodes(const b200fe_hangmesh *mesh, int p_geo, int deform_kind, double amplitude,

@@ -64,16 +64,35 @@ class BoxMesh:
         self.first_cell, self.owned_begin = info.first_cell, info.owned_begin
         self.n_cells, self.n_owned, self.n_ghost = info.n_cells_local, info.n_owned, info.n_ghost
         self.cells, self.h = tuple(info.cells), np.array(list(info.h))
-        nm3 = (p + 1) ** 3
-        self.dof_indices = np.empty((self.n_cells, nm3), dtype=np.uint32)
+        self._dof_indices = None  # host copy of the index table: expanded on first access (see dof_indices)
         self.constrained = np.empty(info.n_constrained, dtype=np.uint32)
         self.ghost_global = np.empty(self.n_ghost, dtype=np.uint64)
         self.ghost_owner = np.empty(self.n_ghost, dtype=np.int32)
         self.cell_xyz = np.empty((self.n_cells, 3), dtype=np.int32)
         self.rank_dof_begin = np.empty(n_ranks + 1, dtype=np.uint64)
         ptr = lambda a: a.ctypes.data_as(C.c_void_p)
-        check(lib.b200fe_boxmesh_fill(self._h, ptr(self.dof_indices), ptr(self.constrained), ptr(self.ghost_global),
+        check(lib.b200fe_boxmesh_fill(self._h, None, ptr(self.constrained), ptr(self.ghost_global),
                                       ptr(self.ghost_owner), ptr(self.cell_xyz), ptr(self.rank_dof_begin)))
+
+    @property
+    def dof_indices(self) -> np.ndarray:
+        """[n_cells][(p+1)^3] index table on the HOST (b200fe_boxmesh_fill), built on first access and kept: the operator
+        takes it from here once it exists (tests edit it), otherwise it lets the device expand its own copy."""
+        if self._dof_indices is None:
+            self._dof_indices = np.empty((self.n_cells, (self.p + 1) ** 3), dtype=np.uint32)
+            check(lib.b200fe_boxmesh_fill(self._h, self._dof_indices.ctypes.data_as(C.c_void_p), None, None, None, None, None))
+        return self._dof_indices
+
+    def dof_indices_device(self, device):
+        """The index table as a device tensor [n_cells][(p+1)^3] (uint32), expanded by a device kernel from 27 numbers per
+        cell (b200fe_boxmesh_dof_indices_device); the host copy, if one was materialised, is uploaded instead."""
+        import torch
+        if self._dof_indices is not None:
+            return torch.from_numpy(np.ascontiguousarray(self._dof_indices)).to(device)
+        out = torch.empty((self.n_cells, (self.p + 1) ** 3), dtype=torch.uint32, device=device)
+        with torch.cuda.device(device):
+            check(lib.b200fe_boxmesh_dof_indices_device(self._h, C.c_void_p(out.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return out
 
     @classmethod
     def bp3_cycle(cls, cycle: int, p: int, **kw):

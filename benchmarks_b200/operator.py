@@ -46,12 +46,13 @@ def _dp(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
-def overlap_permutation(dof_indices: np.ndarray, n_owned: int, one_sided: bool = False):
+def overlap_permutation(dof_indices: np.ndarray, n_owned: int, one_sided: bool = False, touches=None):
     """Cell order [interior half | cells touching a ghost DoF | interior half] and the two sizes
     (deal.II's three colours with overlap_communication_computation).
     one_sided (P2P transport): [all interior cells | cells touching a ghost DoF] -- the ghost values are posted before the
     interior launch and only awaited before the boundary launch, so two launches instead of three hide the exchange."""
-    touches = ((dof_indices >= n_owned) & (dof_indices != INVALID)).any(axis=1)
+    if touches is None:  # (or given: the per-cell flags computed on the device)
+        touches = ((dof_indices >= n_owned) & (dof_indices != INVALID)).any(axis=1)
     interior = np.nonzero(~touches)[0]
     boundary = np.nonzero(touches)[0]
     half = len(interior) if one_sided else len(interior) // 2
@@ -78,13 +79,25 @@ class LaplaceOperator:
         self.kind = {"laplace": OP_LAPLACE, "mass": OP_MASS, "helmholtz": OP_HELMHOLTZ}[kind]
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
         self.basis = basis_1d(p, self.nq, self.quad)
-        idx = mesh.dof_indices
         self.perm = None
         n_phase0 = n_phase1 = 0
-        if overlap and mesh.n_ranks > 1 and not len(getattr(mesh, "hang_dof", ())):  # no split with hanging rows
-            self.perm, n_phase0, n_phase1 = overlap_permutation(idx, mesh.n_owned, one_sided=halo is not None and halo.transport() == "p2p")
-            idx = idx[self.perm]
-        self.dof_indices = torch.from_numpy(np.ascontiguousarray(idx)).to(self.device)
+        want_split = overlap and mesh.n_ranks > 1 and not len(getattr(mesh, "hang_dof", ()))  # no split with hanging rows
+        one_sided = halo is not None and halo.transport() == "p2p"
+        if hasattr(mesh, "dof_indices_device") and mesh.n_local < 2 ** 31:
+            # box meshes: the table is expanded on the device (27 numbers per cell go over PCIe instead of (p+1)^3)
+            idx_dev = mesh.dof_indices_device(self.device)
+            if want_split:
+                signed = idx_dev.view(torch.int32)  # INVALID = -1, valid indices < 2^31
+                touches = (signed >= mesh.n_owned).any(dim=1).cpu().numpy()
+                self.perm, n_phase0, n_phase1 = overlap_permutation(None, mesh.n_owned, one_sided=one_sided, touches=touches)
+                idx_dev = signed[torch.from_numpy(self.perm).to(self.device)].contiguous().view(torch.uint32)
+            self.dof_indices = idx_dev
+        else:
+            idx = mesh.dof_indices
+            if want_split:
+                self.perm, n_phase0, n_phase1 = overlap_permutation(idx, mesh.n_owned, one_sided=one_sided)
+                idx = idx[self.perm]
+            self.dof_indices = torch.from_numpy(np.ascontiguousarray(idx)).to(self.device)
         # geometry: mapping support points -> G, JxW on the device
         ng3 = (p_geo + 1) ** 3
         nodes = torch.empty(mesh.n_cells * 3 * ng3, dtype=torch.float64, device=self.device)
@@ -344,7 +357,12 @@ class PreconditionPMG:
 
 class SolverCG:
     """dealii::SolverCG: solve(A, x, b, preconditioner); preconditioner None = PreconditionIdentity,
-    a tensor holding the inverse diagonal (DiagonalMatrix / Jacobi), a PreconditionChebyshev or a PreconditionPMG."""
+    a tensor holding the inverse diagonal (DiagonalMatrix / Jacobi), a PreconditionChebyshev or a PreconditionPMG.
+
+    One difference from deal.II: the solve always starts from x0 = 0 -- whatever x holds on entry is OVERWRITTEN, not used
+    as an initial guess (dealii::SolverCG would start from r = b - A x).  Every reference driver zeroes the solution
+    before each solve (bp3.cc:271, bp5_kokkos/benchmark.cc:364), so their iteration counts are the cold-start ones; a
+    caller that wants a warm start must solve for the correction: A dx = b - A x0, x = x0 + dx."""
 
     def __init__(self, control: ReductionControl, check_every: int = 8):
         self.control = control

@@ -147,6 +147,13 @@ int b200fe_boxmesh_fill(const b200fe_boxmesh *mesh, uint32_t *h_dof_indices, uin
                         uint64_t *h_ghost_global, int32_t *h_ghost_owner, int32_t *h_cell_xyz,
                         uint64_t *h_rank_dof_begin);
 
+/* The same index table written by a DEVICE kernel into d_dof_indices[n_cells_local][(p+1)^3] (what the operator borrows):
+ * the mesh object keeps, per cell, the local index of the first DoF of each of its 27 entities (vertices, lines, quads,
+ * interior); this uploads those 27 numbers per cell and expands them on the GPU instead of building the (p+1)^3 entries per
+ * cell on the host and copying them over (360 MB for the 64^3-cell, p = 6 mesh).  Bit-identical to b200fe_boxmesh_fill.
+ * Replaces the host loop of CEED_bp/include/portable_laplace_operator.h:304-394.  Synchronises `stream`. */
+int b200fe_boxmesh_dof_indices_device(const b200fe_boxmesh *mesh, uint32_t *d_dof_indices, void *stream);
+
 /* Mapping support points of the owned cells on the DEVICE, d_nodes[cell][3][(p_geo+1)^3]
  * (node index c*ng^2 + b*ng + a, a <-> x), Gauss-Lobatto lattice of MappingQ(p_geo).
  * deform_kind 0: the box itself; 1: x += A sin(f y), y += A sin(f z), z += A sin(f x)

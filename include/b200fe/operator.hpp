@@ -381,8 +381,10 @@ class LaplaceOperator {
     {
         if (mesh.degree != fe_degree) throw Error(B200FE_ERR_INVALID_ARG, "mesh degree != fe_degree");
         const uint32_t nc = mesh.info.n_cells_local;
-        std::vector<uint32_t> idx((size_t)nc * nm3()), con(mesh.info.n_constrained);
-        check(b200fe_boxmesh_fill(mesh.handle(), idx.data(), con.data(), nullptr, nullptr, nullptr, nullptr));
+        std::vector<uint32_t> idx, con(mesh.info.n_constrained);  // idx stays empty: the table is expanded on the device
+        check(b200fe_boxmesh_fill(mesh.handle(), nullptr, con.data(), nullptr, nullptr, nullptr, nullptr));
+        idx_.resize((size_t)nc * nm3());
+        if (nc) check(b200fe_boxmesh_dof_indices_device(mesh.handle(), idx_.data(), nullptr));
         DeviceArray<double> nodes((size_t)nc * 3 * ng3(p_geo));
         check(b200fe_boxmesh_nodes(mesh.handle(), p_geo, deform.amplitude != 0.0, deform.amplitude, deform.frequency, nodes.data(), nullptr));
         init(nc, idx, con, nodes, quad, op_kind, p_geo);
@@ -465,7 +467,7 @@ class LaplaceOperator {
         const bool collocated = quad == Quadrature::GaussLobatto && nq == nm;
         std::vector<double> sv(nm * nq), cg(nq * nq);
         check(b200fe_basis_1d(fe_degree, nq, qk, sv.data(), cg.data(), nullptr, nullptr, nullptr));
-        idx_.upload(idx.data(), idx.size());
+        if (!idx.empty()) idx_.upload(idx.data(), idx.size());
         const size_t nq3 = (size_t)nq * nq * nq;
         if (op_kind & B200FE_OP_LAPLACE) G_.resize((size_t)nc * 6 * nq3);
         JxW_.resize((size_t)nc * nq3);
@@ -500,6 +502,10 @@ class ReductionControl {
 
 struct PreconditionIdentity {};
 
+// dealii::SolverCG as the reference drivers call it.  One difference from deal.II: the solve always starts from x0 = 0 --
+// the contents of x on entry are OVERWRITTEN, not used as an initial guess (dealii::SolverCG starts from r = b - A x).  The
+// reference drivers zero the solution before every solve (bp3.cc:271, bp5_kokkos/benchmark.cc:364), so their iteration
+// counts are the cold-start ones; for a warm start solve for the correction: A dx = b - A x0, x = x0 + dx.
 class SolverCG {
   public:
     explicit SolverCG(ReductionControl &c, int check_every = 8) : control_(c), check_every_(check_every) {}

@@ -93,6 +93,21 @@ def test_exclusive_interior_is_verified_on_the_index_table(oracle_mod, p, name, 
     assert rel(dst.cpu().numpy(), ref1) <= TOL
 
 
+@pytest.mark.parametrize("p,sub,nref,n_ranks,rank,dirichlet", [
+    (1, (2, 1, 1), 1, 1, 0, True), (3, (1, 2, 1), 2, 3, 1, True), (6, (2, 2, 1), 1, 4, 3, True), (8, (1, 1, 1), 1, 2, 0, False),
+    (4, (2, 2, 2), 2, 8, 5, True)])
+def test_index_table_expanded_on_the_device_equals_host_table(p, sub, nref, n_ranks, rank, dirichlet):
+    """b200fe_boxmesh_dof_indices_device (27 entity bases per cell expanded by a kernel) == b200fe_boxmesh_fill, bit for bit;
+    the host table is in turn bit-identical to the oracle's first-touch simulation (tests/test_mesh.py)."""
+    import benchmarks_b200 as b
+    mesh = b.BoxMesh(sub, nref, p, n_ranks=n_ranks, rank=rank, dirichlet=dirichlet)
+    assert mesh._dof_indices is None                       # nothing expanded on the host yet
+    dev = mesh.dof_indices_device(torch.device("cuda", 0))
+    assert mesh._dof_indices is None
+    host = mesh.dof_indices
+    assert dev.shape == host.shape and np.array_equal(dev.cpu().numpy(), host)
+
+
 @pytest.mark.parametrize("p", [1, 2, 4, 7])
 def test_diagonal_rhs_and_dummy(oracle_mod, p):
     import benchmarks_b200 as b
