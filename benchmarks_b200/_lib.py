@@ -69,6 +69,7 @@ _SIGNATURES = {
     "b200fe_op_launch_info": (_i, [_vp, _pi, _pi, _pi, _pi, _pi, _pi]),
     "b200fe_op_kernel_variant": (_i, [_vp, _pi]),
     "b200fe_op_exclusive_interior": (_i, [_vp, _pi]),
+    "b200fe_op_cartesian": (_i, [_vp, _pi]),
     "b200fe_op_timing_enable": (_i, [_vp, _i]),
     "b200fe_op_timing_read": (_i, [_vp, _pd, _pi]),
     "b200fe_launch_count": (C.c_ulonglong, []),

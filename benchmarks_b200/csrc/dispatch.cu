@@ -35,6 +35,8 @@ cudaError_t by_degree(int nq, bool coll, int qop, bool lvec, const double *hB, c
         if (!coll && nq == NM + 1 && qop == LA) return launch_t<NM, NM + 1, false, LA, true>(hB, hD, hW, a, s, info, dry);
         if (!coll && nq == NM && qop == LA) return launch_t<NM, NM, false, LA, true>(hB, hD, hW, a, s, info, dry);
         if (coll && nq == NM && qop == LA) return launch_t<NM, NM, true, LA, true>(hB, hD, hW, a, s, info, dry);
+        constexpr int LC = QOP_LAPLACE | QOP_AFFINE | QOP_CARTESIAN;
+        if (coll && nq == NM && qop == LC) return launch_t<NM, NM, true, LC, true>(hB, hD, hW, a, s, info, dry);
         constexpr int LT = QOP_LAPLACE | QOP_TRILINEAR;
         if (!coll && nq == NM + 1 && qop == LT) return launch_t<NM, NM + 1, false, LT, true>(hB, hD, hW, a, s, info, dry);
         if (!coll && nq == NM && qop == LT) return launch_t<NM, NM, false, LT, true>(hB, hD, hW, a, s, info, dry);

@@ -26,6 +26,8 @@ INST(NM, NM, false, QOP_HELMHOLTZ, true)     // bp5_kokkos Helmholtz (QGauss(p+1
 INST(NM, NM + 1, false, QOP_LAPLACE | QOP_AFFINE, true)
 INST(NM, NM, false, QOP_LAPLACE | QOP_AFFINE, true)
 INST(NM, NM, true, QOP_LAPLACE | QOP_AFFINE, true)
+// ... collocated, axis-aligned cells (deal.II's "cartesian" cell type): separable operator, three 1-D contractions per point
+INST(NM, NM, true, QOP_LAPLACE | QOP_AFFINE | QOP_CARTESIAN, true)
 // ... and for trilinear cells (8 vertices per cell, G rebuilt at every quadrature point)
 INST(NM, NM + 1, false, QOP_LAPLACE | QOP_TRILINEAR, true)
 INST(NM, NM, false, QOP_LAPLACE | QOP_TRILINEAR, true)

@@ -350,6 +350,16 @@ __global__ void expand_indices_kernel(size_t n_entries, int nm, int p, int diric
     }
 }
 
+// *flag = 1 unless every cell's constants are those of an axis-aligned box (vanishing rs, rt, st couplings)
+__global__ void cartesian_check_kernel(uint32_t n_cells, const double *__restrict__ cellG, int *flag)
+{
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n_cells; c += gridDim.x * blockDim.x) {
+        const double *g = cellG + (size_t)c * 8;
+        const double diag = fabs(g[0]) + fabs(g[3]) + fabs(g[5]), off = fabs(g[1]) + fabs(g[2]) + fabs(g[4]);
+        if (!(off <= 1e-14 * diag)) *flag = 1;
+    }
+}
+
 __global__ void set_constrained_kernel(uint32_t n, const uint32_t *__restrict__ list, double value, double *__restrict__ v)
 {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v[list[i]] = value;
@@ -569,7 +579,7 @@ int op_apply_cells(Operator &op, double *d_dst, const double *d_src, uint32_t cb
     const int qop = op.qop | op.otf_flag();
     const bool timed = op.timing && op.ev_used + 2 <= op.ev.size();
     if (timed) B200FE_CUDA_TRY(cudaEventRecord(op.ev[op.ev_used], s));
-    B200FE_CUDA_TRY(launch_sumfact(op.nm, op.nq, op.collocated, qop, true, op.B.data(), op.D.data(), a, s,
+    B200FE_CUDA_TRY(launch_sumfact(op.nm, op.nq, op.collocated, qop, true, op.cartesian ? op.S.data() : op.B.data(), op.D.data(), a, s,
                                    &op.last_launch, false, affine ? op.W.data() : nullptr));
     if (timed) {
         B200FE_CUDA_TRY(cudaEventRecord(op.ev[op.ev_used + 1], s));
@@ -1053,6 +1063,31 @@ int b200fe_op_create(const b200fe_op_desc *d, b200fe_op **out)
         B200FE_CUDA_TRY(cudaMalloc(&op->d_constrained, d->n_constrained * sizeof(uint32_t)));
         B200FE_CUDA_TRY(cudaMemcpy(op->d_constrained, d->h_constrained, d->n_constrained * sizeof(uint32_t), cudaMemcpyHostToDevice));
     }
+    if (d->d_cell_G && coll && d->n_cells) {
+        // axis-aligned cells (deal.II's "cartesian" cell type): the separable kernel.  B200FE_CARTESIAN=0 keeps the general
+        // affine kernel (read at every create: tests switch it).
+        const char *e = std::getenv("B200FE_CARTESIAN");
+        if (!e || std::atoi(e) != 0) {
+            int *d_flag = nullptr, h_flag = 1;
+            B200FE_CUDA_TRY(cudaMalloc(&d_flag, sizeof(int)));
+            cudaMemset(d_flag, 0, sizeof(int));
+            cartesian_check_kernel<<<148 * 4, 256>>>(d->n_cells, d->d_cell_G, d_flag);
+            ++g_launch_count;
+            const cudaError_t ce = cudaMemcpy(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost);
+            cudaFree(d_flag);
+            if (ce != cudaSuccess) return fail_cuda(ce, "cartesian_check_kernel");
+            if (h_flag == 0) {
+                op->cartesian = true;
+                op->S.assign((size_t)nq * nq, 0.0);  // S[q*nq+i] = sum_p D[p][q] w_p D[p][i]
+                for (int q = 0; q < nq; ++q)
+                    for (int i = 0; i < nq; ++i) {
+                        double s = 0.0;
+                        for (int pp = 0; pp < nq; ++pp) s += op->D[pp * nq + q] * d->h_weights[pp] * op->D[pp * nq + i];
+                        op->S[(size_t)q * nq + i] = s;
+                    }
+            }
+        }
+    }
     op_prepare_exclusive(*op);
     *out = reinterpret_cast<b200fe_op *>(op.release());
     return B200FE_OK;
@@ -1301,6 +1336,14 @@ int b200fe_op_kernel_variant(b200fe_op *o, int *even_odd)
     LaunchInfo li{};
     B200FE_CUDA_TRY(launch_sumfact(op.nm, op.nq, op.collocated, op.qop | op.otf_flag(), true, op.B.data(), op.D.data(), a, nullptr, &li, true));
     *even_odd = li.even_odd;
+    return B200FE_OK;
+}
+
+int b200fe_op_cartesian(b200fe_op *o, int *on)
+{
+    Operator *op = reinterpret_cast<Operator *>(o);
+    B200FE_REQUIRE(op && on, "b200fe_op_cartesian: null pointer");
+    *on = op->cartesian ? 1 : 0;
     return B200FE_OK;
 }
 

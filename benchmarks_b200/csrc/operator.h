@@ -21,7 +21,11 @@ struct Operator {
     const double *d_cellG = nullptr;  // borrowed; affine on-the-fly geometry: [cell][8]
     const double *d_cellX = nullptr;  // borrowed; trilinear on-the-fly geometry: [cell][3][2][2][2] vertex coordinates
     std::vector<double> W;            // 1-D quadrature weights (on-the-fly geometry), followed by the points (trilinear)
-    int otf_flag() const { return d_cellG ? QOP_AFFINE : d_cellX ? QOP_TRILINEAR : 0; }
+    // affine cells that are all axis-aligned boxes, collocated operator: the separable kernel (QOP_CARTESIAN) with the 1-D
+    // stiffness matrix S = D^T W D (BK layout, in place of B); decided by b200fe_op_create from the per-cell constants
+    bool cartesian = false;
+    std::vector<double> S;
+    int otf_flag() const { return d_cellG ? (cartesian ? QOP_AFFINE | QOP_CARTESIAN : QOP_AFFINE) : d_cellX ? QOP_TRILINEAR : 0; }
     const double *otf_data() const { return d_cellG ? d_cellG : d_cellX; }
     int otf_stride() const { return d_cellG ? 8 : 24; }
     uint32_t *d_constrained = nullptr;  // owned

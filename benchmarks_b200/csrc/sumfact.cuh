@@ -24,7 +24,12 @@ enum : int { QOP_LAPLACE = 1, QOP_MASS = 2, QOP_HELMHOLTZ = 3,
              QOP_AFFINE = 4,
              // geometry evaluated on the fly for TRILINEAR cells (general hexahedra given by their 8 vertices): the Jacobian
              // at a quadrature point is rebuilt from 24 vertex coordinates per cell and G = JxW K K^T formed in registers
-             QOP_TRILINEAR = 8 };
+             QOP_TRILINEAR = 8,
+             // with QOP_AFFINE, collocated operators: every cell is an axis-aligned box (deal.II's "cartesian" cell type; the
+             // reference's own meshes) -- G is diagonal and separable, so D^T G D u collapses to
+             //   c_rr (S x W x W) u + c_ss (W x S x W) u + c_tt (W x W x S) u,   S = D^T W D  (1-D stiffness matrix, passed as B):
+             // three 1-D contractions per point instead of six, 8 instead of 16 shared-memory accesses per point
+             QOP_CARTESIAN = 16 };
 
 // 1-D matrices in the BK layout: B[q*NM+i] (CEED_BK BK1 serial_kernels.hpp:39),
 // D[p*NQ+n] = derivative of collocation function n at point p (BK3 serial_kernels.hpp:98).

@@ -213,6 +213,8 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
     constexpr bool LAP = L::LAP, MASS = (QOP & QOP_MASS) != 0, AFFINE = L::AFFINE, TRILIN = L::TRILIN, STORED_G = LAP && !AFFINE && !TRILIN;
     static_assert(!(AFFINE && TRILIN), "one on-the-fly geometry at a time");
     static_assert(!COLL || NM == NQ, "collocated operators need nm == nq");
+    constexpr bool CART = (QOP & QOP_CARTESIAN) != 0;
+    static_assert(!CART || (COLL && AFFINE && LVEC && !MASS && !MC), "cartesian kernels: collocated Laplace L-vector operators with per-cell constants");
 
     if (a.skip != nullptr && *a.skip != 0) return;  // uniform across the grid: decided before any barrier
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -408,7 +410,52 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
 
         // ------------------------------------------------------------------ operator at the points
         double w[NQ];
-        if constexpr (LAP) {
+        if constexpr (CART) {
+            // axis-aligned cells (QOP_CARTESIAN): out = c_rr w_q w_r (S v)_p + w_p (c_ss w_r (S v)_q + c_tt w_q (S v)_r), S = m.B
+            // (the three cell constants are fetched first: their latency hides behind the contractions)
+            const double *c8 = a.cellG + (size_t)(active ? e : 0) * 8;
+            const double c_rr = active ? __ldg(c8 + 0) : 0.0, c_ss = active ? __ldg(c8 + 3) : 0.0, c_tt = active ? __ldg(c8 + 5) : 0.0;
+            double sp[NQ];
+            v2::interp<NM, NQ>(m, v, sp);  // S along p from the register column
+#pragma unroll
+            for (int p = 0; p < NQ; ++p) {
+                RQ[p * PSQ + t2] = v[p];
+                RR[p * PSR + ta * RSR + tb] = v[p];
+            }
+            sync_elem();
+            {   // layout Q: thread (p,r) = (ta,tb), column over q, in place
+                double c[NQ], o[NQ];
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) c[q] = RQ[ta * PSQ + q * NQ + tb];
+                v2::interp<NM, NQ>(m, c, o);
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) RQ[ta * PSQ + q * NQ + tb] = o[q];
+            }
+            {   // layout R: thread (p,q) = (ta,tb), row over r, in place
+                double c[NQ], o[NQ];
+#pragma unroll
+                for (int r = 0; r < NQ; ++r) c[r] = RR[ta * PSR + tb * RSR + r];
+                v2::interp<NM, NQ>(m, c, o);
+#pragma unroll
+                for (int r = 0; r < NQ; ++r) RR[ta * PSR + tb * RSR + r] = o[r];
+            }
+            sync_elem();
+            const double wq = m.W[ta], wr = m.W[tb];
+            const double kr = c_rr * wq * wr, ks = c_ss * wr, kt = c_tt * wq;
+            if constexpr (PREFETCH) load_val(nb, nxt_idx, nxt_val, a.in);  // next batch's gathers (indices arrived long ago)
+#pragma unroll
+            for (int p = 0; p < NQ; ++p) {
+                w[p] = fma(kr, sp[p], m.W[p] * fma(ks, RQ[p * PSQ + t2], kt * RR[p * PSR + ta * RSR + tb]));
+                dot_acc = fma(v[p], w[p], dot_acc);  // u.(A u): collocated, so the nodal values are the point values
+            }
+        } else if constexpr (LAP) {
+            [[maybe_unused]] double cg[6];
+            if constexpr (AFFINE) {  // six constants per cell (scaled by the tensor-product quadrature weight in the flux loop);
+                                     // fetched first: the latency hides behind the derivative sweeps
+                const double *c8 = a.cellG + (size_t)(active ? e : 0) * 8;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) cg[c] = active ? __ldg(c8 + c) : 0.0;
+            }
             double gr[NQ];  // d/dr (along p) from the register column; later the r-flux
             v2::deriv<NM, NQ>(m, v, gr);
 #pragma unroll
@@ -440,7 +487,6 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
                     parity ^= 1u;
                 }
             }
-            [[maybe_unused]] double cg[6];
             [[maybe_unused]] double wqr = 0.0;
             // trilinear cells: the columns of J at this thread's (x^, y^) as linear functions of z^ (J[.][2] is constant in z^)
             [[maybe_unused]] double j0a[3], j0b[3], j1a[3], j1b[3], j2c[3];
@@ -467,12 +513,7 @@ __global__ void __launch_bounds__((v2::Layout2<NM, NQ, COLL, QOP>::threads(EPB))
                     j2c[d] = fma(xy, dz1 - dz0, dz0);
                 }
             }
-            if constexpr (AFFINE) {  // six constants per cell, scaled by the tensor-product quadrature weight
-                const double *c8 = a.cellG + (size_t)(active ? e : 0) * 8;
-#pragma unroll
-                for (int c = 0; c < 6; ++c) cg[c] = active ? __ldg(c8 + c) : 0.0;
-                wqr = m.W[ta] * m.W[tb];
-            }
+            if constexpr (AFFINE) wqr = m.W[ta] * m.W[tb];
 #pragma unroll
             for (int p = 0; p < NQ; ++p) {
                 const double qr = gr[p];

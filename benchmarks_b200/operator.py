@@ -69,7 +69,7 @@ class LaplaceOperator:
 
     def __init__(self, mesh: BoxMesh, nq: int | None = None, quad: str = "gauss", kind: str = "laplace",
                  p_geo: int = 1, deform=None, overlap: bool = False, halo=None, with_jxw: bool = True,
-                 device=None, geometry: str = "stored", constraints: str = "faces"):
+                 device=None, geometry: str = "stored", constraints: str = "faces", node_transform=None):
         self.mesh = mesh
         p = mesh.p
         self.p, self.nm = p, p + 1
@@ -103,6 +103,9 @@ class LaplaceOperator:
         nodes = torch.empty(mesh.n_cells * 3 * ng3, dtype=torch.float64, device=self.device)
         kind_d, amp, freq = (0, 0.0, 0.0) if deform is None else (1, float(deform[0]), float(deform[1]))
         mesh.fill_nodes(p_geo, kind_d, amp, freq, _dp(nodes), _sp())
+        if node_transform is not None:
+            # any further mapping of the support points (GridTools::transform): callable on the tensor [cell][3][(p_geo+1)^3]
+            nodes = node_transform(nodes.view(mesh.n_cells, 3, ng3)).contiguous().view(-1)
         if self.perm is not None:
             nodes = nodes.view(mesh.n_cells, 3 * ng3)[torch.from_numpy(self.perm).to(self.device)].contiguous().view(-1)
         nq3 = self.nq ** 3
@@ -111,7 +114,7 @@ class LaplaceOperator:
         self.cell_vertices = None
         if geometry == "affine":  # on-the-fly geometric factors from six per-cell constants
             if p_geo != 1 or deform is not None or self.kind != OP_LAPLACE:
-                raise ValueError("geometry='affine' needs p_geo=1, no deformation and the Laplace operator")
+                raise ValueError("geometry='affine' needs p_geo=1, no deformation (an affine node_transform is fine) and the Laplace operator")
             self.cell_G = torch.empty(mesh.n_cells * 8, dtype=torch.float64, device=self.device)
             check(lib.b200fe_geometry_affine_from_nodes(mesh.n_cells, _dp(nodes), _dp(self.cell_G), _sp()))
         elif geometry == "trilinear":  # general hexahedra: the 8 vertices per cell ARE the geometry (MappingQ1), G rebuilt per point
@@ -237,8 +240,10 @@ class LaplaceOperator:
         check(lib.b200fe_op_kernel_variant(self._h, C.byref(eo)))
         ex = C.c_int()
         check(lib.b200fe_op_exclusive_interior(self._h, C.byref(ex)))
+        ca = C.c_int()
+        check(lib.b200fe_op_cartesian(self._h, C.byref(ca)))
         return dict(zip(keys, [x.value for x in v]), even_odd=eo.value, multi_component=int(self.multi_component_kernel()),
-                    exclusive_interior=ex.value)
+                    exclusive_interior=ex.value, cartesian=ca.value)
 
     def multi_component_kernel(self) -> bool:
         """Vector-valued applies (vmult_components, n_components CG) run ONE cell-kernel launch that fetches the geometric

@@ -360,6 +360,13 @@ int b200fe_op_kernel_variant(b200fe_op *op, int *even_odd);
  * (deal.II's matrix-free loops get the same effect from their cell-interior "pre/post" ranges; no reference file -- the
  * reference kernels scatter everything with Kokkos::atomic_add, CEED_bp/include/bk3_kokkos_kernel.h:372-386.) */
 int b200fe_op_exclusive_interior(b200fe_op *op, int *on);
+/* *on = 1 when the operator runs the separable "cartesian" kernel: collocated Laplace operator with on-the-fly affine
+ * geometry (d_cell_G) whose cells are ALL axis-aligned boxes (checked on the device at b200fe_op_create) -- deal.II
+ * MatrixFree's cartesian cell type, and what every mesh of the reference drivers is (CEED_bp/src/bp3.cc:452-488: cube cells).
+ * G is then diagonal and separable, and D^T G D u = c_rr (S x W x W) u + c_ss (W x S x W) u + c_tt (W x W x S) u with the
+ * 1-D stiffness matrix S = D^T W D: three 1-D contractions per point instead of six.  B200FE_CARTESIAN=0 keeps the general
+ * affine kernel. */
+int b200fe_op_cartesian(b200fe_op *op, int *on);
 
 /* ------------------------------------------------------------------------------------------
  * 5. Conjugate gradients (dealii::SolverCG + ReductionControl as called at CEED_bp/src/bp3.cc:266-285

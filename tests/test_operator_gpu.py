@@ -471,6 +471,8 @@ def test_on_the_fly_affine_geometry_matches_stored_G_and_oracle(oracle_mod, p, d
     mesh = b.BoxMesh(sub, nref, p, p1=p1, p2=p2)
     A_st = b.LaplaceOperator(mesh, nq=nq, quad=quad)
     A_af = b.LaplaceOperator(mesh, nq=nq, quad=quad, geometry="affine")
+    # axis-aligned cells: the collocated operator takes the separable ("cartesian") kernel, the others the general affine one
+    assert A_af.launch_info()["cartesian"] == (1 if quad == "gll" else 0)
     src = np.random.default_rng(p).standard_normal(mesh.n_owned)
     ref = fe.op_apply(src, rd, bas, G)
     d_src = torch.from_numpy(src).cuda()
@@ -488,6 +490,42 @@ def test_on_the_fly_affine_geometry_matches_stored_G_and_oracle(oracle_mod, p, d
         b.SolverCG(ctl).solve(A, x, rhs)
         its.append(ctl.last_step())
     assert abs(its[0] - its[1]) <= 1
+
+
+@pytest.mark.parametrize("p", [1, 2, 3, 5, 6, 7, 8])
+@pytest.mark.parametrize("dq,quad", [(2, "gauss"), (1, "gll")])
+def test_on_the_fly_affine_geometry_on_sheared_cells(oracle_mod, monkeypatch, p, dq, quad):
+    """Parallelepiped (sheared) cells: all six per-cell constants are non-zero, so the coupling terms of the general affine
+    kernel are exercised and the cartesian test must say no; with B200FE_CARTESIAN=0 an axis-aligned mesh also stays on the
+    general affine kernel and gives the cartesian kernel's result."""
+    import benchmarks_b200 as b
+    fe = oracle_mod.fe
+    sub, nref = ((2, 1, 1), 1) if p <= 4 else ((2, 1, 1), 0)
+    nq = p + dq
+    shear_np = lambda P: np.stack([P[..., 0] + 0.3 * P[..., 1] - 0.2 * P[..., 2], P[..., 1] + 0.25 * P[..., 2], P[..., 2] + 0.1 * P[..., 0]], axis=-1)
+    shear_t = lambda N: torch.stack([N[:, 0] + 0.3 * N[:, 1] - 0.2 * N[:, 2], N[:, 1] + 0.25 * N[:, 2], N[:, 2] + 0.1 * N[:, 0]], dim=1)
+    om = fe.BoxMesh(sub, nref)
+    rd = fe.rank_data(om, fe.distribute_dofs(om, p, 1), 0)
+    bas = fe.basis_1d(p, nq, quad)
+    G, _ = fe.geometric_factors(fe.cell_nodes(om, rd["cells"], 1, shear_np), 1, bas)
+    mesh = b.BoxMesh(sub, nref, p)
+    A = b.LaplaceOperator(mesh, nq=nq, quad=quad, geometry="affine", node_transform=shear_t)
+    assert A.launch_info()["cartesian"] == 0
+    src = np.random.default_rng(40 + p).standard_normal(mesh.n_owned)
+    d_src = torch.from_numpy(src).cuda()
+    y = A.initialize_dof_vector()
+    A.vmult(y, d_src)
+    assert rel(y.cpu().numpy(), fe.op_apply(src, rd, bas, G)) <= TOL
+    if quad == "gll":  # same axis-aligned mesh through both kernels
+        A_cart = b.LaplaceOperator(mesh, nq=nq, quad=quad, geometry="affine")
+        monkeypatch.setenv("B200FE_CARTESIAN", "0")
+        A_gen = b.LaplaceOperator(mesh, nq=nq, quad=quad, geometry="affine")
+        monkeypatch.delenv("B200FE_CARTESIAN")
+        assert A_cart.launch_info()["cartesian"] == 1 and A_gen.launch_info()["cartesian"] == 0
+        y1, y2 = A_cart.initialize_dof_vector(), A_gen.initialize_dof_vector()
+        d1, d2 = A_cart.vmult_dot(y1, d_src), A_gen.vmult_dot(y2, d_src)
+        assert rel(y1.cpu().numpy(), y2.cpu().numpy()) <= TOL
+        assert abs(d1.item() - d2.item()) <= 1e-11 * abs(d2.item())
 
 
 @pytest.mark.parametrize("p,quad,dq", [(4, "gauss", 2), (6, "gll", 1)])
