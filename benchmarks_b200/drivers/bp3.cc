@@ -45,7 +45,16 @@ struct LaplaceProblem {
             auto t0 = clk::now();
             BoxMesh mesh = BoxMesh::bp3_cycle(cycle, fe_degree, comm.size, comm.rank);
             std::printf("  Number of cells: %llu |   Number of DoFs: %llu\n", mesh.n_global_active_cells(), mesh.n_dofs());
-            LaplaceOperator<3, fe_degree, nq, double> system_matrix(mesh, quad);
+            // B200FE_GEOMETRY=onthefly: geometric factors rebuilt in the kernel instead of streamed; the
+            // reference's meshes are axis-aligned cubes, so "bp3 <p> <min> <max> 1 gll" then runs the separable kernel
+            const char *geo = std::getenv("B200FE_GEOMETRY");
+            const Geometry geometry = geo && std::string(geo) == "onthefly" ? Geometry::OnTheFly : Geometry::Stored;
+            LaplaceOperator<3, fe_degree, nq, double> system_matrix(mesh, quad, B200FE_OP_LAPLACE, 1, {}, geometry);
+            if (geometry == Geometry::OnTheFly) {
+                int cart = 0;
+                check(b200fe_op_cartesian(system_matrix.handle(), &cart));
+                std::printf("  Geometry on the fly (%s kernel)\n", cart ? "cartesian" : "affine");
+            }
             std::unique_ptr<Halo> halo;
             if (comm.size > 1) {
                 halo = std::make_unique<Halo>(mesh, comm);

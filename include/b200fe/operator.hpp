@@ -367,6 +367,11 @@ struct Deformation {
 };
 
 enum class Quadrature { Gauss, GaussLobatto };
+// Geometric factors of the Laplace operators: Stored = G[cell][6][nq^3] streamed by the cell kernel (the reference's
+// algorithm, portable_laplace_operator.h:239-302); OnTheFly (MappingQ1 meshes) = rebuilt inside the kernel
+// from six constants per cell on undeformed (affine) meshes -- the separable "cartesian" kernel when every cell is an
+// axis-aligned box and the operator is collocated -- or from the 8 vertices per cell on deformed (trilinear) ones.
+enum class Geometry { Stored, OnTheFly };
 
 template <int dim, int fe_degree, int nq, typename number = double>
 class LaplaceOperator {
@@ -376,9 +381,12 @@ class LaplaceOperator {
   public:
     // p_geo: degree of the mapping (MappingQ(p_geo)); op_kind: B200FE_OP_*
     LaplaceOperator(const BoxMesh &mesh, Quadrature quad = Quadrature::Gauss, int op_kind = B200FE_OP_LAPLACE, int p_geo = 1,
-                    Deformation deform = {})
-        : n_dofs_global_(mesh.n_dofs()), n_owned_(mesh.info.n_owned), n_ghost_(mesh.info.n_ghost)
+                    Deformation deform = {}, Geometry geometry = Geometry::Stored)
+        : n_dofs_global_(mesh.n_dofs()), n_owned_(mesh.info.n_owned), n_ghost_(mesh.info.n_ghost), geometry_(geometry)
     {
+        if (geometry == Geometry::OnTheFly && (p_geo != 1 || op_kind != B200FE_OP_LAPLACE))
+            throw Error(B200FE_ERR_INVALID_ARG, "Geometry::OnTheFly: Laplace operators on MappingQ1 meshes");
+        trilinear_ = geometry == Geometry::OnTheFly && deform.amplitude != 0.0;
         if (mesh.degree != fe_degree) throw Error(B200FE_ERR_INVALID_ARG, "mesh degree != fe_degree");
         const uint32_t nc = mesh.info.n_cells_local;
         std::vector<uint32_t> idx, con(mesh.info.n_constrained);  // idx stays empty: the table is expanded on the device
@@ -469,9 +477,21 @@ class LaplaceOperator {
         check(b200fe_basis_1d(fe_degree, nq, qk, sv.data(), cg.data(), nullptr, nullptr, nullptr));
         if (!idx.empty()) idx_.upload(idx.data(), idx.size());
         const size_t nq3 = (size_t)nq * nq * nq;
-        if (op_kind & B200FE_OP_LAPLACE) G_.resize((size_t)nc * 6 * nq3);
-        JxW_.resize((size_t)nc * nq3);
+        const bool otf = geometry_ == Geometry::OnTheFly;
+        if ((op_kind & B200FE_OP_LAPLACE) && !otf) G_.resize((size_t)nc * 6 * nq3);
+        JxW_.resize((size_t)nc * nq3);  // (compute_rhs integrates with it)
         check(b200fe_geometry_from_nodes(p_geo, nq, qk, nc, nodes.data(), G_.data(), JxW_.data(), nullptr));
+        std::vector<double> wts(nq), pts(nq);
+        if (otf) {
+            check(b200fe_basis_1d(fe_degree, nq, qk, nullptr, nullptr, nullptr, pts.data(), wts.data()));
+            if (trilinear_) {  // the vertices ARE the geometry: keep a copy (the operator borrows it)
+                cellX_.resize((size_t)nc * 24);
+                check_cuda(cudaMemcpy(cellX_.data(), nodes.data(), (size_t)nc * 24 * sizeof(double), cudaMemcpyDeviceToDevice), "cudaMemcpy D2D");
+            } else {
+                cellG_.resize((size_t)nc * 8);
+                check(b200fe_geometry_affine_from_nodes(nc, nodes.data(), cellG_.data(), nullptr));
+            }
+        }
         check_cuda(cudaDeviceSynchronize(), "geometry");
         b200fe_op_desc d{};
         d.p = fe_degree; d.nq = nq; d.op_kind = op_kind; d.collocated = collocated;
@@ -479,13 +499,21 @@ class LaplaceOperator {
         d.h_shape_values = sv.data(); d.h_co_shape_gradients = cg.data();
         d.d_dof_indices = idx_.data(); d.d_G = G_.data(); d.d_JxW = JxW_.data();
         d.h_constrained = con.data(); d.n_constrained = (uint32_t)con.size();
+        if (otf) {
+            d.d_G = nullptr;
+            d.h_weights = wts.data(); d.h_points = pts.data();
+            if (trilinear_) d.d_cell_vertices = cellX_.data();
+            else d.d_cell_G = cellG_.data();
+        }
         check(b200fe_op_create(&d, &op_));
     }
     b200fe_op *op_ = nullptr;
     unsigned long long n_dofs_global_;
     uint32_t n_owned_, n_ghost_;
     DeviceArray<uint32_t> idx_;
-    DeviceArray<double> G_, JxW_, inv_diag_;
+    DeviceArray<double> G_, JxW_, inv_diag_, cellG_, cellX_;
+    Geometry geometry_ = Geometry::Stored;
+    bool trilinear_ = false;
 };
 
 class ReductionControl {

@@ -46,6 +46,31 @@ def test_bp3_driver_reproduces_reference_table(golden_dir):
         assert float(got[6]) == pytest.approx(want[4], abs=2e-3)
 
 
+@pytest.mark.parametrize("extra,kernel", [((), "affine"), ((1, "gll"), "cartesian")])
+def test_bp3_driver_with_geometry_on_the_fly_gives_the_same_table(extra, kernel):
+    """C++ host layer, Geometry::OnTheFly (SURVEY 8f.1): same cells / DoFs / CG iteration counts (+-1) and reduction rates
+    as the stored-G run of the same driver; the GLL-collocated variant lands on the separable (cartesian) kernel."""
+    def table(env):
+        exe = os.path.join(DRV, "bp3")
+        if not os.path.exists(exe):
+            subprocess.run(["make", "-C", DRV], check=True)
+        r = subprocess.run([exe, "4", "10000", "150000"] + [str(a) for a in extra], capture_output=True, text=True, timeout=600,
+                           env=dict(os.environ, **env))
+        assert r.returncode == 0, r.stderr
+        out = r.stdout
+        block = out[out.rindex(" cells    dofs    matvec"):]
+        block = block[:block.index("mv_ghost_and_compute")]
+        return out, [l.split() for l in block.splitlines()[1:] if re.match(r"^\s*\d+\s+\d+\s+\d\.\d+e", l)]
+    _, stored = table({})
+    out, otf = table({"B200FE_GEOMETRY": "onthefly"})
+    assert f"Geometry on the fly ({kernel} kernel)" in out
+    assert len(stored) >= 4 and len(stored) == len(otf)
+    for a, b in zip(stored, otf):
+        assert a[0] == b[0] and a[1] == b[1]
+        assert abs(int(a[5]) - int(b[5])) <= 1
+        assert float(a[6]) == pytest.approx(float(b[6]), abs=2e-3)
+
+
 def test_bp3_driver_reports_errors_like_the_reference():
     exe = os.path.join(DRV, "bp3")
     if not os.path.exists(exe):
