@@ -32,4 +32,6 @@ INST(NM, NM, true, QOP_LAPLACE | QOP_AFFINE | QOP_CARTESIAN, true)
 INST(NM, NM + 1, false, QOP_LAPLACE | QOP_TRILINEAR, true)
 INST(NM, NM, false, QOP_LAPLACE | QOP_TRILINEAR, true)
 INST(NM, NM, true, QOP_LAPLACE | QOP_TRILINEAR, true)
+// ... interpolated operators on axis-aligned cells: separable kernel on the nodal values (sumfact_cart.cuh)
+template cudaError_t launch_cart_t<NM>(const double *, const KArgs &, cudaStream_t, LaunchInfo *, bool);
 }  // namespace b200fe

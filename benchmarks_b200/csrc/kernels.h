@@ -25,6 +25,12 @@ cudaError_t launch_sumfact(int nm, int nq, bool coll, int qop, bool lvec, const 
                            const double *hD, const KArgs &a, cudaStream_t s, LaunchInfo *info,
                            bool dry_run, const double *hW = nullptr);
 
+// Separable kernel for axis-aligned cells, interpolated operators (sumfact_cart.cuh).  hKM: the 1-D stiffness matrix K
+// followed by the 1-D mass matrix M, nm*nm doubles each, row-major.  launch_cart_t is instantiated per degree in inst.cu.
+template <int NM>
+cudaError_t launch_cart_t(const double *hKM, const KArgs &a, cudaStream_t s, LaunchInfo *info, bool dry_run);
+cudaError_t launch_cartesian(int nm, const double *hKM, const KArgs &a, cudaStream_t s, LaunchInfo *info, bool dry_run);
+
 // grid multiplier for the persistent launches (env B200FE_GRID_MULT, default 1 = one resident wave)
 int grid_multiplier();
 

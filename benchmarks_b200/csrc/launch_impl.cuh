@@ -6,6 +6,7 @@
 #include "kernels.h"
 #include "sumfact2.cuh"
 #include "sumfact_tpe.cuh"
+#include "sumfact_cart.cuh"
 
 namespace b200fe {
 
@@ -205,6 +206,67 @@ cudaError_t launch_tpe(const double *hB, const double *hD, const KArgs &a, cudaS
     std::memset(m.W, 0, sizeof(m.W));
     std::memset(m.X, 0, sizeof(m.X));
     kern<<<grid, TPB, smem, s>>>(m, a);
+    return cudaGetLastError();
+}
+
+template <int NM>
+cudaError_t launch_cart_t(const double *hKM, const KArgs &a, cudaStream_t s, LaunchInfo *info, bool dry_run)
+{
+    using L = cart::LayoutC<NM>;
+    constexpr int N2 = NM * NM;
+#ifndef B200FE_CART_TPB
+#define B200FE_CART_TPB 128  // target threads per CTA (tuning knob)
+#endif
+    constexpr int EPB = B200FE_CART_TPB / N2 < 1 ? 1 : B200FE_CART_TPB / N2;
+    constexpr int T = EPB * N2, T32 = (T + 31) / 32 * 32;
+#ifdef B200FE_CART_RMIN
+    constexpr int RMIN = B200FE_CART_RMIN;  // tuning knob: one register floor for every degree
+#else
+    // registers the occupancy target must leave.  Measured (profiles/r02z_sweep_table.txt, BP3 apply on ~1.2e7 DoFs, default
+    // floor vs 200 / 255): nm = 5: 54 -> 60 GDoF/s with 150 registers x 3 CTAs; nm = 7: 38 -> 50 and nm = 9: 32 -> 38 with 255 x 2
+    // (the 168-register builds spill ~340 B/thread); nm = 8 (two elements fill four warps exactly) keeps 168 x 3: 62 vs 56
+    constexpr int RMIN = NM <= 4 ? 72 + 10 * NM : NM == 5 ? 160 : NM == 6 ? 224 : NM == 8 ? 152 : 255;
+#endif
+    constexpr int BY_REGS = 65536 / (RMIN * T32), BY_THREADS = 2048 / T32;
+    constexpr int M0 = BY_REGS < BY_THREADS ? BY_REGS : BY_THREADS;
+    constexpr int MINB = M0 < 1 ? 1 : (M0 > 16 ? 16 : M0);
+    auto kern = sumfact_cart_kernel<NM, EPB, MINB>;
+    const size_t smem = L::smem_bytes(EPB);
+    struct Cfg {
+        bool ready = false;
+        int blocks_per_sm = 0, sms = 0, regs = 0;
+    };
+    static Cfg cfg[64];  // per device
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return err;
+    Cfg &c = cfg[dev & 63];
+    if (!c.ready) {
+        err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+        err = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (err != cudaSuccess) return err;
+        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.blocks_per_sm, kern, T, smem);
+        if (err != cudaSuccess) return err;
+        err = cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, dev);
+        if (err != cudaSuccess) return err;
+        cudaFuncAttributes fa;
+        err = cudaFuncGetAttributes(&fa, kern);
+        if (err != cudaSuccess) return err;
+        c.regs = fa.numRegs;
+        if (c.blocks_per_sm < 1) return cudaErrorLaunchOutOfResources;
+        c.ready = true;
+    }
+    const uint32_t n_batches = (a.n_elems + EPB - 1) / EPB;
+    const long long resident = (long long)c.sms * c.blocks_per_sm * grid_multiplier();
+    const int grid = (int)(n_batches < (uint32_t)resident ? n_batches : resident);
+    if (info) *info = LaunchInfo{EPB, grid, T, (int)smem, c.blocks_per_sm, c.regs, 0};
+    if (dry_run || a.n_elems == 0) return cudaSuccess;
+    if (hKM == nullptr) return cudaErrorInvalidValue;
+    CartMats<NM> m;
+    std::memcpy(m.K, hKM, sizeof(m.K));
+    std::memcpy(m.M, hKM + NM * NM, sizeof(m.M));
+    kern<<<grid, T, smem, s>>>(m, a);
     return cudaGetLastError();
 }
 

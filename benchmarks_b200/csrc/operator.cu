@@ -565,6 +565,16 @@ static void op_prepare_exclusive(Operator &op)
     }
 }
 
+// the cell kernel of this operator: the sum-factorisation kernel family, or -- interpolated operator on axis-aligned cells
+// -- the separable kernel on the nodal values (sumfact_cart.cuh)
+static cudaError_t op_launch_kernel(Operator &op, const KArgs &a, cudaStream_t s, LaunchInfo *info, bool dry_run)
+{
+    if (op.cartesian && !op.collocated) return launch_cartesian(op.nm, op.S.data(), a, s, info, dry_run);
+    const int qop = op.qop | op.otf_flag();
+    return launch_sumfact(op.nm, op.nq, op.collocated, qop, true, op.cartesian ? op.S.data() : op.B.data(), op.D.data(), a, s, info, dry_run,
+                          op.otf_flag() ? op.W.data() : nullptr);
+}
+
 int op_apply_cells(Operator &op, double *d_dst, const double *d_src, uint32_t cb, uint32_t ce,
                    double *d_dot, cudaStream_t s, int ncomp)
 {
@@ -576,11 +586,9 @@ int op_apply_cells(Operator &op, double *d_dst, const double *d_src, uint32_t cb
     a.ncomp = ncomp;
     a.comp_stride = op.n_local();
     a.excl_interior = op.d_excl_mask != nullptr;
-    const int qop = op.qop | op.otf_flag();
     const bool timed = op.timing && op.ev_used + 2 <= op.ev.size();
     if (timed) B200FE_CUDA_TRY(cudaEventRecord(op.ev[op.ev_used], s));
-    B200FE_CUDA_TRY(launch_sumfact(op.nm, op.nq, op.collocated, qop, true, op.cartesian ? op.S.data() : op.B.data(), op.D.data(), a, s,
-                                   &op.last_launch, false, affine ? op.W.data() : nullptr));
+    B200FE_CUDA_TRY(op_launch_kernel(op, a, s, &op.last_launch, false));
     if (timed) {
         B200FE_CUDA_TRY(cudaEventRecord(op.ev[op.ev_used + 1], s));
         op.ev_used += 2;
@@ -1063,7 +1071,7 @@ int b200fe_op_create(const b200fe_op_desc *d, b200fe_op **out)
         B200FE_CUDA_TRY(cudaMalloc(&op->d_constrained, d->n_constrained * sizeof(uint32_t)));
         B200FE_CUDA_TRY(cudaMemcpy(op->d_constrained, d->h_constrained, d->n_constrained * sizeof(uint32_t), cudaMemcpyHostToDevice));
     }
-    if (d->d_cell_G && coll && d->n_cells) {
+    if (d->d_cell_G && d->n_cells) {
         // axis-aligned cells (deal.II's "cartesian" cell type): the separable kernel.  B200FE_CARTESIAN=0 keeps the general
         // affine kernel (read at every create: tests switch it).
         const char *e = std::getenv("B200FE_CARTESIAN");
@@ -1076,7 +1084,7 @@ int b200fe_op_create(const b200fe_op_desc *d, b200fe_op **out)
             const cudaError_t ce = cudaMemcpy(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost);
             cudaFree(d_flag);
             if (ce != cudaSuccess) return fail_cuda(ce, "cartesian_check_kernel");
-            if (h_flag == 0) {
+            if (h_flag == 0 && coll) {
                 op->cartesian = true;
                 op->S.assign((size_t)nq * nq, 0.0);  // S[q*nq+i] = sum_p D[p][q] w_p D[p][i]
                 for (int q = 0; q < nq; ++q)
@@ -1084,6 +1092,28 @@ int b200fe_op_create(const b200fe_op_desc *d, b200fe_op **out)
                         double s = 0.0;
                         for (int pp = 0; pp < nq; ++pp) s += op->D[pp * nq + q] * d->h_weights[pp] * op->D[pp * nq + i];
                         op->S[(size_t)q * nq + i] = s;
+                    }
+            } else if (h_flag == 0) {
+                // interpolated operator: 1-D stiffness and mass matrices on the nodal basis (sumfact_cart.cuh),
+                // K = (D B)^T W (D B), M = B^T W B; S = K | M
+                op->cartesian = true;
+                std::vector<double> DB((size_t)nq * nm, 0.0);  // derivative of shape i at point p
+                for (int pp = 0; pp < nq; ++pp)
+                    for (int i = 0; i < nm; ++i) {
+                        double s = 0.0;
+                        for (int n = 0; n < nq; ++n) s += op->D[pp * nq + n] * op->B[n * nm + i];
+                        DB[(size_t)pp * nm + i] = s;
+                    }
+                op->S.assign(2 * (size_t)nm * nm, 0.0);
+                for (int i = 0; i < nm; ++i)
+                    for (int j = 0; j < nm; ++j) {
+                        double k = 0.0, mm = 0.0;
+                        for (int pp = 0; pp < nq; ++pp) {
+                            k += DB[(size_t)pp * nm + i] * d->h_weights[pp] * DB[(size_t)pp * nm + j];
+                            mm += op->B[pp * nm + i] * d->h_weights[pp] * op->B[pp * nm + j];
+                        }
+                        op->S[(size_t)i * nm + j] = k;
+                        op->S[(size_t)nm * nm + (size_t)i * nm + j] = mm;
                     }
             }
         }
@@ -1318,7 +1348,7 @@ int b200fe_op_launch_info(b200fe_op *o, int *elems_per_block, int *num_blocks, i
     Operator &op = *reinterpret_cast<Operator *>(o);
     KArgs a{op.n_cells, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     LaunchInfo li{};
-    B200FE_CUDA_TRY(launch_sumfact(op.nm, op.nq, op.collocated, op.qop | op.otf_flag(), true, op.B.data(), op.D.data(), a, nullptr, &li, true));
+    B200FE_CUDA_TRY(op_launch_kernel(op, a, nullptr, &li, true));
     if (elems_per_block) *elems_per_block = li.elems_per_block;
     if (num_blocks) *num_blocks = li.num_blocks;
     if (threads_per_block) *threads_per_block = li.threads_per_block;
@@ -1334,7 +1364,7 @@ int b200fe_op_kernel_variant(b200fe_op *o, int *even_odd)
     Operator &op = *reinterpret_cast<Operator *>(o);
     KArgs a{op.n_cells, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     LaunchInfo li{};
-    B200FE_CUDA_TRY(launch_sumfact(op.nm, op.nq, op.collocated, op.qop | op.otf_flag(), true, op.B.data(), op.D.data(), a, nullptr, &li, true));
+    B200FE_CUDA_TRY(op_launch_kernel(op, a, nullptr, &li, true));
     *even_odd = li.even_odd;
     return B200FE_OK;
 }

@@ -46,10 +46,11 @@ def test_bp3_driver_reproduces_reference_table(golden_dir):
         assert float(got[6]) == pytest.approx(want[4], abs=2e-3)
 
 
-@pytest.mark.parametrize("extra,kernel", [((), "affine"), ((1, "gll"), "cartesian")])
+@pytest.mark.parametrize("extra,kernel", [((), "cartesian"), ((1, "gll"), "cartesian")])
 def test_bp3_driver_with_geometry_on_the_fly_gives_the_same_table(extra, kernel):
     """C++ host layer, Geometry::OnTheFly (SURVEY 8f.1): same cells / DoFs / CG iteration counts (+-1) and reduction rates
-    as the stored-G run of the same driver; the GLL-collocated variant lands on the separable (cartesian) kernel."""
+    as the stored-G run of the same driver; the reference's cube cells land on the separable (cartesian) kernels: the nodal
+    one for QGauss(p+2), the collocated one for GLL."""
     def table(env):
         exe = os.path.join(DRV, "bp3")
         if not os.path.exists(exe):

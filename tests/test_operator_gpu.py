@@ -471,8 +471,9 @@ def test_on_the_fly_affine_geometry_matches_stored_G_and_oracle(oracle_mod, p, d
     mesh = b.BoxMesh(sub, nref, p, p1=p1, p2=p2)
     A_st = b.LaplaceOperator(mesh, nq=nq, quad=quad)
     A_af = b.LaplaceOperator(mesh, nq=nq, quad=quad, geometry="affine")
-    # axis-aligned cells: the collocated operator takes the separable ("cartesian") kernel, the others the general affine one
-    assert A_af.launch_info()["cartesian"] == (1 if quad == "gll" else 0)
+    # axis-aligned cells: the separable ("cartesian") kernels -- three contractions at the points for the collocated operator,
+    # seven on the nodal values for the interpolated ones
+    assert A_af.launch_info()["cartesian"] == 1
     src = np.random.default_rng(p).standard_normal(mesh.n_owned)
     ref = fe.op_apply(src, rd, bas, G)
     d_src = torch.from_numpy(src).cuda()
@@ -516,7 +517,7 @@ def test_on_the_fly_affine_geometry_on_sheared_cells(oracle_mod, monkeypatch, p,
     y = A.initialize_dof_vector()
     A.vmult(y, d_src)
     assert rel(y.cpu().numpy(), fe.op_apply(src, rd, bas, G)) <= TOL
-    if quad == "gll":  # same axis-aligned mesh through both kernels
+    if True:  # same axis-aligned mesh through the separable and the general affine kernel
         A_cart = b.LaplaceOperator(mesh, nq=nq, quad=quad, geometry="affine")
         monkeypatch.setenv("B200FE_CARTESIAN", "0")
         A_gen = b.LaplaceOperator(mesh, nq=nq, quad=quad, geometry="affine")

@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--json", default=None)
     ap.add_argument("--mass", action="store_true", help="also BP1 (mass, QGauss(p+2)) and the bp5_kokkos Helmholtz operator")
+    ap.add_argument("--geometry", default="stored", help="stored | affine (on-the-fly; the cube cells of these meshes take the separable kernels)")
     args = ap.parse_args()
     try:
         peak = float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"])
@@ -36,7 +37,7 @@ def main():
                          ("bp1", dict(quad="gauss", nq=p + 2, kind="mass")), ("helm", dict(quad="gauss", nq=p + 1, kind="helmholtz"))):
             if name in ("bp1", "helm") and not args.mass:
                 continue
-            op = b.LaplaceOperator(mesh, with_jxw=name in ("bp1", "helm"), **kw)
+            op = b.LaplaceOperator(mesh, with_jxw=name in ("bp1", "helm"), geometry=args.geometry if name not in ("bp1", "helm") else "stored", **kw)
             src = torch.rand(mesh.n_owned, dtype=torch.float64, device="cuda")
             dst = torch.empty_like(src)
             for _ in range(3):
