@@ -222,10 +222,9 @@ cudaError_t launch_cart_t(const double *hKM, const KArgs &a, cudaStream_t s, Lau
 #ifdef B200FE_CART_RMIN
     constexpr int RMIN = B200FE_CART_RMIN;  // tuning knob: one register floor for every degree
 #else
-    // registers the occupancy target must leave.  Measured (profiles/r02z_sweep_table.txt, BP3 apply on ~1.2e7 DoFs, default
-    // floor vs 200 / 255): nm = 5: 54 -> 60 GDoF/s with 150 registers x 3 CTAs; nm = 7: 38 -> 50 and nm = 9: 32 -> 38 with 255 x 2
-    // (the 168-register builds spill ~340 B/thread); nm = 8 (two elements fill four warps exactly) keeps 168 x 3: 62 vs 56
-    constexpr int RMIN = NM <= 4 ? 72 + 10 * NM : NM == 5 ? 160 : NM == 6 ? 224 : NM == 8 ? 152 : 255;
+    // registers the occupancy target must leave: what the packed even-odd build needs without spilling (ptxas: 89 / 103 /
+    // 116 / 149 / 198 registers at nm = 5 ... 9; the first build with full matrices wanted > 255 at nm = 7, 9)
+    constexpr int RMIN = NM <= 4 ? 72 + 10 * NM : NM == 5 ? 96 : NM == 6 ? 104 : NM == 7 ? 120 : NM == 8 ? 152 : 168;  // (nm = 9: 4 CTAs of 3 warps cap at 168, 68 B/thread spilled)
 #endif
     constexpr int BY_REGS = 65536 / (RMIN * T32), BY_THREADS = 2048 / T32;
     constexpr int M0 = BY_REGS < BY_THREADS ? BY_REGS : BY_THREADS;
@@ -264,8 +263,8 @@ cudaError_t launch_cart_t(const double *hKM, const KArgs &a, cudaStream_t s, Lau
     if (dry_run || a.n_elems == 0) return cudaSuccess;
     if (hKM == nullptr) return cudaErrorInvalidValue;
     CartMats<NM> m;
-    std::memcpy(m.K, hKM, sizeof(m.K));
-    std::memcpy(m.M, hKM + NM * NM, sizeof(m.M));
+    // (b200fe_op_create only selects this kernel for symmetric, point-symmetric K and M; refuse anything else)
+    if (m.K.fill(hKM) > 1e-10 || m.M.fill(hKM + NM * NM) > 1e-10) return cudaErrorInvalidValue;
     kern<<<grid, T, smem, s>>>(m, a);
     return cudaGetLastError();
 }

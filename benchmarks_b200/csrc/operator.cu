@@ -8,6 +8,7 @@
 //                        bakeoff_problems_dealii/include/portable_laplace_operator.h:227-258)
 //   compute_diagonal  -> b200fe_op_diagonal       (bp5_kokkos/benchmark.cc:218-251)
 //   compute_rhs       -> b200fe_op_rhs_one        (CEED_bp/src/bp3.cc:184-239)
+#include <cmath>
 #include <cstring>
 #include <memory>
 
@@ -1115,6 +1116,16 @@ int b200fe_op_create(const b200fe_op_desc *d, b200fe_op **out)
                         op->S[(size_t)i * nm + j] = k;
                         op->S[(size_t)nm * nm + (size_t)i * nm + j] = mm;
                     }
+                // the kernel contracts through the even-odd split: needs the point symmetry of a real basis
+                double viol = 0.0, big = 0.0;
+                for (int m2 = 0; m2 < 2; ++m2)
+                    for (int i = 0; i < nm; ++i)
+                        for (int j = 0; j < nm; ++j) {
+                            const double a1 = op->S[(size_t)m2 * nm * nm + (size_t)i * nm + j], a2 = op->S[(size_t)m2 * nm * nm + (size_t)(nm - 1 - i) * nm + (nm - 1 - j)];
+                            big = std::max(big, std::fabs(a1));
+                            viol = std::max(viol, std::fabs(a1 - a2));
+                        }
+                if (!(viol <= 1e-11 * big)) { op->cartesian = false; op->S.clear(); }
             }
         }
     }
