@@ -63,17 +63,17 @@ cudaError_t launch_sumfact(int nm, int nq, bool coll, int qop, bool lvec, const 
     }
 }
 
-cudaError_t launch_cartesian(int nm, const double *hKM, const KArgs &a, cudaStream_t s, LaunchInfo *info, bool dry)
+cudaError_t launch_cartesian(int nm, int qop, const double *hKM, const KArgs &a, cudaStream_t s, LaunchInfo *info, bool dry)
 {
     switch (nm - 1) {
-        case 1: return launch_cart_t<2>(hKM, a, s, info, dry);
-        case 2: return launch_cart_t<3>(hKM, a, s, info, dry);
-        case 3: return launch_cart_t<4>(hKM, a, s, info, dry);
-        case 4: return launch_cart_t<5>(hKM, a, s, info, dry);
-        case 5: return launch_cart_t<6>(hKM, a, s, info, dry);
-        case 6: return launch_cart_t<7>(hKM, a, s, info, dry);
-        case 7: return launch_cart_t<8>(hKM, a, s, info, dry);
-        case 8: return launch_cart_t<9>(hKM, a, s, info, dry);
+        case 1: return launch_cart_t<2>(qop, hKM, a, s, info, dry);
+        case 2: return launch_cart_t<3>(qop, hKM, a, s, info, dry);
+        case 3: return launch_cart_t<4>(qop, hKM, a, s, info, dry);
+        case 4: return launch_cart_t<5>(qop, hKM, a, s, info, dry);
+        case 5: return launch_cart_t<6>(qop, hKM, a, s, info, dry);
+        case 6: return launch_cart_t<7>(qop, hKM, a, s, info, dry);
+        case 7: return launch_cart_t<8>(qop, hKM, a, s, info, dry);
+        case 8: return launch_cart_t<9>(qop, hKM, a, s, info, dry);
         default: return cudaErrorInvalidValue;
     }
 }

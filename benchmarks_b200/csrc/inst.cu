@@ -33,5 +33,5 @@ INST(NM, NM + 1, false, QOP_LAPLACE | QOP_TRILINEAR, true)
 INST(NM, NM, false, QOP_LAPLACE | QOP_TRILINEAR, true)
 INST(NM, NM, true, QOP_LAPLACE | QOP_TRILINEAR, true)
 // ... interpolated operators on axis-aligned cells: separable kernel on the nodal values (sumfact_cart.cuh)
-template cudaError_t launch_cart_t<NM>(const double *, const KArgs &, cudaStream_t, LaunchInfo *, bool);
+template cudaError_t launch_cart_t<NM>(int, const double *, const KArgs &, cudaStream_t, LaunchInfo *, bool);
 }  // namespace b200fe

@@ -27,9 +27,10 @@ cudaError_t launch_sumfact(int nm, int nq, bool coll, int qop, bool lvec, const 
 
 // Separable kernel for axis-aligned cells, interpolated operators (sumfact_cart.cuh).  hKM: the 1-D stiffness matrix K
 // followed by the 1-D mass matrix M, nm*nm doubles each, row-major.  launch_cart_t is instantiated per degree in inst.cu.
+// qop: QOP_LAPLACE, QOP_MASS or QOP_HELMHOLTZ (mass term = det J * M x M x M, KArgs::cellG[e][6]).
 template <int NM>
-cudaError_t launch_cart_t(const double *hKM, const KArgs &a, cudaStream_t s, LaunchInfo *info, bool dry_run);
-cudaError_t launch_cartesian(int nm, const double *hKM, const KArgs &a, cudaStream_t s, LaunchInfo *info, bool dry_run);
+cudaError_t launch_cart_t(int qop, const double *hKM, const KArgs &a, cudaStream_t s, LaunchInfo *info, bool dry_run);
+cudaError_t launch_cartesian(int nm, int qop, const double *hKM, const KArgs &a, cudaStream_t s, LaunchInfo *info, bool dry_run);
 
 // grid multiplier for the persistent launches (env B200FE_GRID_MULT, default 1 = one resident wave)
 int grid_multiplier();

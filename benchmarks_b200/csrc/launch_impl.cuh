@@ -209,8 +209,8 @@ cudaError_t launch_tpe(const double *hB, const double *hD, const KArgs &a, cudaS
     return cudaGetLastError();
 }
 
-template <int NM>
-cudaError_t launch_cart_t(const double *hKM, const KArgs &a, cudaStream_t s, LaunchInfo *info, bool dry_run)
+template <int NM, int QOP>
+cudaError_t launch_cart_q(const double *hKM, const KArgs &a, cudaStream_t s, LaunchInfo *info, bool dry_run)
 {
     using L = cart::LayoutC<NM>;
     constexpr int N2 = NM * NM;
@@ -229,7 +229,7 @@ cudaError_t launch_cart_t(const double *hKM, const KArgs &a, cudaStream_t s, Lau
     constexpr int BY_REGS = 65536 / (RMIN * T32), BY_THREADS = 2048 / T32;
     constexpr int M0 = BY_REGS < BY_THREADS ? BY_REGS : BY_THREADS;
     constexpr int MINB = M0 < 1 ? 1 : (M0 > 16 ? 16 : M0);
-    auto kern = sumfact_cart_kernel<NM, EPB, MINB>;
+    auto kern = sumfact_cart_kernel<NM, EPB, MINB, QOP>;
     const size_t smem = L::smem_bytes(EPB);
     struct Cfg {
         bool ready = false;
@@ -267,6 +267,15 @@ cudaError_t launch_cart_t(const double *hKM, const KArgs &a, cudaStream_t s, Lau
     if (m.K.fill(hKM) > 1e-10 || m.M.fill(hKM + NM * NM) > 1e-10) return cudaErrorInvalidValue;
     kern<<<grid, T, smem, s>>>(m, a);
     return cudaGetLastError();
+}
+
+template <int NM>
+cudaError_t launch_cart_t(int qop, const double *hKM, const KArgs &a, cudaStream_t s, LaunchInfo *info, bool dry_run)
+{
+    if (qop == QOP_LAPLACE) return launch_cart_q<NM, QOP_LAPLACE>(hKM, a, s, info, dry_run);
+    if (qop == QOP_MASS) return launch_cart_q<NM, QOP_MASS>(hKM, a, s, info, dry_run);
+    if (qop == QOP_HELMHOLTZ) return launch_cart_q<NM, QOP_HELMHOLTZ>(hKM, a, s, info, dry_run);
+    return cudaErrorInvalidValue;
 }
 
 template <int NM, int NQ, bool COLL, int QOP, bool LVEC>

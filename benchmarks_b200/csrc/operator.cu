@@ -351,6 +351,37 @@ __global__ void expand_indices_kernel(size_t n_entries, int nm, int p, int diric
     }
 }
 
+// Axis-aligned cells: diagonal and int phi_i of the separable operator from the diagonals of the 1-D matrices.
+struct CartVecs { double dk[9], dm[9], mv[9]; };  // diag K, diag M, m = B^T w (nm <= 9 entries each)
+__global__ void cart_diagonal_kernel(const __grid_constant__ CartVecs v, size_t n_entries, int nm, int qop, const double *__restrict__ cellG,
+                                     const uint32_t *__restrict__ idx, double *diag)
+{
+    const int nm3 = nm * nm * nm;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n_entries; t += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t id = idx[t];
+        if (id == kInvalidIndex) continue;
+        const size_t cell = t / nm3;
+        const int l = (int)(t - cell * nm3), k = l % nm, j = (l / nm) % nm, i = l / (nm * nm);
+        const double *g = cellG + cell * 8;
+        double d = 0.0;
+        if (qop & QOP_LAPLACE) d = g[0] * v.dk[i] * v.dm[j] * v.dm[k] + g[3] * v.dm[i] * v.dk[j] * v.dm[k] + g[5] * v.dm[i] * v.dm[j] * v.dk[k];
+        if (qop & QOP_MASS) d += g[6] * v.dm[i] * v.dm[j] * v.dm[k];
+        atomicAdd(diag + id, d);
+    }
+}
+__global__ void cart_rhs_kernel(const __grid_constant__ CartVecs v, size_t n_entries, int nm, const double *__restrict__ cellG,
+                                const uint32_t *__restrict__ idx, double *b)
+{
+    const int nm3 = nm * nm * nm;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n_entries; t += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t id = idx[t];
+        if (id == kInvalidIndex) continue;
+        const size_t cell = t / nm3;
+        const int l = (int)(t - cell * nm3), k = l % nm, j = (l / nm) % nm, i = l / (nm * nm);
+        atomicAdd(b + id, cellG[cell * 8 + 6] * v.mv[i] * v.mv[j] * v.mv[k]);
+    }
+}
+
 // *flag = 1 unless every cell's constants are those of an axis-aligned box (vanishing rs, rt, st couplings)
 __global__ void cartesian_check_kernel(uint32_t n_cells, const double *__restrict__ cellG, int *flag)
 {
@@ -570,10 +601,21 @@ static void op_prepare_exclusive(Operator &op)
 // -- the separable kernel on the nodal values (sumfact_cart.cuh)
 static cudaError_t op_launch_kernel(Operator &op, const KArgs &a, cudaStream_t s, LaunchInfo *info, bool dry_run)
 {
-    if (op.cartesian && !op.collocated) return launch_cartesian(op.nm, op.S.data(), a, s, info, dry_run);
+    if (op.cartesian && !op.collocated) return launch_cartesian(op.nm, op.qop, op.S.data(), a, s, info, dry_run);
     const int qop = op.qop | op.otf_flag();
     return launch_sumfact(op.nm, op.nq, op.collocated, qop, true, op.cartesian ? op.S.data() : op.B.data(), op.D.data(), a, s, info, dry_run,
                           op.otf_flag() ? op.W.data() : nullptr);
+}
+
+static CartVecs cart_vecs(const Operator &op)
+{
+    CartVecs v{};
+    for (int i = 0; i < op.nm; ++i) {
+        v.dk[i] = op.S[(size_t)i * op.nm + i];
+        v.dm[i] = op.S[(size_t)op.nm * op.nm + (size_t)i * op.nm + i];
+        v.mv[i] = op.mvec[i];
+    }
+    return v;
 }
 
 int op_apply_cells(Operator &op, double *d_dst, const double *d_src, uint32_t cb, uint32_t ce,
@@ -1029,12 +1071,13 @@ int b200fe_op_create(const b200fe_op_desc *d, b200fe_op **out)
     const bool trilinear = d->d_cell_vertices != nullptr;
     const bool affine = d->d_cell_G != nullptr || trilinear;  // on-the-fly geometry of either kind
     B200FE_REQUIRE(!(d->d_cell_G && trilinear), "b200fe_op_create: d_cell_G and d_cell_vertices are mutually exclusive");
-    if (affine && d->op_kind != B200FE_OP_LAPLACE)
-        return fail(B200FE_ERR_UNSUPPORTED, "b200fe_op_create: on-the-fly geometry is built for the Laplace operators only");
+    if (trilinear && d->op_kind != B200FE_OP_LAPLACE)
+        return fail(B200FE_ERR_UNSUPPORTED, "b200fe_op_create: trilinear on-the-fly geometry is built for the Laplace operators only");
+    // (mass / Helmholtz with d_cell_G: axis-aligned cells only -- checked below, once the constants have been looked at)
     B200FE_REQUIRE(!affine || d->h_weights, "b200fe_op_create: on-the-fly geometry needs the 1-D quadrature weights");
     B200FE_REQUIRE(!trilinear || d->h_points, "b200fe_op_create: trilinear geometry needs the 1-D quadrature points");
     B200FE_REQUIRE(!(d->op_kind & B200FE_OP_LAPLACE) || d->n_cells == 0 || d->d_G || affine, "b200fe_op_create: G missing");
-    B200FE_REQUIRE(!(d->op_kind & B200FE_OP_MASS) || d->n_cells == 0 || d->d_JxW, "b200fe_op_create: JxW missing");
+    B200FE_REQUIRE(!(d->op_kind & B200FE_OP_MASS) || d->n_cells == 0 || d->d_JxW || d->d_cell_G, "b200fe_op_create: JxW missing");
     B200FE_REQUIRE(d->n_constrained == 0 || d->h_constrained, "b200fe_op_create: constrained list missing");
     B200FE_REQUIRE((uint64_t)d->n_phase0 + d->n_phase1 <= d->n_cells, "b200fe_op_create: phase split exceeds n_cells");
 
@@ -1085,28 +1128,20 @@ int b200fe_op_create(const b200fe_op_desc *d, b200fe_op **out)
             const cudaError_t ce = cudaMemcpy(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost);
             cudaFree(d_flag);
             if (ce != cudaSuccess) return fail_cuda(ce, "cartesian_check_kernel");
-            if (h_flag == 0 && coll) {
-                op->cartesian = true;
-                op->S.assign((size_t)nq * nq, 0.0);  // S[q*nq+i] = sum_p D[p][q] w_p D[p][i]
-                for (int q = 0; q < nq; ++q)
-                    for (int i = 0; i < nq; ++i) {
-                        double s = 0.0;
-                        for (int pp = 0; pp < nq; ++pp) s += op->D[pp * nq + q] * d->h_weights[pp] * op->D[pp * nq + i];
-                        op->S[(size_t)q * nq + i] = s;
-                    }
-            } else if (h_flag == 0) {
-                // interpolated operator: 1-D stiffness and mass matrices on the nodal basis (sumfact_cart.cuh),
-                // K = (D B)^T W (D B), M = B^T W B; S = K | M
+            if (h_flag == 0) {
+                // 1-D stiffness and mass matrices on the nodal basis, K = (D B)^T W (D B), M = B^T W B (collocated: B = I, so
+                // K = D^T W D and M = diag(w)), and m = B^T w; S = K | M, nm*nm doubles each
                 op->cartesian = true;
                 std::vector<double> DB((size_t)nq * nm, 0.0);  // derivative of shape i at point p
                 for (int pp = 0; pp < nq; ++pp)
                     for (int i = 0; i < nm; ++i) {
-                        double s = 0.0;
-                        for (int n = 0; n < nq; ++n) s += op->D[pp * nq + n] * op->B[n * nm + i];
-                        DB[(size_t)pp * nm + i] = s;
+                        double t = 0.0;
+                        for (int n = 0; n < nq; ++n) t += op->D[pp * nq + n] * op->B[n * nm + i];
+                        DB[(size_t)pp * nm + i] = t;
                     }
                 op->S.assign(2 * (size_t)nm * nm, 0.0);
-                for (int i = 0; i < nm; ++i)
+                op->mvec.assign(nm, 0.0);
+                for (int i = 0; i < nm; ++i) {
                     for (int j = 0; j < nm; ++j) {
                         double k = 0.0, mm = 0.0;
                         for (int pp = 0; pp < nq; ++pp) {
@@ -1116,7 +1151,9 @@ int b200fe_op_create(const b200fe_op_desc *d, b200fe_op **out)
                         op->S[(size_t)i * nm + j] = k;
                         op->S[(size_t)nm * nm + (size_t)i * nm + j] = mm;
                     }
-                // the kernel contracts through the even-odd split: needs the point symmetry of a real basis
+                    for (int pp = 0; pp < nq; ++pp) op->mvec[i] += op->B[pp * nm + i] * d->h_weights[pp];
+                }
+                // the separable kernels contract through the even-odd split: needs the point symmetry of a real basis
                 double viol = 0.0, big = 0.0;
                 for (int m2 = 0; m2 < 2; ++m2)
                     for (int i = 0; i < nm; ++i)
@@ -1125,10 +1162,12 @@ int b200fe_op_create(const b200fe_op_desc *d, b200fe_op **out)
                             big = std::max(big, std::fabs(a1));
                             viol = std::max(viol, std::fabs(a1 - a2));
                         }
-                if (!(viol <= 1e-11 * big)) { op->cartesian = false; op->S.clear(); }
+                if (!(viol <= 1e-11 * big)) { op->cartesian = false; op->S.clear(); op->mvec.clear(); }
             }
         }
     }
+    if (d->d_cell_G && d->op_kind != B200FE_OP_LAPLACE && !op->cartesian)
+        return fail(B200FE_ERR_UNSUPPORTED, "b200fe_op_create: mass / Helmholtz operators with on-the-fly geometry need axis-aligned cells");
     op_prepare_exclusive(*op);
     *out = reinterpret_cast<b200fe_op *>(op.release());
     return B200FE_OK;
@@ -1278,8 +1317,10 @@ int b200fe_op_diagonal(b200fe_op *o, double *d_diag, void *stream)
 {
     B200FE_REQUIRE(o && d_diag, "b200fe_op_diagonal: null pointer");
     Operator &op = *reinterpret_cast<Operator *>(o);
-    B200FE_REQUIRE(!(op.qop & QOP_LAPLACE) || op.d_G, "b200fe_op_diagonal: needs the stored geometric factors (d_G)");
+    B200FE_REQUIRE(!(op.qop & QOP_LAPLACE) || op.d_G || op.cartesian, "b200fe_op_diagonal: needs the stored geometric factors (d_G) or axis-aligned cells");
     cudaStream_t s = (cudaStream_t)stream;
+    if (op.cartesian && op.has_constraints())
+        return fail(B200FE_ERR_UNSUPPORTED, "b200fe_op_diagonal: constrained operators need the stored geometric factors");
     if (op.has_constraints()) {
         if (op.n_hang == 0)
             return fail(B200FE_ERR_UNSUPPORTED, "b200fe_op_diagonal: an operator with face-structured constraints also needs the constraint rows "
@@ -1287,7 +1328,12 @@ int b200fe_op_diagonal(b200fe_op *o, double *d_diag, void *stream)
         return op_diagonal_constrained(op, d_diag, s);
     }
     B200FE_CUDA_TRY(cudaMemsetAsync(d_diag, 0, sizeof(double) * op.n_local(), s));
-    if (op.n_cells) {
+    if (op.n_cells && op.cartesian) {
+        const size_t n_entries = (size_t)op.n_cells * op.nm * op.nm * op.nm;
+        cart_diagonal_kernel<<<(unsigned)std::min<size_t>((n_entries + 255) / 256, 148u * 16u), 256, 0, s>>>(cart_vecs(op), n_entries, op.nm, op.qop, op.d_cellG,
+                                                                                                            op.d_idx, d_diag);
+        B200FE_CUDA_TRY(cudaGetLastError());
+    } else if (op.n_cells) {
         diagonal_kernel<<<std::min<uint32_t>(op.n_cells, 148u * 8u), 128, 0, s>>>(op.n_cells, op.nm, op.nq, op.qop, op.d_mats, op.d_G, op.d_JxW, op.d_idx, d_diag, nullptr);
         B200FE_CUDA_TRY(cudaGetLastError());
     }
@@ -1304,10 +1350,14 @@ int b200fe_op_rhs_one(b200fe_op *o, double *d_b, void *stream)
 {
     B200FE_REQUIRE(o && d_b, "b200fe_op_rhs_one: null pointer");
     Operator &op = *reinterpret_cast<Operator *>(o);
-    B200FE_REQUIRE(op.d_JxW || op.n_cells == 0, "b200fe_op_rhs_one: the operator was created without JxW");
+    B200FE_REQUIRE(op.d_JxW || op.cartesian || op.n_cells == 0, "b200fe_op_rhs_one: the operator was created without JxW");
     cudaStream_t s = (cudaStream_t)stream;
     B200FE_CUDA_TRY(cudaMemsetAsync(d_b, 0, sizeof(double) * op.n_local(), s));
-    if (op.n_cells) {
+    if (op.n_cells && op.cartesian && !op.d_JxW) {  // axis-aligned cells: int phi_i = det J * m_i m_j m_k
+        const size_t n_entries = (size_t)op.n_cells * op.nm * op.nm * op.nm;
+        cart_rhs_kernel<<<(unsigned)std::min<size_t>((n_entries + 255) / 256, 148u * 16u), 256, 0, s>>>(cart_vecs(op), n_entries, op.nm, op.d_cellG, op.d_idx, d_b);
+        B200FE_CUDA_TRY(cudaGetLastError());
+    } else if (op.n_cells) {
         rhs_one_kernel<<<std::min<uint32_t>(op.n_cells, 148u * 8u), 128, 0, s>>>(op.n_cells, op.nm, op.nq, op.d_mats, op.d_JxW, op.d_idx, d_b);
         B200FE_CUDA_TRY(cudaGetLastError());
     }

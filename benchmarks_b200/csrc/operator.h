@@ -24,7 +24,8 @@ struct Operator {
     // affine cells that are all axis-aligned boxes, collocated operator: the separable kernel (QOP_CARTESIAN) with the 1-D
     // stiffness matrix S = D^T W D (BK layout, in place of B); decided by b200fe_op_create from the per-cell constants
     bool cartesian = false;
-    std::vector<double> S;
+    std::vector<double> S;     // K | M: the 1-D stiffness and mass matrices on the nodal basis, nm*nm doubles each
+    std::vector<double> mvec;  // m = B^T w (int of the 1-D shape functions): rhs of the separable operators
     int otf_flag() const { return d_cellG ? (cartesian ? QOP_AFFINE | QOP_CARTESIAN : QOP_AFFINE) : d_cellX ? QOP_TRILINEAR : 0; }
     const double *otf_data() const { return d_cellG ? d_cellG : d_cellX; }
     int otf_stride() const { return d_cellG ? 8 : 24; }

@@ -100,9 +100,13 @@ __device__ __forceinline__ void mat_col(const SymEo<NM> &A, const double (&in)[N
 }
 }  // namespace cart
 
-template <int NM, int EPB, int MINB>
+// QOP: QOP_LAPLACE, QOP_MASS or QOP_HELMHOLTZ -- the mass term of an affine cell is separable as well, det J (M x M x M), so
+// the Helmholtz operator costs no contraction more than the Laplacian (c_m a2 joins the sum under M_i) and the mass operator
+// three in total.
+template <int NM, int EPB, int MINB, int QOP = QOP_LAPLACE>
 __global__ void __launch_bounds__(EPB *NM *NM, MINB) sumfact_cart_kernel(const __grid_constant__ CartMats<NM> m, const KArgs a)
 {
+    constexpr bool LAP = (QOP & QOP_LAPLACE) != 0, MASS = (QOP & QOP_MASS) != 0;
     using L = cart::LayoutC<NM>;
     constexpr int N2 = L::N2, M3 = L::M3, RA = L::RA, PA = L::PA;
     if (a.skip != nullptr && *a.skip != 0) return;  // uniform across the grid
@@ -138,7 +142,9 @@ __global__ void __launch_bounds__(EPB *NM *NM, MINB) sumfact_cart_kernel(const _
         const uint32_t nb = eb + gridDim.x;
         load_idx(nb, nxt_idx);  // next batch's index rows; the dependent gathers are issued after the first sweep
         const double *c8 = a.cellG + (size_t)(active ? e : 0) * 8;
-        const double c_rr = active ? __ldg(c8 + 0) : 0.0, c_ss = active ? __ldg(c8 + 3) : 0.0, c_tt = active ? __ldg(c8 + 5) : 0.0;
+        [[maybe_unused]] const double c_rr = (LAP && active) ? __ldg(c8 + 0) : 0.0, c_ss = (LAP && active) ? __ldg(c8 + 3) : 0.0,
+                                      c_tt = (LAP && active) ? __ldg(c8 + 5) : 0.0;
+        [[maybe_unused]] const double c_m = (MASS && active) ? __ldg(c8 + 6) : 0.0;  // det J
 
         // layout P: thread (j,k) = (ta,tb) owns the column over i -> X1[i][j][k]
 #pragma unroll
@@ -151,41 +157,57 @@ __global__ void __launch_bounds__(EPB *NM *NM, MINB) sumfact_cart_kernel(const _
             cart::mat_col<NM>(m.M, u, o);
 #pragma unroll
             for (int k = 0; k < NM; ++k) X1[ta * PA + tb * RA + k] = o[k];
-            cart::mat_col<NM>(m.K, u, o);
+            if constexpr (LAP) {
+                cart::mat_col<NM>(m.K, u, o);
 #pragma unroll
-            for (int k = 0; k < NM; ++k) X2[ta * PA + tb * RA + k] = o[k];
+                for (int k = 0; k < NM; ++k) X2[ta * PA + tb * RA + k] = o[k];
+            }
         }
         __syncthreads();
         load_val(nxt_idx, nxt_val);  // next batch's gathers (indices arrived during the first sweep)
         {   // layout Q: thread (i,k) = (ta,tb), column over j:  a2 = M a -> X1,  t = c_ss K a + c_tt M b -> X2
-            // (one input column live at a time: three columns of registers at the peak, not four)
-            double x[NM], o[NM], t[NM];
+            double x[NM], o[NM];
+            if constexpr (LAP) {
+                double t[NM];
 #pragma unroll
-            for (int j = 0; j < NM; ++j) x[j] = X2[ta * PA + j * RA + tb];
-            cart::mat_col<NM>(m.M, x, o);
+                for (int j = 0; j < NM; ++j) x[j] = X2[ta * PA + j * RA + tb];
+                cart::mat_col<NM>(m.M, x, o);
 #pragma unroll
-            for (int j = 0; j < NM; ++j) o[j] *= c_tt;
+                for (int j = 0; j < NM; ++j) o[j] *= c_tt;
 #pragma unroll
-            for (int j = 0; j < NM; ++j) x[j] = X1[ta * PA + j * RA + tb];
-            cart::mat_col<NM>(m.K, x, t);
+                for (int j = 0; j < NM; ++j) x[j] = X1[ta * PA + j * RA + tb];
+                cart::mat_col<NM>(m.K, x, t);
 #pragma unroll
-            for (int j = 0; j < NM; ++j) X2[ta * PA + j * RA + tb] = fma(c_ss, t[j], o[j]);
-            cart::mat_col<NM>(m.M, x, o);
+                for (int j = 0; j < NM; ++j) t[j] = fma(c_ss, t[j], o[j]);
+                cart::mat_col<NM>(m.M, x, o);
 #pragma unroll
-            for (int j = 0; j < NM; ++j) X1[ta * PA + j * RA + tb] = o[j];
+                for (int j = 0; j < NM; ++j) {
+                    X2[ta * PA + j * RA + tb] = MASS ? fma(c_m, o[j], t[j]) : t[j];  // Helmholtz: + det J * M_j M_k u under M_i
+                    X1[ta * PA + j * RA + tb] = o[j];
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < NM; ++j) x[j] = X1[ta * PA + j * RA + tb];
+                cart::mat_col<NM>(m.M, x, o);
+#pragma unroll
+                for (int j = 0; j < NM; ++j) X1[ta * PA + j * RA + tb] = o[j];
+            }
         }
         __syncthreads();
         {   // layout P again: out = c_rr K a2 + M t along i; scatter
-            double x[NM], o1[NM], o2[NM];
+            double x[NM], o2[NM];
+            [[maybe_unused]] double o1[NM];
 #pragma unroll
             for (int i = 0; i < NM; ++i) x[i] = X1[i * PA + ta * RA + tb];
-            cart::mat_col<NM>(m.K, x, o1);
+            if constexpr (LAP) {
+                cart::mat_col<NM>(m.K, x, o1);
 #pragma unroll
-            for (int i = 0; i < NM; ++i) x[i] = X2[i * PA + ta * RA + tb];
+                for (int i = 0; i < NM; ++i) x[i] = X2[i * PA + ta * RA + tb];
+            }
             cart::mat_col<NM>(m.M, x, o2);
 #pragma unroll
             for (int i = 0; i < NM; ++i) {
-                const double w = fma(c_rr, o1[i], o2[i]);
+                const double w = LAP ? fma(c_rr, o1[i], o2[i]) : c_m * o2[i];
                 dot_acc = fma(cur_val[i], w, dot_acc);  // u.(A u) from the nodal values (masked entries carry u = 0)
                 if (cur_idx[i] != kInvalidIndex) {
                     if (excl_t2 && i >= 1 && i <= NM - 2) a.out[cur_idx[i]] = w;  // cell-interior DoF: sole writer

@@ -31,7 +31,10 @@ void test(const unsigned int s, const bool short_output)
     if (remainder > 7) sub[0] = 2;
     const double p1[3] = {0, 0, 0}, p2[3] = {(double)sub[0], (double)sub[1], (double)sub[2]};
     BoxMesh mesh(sub, (int)n_refine, fe_degree, p1, p2, 1, 0, B200FE_PARTITION_BLOCKS);
-    LaplaceOperator<3, fe_degree, n_q_points, double> helmholtz(mesh, Quadrature::Gauss, B200FE_OP_HELMHOLTZ);
+    // B200FE_GEOMETRY=onthefly: the mesh is a box of unit cubes -> separable Helmholtz kernel, no G / JxW in memory
+    const char *geo = std::getenv("B200FE_GEOMETRY");
+    const Geometry geometry = geo && std::string(geo) == "onthefly" ? Geometry::OnTheFly : Geometry::Stored;
+    LaplaceOperator<3, fe_degree, n_q_points, double> helmholtz(mesh, Quadrature::Gauss, B200FE_OP_HELMHOLTZ, 1, {}, geometry);
     Vector solution, rhs;
     helmholtz.initialize_dof_vector(solution);
     rhs.reinit(solution);

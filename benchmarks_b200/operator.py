@@ -113,8 +113,9 @@ class LaplaceOperator:
         self.cell_G = None
         self.cell_vertices = None
         if geometry == "affine":  # on-the-fly geometric factors from six per-cell constants
-            if p_geo != 1 or deform is not None or self.kind != OP_LAPLACE:
-                raise ValueError("geometry='affine' needs p_geo=1, no deformation (an affine node_transform is fine) and the Laplace operator")
+            if p_geo != 1 or deform is not None:
+                raise ValueError("geometry='affine' needs p_geo=1 and no deformation (an affine node_transform is fine); "
+                                 "mass / Helmholtz operators additionally need axis-aligned cells")
             self.cell_G = torch.empty(mesh.n_cells * 8, dtype=torch.float64, device=self.device)
             check(lib.b200fe_geometry_affine_from_nodes(mesh.n_cells, _dp(nodes), _dp(self.cell_G), _sp()))
         elif geometry == "trilinear":  # general hexahedra: the 8 vertices per cell ARE the geometry (MappingQ1), G rebuilt per point
@@ -124,7 +125,7 @@ class LaplaceOperator:
         elif geometry != "stored":
             raise ValueError(geometry)
         need_G = bool(self.kind & OP_LAPLACE) and geometry == "stored"
-        need_J = bool(self.kind & OP_MASS) or with_jxw
+        need_J = (bool(self.kind & OP_MASS) and geometry == "stored") or with_jxw
         self.G = torch.empty(mesh.n_cells * 6 * nq3, dtype=torch.float64, device=self.device) if need_G else None
         self.JxW = torch.empty(mesh.n_cells * nq3, dtype=torch.float64, device=self.device) if need_J else None
         if self.G is not None or self.JxW is not None:
@@ -256,7 +257,8 @@ class LaplaceOperator:
     def algorithmic_bytes(self) -> int:
         nq3, nm3 = self.nq ** 3, self.nm ** 3
         g_bytes = 64 if self.geometry == "affine" else 192 if self.geometry == "trilinear" else 48 * nq3
-        per_cell = 4 * nm3 + (g_bytes if self.kind & OP_LAPLACE else 0) + (8 * nq3 if self.kind & OP_MASS else 0)
+        jxw_bytes = 8 * nq3 if self.geometry == "stored" else (0 if self.kind & OP_LAPLACE else 64)  # on the fly: det J among the cell constants
+        per_cell = 4 * nm3 + (g_bytes if self.kind & OP_LAPLACE else 0) + (jxw_bytes if self.kind & OP_MASS else 0)
         return self.mesh.n_cells * per_cell + 32 * self.mesh.n_owned
 
     def __del__(self):

@@ -384,8 +384,8 @@ class LaplaceOperator {
                     Deformation deform = {}, Geometry geometry = Geometry::Stored)
         : n_dofs_global_(mesh.n_dofs()), n_owned_(mesh.info.n_owned), n_ghost_(mesh.info.n_ghost), geometry_(geometry)
     {
-        if (geometry == Geometry::OnTheFly && (p_geo != 1 || op_kind != B200FE_OP_LAPLACE))
-            throw Error(B200FE_ERR_INVALID_ARG, "Geometry::OnTheFly: Laplace operators on MappingQ1 meshes");
+        if (geometry == Geometry::OnTheFly && (p_geo != 1 || (op_kind != B200FE_OP_LAPLACE && deform.amplitude != 0.0)))
+            throw Error(B200FE_ERR_INVALID_ARG, "Geometry::OnTheFly: MappingQ1 meshes; mass / Helmholtz operators on undeformed (axis-aligned) cells only");
         trilinear_ = geometry == Geometry::OnTheFly && deform.amplitude != 0.0;
         if (mesh.degree != fe_degree) throw Error(B200FE_ERR_INVALID_ARG, "mesh degree != fe_degree");
         const uint32_t nc = mesh.info.n_cells_local;
@@ -479,8 +479,10 @@ class LaplaceOperator {
         const size_t nq3 = (size_t)nq * nq * nq;
         const bool otf = geometry_ == Geometry::OnTheFly;
         if ((op_kind & B200FE_OP_LAPLACE) && !otf) G_.resize((size_t)nc * 6 * nq3);
-        JxW_.resize((size_t)nc * nq3);  // (compute_rhs integrates with it)
-        check(b200fe_geometry_from_nodes(p_geo, nq, qk, nc, nodes.data(), G_.data(), JxW_.data(), nullptr));
+        // JxW: streamed by the stored-geometry mass terms and read by compute_rhs; the separable kernels of undeformed meshes
+        // need neither (det J is among the cell constants)
+        if (!otf || trilinear_) JxW_.resize((size_t)nc * nq3);
+        if (G_.size() || JxW_.size()) check(b200fe_geometry_from_nodes(p_geo, nq, qk, nc, nodes.data(), G_.data(), JxW_.data(), nullptr));
         std::vector<double> wts(nq), pts(nq);
         if (otf) {
             check(b200fe_basis_1d(fe_degree, nq, qk, nullptr, nullptr, nullptr, pts.data(), wts.data()));

@@ -80,6 +80,21 @@ def test_bp3_driver_reports_errors_like_the_reference():
     assert r.returncode == 1 and "Expected at least one argument" in r.stdout
 
 
+def test_bp5_driver_with_geometry_on_the_fly_gives_the_same_row():
+    """bp5_kokkos protocol with Geometry::OnTheFly: the unit-cube mesh takes the separable Helmholtz kernel (no G, no JxW,
+    diagonal and rhs from the 1-D matrices) -- same DoFs and Jacobi-CG iteration count as the stored-geometry run."""
+    def row(env):
+        exe = os.path.join(DRV, "bp5")
+        if not os.path.exists(exe):
+            subprocess.run(["make", "-C", DRV], check=True)
+        r = subprocess.run([exe, "4", "14", "1"], capture_output=True, text=True, timeout=600, env=dict(os.environ, **env))
+        assert r.returncode == 0, r.stderr
+        return [x.strip() for x in r.stdout.strip().splitlines()[-1].split("|")]
+    a, b = row({}), row({"B200FE_GEOMETRY": "onthefly"})
+    assert a[:4] == b[:4]                       # p, q, cells, DoFs
+    assert abs(int(a[6]) - int(b[6])) <= 1      # CG iterations
+
+
 def test_bp5_driver_helmholtz_jacobi_matches_c_oracle(oracle_mod):
     """bp5_kokkos protocol (Helmholtz, QGauss(p+1), Jacobi CG capped at 100 iterations, rhs = i % 8): the C++ driver's
     iteration count and DoF count against the C oracle on the same mesh (s = 3: 1 x 1 x 7 cells, p = 3)."""

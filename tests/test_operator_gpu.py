@@ -493,6 +493,48 @@ def test_on_the_fly_affine_geometry_matches_stored_G_and_oracle(oracle_mod, p, d
     assert abs(its[0] - its[1]) <= 1
 
 
+@pytest.mark.parametrize("p", [1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("dq,kind", [(2, "mass"), (1, "helmholtz")])
+def test_separable_mass_and_helmholtz_on_axis_aligned_cells(oracle_mod, p, dq, kind):
+    """BP1 (mass, QGauss(p+2)) and bp5_kokkos' Helmholtz operator (QGauss(p+1)) with the geometry on the fly: on axis-aligned
+    cells the mass term det J (M x M x M) is separable too.  Apply, diagonal (Jacobi) and rhs against the oracle and against
+    the stored-geometry operator; sheared cells are refused for these operators."""
+    import benchmarks_b200 as b
+    fe = oracle_mod.fe
+    sub, nref = ((3, 2, 1), 1) if p <= 4 else ((3, 1, 1), 0)
+    p1, p2 = (0.0, -1.0, 0.5), (1.3, 0.2, 1.0)   # cells 0.217 x 0.3 x 0.25: anisotropic, off-origin
+    nq = p + dq
+    om = fe.BoxMesh(sub, nref, p1=p1, p2=p2)
+    rd = fe.rank_data(om, fe.distribute_dofs(om, p, 1), 0)
+    bas = fe.basis_1d(p, nq, "gauss")
+    G, JxW = fe.geometric_factors(fe.cell_nodes(om, rd["cells"], 1), 1, bas)
+    lap, mass = kind != "mass", True
+    mesh = b.BoxMesh(sub, nref, p, p1=p1, p2=p2)
+    A = b.LaplaceOperator(mesh, nq=nq, quad="gauss", kind=kind, geometry="affine", with_jxw=False)
+    assert A.launch_info()["cartesian"] == 1 and A.JxW is None and A.G is None
+    src = np.random.default_rng(70 + p).standard_normal(mesh.n_owned)
+    ref = fe.op_apply(src, rd, bas, G, JxW, laplace=lap, mass=mass)
+    y = A.initialize_dof_vector()
+    dot = A.vmult_dot(y, torch.from_numpy(src).cuda())
+    assert rel(y.cpu().numpy(), ref) <= TOL
+    assert abs(dot.item() - float(src @ ref)) <= 1e-11 * np.abs(src).dot(np.abs(ref))
+    assert rel(A.compute_diagonal().cpu().numpy(), fe.op_diagonal(rd, bas, G, JxW, laplace=lap, mass=mass)) <= 1e-11
+    assert rel(A.compute_rhs().cpu().numpy(), fe.rhs_one(rd, bas, JxW)) <= TOL
+    # Jacobi-preconditioned CG: same iteration count as the stored-geometry operator
+    A_st = b.LaplaceOperator(mesh, nq=nq, quad="gauss", kind=kind)
+    rhs = A_st.compute_rhs()
+    its = []
+    for op in (A_st, A):
+        x = op.initialize_dof_vector()
+        ctl = b.ReductionControl(5000, 1e-16, 1e-9)
+        b.SolverCG(ctl).solve(op, x, rhs, op.get_matrix_diagonal_inverse())
+        its.append(ctl.last_step())
+    assert abs(its[0] - its[1]) <= 1
+    shear_t = lambda N: torch.stack([N[:, 0] + 0.3 * N[:, 1], N[:, 1], N[:, 2]], dim=1)
+    with pytest.raises(b.B200feError):
+        b.LaplaceOperator(mesh, nq=nq, quad="gauss", kind=kind, geometry="affine", with_jxw=False, node_transform=shear_t)
+
+
 @pytest.mark.parametrize("p", [1, 2, 3, 5, 6, 7, 8])
 @pytest.mark.parametrize("dq,quad", [(2, "gauss"), (1, "gll")])
 def test_on_the_fly_affine_geometry_on_sheared_cells(oracle_mod, monkeypatch, p, dq, quad):

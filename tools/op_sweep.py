@@ -37,7 +37,7 @@ def main():
                          ("bp1", dict(quad="gauss", nq=p + 2, kind="mass")), ("helm", dict(quad="gauss", nq=p + 1, kind="helmholtz"))):
             if name in ("bp1", "helm") and not args.mass:
                 continue
-            op = b.LaplaceOperator(mesh, with_jxw=name in ("bp1", "helm"), geometry=args.geometry if name not in ("bp1", "helm") else "stored", **kw)
+            op = b.LaplaceOperator(mesh, with_jxw=name in ("bp1", "helm") and args.geometry == "stored", geometry=args.geometry, **kw)
             src = torch.rand(mesh.n_owned, dtype=torch.float64, device="cuda")
             dst = torch.empty_like(src)
             for _ in range(3):
