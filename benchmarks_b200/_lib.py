@@ -103,6 +103,7 @@ _SIGNATURES = {
     "b200fe_halo_set_transport": (_i, [_vp, _i]),
     "b200fe_halo_status": (_i, [_vp]),
     "b200fe_halo_exchange_raw": (_i, [_vp, _vp, _vp, _vp]),
+    "b200fe_halo_exchange_raw_rounds": (_i, [_vp, _vp, _vp, _i, _vp]),
 }
 for _name, (_res, _args) in _SIGNATURES.items():
     _f = getattr(lib, _name)

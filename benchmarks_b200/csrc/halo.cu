@@ -443,6 +443,17 @@ int b200fe_halo_exchange_raw(b200fe_halo *halo, const double *d_send, double *d_
     return B200FE_OK;
 }
 
+int b200fe_halo_exchange_raw_rounds(b200fe_halo *halo, const double *d_send, double *d_recv, int n_rounds, void *stream)
+{
+    B200FE_REQUIRE(halo && d_send && d_recv && n_rounds >= 1, "b200fe_halo_exchange_raw_rounds: bad arguments");
+    Halo &h = *reinterpret_cast<Halo *>(halo);
+    if (h.n_ranks == 1) return B200FE_OK;
+    if (h.use_p2p && (size_t)h.n_ghost * sizeof(double) < (size_t)1 << 30) return p2p_update_rounds(h, d_send, d_recv, n_rounds, (cudaStream_t)stream);
+    for (int r = 0; r < n_rounds; ++r)
+        if (int rc = b200fe_halo_exchange_raw(halo, d_send, d_recv, stream)) return rc;
+    return B200FE_OK;
+}
+
 int b200fe_halo_transport(b200fe_halo *halo, int *p2p_available, int *p2p_in_use)
 {
     B200FE_REQUIRE(halo, "b200fe_halo_transport: null pointer");

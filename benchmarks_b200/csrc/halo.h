@@ -53,6 +53,7 @@ int p2p_compress_send(Halo &h, double *d_v, int ncomp, size_t stride, cudaStream
 int p2p_compress_wait(Halo &h, double *d_v, int ncomp, size_t stride, cudaStream_t s);
 // whole rounds (post + complete back to back; one single-block kernel for small messages)
 int p2p_update(Halo &h, double *d_v, int ncomp, size_t stride, const double *d_raw_send, double *d_raw_recv, cudaStream_t s);
+int p2p_update_rounds(Halo &h, const double *d_raw_send, double *d_raw_recv, int n_rounds, cudaStream_t s);
 int p2p_compress(Halo &h, double *d_v, int ncomp, size_t stride, cudaStream_t s);
 int p2p_allreduce(Halo &h, double *d_vals, int count, cudaStream_t s);
 int p2p_status(Halo &h);

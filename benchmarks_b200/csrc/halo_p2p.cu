@@ -329,45 +329,57 @@ __device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned l
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// n_rounds > 1 (raw exchanges only): that many consecutive rounds of the same buffers inside ONE launch -- the exchange as a
+// device-resident loop would issue it (no launch between rounds; a round then costs the NVLink hop and the polling, not the
+// 3 us launch-to-launch gap of dependent kernels).  Epochs, window halves and acknowledgements advance exactly as over launches.
 __global__ void __launch_bounds__(1024) p2p_round_ll_kernel(DevState *st, Ctrl *my, int mode, double *v, uint32_t n_owned, uint32_t n_out, uint32_t n_in,
                                                              const uint32_t *__restrict__ send_idx, int ncomp, size_t stride,
-                                                             const double *__restrict__ raw_send, const ulonglong2 *win, double *raw_recv)
+                                                             const double *__restrict__ raw_send, const ulonglong2 *win, double *raw_recv,
+                                                             int n_rounds)
 {
-    __shared__ uint32_t s_off[kMaxEntries], s_cnt[kMaxEntries];
+    // the peer table of this launch in shared memory: read from device memory once, not once per element and round
+    __shared__ uint32_t s_off[kMaxEntries], s_cnt[kMaxEntries], s_cstride[kMaxEntries];
+    __shared__ ulonglong2 *s_dst[kMaxEntries];
+    __shared__ unsigned long long s_dhalf[kMaxEntries];
     const int n = st->n_entries, tid = threadIdx.x;
-    const unsigned long long epoch = (mode == MODE_UPDATE ? st->upd_send_epoch : st->cmp_send_epoch) + 1;
-    const unsigned long long par = epoch & 1ull, tag = (epoch & 0xFFFFFFFFull) << 32;
+    const unsigned long long epoch0 = (mode == MODE_UPDATE ? st->upd_send_epoch : st->cmp_send_epoch);
+    const unsigned long long half = mode == MODE_UPDATE ? st->ll_recv_half : st->ll_back_half;
     bool in_k = false;
+    unsigned long long *ack_out = nullptr;
     if (tid < n) {
         const EntryDev &e = st->e[tid];
         s_off[tid] = mode == MODE_UPDATE ? e.send_off : e.recv_off;
         s_cnt[tid] = mode == MODE_UPDATE ? e.send_cnt : e.recv_cnt;
+        s_dst[tid] = mode == MODE_UPDATE ? e.peer_ll_recv : e.peer_ll_back;
+        s_dhalf[tid] = mode == MODE_UPDATE ? e.peer_ll_recv_half : e.peer_ll_back_half;
+        s_cstride[tid] = mode == MODE_UPDATE ? e.peer_n_ghost : e.peer_n_send;
         in_k = (mode == MODE_UPDATE ? e.recv_cnt : e.send_cnt) != 0;
-        if (s_cnt[tid] && epoch > 2) spin_until(mode == MODE_UPDATE ? &my->upd_ack[tid] : &my->cmp_ack[tid], epoch - 2, &st->error);
+        ack_out = mode == MODE_UPDATE ? e.peer_upd_ack : e.peer_cmp_ack;
     }
+  for (int round = 0; round < n_rounds; ++round) {
+    const unsigned long long epoch = epoch0 + 1 + (unsigned long long)round;
+    const unsigned long long par = epoch & 1ull, tag = (epoch & 0xFFFFFFFFull) << 32;
+    // the peer must have consumed the message that used this half of its window (two epochs ago)
+    if (tid < n && s_cnt[tid] && epoch > 2) spin_until(mode == MODE_UPDATE ? &my->upd_ack[tid] : &my->cmp_ack[tid], epoch - 2, &st->error);
     __syncthreads();
     const uint32_t total_out = n_out * (uint32_t)ncomp;
     for (uint32_t i = tid; i < total_out; i += blockDim.x) {
         const uint32_t c = i / n_out, j = i - c * n_out;
         const int k = find_entry(s_off, s_cnt, n, j);
         if (k < 0) continue;
-        const EntryDev &e = st->e[k];
         double x;
-        ulonglong2 *dst;
         if (mode == MODE_UPDATE) {
             x = raw_send ? raw_send[j] : v[c * stride + send_idx[j]];
-            dst = e.peer_ll_recv + par * e.peer_ll_recv_half + (size_t)c * e.peer_n_ghost + (j - s_off[k]);
         } else {
             double *g = v + c * stride + n_owned + j;
             x = *g;
             *g = 0.0;
-            dst = e.peer_ll_back + par * e.peer_ll_back_half + (size_t)c * e.peer_n_send + (j - s_off[k]);
         }
+        ulonglong2 *dst = s_dst[k] + par * s_dhalf[k] + (size_t)c * s_cstride[k] + (j - s_off[k]);
         const unsigned long long bits = (unsigned long long)__double_as_longlong(x);
         st_relaxed_sys_v2(dst, tag | (bits & 0xFFFFFFFFull), tag | (bits >> 32));
     }
     // receive: every element carries its own flag
-    const unsigned long long half = mode == MODE_UPDATE ? st->ll_recv_half : st->ll_back_half;
     const uint32_t total_in = n_in * (uint32_t)ncomp;
     for (uint32_t i = tid; i < total_in; i += blockDim.x) {
         const uint32_t c = i / n_in, j = i - c * n_in;
@@ -391,11 +403,10 @@ __global__ void __launch_bounds__(1024) p2p_round_ll_kernel(DevState *st, Ctrl *
         }
     }
     __syncthreads();  // every element of this round has been read: the senders may reuse this half two rounds from now
-    if (tid < n && in_k) {
-        const EntryDev &e = st->e[tid];
-        st_relaxed_sys(mode == MODE_UPDATE ? e.peer_upd_ack : e.peer_cmp_ack, epoch);
-    }
+    if (tid < n && in_k) st_relaxed_sys(ack_out, epoch);
+  }  // rounds
     if (tid == 0) {
+        const unsigned long long epoch = epoch0 + (unsigned long long)n_rounds;
         if (mode == MODE_UPDATE) { st->upd_send_epoch = epoch; st->upd_wait_epoch = epoch; }
         else { st->cmp_send_epoch = epoch; st->cmp_wait_epoch = epoch; }
     }
@@ -652,7 +663,7 @@ int p2p_update(Halo &h, double *v, int ncomp, size_t stride, const double *raw_s
     if (ncomp > p.comps) return fail(B200FE_ERR_UNSUPPORTED, "P2P halo: %d components exceed the window (%d)", ncomp, p.comps);
     if (ncomp <= p.ll_max_comps && ll_enabled()) {
         p2p_round_ll_kernel<<<1, ll_threads(std::max(h.n_send, h.n_ghost), ncomp), 0, s>>>(p.d_state, (Ctrl *)p.window, MODE_UPDATE, v, h.n_owned, h.n_send, h.n_ghost, h.d_send_idx, ncomp, stride,
-                                               raw_send, p.ll_recv, raw_recv);
+                                               raw_send, p.ll_recv, raw_recv, 1);
         B200FE_CUDA_TRY(cudaGetLastError());
         return B200FE_OK;
     }
@@ -666,13 +677,28 @@ int p2p_update(Halo &h, double *v, int ncomp, size_t stride, const double *raw_s
     return p2p_update_wait(h, v, ncomp, stride, raw_recv, s);
 }
 
+// n_rounds raw exchange rounds in one launch when the low-latency round applies, else launch by launch
+int p2p_update_rounds(Halo &h, const double *raw_send, double *raw_recv, int n_rounds, cudaStream_t s)
+{
+    P2P &p = *h.p2p;
+    if (1 <= p.ll_max_comps && ll_enabled()) {
+        p2p_round_ll_kernel<<<1, ll_threads(std::max(h.n_send, h.n_ghost), 1), 0, s>>>(p.d_state, (Ctrl *)p.window, MODE_UPDATE, nullptr, h.n_owned, h.n_send, h.n_ghost,
+                                                                                      h.d_send_idx, 1, 0, raw_send, p.ll_recv, raw_recv, n_rounds);
+        B200FE_CUDA_TRY(cudaGetLastError());
+        return B200FE_OK;
+    }
+    for (int r = 0; r < n_rounds; ++r)
+        if (int rc = p2p_update(h, nullptr, 1, 0, raw_send, raw_recv, s)) return rc;
+    return B200FE_OK;
+}
+
 int p2p_compress(Halo &h, double *v, int ncomp, size_t stride, cudaStream_t s)
 {
     P2P &p = *h.p2p;
     if (ncomp > p.comps) return fail(B200FE_ERR_UNSUPPORTED, "P2P halo: %d components exceed the window (%d)", ncomp, p.comps);
     if (ncomp <= p.ll_max_comps && ll_enabled()) {
         p2p_round_ll_kernel<<<1, ll_threads(std::max(h.n_send, h.n_ghost), ncomp), 0, s>>>(p.d_state, (Ctrl *)p.window, MODE_COMPRESS, v, h.n_owned, h.n_ghost, h.n_send, h.d_send_idx, ncomp, stride,
-                                               nullptr, p.ll_back, nullptr);
+                                               nullptr, p.ll_back, nullptr, 1);
         B200FE_CUDA_TRY(cudaGetLastError());
         return B200FE_OK;
     }

@@ -12,7 +12,8 @@ Same Cartesian decomposition (MPI_Dims_create / MPI_Cart_shift semantics, phalox
 non-periodic boundaries dropped, duplicates kept), same message schedule ((warmup + nMsg) rounds of
 "receive from all, send to all, complete", clock after a barrier at msg == warmup) and the same output line
 (:148-154).  Two timings are printed: `sync` completes every round on the host like MPI_Waitall,
-`stream` enqueues all rounds on the CUDA stream and times them with CUDA events (the GPU-native way)."""
+`stream` enqueues all rounds on the CUDA stream and times them with CUDA events (the GPU-native way); with the P2P
+transport `launch` runs the nMsg rounds inside one kernel launch (b200fe_halo_exchange_raw_rounds; small messages)."""
 import ctypes as C
 import os
 import sys
@@ -127,6 +128,22 @@ def run_config(dim, KB, nMsg, periodic, warmup, print_topo, rank, world, gloo):
 
     def run_transport(transport):
         results = {}
+        if transport == "p2p":
+            # "launch": the nMsg rounds inside ONE kernel launch (b200fe_halo_exchange_raw_rounds) -- the exchange as a
+            # device-resident loop issues it; no launch gap between rounds: the latency floor of the NVLink fabric
+            recv.zero_()
+            torch.cuda.synchronize()
+            dist.barrier()
+            check(lib.b200fe_halo_exchange_raw_rounds(h, C.c_void_p(send.data_ptr()), C.c_void_p(recv.data_ptr()), max(warmup, 1), sp))
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            check(lib.b200fe_halo_exchange_raw_rounds(h, C.c_void_p(send.data_ptr()), C.c_void_p(recv.data_ptr()), nMsg, sp))
+            e1.record()
+            torch.cuda.synchronize()
+            results["launch"] = (e0.elapsed_time(e1) * 1e-3, payload_ok() and lib.b200fe_halo_status(h) == 0)
         for mode in ("sync", "stream"):
             recv.zero_()
             torch.cuda.synchronize()

@@ -483,6 +483,12 @@ int b200fe_halo_status(b200fe_halo *halo);
  * d_recv[recv_offset[k] .. +recv_count[k]) is filled from it.  A halo created with
  * h_send_indices = NULL ("raw mode") supports only this call; the same peer may appear twice. */
 int b200fe_halo_exchange_raw(b200fe_halo *halo, const double *d_send, double *d_recv, void *stream);
+/* n_rounds consecutive rounds of the same exchange.  With the P2P transport and messages small enough for the low-latency
+ * round (< 4096 doubles per direction on every rank) all rounds run inside ONE kernel launch -- the exchange as a
+ * device-resident solver loop would issue it: a round then costs the NVLink hop and the polling instead of the launch-to-launch
+ * gap of dependent kernels (p-halox "launch" mode: the latency floor of the fabric).  Otherwise the same as n_rounds calls of
+ * b200fe_halo_exchange_raw. */
+int b200fe_halo_exchange_raw_rounds(b200fe_halo *halo, const double *d_send, double *d_recv, int n_rounds, void *stream);
 
 #ifdef __cplusplus
 }
