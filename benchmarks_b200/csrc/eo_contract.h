@@ -174,5 +174,57 @@ B200FE_UNROLL
     }
 }
 
+// A square matrix that is symmetric AND point-symmetric (A = A^T, A(n-1-i, n-1-j) = A(i,j): the 1-D stiffness and mass
+// matrices of a real basis on symmetric points): its even and odd halves are symmetric again and are stored packed (upper
+// triangle, by rows).  sumfact_cart.cuh contracts with these.
+template <int N>
+struct SymEo {
+    static constexpr int H = (N + 1) / 2, L = N / 2;
+    double e[H * (H + 1) / 2];                      // even half  Ae[q][i], q <= i < H, packed by rows
+    double o[L * (L + 1) / 2 > 0 ? L * (L + 1) / 2 : 1];  // odd half Ao[q][i], q <= i < L
+    static B200FE_CHD int at(int n, int r, int c) { return r <= c ? r * n - r * (r - 1) / 2 + (c - r) : c * n - c * (c - 1) / 2 + (r - c); }
+    // from the full row-major matrix; returns the largest violation of A = A^T and A(n-1-i, n-1-j) = A(i,j), relative
+    double fill(const double *A)
+    {
+        double viol = 0.0, big = 0.0;
+        auto ab = [](double x) { return x < 0 ? -x : x; };
+        for (int i = 0; i < N; ++i)
+            for (int j = 0; j < N; ++j) {
+                const double a = A[i * N + j];
+                if (ab(a) > big) big = ab(a);
+                if (ab(a - A[j * N + i]) > viol) viol = ab(a - A[j * N + i]);
+                if (ab(a - A[(N - 1 - i) * N + (N - 1 - j)]) > viol) viol = ab(a - A[(N - 1 - i) * N + (N - 1 - j)]);
+            }
+        for (int q = 0; q < H; ++q)
+            for (int i = q; i < H; ++i) e[at(H, q, i)] = (N % 2 && i == L) ? A[q * N + i] : 0.5 * (A[q * N + i] + A[q * N + N - 1 - i]);
+        for (int q = 0; q < L; ++q)
+            for (int i = q; i < L; ++i) o[at(L, q, i)] = 0.5 * (A[q * N + i] - A[q * N + N - 1 - i]);
+        if (L == 0) o[0] = 0.0;
+        return big > 0 ? viol / big : 0.0;
+    }
+};
+
+
+// out = A in through the even-odd split, A given by its packed halves
+template <int N>
+B200FE_HD void sym_apply(const SymEo<N> &A, const double (&in)[N], double (&out)[N])
+{
+    constexpr int H = SymEo<N>::H, L = SymEo<N>::L;
+    double ev[H], od[H];
+    split<N>(in, ev, od);
+B200FE_UNROLL
+    for (int q = 0; q < H; ++q) {
+        double se = 0.0, so = 0.0;
+B200FE_UNROLL
+        for (int i = 0; i < H; ++i) se = fma(A.e[SymEo<N>::at(H, q, i)], ev[i], se);
+        if (q < L) {
+B200FE_UNROLL
+            for (int i = 0; i < L; ++i) so = fma(A.o[SymEo<N>::at(L, q, i)], od[i], so);
+        }
+        out[q] = se + so;
+        if (q != N - 1 - q) out[N - 1 - q] = se - so;
+    }
+}
+
 }  // namespace eo
 }  // namespace b200fe

@@ -55,9 +55,49 @@ void check(int quad)
     dev(out_q, ref_q, NQ);
 }
 
+// the packed symmetric even-odd halves of the nodal 1-D stiffness and mass matrices (sumfact_cart.cuh) against plain products;
+// K = (D B)^T W (D B), M = B^T W B as b200fe_op_create builds them
+template <int NM, int NQ>
+void check_sym(int quad)
+{
+    const int p = NM - 1;
+    std::vector<double> sv(NM * NQ), cg(NQ * NQ), w(NQ), B(NQ * NM), D(NQ * NQ), DB(NQ * NM), K(NM * NM), M(NM * NM);
+    if (b200fe_basis_1d(p, NQ, quad, sv.data(), cg.data(), nullptr, nullptr, w.data())) { std::printf("basis failed\n"); worst = 1; return; }
+    for (int q = 0; q < NQ; ++q) {
+        for (int i = 0; i < NM; ++i) B[q * NM + i] = sv[i * NQ + q];
+        for (int n = 0; n < NQ; ++n) D[q * NQ + n] = cg[n * NQ + q];
+    }
+    for (int q = 0; q < NQ; ++q)
+        for (int i = 0; i < NM; ++i) { double s = 0; for (int n = 0; n < NQ; ++n) s += D[q * NQ + n] * B[n * NM + i]; DB[q * NM + i] = s; }
+    for (int i = 0; i < NM; ++i)
+        for (int j = 0; j < NM; ++j) {
+            double k = 0, m = 0;
+            for (int q = 0; q < NQ; ++q) { k += DB[q * NM + i] * w[q] * DB[q * NM + j]; m += B[q * NM + i] * w[q] * B[q * NM + j]; }
+            K[i * NM + j] = k; M[i * NM + j] = m;
+        }
+    double in[NM], out[NM];
+    for (int i = 0; i < NM; ++i) in[i] = std::sin(0.7 + 2.9 * i) - 0.2 * i;
+    for (const std::vector<double> *A : {&K, &M}) {
+        eo::SymEo<NM> h;
+        const double sym = h.fill(A->data());
+        if (sym > worst_sym) worst_sym = sym;
+        eo::sym_apply<NM>(h, in, out);
+        double big = 0, d = 0;
+        for (int i = 0; i < NM; ++i) {
+            double s = 0;
+            for (int j = 0; j < NM; ++j) s += (*A)[i * NM + j] * in[j];
+            big = std::fmax(big, std::fabs(s)); d = std::fmax(d, std::fabs(out[i] - s));
+        }
+        if (d / big > worst) worst = d / big;
+    }
+}
+
 template <int P>
 void degree()
 {
+    check_sym<P + 1, P + 2>(B200FE_QUAD_GAUSS);
+    check_sym<P + 1, P + 1>(B200FE_QUAD_GAUSS);
+    check_sym<P + 1, P + 1>(B200FE_QUAD_GLL);
     check<P + 1, P + 2>(B200FE_QUAD_GAUSS);
     check<P + 1, P + 1>(B200FE_QUAD_GAUSS);
     check<P + 1, P + 1>(B200FE_QUAD_GLL);

@@ -33,37 +33,10 @@ namespace b200fe {
 // multiply-adds this is what keeps the kernel in registers: ptxas keeps loop-invariant matrix entries that do not fit the
 // uniform register file in ordinary registers -- with the full matrices the nm = 7, 9 builds wanted > 255 registers and
 // spilled ~340 B/thread at the 168-register cap.
-template <int N>
-struct SymEo {
-    static constexpr int H = (N + 1) / 2, L = N / 2;
-    double e[H * (H + 1) / 2];                      // even half  Ae[q][i], q <= i < H, packed by rows
-    double o[L * (L + 1) / 2 > 0 ? L * (L + 1) / 2 : 1];  // odd half Ao[q][i], q <= i < L
-    static constexpr __host__ __device__ int at(int n, int r, int c) { return r <= c ? r * n - r * (r - 1) / 2 + (c - r) : c * n - c * (c - 1) / 2 + (r - c); }
-    // from the full row-major matrix; returns the largest violation of A = A^T and A(n-1-i, n-1-j) = A(i,j), relative
-    double fill(const double *A)
-    {
-        double viol = 0.0, big = 0.0;
-        auto ab = [](double x) { return x < 0 ? -x : x; };
-        for (int i = 0; i < N; ++i)
-            for (int j = 0; j < N; ++j) {
-                const double a = A[i * N + j];
-                if (ab(a) > big) big = ab(a);
-                if (ab(a - A[j * N + i]) > viol) viol = ab(a - A[j * N + i]);
-                if (ab(a - A[(N - 1 - i) * N + (N - 1 - j)]) > viol) viol = ab(a - A[(N - 1 - i) * N + (N - 1 - j)]);
-            }
-        for (int q = 0; q < H; ++q)
-            for (int i = q; i < H; ++i) e[at(H, q, i)] = (N % 2 && i == L) ? A[q * N + i] : 0.5 * (A[q * N + i] + A[q * N + N - 1 - i]);
-        for (int q = 0; q < L; ++q)
-            for (int i = q; i < L; ++i) o[at(L, q, i)] = 0.5 * (A[q * N + i] - A[q * N + N - 1 - i]);
-        if (L == 0) o[0] = 0.0;
-        return big > 0 ? viol / big : 0.0;
-    }
-};
-
 template <int NM>
 struct CartMats {
-    SymEo<NM> K;  // 1-D stiffness matrix
-    SymEo<NM> M;  // 1-D mass matrix
+    eo::SymEo<NM> K;  // 1-D stiffness matrix
+    eo::SymEo<NM> M;  // 1-D mass matrix
 };
 
 namespace cart {
@@ -80,23 +53,9 @@ struct LayoutC {
 
 // out = A in  (packed even-odd halves in the constant bank, register column)
 template <int NM>
-__device__ __forceinline__ void mat_col(const SymEo<NM> &A, const double (&in)[NM], double (&out)[NM])
+__device__ __forceinline__ void mat_col(const eo::SymEo<NM> &A, const double (&in)[NM], double (&out)[NM])
 {
-    constexpr int H = SymEo<NM>::H, L = SymEo<NM>::L;
-    double ev[H], od[H];
-    eo::split<NM>(in, ev, od);
-#pragma unroll
-    for (int q = 0; q < H; ++q) {
-        double se = 0.0, so = 0.0;
-#pragma unroll
-        for (int i = 0; i < H; ++i) se = fma(A.e[SymEo<NM>::at(H, q, i)], ev[i], se);
-        if (q < L) {
-#pragma unroll
-            for (int i = 0; i < L; ++i) so = fma(A.o[SymEo<NM>::at(L, q, i)], od[i], so);
-        }
-        out[q] = se + so;
-        if (q != NM - 1 - q) out[NM - 1 - q] = se - so;
-    }
+    eo::sym_apply<NM>(A, in, out);
 }
 }  // namespace cart
 
