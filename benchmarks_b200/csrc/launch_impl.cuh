@@ -52,6 +52,9 @@ constexpr int v2_rmin(int nq, bool coll, int qop, bool eo = false)
     if (!(qop & QOP_LAPLACE)) return 64 + 12 * nq;  // mass only: no G buffer, registers are the limit
     // separable kernel for axis-aligned cells: no G stream to wait for, three contractions -- the even-odd build needs 108
     // registers at nq = 7 and 167 at nq = 9; more resident CTAs hide the gather latency
+#ifdef B200FE_CART_COLL_RMIN
+    if (qop & QOP_CARTESIAN) return B200FE_CART_COLL_RMIN;  // tuning knob
+#endif
     if (qop & QOP_CARTESIAN) return nq <= 6 ? 96 : nq == 7 ? 112 : nq == 8 ? 128 : 168;
     if (nq <= 6) return (qop & (QOP_AFFINE | QOP_TRILINEAR)) ? 128 : 96;  // on-the-fly kernels keep the cell constants + weights live
 #ifdef B200FE_V2_RMIN_HI
