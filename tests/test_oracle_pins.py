@@ -287,3 +287,51 @@ def test_p_transfer_oracle_is_exact_for_coarse_polynomials_and_adjoint():
         rng = np.random.default_rng(pf)
         u, r = rng.standard_normal(rc["n_owned"]), rng.standard_normal(rf["n_owned"])
         assert abs(P(u) @ r - u @ R(r)) <= 1e-11 * np.abs(P(u)).dot(np.abs(r))
+
+
+@pytest.mark.parametrize("p,dq,quad", [(1, 2, "gauss"), (3, 2, "gauss"), (4, 1, "gauss"), (6, 1, "gll"), (8, 2, "gauss"), (5, 1, "gll")])
+def test_separable_form_of_the_operator_on_axis_aligned_cells(oracle_mod, p, dq, quad):
+    """The identity behind the separable ("cartesian") kernels, checked on the CPU against the oracle's cell kernel
+    B^T D^T G D B (+ B^T JxW B): on an axis-aligned box cell the cell matrix is
+        c_rr K x M x M + c_ss M x K x M + c_tt M x M x K  (+ det J M x M x M),   K = (D B)^T W (D B),  M = B^T W B,
+    with c = det J diag(1/hz^2, 1/hy^2, 1/hx^2) (r <-> slowest local index <-> z); K and M are symmetric and point-symmetric
+    (what the packed even-odd halves of csrc/eo_contract.h rely on); diagonal and int phi_i follow from diag K, diag M and
+    m = B^T w.  Same formulas as b200fe_op_create / sumfact_cart.cuh / cart_diagonal_kernel / cart_rhs_kernel."""
+    fe = oracle_mod.fe
+    nq = p + dq
+    bas = fe.basis_1d(p, nq, quad)
+    B, D, w = bas["B"], bas["D"], bas["wq"]
+    om = fe.BoxMesh((2, 1, 1), 0, p1=(0.0, -1.0, 0.5), p2=(0.6, -0.3, 0.9))   # two cells 0.3 x 0.7 x 0.4
+    rd = fe.rank_data(om, fe.distribute_dofs(om, p, 1), 0)
+    G, JxW = fe.geometric_factors(fe.cell_nodes(om, rd["cells"], 1), 1, bas)
+    hx, hy, hz = 0.3, 0.7, 0.4
+    det = hx * hy * hz
+    c_rr, c_ss, c_tt = det / hz ** 2, det / hy ** 2, det / hx ** 2
+    DB = D @ B
+    K, M, m = DB.T @ (w[:, None] * DB), B.T @ (w[:, None] * B), B.T @ w
+    for A in (K, M):
+        assert np.abs(A - A.T).max() <= 1e-13 * np.abs(A).max()
+        assert np.abs(A - A[::-1, ::-1]).max() <= 1e-12 * np.abs(A).max()
+    nm = p + 1
+    u = np.random.default_rng(p).standard_normal((len(rd["cells"]), nm, nm, nm))
+    lap = (c_rr * np.einsum("ai,bj,ck,eijk->eabc", K, M, M, u) + c_ss * np.einsum("ai,bj,ck,eijk->eabc", M, K, M, u)
+           + c_tt * np.einsum("ai,bj,ck,eijk->eabc", M, M, K, u))
+    mass = det * np.einsum("ai,bj,ck,eijk->eabc", M, M, M, u)
+    for kw, want in ((dict(laplace=True), lap), (dict(laplace=False, mass=True), mass), (dict(laplace=True, mass=True), lap + mass)):
+        ref = fe.cell_kernel(u, bas, G, JxW, **kw)
+        assert np.abs(ref - want).max() <= 1e-12 * np.abs(ref).max()
+    # diagonal and rhs of the assembled operator
+    dk, dm = np.diag(K), np.diag(M)
+    diag_cell = (c_rr * np.einsum("a,b,c->abc", dk, dm, dm) + c_ss * np.einsum("a,b,c->abc", dm, dk, dm) + c_tt * np.einsum("a,b,c->abc", dm, dm, dk)
+                 + det * np.einsum("a,b,c->abc", dm, dm, dm)).ravel()
+    idx = rd["dof_indices"]
+    valid = idx != 0xFFFFFFFF
+    n_local = rd["n_owned"] + rd["n_ghost"]
+    diag = np.bincount(idx[valid].astype(np.int64), weights=np.tile(diag_cell, (idx.shape[0], 1))[valid], minlength=n_local)
+    diag[rd["constrained"]] = 1.0
+    ref_diag = fe.op_diagonal(rd, bas, G, JxW, laplace=True, mass=True)
+    assert np.abs(diag - ref_diag).max() <= 1e-11 * np.abs(ref_diag).max()
+    rhs_cell = det * np.einsum("a,b,c->abc", m, m, m).ravel()
+    rhs = np.bincount(idx[valid].astype(np.int64), weights=np.tile(rhs_cell, (idx.shape[0], 1))[valid], minlength=n_local)
+    ref_rhs = fe.rhs_one(rd, bas, JxW)
+    assert np.abs(rhs - ref_rhs).max() <= 1e-12 * np.abs(ref_rhs).max()
