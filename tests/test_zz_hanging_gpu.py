@@ -254,3 +254,34 @@ def test_face_structured_constraints_equal_rows(oracle_mod, p):
         b.SolverCG(ctl).solve(op, xv, rhs)
         its.append(ctl.last_step())
     assert abs(its[0] - its[1]) <= 1
+
+
+@pytest.mark.parametrize("p,dq,quad,kind", [(2, 2, "gauss", "laplace"), (4, 1, "gll", "laplace"), (3, 1, "gauss", "helmholtz"), (6, 1, "gll", "laplace")])
+@pytest.mark.parametrize("constraints", ["rows", "faces"])
+def test_separable_kernels_under_hanging_node_constraints(oracle_mod, p, dq, quad, kind, constraints):
+    """Undeformed two-level mesh: parents and children are axis-aligned boxes of two sizes, so the geometry can be evaluated
+    on the fly by the separable kernels (six constants per cell); C^T A C around them (distribute / condense, exclusive
+    interior stores) must equal the oracle's constrained operator and the stored-geometry one."""
+    import benchmarks_b200 as b
+    sub, nref, lo, hi = ((2, 2, 1), 0, (0, 0, 0), (1, 2, 1)) if p >= 6 else ((1, 1, 1), 1, (1, 0, 1), (2, 1, 2))
+    fe, ho, rd, bas, G, JxW, mesh, A_st = _setup(oracle_mod, p, sub, nref, lo, hi, p + dq, quad, kind, p_geo=1, deform=None, constraints=constraints)
+    A = b.LaplaceOperator(mesh, nq=p + dq, quad=quad, kind=kind, p_geo=1, geometry="affine", with_jxw=False, constraints=constraints)
+    assert A.launch_info()["cartesian"] == 1 and len(mesh.hang_dof) > 0
+    src = np.random.default_rng(300 + p).standard_normal(mesh.n_owned)
+    ref = ho.op_apply(rd, bas, G, src, JxW, laplace=kind != "mass", mass=kind != "laplace")
+    d_src = torch.from_numpy(src).cuda()
+    y, y_st = torch.full((mesh.n_owned,), -2.0, dtype=torch.float64, device="cuda"), A_st.initialize_dof_vector()
+    A.vmult(y, d_src)
+    A_st.vmult(y_st, d_src)
+    assert rel(y.cpu().numpy(), ref) <= TOL
+    assert rel(y.cpu().numpy(), y_st.cpu().numpy()) <= TOL
+    assert rel(A.compute_rhs().cpu().numpy(), ho.rhs_one(rd, bas, JxW)) <= TOL
+    # CG on the constrained operator: same iteration count with either geometry
+    rhs = A_st.compute_rhs()
+    its = []
+    for op in (A_st, A):
+        x = op.initialize_dof_vector()
+        ctl = b.ReductionControl(5000, 1e-16, 1e-9)
+        b.SolverCG(ctl).solve(op, x, rhs)
+        its.append(ctl.last_step())
+    assert abs(its[0] - its[1]) <= 1
