@@ -268,7 +268,11 @@ typedef struct {
      * G(q) = cell_G * w_p w_q w_r with DEVICE d_cell_G[cell][8] = {det J * K K^T (rr,rs,rt,ss,st,tt), det J, 0}
      * (b200fe_geometry_affine_from_nodes) and the HOST 1-D weights h_weights[nq].  Results equal the
      * stored-G path to rounding on parallelepiped cells; algorithmic bytes drop to 4 nm^3 + 64 per cell.
-     * d_G may still be given (needed by b200fe_op_diagonal).  BORROWED. */
+     * d_G may still be given (needed by b200fe_op_diagonal on parallelepiped cells).  When every cell turns out to be an
+     * axis-aligned box (checked on the device; b200fe_op_cartesian) the separable kernels run instead, and then
+     *  - the mass and Helmholtz operators are accepted with d_cell_G as well (their mass term is det J (M x M x M); d_JxW
+     *    may be NULL), on any other cell shape they are refused with B200FE_ERR_UNSUPPORTED;
+     *  - b200fe_op_diagonal and b200fe_op_rhs_one need neither d_G nor d_JxW (unconstrained operators).  BORROWED. */
     const double *d_cell_G;
     const double *h_weights;
     /* Optional: geometry evaluated on the fly for TRILINEAR cells (general hexahedra, the MappingQ1 case of SURVEY.md 8f.1):
