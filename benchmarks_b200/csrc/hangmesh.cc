@@ -20,6 +20,7 @@
 // fine level: the refined box with 2p intervals per coarse cell), so the first-touch sweep is a plain array walk
 // (no hashing): ~2e8 lookups per second, 0.5 GB for the 2 x 67 M lattices of config C5.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <memory>
@@ -115,6 +116,15 @@ std::vector<double> trace_weights(int p, const std::vector<double> &t)
 int HangMesh::build()
 {
     meshdetail::use_setup_threads();
+    // B200FE_SETUP_TRACE=1: wall time of the build phases on stderr
+    static const bool trace = [] { const char *e = std::getenv("B200FE_SETUP_TRACE"); return e && std::atoi(e) != 0; }();
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!trace) return;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[b200fe setup] hanging mesh rank %d: %-28s %7.1f ms\n", rank, what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
     const int nm = p + 1, nm3 = nm * nm * nm;
     for (int d = 0; d < 3; ++d) {
         cells[d] = (int64_t)sub[d] << nref;
@@ -157,6 +167,7 @@ int HangMesh::build()
         i += 8;
     }
 
+    lap("curve + partition");
     // ---- dense lattices (H1) ------------------------------------------------------------------------------------
     const int64_t d0[3] = {cells[0] * p + 1, cells[1] * p + 1, cells[2] * p + 1};
     const int64_t d1[3] = {2 * (int64_t)(hi[0] - lo[0]) * p + 1, 2 * (int64_t)(hi[1] - lo[1]) * p + 1, 2 * (int64_t)(hi[2] - lo[2]) * p + 1};
@@ -182,6 +193,7 @@ int HangMesh::build()
     std::vector<int> la(nm3), lb(nm3), lc(nm3);
     for (int hh = 0; hh < nm3; ++hh) { const int l = h2l[hh]; la[hh] = l % nm; lb[hh] = (l / nm) % nm; lc[hh] = l / (nm * nm); }
 
+    lap("lattices");
     // ---- first-touch numbering: ranks one after the other, inside a rank level by level (H3, H4) ---------------
     // rank cell ranges on the curve are contiguous; iterate each twice (level 0, then level 1)
     std::vector<uint64_t> rank_cell_begin(nranks + 1, N);
@@ -212,6 +224,7 @@ int HangMesh::build()
     owned_end = rank_dof_begin[rank + 1];
     first_cell = rank_cell_begin[rank];
 
+    lap("first-touch numbering");
     // ---- local cells in iterator order --------------------------------------------------------------------------
     std::vector<uint64_t> mine;
     for (int lvl = 0; lvl <= 1; ++lvl)
@@ -224,6 +237,10 @@ int HangMesh::build()
     const int64_t fmax[3] = {cells[0] * twop, cells[1] * twop, cells[2] * twop};
     // hanging test for an absolute fine lattice point: is it on the closure of an unrefined base cell?  Returns that cell.
     auto unrefined_neighbour = [&](const int64_t F[3], int64_t K[3]) -> bool {
+        // a point strictly inside the refined box has refined cells all around it (the refined region is a box)
+        if (F[0] > (int64_t)lo[0] * twop && F[0] < (int64_t)hi[0] * twop && F[1] > (int64_t)lo[1] * twop && F[1] < (int64_t)hi[1] * twop &&
+            F[2] > (int64_t)lo[2] * twop && F[2] < (int64_t)hi[2] * twop)
+            return false;
         int64_t cand[3][2];
         int nc[3];
         for (int d = 0; d < 3; ++d) {
@@ -260,6 +277,7 @@ int HangMesh::build()
         }
     }
 
+    lap("local indices + flags");
     // ---- hanging rows needed by this rank (H2): unique hanging DoFs of the local cells, sorted by global index ----
     struct Row { uint32_t g; int64_t F[3]; };
     std::vector<Row> rows;
@@ -283,8 +301,10 @@ int HangMesh::build()
         if (!unrefined_neighbour(r.F, K)) return fail(B200FE_ERR_INVALID_ARG, "hanging mesh: internal error (row without an unrefined neighbour)");
         const double *w0 = &W[(size_t)(r.F[0] - K[0] * twop) * nm], *w1 = &W[(size_t)(r.F[1] - K[1] * twop) * nm], *w2 = &W[(size_t)(r.F[2] - K[2] * twop) * nm];
         std::vector<std::pair<uint32_t, double>> ent;
-        for (int cc = 0; cc < nm; ++cc)
-            for (int b = 0; b < nm; ++b)
+        for (int cc = 0; cc < nm; ++cc) {
+            if (w2[cc] == 0.0) continue;  // (unit rows of W on a face / edge: a zero factor makes the product vanish)
+            for (int b = 0; b < nm; ++b) {
+                if (w1[b] == 0.0) continue;
                 for (int a = 0; a < nm; ++a) {
                     const double w = w0[a] * w1[b] * w2[cc];
                     if (!(std::fabs(w) > 1e-14)) continue;
@@ -294,11 +314,14 @@ int HangMesh::build()
                     if (g == kNone) return fail(B200FE_ERR_INVALID_ARG, "hanging mesh: internal error (unnumbered parent)");
                     ent.emplace_back(g, w);
                 }
+            }
+        }
         std::sort(ent.begin(), ent.end());
         for (auto &e : ent) { col_g.push_back(e.first); wgt.push_back(e.second); }
         row_ptr_g.push_back((uint32_t)col_g.size());
     }
 
+    lap("hanging rows");
     // ---- ghosts: non-owned DoFs of the local cells and non-owned parents of the rows ----------------------------
     std::vector<uint64_t> cand;
     for (uint32_t g : gidx)
@@ -320,10 +343,17 @@ int HangMesh::build()
 
     dof_indices.resize(gidx.size());
     std::vector<uint32_t> cons;
-    for (size_t i = 0; i < gidx.size(); ++i) {
-        const uint32_t loc = local_of(gidx[i]);
-        dof_indices[i] = flag[i] == 1 ? B200FE_INVALID_INDEX : loc;
-        if (flag[i] != 0 && loc < n_owned) cons.push_back(loc);
+#pragma omp parallel
+    {
+        std::vector<uint32_t> my_cons;
+#pragma omp for schedule(static) nowait
+        for (int64_t i = 0; i < (int64_t)gidx.size(); ++i) {
+            const uint32_t loc = local_of(gidx[i]);
+            dof_indices[i] = flag[i] == 1 ? B200FE_INVALID_INDEX : loc;
+            if (flag[i] != 0 && loc < n_owned) my_cons.push_back(loc);
+        }
+#pragma omp critical
+        cons.insert(cons.end(), my_cons.begin(), my_cons.end());
     }
     std::sort(cons.begin(), cons.end());
     cons.erase(std::unique(cons.begin(), cons.end()), cons.end());
@@ -335,6 +365,7 @@ int HangMesh::build()
     for (size_t i = 0; i < col_g.size(); ++i) hang_col[i] = local_of(col_g[i]);
     hang_w.swap(wgt);
 
+    lap("ghosts + local table");
     // ---- face-structured form of the same rows ------------------------------------------------------------------
     // Every hanging DoF of a box-refined mesh lies on a face shared by an unrefined cell K and a refined cell; its
     // (2p+1)^2 fine nodes are the tensor-product interpolation W (x) W of the (p+1)^2 coarse face nodes.  Blocks in
@@ -399,6 +430,7 @@ int HangMesh::build()
         }
         if (n_claimed != rows.size()) return fail(B200FE_ERR_INVALID_ARG, "hanging mesh: internal error (%zu of %zu hanging DoFs lie on a hanging face)", n_claimed, rows.size());
     }
+    lap("face blocks");
     return B200FE_OK;
 }
 
