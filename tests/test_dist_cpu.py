@@ -127,6 +127,21 @@ def test_overlap_permutation_splits_cells():
     assert n1 > 0
 
 
+@pytest.mark.parametrize("one_sided", [False, True])
+def test_overlap_permutation_from_per_cell_flags_equals_the_table_path(one_sided):
+    """The operator computes the "touches a ghost DoF" flags on the device from the device-side index table (signed view:
+    INVALID = -1, valid indices < 2^31) and hands them to overlap_permutation: same permutation as from the host table."""
+    import benchmarks_b200 as b
+    for rank in range(3):
+        mesh = b.BoxMesh((2, 1, 1), 2, 3, n_ranks=3, rank=rank)
+        idx = mesh.dof_indices
+        ref = b.overlap_permutation(idx, mesh.n_owned, one_sided=one_sided)
+        signed = torch.from_numpy(idx).view(torch.int32)              # what LaplaceOperator does on the device tensor
+        touches = (signed >= mesh.n_owned).any(dim=1).numpy()
+        got = b.overlap_permutation(None, mesh.n_owned, one_sided=one_sided, touches=touches)
+        assert np.array_equal(ref[0], got[0]) and ref[1:] == got[1:]
+
+
 def _worker_hanging(rank, world, port, sub, nref, p, lo, hi, q):
     """Same emulation on a two-level mesh with hanging nodes: the ghost set must also carry the parents of the
     hanging DoFs, and distribute / condense run between the exchanges (the sequence of b200fe_op_vmult)."""
